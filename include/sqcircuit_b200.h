@@ -1,0 +1,208 @@
+/*
+ * sqcircuit_b200 — C ABI of the B200-native diagonalisation hot path.
+ *
+ * The reference (stanfordLINQS/SQcircuit) is pure Python; its hot path is
+ *   Circuit._build_op_memory / _build_exp_ops        circuit.py:1621-1714   (operators)
+ *   Circuit._get_LC_hamil / _get_inductive_hamil /
+ *   Circuit.hamiltonian                              circuit.py:1731-1829, 2147-2164
+ *   Circuit._diag_np  (scipy.sparse.linalg.eigs)     circuit.py:1938-1986
+ *   Circuit.matrix_elements / dec_rate               circuit.py:2397-2647
+ *   Sweep.sweepFlux / sweepCharge                    sweep.py:71-148
+ * Each entry point below names the reference code it replaces.  A maintainer
+ * binds them with ctypes; no torch types cross this ABI:
+ * plain device pointers, sizes and a cudaStream_t passed as void*.
+ *
+ * Conventions
+ *   - complex128 everywhere, interleaved (re, im) doubles  == torch.complex128.
+ *   - a "block" is a set of state vectors per sweep point:  data[b][v][n],
+ *     n fastest (n < N = prod(mode dims), reference Kronecker order: mode 0
+ *     slowest), v < count(b), b < B.  See sqc_block_t.
+ *   - small matrices per sweep point are row-major with a fixed leading dim.
+ *   - every function returns 0 on success, a cudaError_t (>0) on a CUDA
+ *     failure or a negative SQC_E* code on invalid arguments.
+ */
+#ifndef SQCIRCUIT_B200_H
+#define SQCIRCUIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQC_MAX_MODES 8
+#define SQC_MAX_TERMS 16      /* junction-like terms (distinct rows of W) */
+#define SQC_EINVAL   (-1)
+#define SQC_ELIMIT   (-2)
+
+/* A batch of state-vector blocks living in one allocation. */
+typedef struct {
+    void*          ptr;        /* device, complex128 */
+    int64_t        stride_b;   /* complex elements between consecutive sweep points */
+    const int32_t* off;        /* device[B] first vector index per point, or NULL (0) */
+    const int32_t* cnt;        /* device[B] number of vectors per point, or NULL (cnt_fixed) */
+    int32_t        cnt_fixed;  /* count when cnt == NULL; always the maximum count */
+} sqc_block_t;
+
+/* Tensor-product space of the truncated modes (circuit.py:1340-1379). */
+typedef struct {
+    int32_t n_modes;
+    int32_t dims[SQC_MAX_MODES];      /* m_i (charge modes: 2*trunc-1) */
+    int32_t harmonic[SQC_MAX_MODES];  /* 1: Fock basis, 0: charge basis */
+} sqc_space_t;
+
+/* Potential part of a Hermitian circuit operator, expressed in the basis where
+ * every harmonic mode is rotated to the eigenbasis of its truncated (a + a^dag)
+ * ("x basis"; displacement operators D(alpha), alpha imaginary, are diagonal
+ * there) and charge modes stay in the charge basis:
+ *
+ *   (P z)(i) = [ g0(b) + sum_m g_m(b) lam_m[i_m] + diag(i) ] z(i)
+ *            + sum_t  a_t(b) ph_t(i) z(i - sh_t) + conj(a_t(b) ph_t(i)) z(i + sh_t)
+ *   ph_t(i)  = prod_{m harmonic} etab[t][m][i_m],      sh_t = integer shift on charge modes
+ *
+ * This is sum_j -EJ_j cos(phi_j) plus the external-flux inductor terms of
+ * Circuit._get_inductive_hamil (circuit.py:1788-1829) for a_t = -EJ e^{i phi_ext}/2,
+ * and the cos/sin/sin_half operators of the noise code for other a_t. */
+typedef struct {
+    int32_t        n_terms;
+    int32_t        shift[SQC_MAX_TERMS][SQC_MAX_MODES]; /* per-mode index shift (charge modes) */
+    const double*  lam;        /* device[sum dims]  x-basis eigenvalues per mode (0 for charge) */
+    const void*    etab;       /* device complex [(B or 1)][n_terms][sum dims] */
+    int64_t        etab_stride_b; /* 0 when shared by all sweep points */
+    const double*  g;          /* device[B][1 + n_modes]  linear coefficients */
+    const void*    a;          /* device complex [B][n_terms] */
+    const double*  diag;       /* optional device[(B or 1)][N] extra real diagonal, or NULL */
+    int64_t        diag_stride_b;
+} sqc_potential_t;
+
+/* ---- library ---------------------------------------------------------- */
+int         sqc_abi_version(void);
+const char* sqc_error_string(int code);
+/* number of kernels launched by this library since load (bench.py gpu_launches) */
+int64_t     sqc_launch_count(void);
+
+/* ---- (1) operator construction ---------------------------------------- */
+/* x-basis of one harmonic mode: eigen-decomposition of the truncated a + a^dag
+ * (real symmetric tridiagonal, m x m).  Replaces qt.displace(N, alpha).expm()
+ * (circuit.py:1707-1708): D(i s) = V diag(exp(i s lam)) V^T.
+ * V is row-major V[n][i] = <Fock n | x_i>, lam ascending.  m <= 112. */
+int sqc_xbasis(int32_t m, double* V, double* lam, void* stream);
+
+/* Phase tables etab[t][off_m + i] = exp(i * s[t][m] * lam_m[i]) for harmonic modes
+ * (1 for charge modes).  s = phi_zp_m * wTrans[t][m]  (circuit.py:1603-1619).
+ * s: device[(B or 1)][n_terms][n_modes]. */
+int sqc_phase_tables(const sqc_space_t* sp, int32_t n_terms, const double* lam,
+                     const double* s, int64_t s_stride_b, void* etab,
+                     int64_t etab_stride_b, int32_t B, void* stream);
+
+/* Diagonal of the LC Hamiltonian (circuit.py:1731-1757) in the Fock/charge basis:
+ *   d(i) = sum_{m harm} omega_m i_m + sum_{m<=m' charge} q[m][m'] (n_m - ng_m)(n_m' - ng_m')
+ * omega: device[(B or 1)][n_modes], q: device[(B or 1)][n_modes][n_modes] (upper triangle,
+ * diagonal already halved as in _get_quadratic_cInvTrans, charge unit (2e)^2/hbar folded in),
+ * ng: device[(B or 1)][n_modes].  out: device[(B or 1)][N]. */
+int sqc_lc_diagonal(const sqc_space_t* sp, const double* omega, const double* q,
+                    const double* ng, int64_t param_stride_b, double* out,
+                    int32_t B_out, void* stream);
+
+/* ---- (2) matrix-free operator apply ------------------------------------ */
+/* Y = (accumulate ? Y : 0) + diag .* X */
+int sqc_diag_mul(sqc_block_t X, sqc_block_t Y, const double* diag, int64_t diag_stride_b,
+                 int64_t N, int32_t B, int32_t accumulate, void* stream);
+
+/* Mode-wise contraction  Z[.., i, ..] = sum_k Mat[i][k] X[.., k, ..]  (transpose: Mat[k][i])
+ * along mode `mode` of every vector in the block; optional epilogue
+ * Z += ediag .* EX (used to add the LC diagonal on the way back to the Fock basis).
+ * Mat: device[(B or 1)][m][m] real.  In-place (Z == X) is allowed.
+ * impl: 0 = FP64 tensor-core (DMMA) kernel, 1 = plain FP64 SIMT kernel. */
+int sqc_mode_transform(const sqc_space_t* sp, int32_t mode, const double* Mat,
+                       int64_t mat_stride_b, int32_t transpose, sqc_block_t X, sqc_block_t Z,
+                       const double* ediag, int64_t ediag_stride_b, sqc_block_t EX,
+                       int32_t B, int32_t impl, void* stream);
+
+/* Z = P X with P as documented at sqc_potential_t (X, Z in the x/charge basis). */
+int sqc_potential_apply(const sqc_space_t* sp, const sqc_potential_t* pot, sqc_block_t X,
+                        sqc_block_t Z, int32_t B, void* stream);
+
+/* Y = (accumulate ? Y : 0) + c_dn(b) * (a_m X) + c_up(b) * (a_m^dag X) on harmonic mode m
+ * (charge / flux operators of harmonic modes, circuit.py:1471-1524).  c_*: device complex[B]. */
+int sqc_ladder_apply(const sqc_space_t* sp, int32_t mode, const void* c_dn, const void* c_up,
+                     sqc_block_t X, sqc_block_t Y, int32_t B, int32_t accumulate, void* stream);
+
+/* ---- (3) batched block-Davidson building blocks ------------------------- */
+/* C[b][i][j] = sum_n conj(A[b][i][n]) Bm[b][j][n]    (Rayleigh-Ritz projections, Gram
+ * matrices; FP64 tensor cores).  C: device complex [B][ldr][ldc] row-major, rows >= count(A)
+ * and columns >= count(Bm) are written as zero up to (A.cnt_fixed, Bm.cnt_fixed).
+ * work: device scratch of sqc_gram_work_bytes() bytes (split-N partial sums), or NULL when
+ * that returns 0.  impl: 0 = DMMA, 1 = SIMT reference. */
+int64_t sqc_gram_work_bytes(int32_t B, int32_t na_max, int32_t nb_max, int64_t N);
+int sqc_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int32_t B, void* C, int32_t ldr,
+             int32_t ldc, void* work, int32_t impl, void* stream);
+
+/* Out[b][j][n] (op)= sum_i Cf[b][j][i] A[b][i][n],  i < count(A), j < count(Out);
+ * op: 0 assign, 1 subtract from Out.  Cf: device complex [B][ldr][ldc]; the coefficient of
+ * A_i in Out_j is Cf[j][i] (trans = 0) or Cf[i][j] (trans = 1). */
+int sqc_block_update(sqc_block_t A, const void* Cf, int32_t ldr, int32_t ldc, int32_t trans,
+                     sqc_block_t Out, int64_t N, int32_t B, int32_t op, void* stream);
+
+/* In-place T[b][j][n] <- sum_i Cq[b][j][i] T[b][i][n], i < count(T) (<= 16), j < nout[b]. */
+int sqc_block_rightmul(sqc_block_t T, const void* Cq, int32_t ldr, int32_t ldc,
+                       const int32_t* nout, int64_t N, int32_t B, void* stream);
+
+/* Batched Hermitian eigensolver (parallel cyclic Jacobi, one CTA per matrix).
+ * A: device complex [B][ld][ld] (read only; full Hermitian storage), n: device[B] sizes or
+ * NULL (n_fixed).  w: device[B][ld] ascending eigenvalues (entries >= n set to +inf),
+ * Zt: device complex [B][ld][ld], Zt[j][i] = component i of eigenvector j.  ld <= 112. */
+int sqc_heev(const void* A, const int32_t* n, int32_t n_fixed, int32_t ld, double* w, void* Zt,
+             int32_t B, void* stream);
+
+/* rn2[b][j] = || HX_j - theta[b][j] X_j ||^2,  j < p. */
+int sqc_residual_norms(sqc_block_t X, sqc_block_t HX, const double* theta, int32_t ld_theta,
+                       int64_t N, int32_t B, double* rn2, void* stream);
+
+/* Davidson bookkeeping for one iteration (one small CTA per sweep point); see
+ * sqcircuit_b200/eigensolver.py for the algorithm.  All arrays device, per point. */
+typedef struct {
+    int32_t  p, k, mmax, ldg;   /* block size, wanted pairs, max basis, leading dim of G/Cf */
+    double   tol_rel;           /* residual tolerance relative to max(|theta_0..k-1|, floor_abs) */
+    double   tol_abs_floor;
+    int32_t* msz;               /* [B] basis size */
+    int32_t* nact;              /* [B] number of new (active) vectors */
+    int32_t* act;               /* [B][p] Ritz index of each active vector */
+    int32_t* restart;           /* [B] restart flag for this iteration */
+    int32_t* done;              /* [B] converged flag */
+    int32_t* n_not_done;        /* [1] counter (zeroed by the callee) */
+    double*  theta;             /* [B][ldg] Ritz values */
+    double*  rn2;               /* [B][p] squared residual norms */
+    double*  resmax;            /* [B] max relative residual over the k wanted pairs */
+    double*  den_floor;         /* [B] preconditioner denominator floor */
+    void*    G;                 /* [B][ldg][ldg] projected Hamiltonian */
+} sqc_davidson_state_t;
+
+int sqc_davidson_decide(const sqc_davidson_state_t* st, int32_t B, void* stream);
+
+/* restart: where restart[b], V[b][0..p) <- X[b], W[b][0..p) <- HX[b]. */
+int sqc_restart_copy(sqc_block_t X, sqc_block_t HX, sqc_block_t V, sqc_block_t W,
+                     const int32_t* restart, int64_t N, int32_t B, void* stream);
+
+/* T[b][jj] = (HX_a - theta_a X_a) / clamp(d - theta_a),  a = act[b][jj], jj < nact[b];
+ * T addresses the free tail of the basis (T.off = msz). d: device[(B or 1)][N]. */
+int sqc_precond_residual(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                         int32_t ld_theta, const int32_t* act, int32_t ld_act,
+                         const double* d, int64_t d_stride_b, const double* den_floor,
+                         int64_t N, int32_t B, void* stream);
+
+/* SVQB coefficients from the Gram matrix S = T^H T of the new block:
+ * Cq[j][i] = D_i U_ij sigma_j^-1/2 over directions with sigma_j > drop * sigma_max;
+ * nact[b] <- number kept; mtot[b] <- msz[b] + nact[b] when both pointers are given.
+ * S: [B][ld][ld] (read only), Cq: [B][ld][ld], ld <= 16. */
+int sqc_svqb_coeffs(const void* S, int32_t ld, int32_t* nact, double drop, void* Cq,
+                    const int32_t* msz, int32_t* mtot, int32_t B, void* stream);
+
+/* G[b][i][msz+j] = S[b][i][j], G[b][msz+j][i] = conj(.), i < msz+nact, j < nact; msz += nact. */
+int sqc_davidson_insert(const sqc_davidson_state_t* st, const void* S, int32_t ldr, int32_t ldc,
+                        int32_t B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQCIRCUIT_B200_H */

@@ -678,14 +678,23 @@ def transmon():
     return OCircuit({(0, 1): [OCap(20, 'GHz'), OJJ(15.0, 'GHz', A=1e-7)]})
 
 
-def subspace_overlap(v_ref: np.ndarray, v: np.ndarray, w_ref: np.ndarray, rel_gap=1e-7):
+def subspace_overlap(v_ref: np.ndarray, v: np.ndarray, w_ref: np.ndarray, rel_gap=1e-7,
+                     w_next=None):
     """Phase/degeneracy-invariant eigenvector comparison.
 
     For each reference eigenvector i, the squared norm of its projection on the
     span of the computed vectors whose reference eigenvalues lie in the same
-    (near-)degenerate cluster.  Returns the minimum over i.
+    (near-)degenerate cluster.  Returns the minimum over i.  If ``w_next`` (the first
+    eigenvalue that was NOT requested) is given and it is within ``rel_gap`` of the last
+    requested one, the trailing cluster is cut by the request and is skipped.
     """
     k = v_ref.shape[1]
+    if w_next is not None:
+        sc = max(1.0, float(np.max(np.abs(w_ref))))
+        while k > 1 and abs(w_next - w_ref[k - 1]) <= rel_gap * sc:
+            w_next = w_ref[k - 1]
+            k -= 1
+        v_ref, v, w_ref = v_ref[:, :k], v[:, :k], w_ref[:k]
     scale = max(1.0, float(np.max(np.abs(w_ref))))
     clusters = []
     start = 0

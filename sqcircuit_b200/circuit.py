@@ -1,0 +1,292 @@
+"""Circuit: the reference's user-facing class for the diagonalisation path, backed by the
+batched GPU solver.
+
+API parity (reference circuit.py): ``Circuit(elements, flux_dist)``, ``set_trunc_nums``,
+``set_charge_offset``, ``set_charge_noise``, ``trunc_nums``, ``truncate_circuit``, ``diag``,
+``efreqs``, ``evecs``, ``hamiltonian``, ``matrix_elements``, ``dec_rate``,
+``check_convergence``, ``update`` and the transformation attributes (``S, R, C, L, W, B,
+wTrans, cInvTrans, lTrans, omega, loops``).  New: ``sweep_diag`` solves all points of a flux /
+gate-charge sweep in one batched call (what ``Sweep.sweepFlux`` loops over in the reference).
+"""
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import units as unt
+from .eigensolver import DENSE_MAX, solve_davidson, solve_dense
+from .elements import Capacitor, Charge, Inductor, Junction, Loop
+from .exceptions import CircuitStateError
+from .noise_ops import SweepNoise
+from .operators import CircuitOperators, HamiltonianOperator
+from .settings import get_device, get_optim_mode
+from .topology import assemble, transform
+
+_KERNELS = {}
+
+
+def default_kernels(device=None):
+    """The CUDA kernel backend for ``device`` (raises if the extension is not built)."""
+    from .kernels import Kernels
+    device = device or get_device()
+    if device not in _KERNELS:
+        _KERNELS[device] = Kernels(device)
+    return _KERNELS[device]
+
+
+class Ket(np.ndarray):
+    """Column state vector with the few Qobj-like accessors the reference's users touch."""
+
+    def __new__(cls, data, dims=None):
+        obj = np.asarray(data, dtype=complex).reshape(-1, 1).view(cls)
+        obj.dims = dims
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.dims = getattr(obj, 'dims', None)
+
+    def full(self):
+        return np.asarray(self)
+
+    def dag(self):
+        return np.asarray(self).conj().T
+
+
+@dataclass
+class SweepResult:
+    efreqs: torch.Tensor        # [B][k] in the package frequency unit (GHz by default)
+    evals_rad: torch.Tensor     # [B][k] rad/s
+    evecs: torch.Tensor         # [B][k][N]
+    iterations: int
+    converged: bool
+    resmax: torch.Tensor
+    noise: SweepNoise = None
+
+    def matrix_elements(self, ctype, nodes, states):
+        return self.noise.matrix_elements(ctype, nodes, states)
+
+    def dec_rate(self, dec_type, states, total=True):
+        return self.noise.dec_rate(dec_type, states, total)
+
+
+class Circuit:
+    def __init__(self, elements, flux_dist='junctions', kernels=None):
+        self.elements = OrderedDict((k, elements[k]) for k in elements.keys())
+        if flux_dist not in ('junctions', 'inductors', 'all'):
+            raise ValueError("flux_dist option must either be 'junctions', 'inductors', or 'all'.")
+        self.flux_dist = flux_dist
+        self._kern = kernels
+        self._analyse()
+        self.charge_islands = {i: Charge() for i in range(self.n) if self._is_charge_mode(i)}
+        self.m: List[int] = []
+        self.ms: List[int] = []
+        self._ops = None
+        self._efreqs = np.array([])
+        self._evecs = []
+        self._last = None
+
+    # ---- topology ---------------------------------------------------------------------------
+    def _analyse(self):
+        top = assemble(self.elements, self.flux_dist)
+        top = transform(top, remove_uncoupled=not get_optim_mode())
+        self._top = top
+        self.loops = top.loops
+        self.C, self.L, self.W, self.B = top.C, top.L, top.W, top.B
+        self.S, self.R = top.S, top.R
+        self.cInvTrans, self.lTrans, self.wTrans = top.cInvTrans, top.lTrans, top.wTrans
+        self.omega = top.omega
+        self.n = top.n
+        self.num_jun_without_ind = top.n_jj_without_ind
+        self.partial_mats = top.partial_mats
+        self.elem_keys = {Inductor: top.ind_keys, Junction: top.jj_keys}
+
+    def update(self):
+        """Re-read element values after in-place changes (circuit.py:397-440)."""
+        self._analyse()
+        self._ops = None
+        self._efreqs = np.array([])
+        self._evecs = []
+        self._last = None
+
+    def _is_charge_mode(self, i):
+        if i >= self.n:
+            raise ValueError(f'The circuit only has {self.n} modes!')
+        return self.omega[i] == 0
+
+    # ---- truncation / offsets (circuit.py:1340-1422) ------------------------------------------
+    def set_trunc_nums(self, nums):
+        if not isinstance(nums, list):
+            raise ValueError('The input must be be a python list')
+        if len(nums) != self.n:
+            raise ValueError('The number of modes (length of the input) must be equal to the number of nodes.')
+        self.m = [2 * nums[i] - 1 if self._is_charge_mode(i) else nums[i] for i in range(self.n)]
+        self.ms = [x for x in self.m if x != 1]
+        self._ops = None
+
+    @property
+    def trunc_nums(self):
+        return [int((self.m[i] + 1) / 2) if self._is_charge_mode(i) else self.m[i] for i in range(self.n)]
+
+    def truncate_circuit(self, K):
+        if not isinstance(K, int):
+            raise ValueError('The total truncation number must be an integer.')
+        if K < 1:
+            raise ValueError('The total truncation number must be >=1.')
+        avg = K ** (1 / len(self.omega))
+        nums = [int(np.floor(avg)) if self.omega[i] != 0 else int(np.floor((avg + 1) / 2))
+                for i in range(len(self.omega))]
+        self.set_trunc_nums(nums)
+        return nums
+
+    def set_charge_offset(self, mode, ng):
+        if not isinstance(mode, int):
+            raise ValueError('Mode number should be an integer.')
+        if mode - 1 not in self.charge_islands:
+            raise ValueError('The specified mode is not a charge mode.')
+        self.charge_islands[mode - 1].set_offset(ng)
+
+    def set_charge_noise(self, mode, amp):
+        if not isinstance(mode, int):
+            raise ValueError('The mode number should be an integer.')
+        if mode - 1 not in self.charge_islands:
+            raise ValueError('The specified mode is not a charge mode.')
+        self.charge_islands[mode - 1].set_noise(amp)
+
+    # ---- GPU plan ---------------------------------------------------------------------------------
+    def _operators(self):
+        if len(self.m) == 0:
+            raise CircuitStateError('Please specify the truncation number for each mode.')
+        if self._ops is None:
+            kern = self._kern or default_kernels()
+            self._ops = CircuitOperators(kern, self._top, self.m)
+        return self._ops
+
+    def _current_point(self):
+        lv = np.array([[float(np.asarray(_to_float(lp.value()))) for lp in self.loops]], dtype=float) \
+            if self.loops else np.zeros((1, 0))
+        ng = np.array([[float(self.charge_islands[i].value()) if i in self.charge_islands else 0.0
+                        for i in range(self.n)]], dtype=float)
+        return lv, ng
+
+    def sweep_diag(self, n_eig, loop_fluxes: Optional[Dict] = None,
+                   charge_offsets: Optional[Dict[int, Sequence[float]]] = None, tol=1e-9,
+                   block_size=None, max_basis=None, maxit=300, stats=None) -> SweepResult:
+        """Diagonalise at every point of a sweep in one batched GPU solve.
+
+        loop_fluxes: {Loop: array[B]} external fluxes in units of Phi0 (as Loop.set_flux);
+        charge_offsets: {mode (1-based): array[B]} gate charges (as set_charge_offset).
+        Parameters not listed keep their current value.  Arrays must share the length B.
+        """
+        if not isinstance(n_eig, int):
+            raise ValueError('n_eig (number of eigenvalues) should be an integer.')
+        ops = self._operators()
+        lv0, ng0 = self._current_point()
+        sizes = [len(v) for v in (loop_fluxes or {}).values()] + [len(v) for v in (charge_offsets or {}).values()]
+        B = sizes[0] if sizes else 1
+        if any(s != B for s in sizes):
+            raise ValueError('all sweep arrays must have the same length')
+        lv = np.repeat(lv0, B, axis=0)
+        for lp, vals in (loop_fluxes or {}).items():
+            lv[:, self.loops.index(lp)] = 2 * np.pi * np.asarray(vals, dtype=float)
+        if charge_offsets:
+            ng = np.repeat(ng0, B, axis=0)
+            for mode, vals in charge_offsets.items():
+                if mode - 1 not in self.charge_islands:
+                    raise ValueError('The specified mode is not a charge mode.')
+                ng[:, mode - 1] = np.asarray(vals, dtype=float)
+        else:
+            ng = ng0
+        hop = HamiltonianOperator(ops, lv, ng)
+        kern = ops.kern
+        if ops.N <= DENSE_MAX:
+            res = solve_dense(kern, hop, B, ops.N, n_eig)
+        else:
+            res = solve_davidson(kern, hop, B, ops.N, n_eig, hop.diag, p=block_size, mmax=max_basis,
+                                 tol=tol, maxit=maxit, stats=stats)
+            if not res.converged:
+                raise RuntimeError(f'batched Davidson did not converge in {maxit} iterations '
+                                   f'(worst relative residual {float(res.resmax.max()):.2e})')
+        out = SweepResult(res.evals / (2 * np.pi * unt.get_unit_freq()), res.evals, res.evecs,
+                          res.iterations, res.converged, res.resmax)
+        out.noise = SweepNoise(kern, ops, hop, res.evals, res.evecs, self)
+        return out
+
+    # ---- single-point API of the reference -----------------------------------------------------------
+    def diag(self, n_eig):
+        """circuit.py:2016-2049."""
+        if len(self.m) == 0:
+            raise CircuitStateError('Please specify the truncation number for each mode.')
+        if not isinstance(n_eig, int):
+            raise ValueError('n_eig (number of eigenvalues) should be an integer.')
+        res = self.sweep_diag(n_eig)
+        self._last = res
+        ev = res.evecs[0]
+        if get_optim_mode():
+            self._efreqs = res.evals_rad[0]
+            self._evecs = ev
+            return res.efreqs[0], ev
+        dims = [self.ms, len(self.ms) * [1]]
+        self._efreqs = res.evals_rad[0].cpu().numpy()
+        vecs = ev.cpu().numpy()
+        self._evecs = [Ket(vecs[i], dims) for i in range(vecs.shape[0])]
+        return self._efreqs / (2 * np.pi * unt.get_unit_freq()), self._evecs
+
+    @property
+    def efreqs(self):
+        if len(self._efreqs) == 0:
+            raise CircuitStateError('Please diagonalize the circuit first.')
+        return self._efreqs / (2 * np.pi * unt.get_unit_freq())
+
+    @property
+    def evecs(self):
+        if len(self._evecs) == 0:
+            raise CircuitStateError('Please diagonalize the circuit first.')
+        return self._evecs
+
+    def hamiltonian(self):
+        """Dense Hamiltonian matrix (rad/s) at the current parameter point, produced by applying
+        the matrix-free operator to the identity (debug / parity helper)."""
+        ops = self._operators()
+        lv, ng = self._current_point()
+        hop = HamiltonianOperator(ops, lv, ng)
+        from .kernels import BlockView
+        N = ops.N
+        eye = torch.eye(N, dtype=torch.complex128, device=ops.device).unsqueeze(0).contiguous()
+        out = torch.empty_like(eye)
+        hop.apply(BlockView(eye), BlockView(out))
+        return out[0].cpu().numpy().T
+
+    def matrix_elements(self, ctype, nodes, states):
+        if self._last is None:
+            raise CircuitStateError('Please diagonalize the circuit first.')
+        if ctype not in ('capacitive', 'inductive'):
+            raise ValueError("The coupling type must be either 'capacitive' or 'inductive'.")
+        return complex(self._last.matrix_elements(ctype, nodes, states)[0])
+
+    def dec_rate(self, dec_type, states, total=True):
+        if self._last is None:
+            raise CircuitStateError('Please diagonalize the circuit first.')
+        return float(self._last.dec_rate(dec_type, states, total)[0])
+
+    def check_convergence(self, eig_vec_idx=1, t=10, threshold=1e-5):
+        """circuit.py:2090-2118."""
+        if self._last is None:
+            raise CircuitStateError('Must call circuit.diag before testing convergence.')
+        v = self._last.evecs[0, eig_vec_idx].cpu().numpy().reshape(self.m)
+        sub = v[(slice(-t),) * len(self.m)]
+        eps = 1 - np.sum(np.abs(sub) ** 2)
+        return (eps < threshold), eps
+
+    def coord_transform(self, var_type):
+        var_type = var_type.lower()
+        if var_type == 'charge':
+            return np.linalg.inv(self.R)
+        if var_type == 'flux':
+            return np.linalg.inv(self.S)
+        raise ValueError("The input must be either 'charge' or 'flux'.")
+
+
+def _to_float(v):
+    return v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v

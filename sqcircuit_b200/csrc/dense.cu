@@ -1,0 +1,500 @@
+// Tall-skinny batched linear algebra of the block-Davidson solver:
+//   Gram / Rayleigh-Ritz projections (FP64 tensor cores), basis updates,
+//   residual norms, preconditioned residuals, restart copies.
+// Replaces the ARPACK call in Circuit._diag_np (reference circuit.py:1962-1969).
+#include "common.cuh"
+
+long long g_sqc_launches = 0;
+
+// =====================================================================================
+// Gram:  C[b][i][j] = sum_n conj(A[b][i][n]) B[b][j][n]
+//
+// Real formulation on the interleaved data (K index t runs over the 2N doubles of a vector):
+//   Re C = A_r . B_r^T           Im C = A_r . B'_r^T,   B'[2n] = Im b_n, B'[2n+1] = -Re b_n
+// so one DMMA B-fragment plus a lane-xor shuffle feeds both the real and the imaginary tile.
+// CTA = 4 warps; the warps split the K range of every staged chunk and each warp keeps all
+// (NAT x 2*NBT) 8x8 accumulator tiles; a final shared-memory reduction combines the warps.
+// =====================================================================================
+#define GRAM_THREADS 128
+#define GRAM_CH 32                  // complex elements per staged chunk
+#define GRAM_LD (2 * GRAM_CH + 4)   // doubles per smem row: 68 == 4 (mod 16) -> conflict-free frags
+
+template <int NAT, int NBT>
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, int nsplit, cplx* __restrict__ C,
+                 int ldr, int ldc, cplx* __restrict__ work) {
+    constexpr int NA = NAT * 8, NB = NBT * 8;
+    extern __shared__ double smem[];
+    double* sA[2] = {smem, smem + (NA + NB) * GRAM_LD};
+    double* sB[2] = {sA[0] + NA * GRAM_LD, sA[1] + NA * GRAM_LD};
+
+    const int b = blockIdx.x / nsplit, split = blockIdx.x % nsplit;
+    const int na = min(blk_count(A, b), NA), nb = min(blk_count(Bm, b), NB);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+    cplx* out = (nsplit == 1) ? C + (int64_t)b * ldr * ldc
+                              : work + ((int64_t)b * nsplit + split) * (NA * NB);
+    const int out_ld = (nsplit == 1) ? ldc : NB;
+    const int out_rows = (nsplit == 1) ? min(A.cnt_fixed, ldr) : NA;
+    const int out_cols = (nsplit == 1) ? min(Bm.cnt_fixed, ldc) : NB;
+
+    if (na == 0 || nb == 0) {
+        for (int e = tid; e < out_rows * out_cols; e += GRAM_THREADS)
+            out[(e / out_cols) * out_ld + (e % out_cols)] = cmake(0.0, 0.0);
+        return;
+    }
+    const cplx* a0 = blk_vec(A, b, 0, N);
+    const cplx* b0 = blk_vec(Bm, b, 0, N);
+
+    const int64_t nchunks = (N + GRAM_CH - 1) / GRAM_CH;
+    const int64_t c_lo = nchunks * split / nsplit, c_hi = nchunks * (split + 1) / nsplit;
+
+    double acc[NAT][2 * NBT][2];
+#pragma unroll
+    for (int i = 0; i < NAT; ++i)
+#pragma unroll
+        for (int j = 0; j < 2 * NBT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto stage = [&](int buf, int64_t chunk) {
+        const int64_t n0 = chunk * GRAM_CH;
+        // rows of A then rows of B; GRAM_CH complex (16 B) elements per row
+        for (int e = tid; e < (NA + NB) * GRAM_CH; e += GRAM_THREADS) {
+            const int r = e / GRAM_CH, c = e % GRAM_CH;
+            const bool isA = r < NA;
+            const int rr = isA ? r : r - NA;
+            double* dst = (isA ? sA[buf] : sB[buf]) + rr * GRAM_LD + 2 * c;
+            const bool valid = (n0 + c < N) && (isA ? rr < na : rr < nb);
+            if (valid) {
+                cp_async16(dst, (isA ? a0 : b0) + (int64_t)rr * N + n0 + c);
+            } else {
+                dst[0] = 0.0;
+                dst[1] = 0.0;
+            }
+        }
+        cp_async_commit();
+    };
+
+    if (c_lo < c_hi) stage(0, c_lo);
+    for (int64_t ch = c_lo; ch < c_hi; ++ch) {
+        const int buf = (int)((ch - c_lo) & 1);
+        if (ch + 1 < c_hi) {
+            stage(buf ^ 1, ch + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        // 2*GRAM_CH doubles = 16 k-steps of 4; warp w takes k-steps w, w+4, ...
+#pragma unroll
+        for (int ks = 0; ks < (2 * GRAM_CH / 4) / 4; ++ks) {
+            const int k0 = 4 * (warp + 4 * ks);
+            double af[NAT];
+#pragma unroll
+            for (int i = 0; i < NAT; ++i) af[i] = sA[buf][(8 * i + g) * GRAM_LD + k0 + t];
+#pragma unroll
+            for (int j = 0; j < NBT; ++j) {
+                const double bf = sB[buf][(8 * j + g) * GRAM_LD + k0 + t];
+                // primed fragment: element t of B' is  (t even) ? B[t+1] : -B[t-1]
+                double bp = __shfl_xor_sync(0xffffffffu, bf, 1);
+                bp = (t & 1) ? -bp : bp;
+#pragma unroll
+                for (int i = 0; i < NAT; ++i) {
+                    dmma884(acc[i][j][0], acc[i][j][1], af[i], bf);
+                    dmma884(acc[i][NBT + j][0], acc[i][NBT + j][1], af[i], bp);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // cross-warp reduction through shared memory: red[warp][row][2*NB]
+    double* red = smem;  // 4 * NA * 2NB doubles  <= staging size (checked on the host)
+#pragma unroll
+    for (int i = 0; i < NAT; ++i)
+#pragma unroll
+        for (int j = 0; j < 2 * NBT; ++j) {
+            double* p = red + ((warp * NA + 8 * i + g) * (2 * NB)) + 8 * j + 2 * t;
+            p[0] = acc[i][j][0];
+            p[1] = acc[i][j][1];
+        }
+    __syncthreads();
+    for (int e = tid; e < out_rows * out_cols; e += GRAM_THREADS) {
+        const int r = e / out_cols, c = e % out_cols;
+        double re = 0.0, im = 0.0;
+        if (r < NA && c < NB) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                re += red[(w * NA + r) * (2 * NB) + c];
+                im += red[(w * NA + r) * (2 * NB) + NB + c];
+            }
+        }
+        out[r * out_ld + c] = cmake(re, im);
+    }
+}
+
+__global__ void gram_reduce_kernel(const cplx* __restrict__ work, int nsplit, int NA, int NB,
+                                   cplx* __restrict__ C, int ldr, int ldc, int rows, int cols) {
+    const int b = blockIdx.x;
+    for (int e = threadIdx.x; e < rows * cols; e += blockDim.x) {
+        const int r = e / cols, c = e % cols;
+        double re = 0.0, im = 0.0;
+        if (r < NA && c < NB)
+            for (int s = 0; s < nsplit; ++s) {
+                const cplx v = work[((int64_t)b * nsplit + s) * (NA * NB) + r * NB + c];
+                re += v.x;
+                im += v.y;
+            }
+        C[(int64_t)b * ldr * ldc + r * ldc + c] = cmake(re, im);
+    }
+}
+
+// plain SIMT reference (one warp per output element); used by tests to cross-check the DMMA path
+__global__ void gram_ref_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, cplx* __restrict__ C,
+                                int ldr, int ldc) {
+    const int rows = min(A.cnt_fixed, ldr), cols = min(Bm.cnt_fixed, ldc);
+    const int b = blockIdx.x / (rows * cols);
+    const int e = blockIdx.x % (rows * cols);
+    const int i = e / cols, j = e % cols;
+    const int na = blk_count(A, b), nb = blk_count(Bm, b);
+    double re = 0.0, im = 0.0;
+    if (i < na && j < nb) {
+        const cplx* a = blk_vec(A, b, i, N);
+        const cplx* c = blk_vec(Bm, b, j, N);
+        cplx acc = cmake(0.0, 0.0);
+        for (int64_t n = threadIdx.x; n < N; n += blockDim.x) cfmac(acc, a[n], c[n]);
+        re = acc.x;
+        im = acc.y;
+    }
+    __shared__ double sr[32], si[32];
+    re = warp_sum(re);
+    im = warp_sum(im);
+    if ((threadIdx.x & 31) == 0) {
+        sr[threadIdx.x >> 5] = re;
+        si[threadIdx.x >> 5] = im;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0, m = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) {
+            r += sr[w];
+            m += si[w];
+        }
+        C[(int64_t)b * ldr * ldc + i * ldc + j] = cmake(r, m);
+    }
+}
+
+static int gram_nsplit(int B, int64_t N) {
+    // enough CTAs to fill 148 SMs x 3 resident CTAs, but never split below 8 chunks per CTA
+    int want = (148 * 3 + B - 1) / B;
+    int64_t nchunks = (N + GRAM_CH - 1) / GRAM_CH;
+    int64_t maxs = nchunks / 8 > 0 ? nchunks / 8 : 1;
+    if (want > maxs) want = (int)maxs;
+    if (want < 1) want = 1;
+    if (want > 64) want = 64;
+    return want;
+}
+static void gram_tiles(int na_max, int nb_max, int* nat, int* nbt) {
+    *nat = (na_max + 7) / 8;
+    if (*nat < 1) *nat = 1;
+    if (*nat > 2 && (*nat & 1)) ++*nat;  // instantiated: 1,2,4,6,8
+    if (*nat == 3) *nat = 4;
+    *nbt = nb_max > 8 ? 2 : 1;
+}
+
+extern "C" int64_t sqc_gram_work_bytes(int32_t B, int32_t na_max, int32_t nb_max, int64_t N) {
+    int nat, nbt;
+    gram_tiles(na_max, nb_max, &nat, &nbt);
+    int ns = gram_nsplit(B, N);
+    if (ns == 1) return 0;
+    return (int64_t)B * ns * (nat * 8) * (nbt * 8) * (int64_t)sizeof(cplx);
+}
+
+template <int NAT, int NBT>
+static int launch_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int B, cplx* C, int ldr, int ldc,
+                       cplx* work, cudaStream_t st) {
+    const int ns = gram_nsplit(B, N);
+    if (ns > 1 && !work) return SQC_EINVAL;
+    size_t stage_bytes = 2 * (size_t)(NAT * 8 + NBT * 8) * GRAM_LD * sizeof(double);
+    size_t red_bytes = 4 * (size_t)(NAT * 8) * (2 * NBT * 8) * sizeof(double);
+    size_t smem = stage_bytes > red_bytes ? stage_bytes : red_bytes;
+    auto kern = gram_dmma_kernel<NAT, NBT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<B * ns, GRAM_THREADS, smem, st>>>(A, Bm, N, ns, C, ldr, ldc, work);
+    SQC_LAUNCHED();
+    if (ns > 1) {
+        int rows = A.cnt_fixed < ldr ? A.cnt_fixed : ldr, cols = Bm.cnt_fixed < ldc ? Bm.cnt_fixed : ldc;
+        gram_reduce_kernel<<<B, 128, 0, st>>>(work, ns, NAT * 8, NBT * 8, C, ldr, ldc, rows, cols);
+        SQC_LAUNCHED();
+    }
+    return 0;
+}
+
+extern "C" int sqc_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int32_t B, void* C, int32_t ldr,
+                        int32_t ldc, void* work, int32_t impl, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || N <= 0 || A.cnt_fixed <= 0 || Bm.cnt_fixed <= 0) return SQC_EINVAL;
+    if (impl == 1) {
+        int rows = A.cnt_fixed < ldr ? A.cnt_fixed : ldr, cols = Bm.cnt_fixed < ldc ? Bm.cnt_fixed : ldc;
+        gram_ref_kernel<<<B * rows * cols, 128, 0, st>>>(A, Bm, N, (cplx*)C, ldr, ldc);
+        SQC_LAUNCHED();
+        return 0;
+    }
+    if (A.cnt_fixed > 64 || Bm.cnt_fixed > 16) return SQC_ELIMIT;
+    int nat, nbt;
+    gram_tiles(A.cnt_fixed, Bm.cnt_fixed, &nat, &nbt);
+#define GRAM_CASE(a, b_) \
+    if (nat == a && nbt == b_) return launch_gram<a, b_>(A, Bm, N, B, (cplx*)C, ldr, ldc, (cplx*)work, st)
+    GRAM_CASE(1, 1); GRAM_CASE(2, 1); GRAM_CASE(4, 1); GRAM_CASE(6, 1); GRAM_CASE(8, 1);
+    GRAM_CASE(1, 2); GRAM_CASE(2, 2); GRAM_CASE(4, 2); GRAM_CASE(6, 2); GRAM_CASE(8, 2);
+#undef GRAM_CASE
+    return SQC_ELIMIT;
+}
+
+// =====================================================================================
+// Block update:  Out[b][j][n] (op)= sum_i Cf[b][j][i] A[b][i][n]
+// One thread per n; NB accumulators in registers; coefficients broadcast from shared memory.
+// =====================================================================================
+#define UPD_THREADS 128
+
+template <int NB>
+__global__ void __launch_bounds__(UPD_THREADS)
+block_update_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, int ldc, int trans,
+                    sqc_block_t Out, int64_t N, int nchunk, int op) {
+    extern __shared__ double smem[];
+    cplx* sC = reinterpret_cast<cplx*>(smem);  // [na][NB]  (i-major so that j is contiguous)
+    const int b = blockIdx.x / nchunk;
+    const int64_t n = (int64_t)(blockIdx.x % nchunk) * UPD_THREADS + threadIdx.x;
+    const int na = blk_count(A, b), nb = min(blk_count(Out, b), NB);
+    if (nb == 0) return;
+    if (na == 0 && op == 1) return;
+    const cplx* cf = Cf + (int64_t)b * ldr * ldc;
+    for (int e = threadIdx.x; e < na * NB; e += UPD_THREADS) {
+        const int i = e / NB, j = e % NB;
+        sC[e] = (j < nb) ? (trans ? cf[i * ldc + j] : cf[j * ldc + i]) : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    if (n >= N) return;
+    cplx acc[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[j] = cmake(0.0, 0.0);
+    const cplx* a = blk_vec(A, b, 0, N) + n;
+#pragma unroll 2
+    for (int i = 0; i < na; ++i) {
+        const cplx av = a[(int64_t)i * N];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) cfma(acc[j], sC[i * NB + j], av);
+    }
+    cplx* o = blk_vec(Out, b, 0, N) + n;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        if (j < nb) {
+            if (op == 1) {
+                cplx v = o[(int64_t)j * N];
+                o[(int64_t)j * N] = csub(v, acc[j]);
+            } else {
+                o[(int64_t)j * N] = acc[j];
+            }
+        }
+    }
+}
+
+extern "C" int sqc_block_update(sqc_block_t A, const void* Cf, int32_t ldr, int32_t ldc, int32_t trans,
+                                sqc_block_t Out, int64_t N, int32_t B, int32_t op, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || N <= 0 || Out.cnt_fixed <= 0 || Out.cnt_fixed > 16 || A.cnt_fixed > 128) return SQC_EINVAL;
+    const int nchunk = (int)((N + UPD_THREADS - 1) / UPD_THREADS);
+    const int64_t grid = (int64_t)B * nchunk;
+    if (grid > 0x7fffffffLL) return SQC_ELIMIT;
+    const int nbm = Out.cnt_fixed;
+#define UPD_CASE(NBv)                                                                              \
+    if (nbm <= NBv) {                                                                              \
+        size_t smem = (size_t)(A.cnt_fixed > 0 ? A.cnt_fixed : 1) * NBv * sizeof(cplx);             \
+        auto kern = block_update_kernel<NBv>;                                                      \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return (int)e;                                                       \
+        kern<<<(unsigned)grid, UPD_THREADS, smem, st>>>(A, (const cplx*)Cf, ldr, ldc, trans, Out, N, nchunk, op); \
+        SQC_LAUNCHED();                                                                            \
+        return 0;                                                                                  \
+    }
+    UPD_CASE(4) UPD_CASE(8) UPD_CASE(12) UPD_CASE(16)
+#undef UPD_CASE
+    return SQC_ELIMIT;
+}
+
+// In-place right multiplication of a (<=16 vector) block by a small matrix.
+__global__ void __launch_bounds__(UPD_THREADS)
+block_rightmul_kernel(sqc_block_t T, const cplx* __restrict__ Cq, int ldr, int ldc,
+                      const int32_t* __restrict__ nout, int64_t N, int nchunk) {
+    __shared__ cplx sC[16 * 16];  // [j][i]
+    const int b = blockIdx.x / nchunk;
+    const int64_t n = (int64_t)(blockIdx.x % nchunk) * UPD_THREADS + threadIdx.x;
+    const int nin = min(blk_count(T, b), 16), no = min(nout[b], 16);
+    if (nin == 0) return;
+    const cplx* cq = Cq + (int64_t)b * ldr * ldc;
+    for (int e = threadIdx.x; e < 256; e += UPD_THREADS) {
+        const int j = e >> 4, i = e & 15;
+        sC[e] = (j < no && i < nin) ? cq[j * ldc + i] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    if (n >= N) return;
+    cplx* tp = blk_vec(T, b, 0, N) + n;
+    cplx tin[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tin[i] = (i < nin) ? tp[(int64_t)i * N] : cmake(0.0, 0.0);
+    for (int j = 0; j < nin; ++j) {   // vectors j >= nout are zeroed (dropped directions)
+        cplx acc = cmake(0.0, 0.0);
+        if (j < no) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cfma(acc, sC[j * 16 + i], tin[i]);
+        }
+        tp[(int64_t)j * N] = acc;
+    }
+}
+
+extern "C" int sqc_block_rightmul(sqc_block_t T, const void* Cq, int32_t ldr, int32_t ldc,
+                                  const int32_t* nout, int64_t N, int32_t B, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || N <= 0 || T.cnt_fixed <= 0 || T.cnt_fixed > 16 || !nout) return SQC_EINVAL;
+    const int nchunk = (int)((N + UPD_THREADS - 1) / UPD_THREADS);
+    const int64_t grid = (int64_t)B * nchunk;
+    if (grid > 0x7fffffffLL) return SQC_ELIMIT;
+    block_rightmul_kernel<<<(unsigned)grid, UPD_THREADS, 0, st>>>(T, (const cplx*)Cq, ldr, ldc, nout, N, nchunk);
+    SQC_LAUNCHED();
+    return 0;
+}
+
+// =====================================================================================
+// residual norms, preconditioned residuals, restart copies, diag multiply
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+residual_norms_kernel(sqc_block_t X, sqc_block_t HX, const double* __restrict__ theta, int ld_theta,
+                      int64_t N, int p, double* __restrict__ rn2) {
+    const int b = blockIdx.x / p, j = blockIdx.x % p;
+    double s = 0.0;
+    if (j < blk_count(X, b)) {
+        const double th = theta[(int64_t)b * ld_theta + j];
+        const cplx* x = blk_vec(X, b, j, N);
+        const cplx* hx = blk_vec(HX, b, j, N);
+        for (int64_t n = threadIdx.x; n < N; n += 256) {
+            const cplx a = x[n], h = hx[n];
+            const double rr = h.x - th * a.x, ri = h.y - th * a.y;
+            s = fma(rr, rr, s);
+            s = fma(ri, ri, s);
+        }
+    }
+    __shared__ double sh[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += sh[w];
+        rn2[(int64_t)b * p + j] = tot;
+    }
+}
+
+extern "C" int sqc_residual_norms(sqc_block_t X, sqc_block_t HX, const double* theta,
+                                  int32_t ld_theta, int64_t N, int32_t B, double* rn2, void* stream) {
+    if (B <= 0 || N <= 0 || X.cnt_fixed <= 0) return SQC_EINVAL;
+    const int p = X.cnt_fixed;
+    residual_norms_kernel<<<B * p, 256, 0, (cudaStream_t)stream>>>(X, HX, theta, ld_theta, N, p, rn2);
+    SQC_LAUNCHED();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+precond_residual_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* __restrict__ theta,
+                        int ld_theta, const int32_t* __restrict__ act, int ld_act,
+                        const double* __restrict__ d, int64_t d_stride_b,
+                        const double* __restrict__ den_floor, int64_t N, int pmax, int nchunk) {
+    const int vec = blockIdx.x / nchunk;
+    const int b = vec / pmax, jj = vec % pmax;
+    if (jj >= blk_count(T, b)) return;
+    const int64_t n = (int64_t)(blockIdx.x % nchunk) * 256 + threadIdx.x;
+    if (n >= N) return;
+    const int a = act[(int64_t)b * ld_act + jj];
+    const double th = theta[(int64_t)b * ld_theta + a];
+    const double fl = den_floor[b];
+    const cplx xv = blk_vec(X, b, a, N)[n], hv = blk_vec(HX, b, a, N)[n];
+    double den = d[(int64_t)b * d_stride_b + n] - th;
+    if (fabs(den) < fl) den = (den < 0.0) ? -fl : fl;
+    const double inv = 1.0 / den;
+    blk_vec(T, b, jj, N)[n] = cmake((hv.x - th * xv.x) * inv, (hv.y - th * xv.y) * inv);
+}
+
+extern "C" int sqc_precond_residual(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                                    int32_t ld_theta, const int32_t* act, int32_t ld_act,
+                                    const double* d, int64_t d_stride_b, const double* den_floor,
+                                    int64_t N, int32_t B, void* stream) {
+    if (B <= 0 || N <= 0 || T.cnt_fixed <= 0) return SQC_EINVAL;
+    const int nchunk = (int)((N + 255) / 256);
+    const int64_t grid = (int64_t)B * T.cnt_fixed * nchunk;
+    if (grid > 0x7fffffffLL) return SQC_ELIMIT;
+    precond_residual_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        X, HX, T, theta, ld_theta, act, ld_act, d, d_stride_b, den_floor, N, T.cnt_fixed, nchunk);
+    SQC_LAUNCHED();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+restart_copy_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t V, sqc_block_t W,
+                    const int32_t* __restrict__ restart, int64_t N, int p, int nchunk) {
+    const int vec = blockIdx.x / nchunk;
+    const int b = vec / p, j = vec % p;
+    if (!restart[b]) return;
+    const int64_t n = (int64_t)(blockIdx.x % nchunk) * 256 + threadIdx.x;
+    if (n >= N) return;
+    blk_vec(V, b, j, N)[n] = blk_vec(X, b, j, N)[n];
+    blk_vec(W, b, j, N)[n] = blk_vec(HX, b, j, N)[n];
+}
+
+extern "C" int sqc_restart_copy(sqc_block_t X, sqc_block_t HX, sqc_block_t V, sqc_block_t W,
+                                const int32_t* restart, int64_t N, int32_t B, void* stream) {
+    if (B <= 0 || N <= 0 || X.cnt_fixed <= 0) return SQC_EINVAL;
+    const int p = X.cnt_fixed;
+    const int nchunk = (int)((N + 255) / 256);
+    const int64_t grid = (int64_t)B * p * nchunk;
+    if (grid > 0x7fffffffLL) return SQC_ELIMIT;
+    restart_copy_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(X, HX, V, W, restart, N, p, nchunk);
+    SQC_LAUNCHED();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+diag_mul_kernel(sqc_block_t X, sqc_block_t Y, const double* __restrict__ diag, int64_t diag_stride_b,
+                int64_t N, int vmax, int nchunk, int accumulate) {
+    const int vec = blockIdx.x / nchunk;
+    const int b = vec / vmax, v = vec % vmax;
+    if (v >= blk_count(X, b)) return;
+    const int64_t n = (int64_t)(blockIdx.x % nchunk) * 256 + threadIdx.x;
+    if (n >= N) return;
+    const double dv = diag[(int64_t)b * diag_stride_b + n];
+    const cplx x = blk_vec(X, b, v, N)[n];
+    cplx* y = blk_vec(Y, b, v, N) + n;
+    cplx r = cmake(dv * x.x, dv * x.y);
+    if (accumulate) r = cadd(r, *y);
+    *y = r;
+}
+
+extern "C" int sqc_diag_mul(sqc_block_t X, sqc_block_t Y, const double* diag, int64_t diag_stride_b,
+                            int64_t N, int32_t B, int32_t accumulate, void* stream) {
+    if (B <= 0 || N <= 0 || X.cnt_fixed <= 0) return SQC_EINVAL;
+    const int nchunk = (int)((N + 255) / 256);
+    const int64_t grid = (int64_t)B * X.cnt_fixed * nchunk;
+    if (grid > 0x7fffffffLL) return SQC_ELIMIT;
+    diag_mul_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(X, Y, diag, diag_stride_b, N,
+                                                                     X.cnt_fixed, nchunk, accumulate);
+    SQC_LAUNCHED();
+    return 0;
+}
+
+extern "C" int sqc_abi_version(void) { return 1; }
+extern "C" int64_t sqc_launch_count(void) { return g_sqc_launches; }
+extern "C" const char* sqc_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code == SQC_EINVAL) return "sqcircuit_b200: invalid argument";
+    if (code == SQC_ELIMIT) return "sqcircuit_b200: size outside the supported range";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "sqcircuit_b200: unknown error";
+}

@@ -1,0 +1,472 @@
+// Small dense per-sweep-point kernels: batched Hermitian Jacobi eigensolver (Rayleigh-Ritz,
+// SVQB, x-basis of the harmonic modes, direct diagonalisation of small Hamiltonians) and the
+// block-Davidson bookkeeping.  One CTA per sweep point.
+#include <math.h>
+#include "common.cuh"
+
+#define JAC_THREADS 256
+#define JAC_MAX_SWEEPS 30
+#define JAC_BIG 1.0e300
+
+// Parallel cyclic (round-robin) two-sided Jacobi for an n x n Hermitian matrix.
+//   A  : np x np complex, leading dim lda (shared memory), np even, rows/cols >= n are padding
+//   Zt : np rows of length ldz (shared or global); on exit row j = eigenvector of A[j][j]
+//   rot: 4*np/2 doubles of shared scratch, prs: np ints of shared scratch, red: 64 doubles
+// All threads of the CTA must call.  Eigenvalues are left on the diagonal of A (unsorted).
+__device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, double* rot,
+                            int* prs, double* red) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int half = np >> 1;
+    // padding + identity
+    for (int e = tid; e < np * np; e += nt) {
+        const int r = e / np, c = e % np;
+        if (r >= n || c >= n) A[r * lda + c] = (r == c) ? cmake(JAC_BIG, 0.0) : cmake(0.0, 0.0);
+        Zt[r * ldz + c] = (r == c) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+    bool polish = false;
+    for (int sweep = 0; sweep < JAC_MAX_SWEEPS; ++sweep) {
+        // convergence test: off-diagonal vs diagonal Frobenius mass (real rows only)
+        double off = 0.0, dg = 0.0;
+        for (int e = tid; e < n * n; e += nt) {
+            const int r = e / n, c = e % n;
+            const cplx v = A[r * lda + c];
+            const double m2 = v.x * v.x + v.y * v.y;
+            if (r == c) dg += m2; else off += m2;
+        }
+        off = warp_sum(off);
+        dg = warp_sum(dg);
+        if ((tid & 31) == 0) {
+            red[tid >> 5] = off;
+            red[32 + (tid >> 5)] = dg;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double o = 0.0, d = 0.0;
+            for (int w = 0; w < (nt >> 5); ++w) {
+                o += red[w];
+                d += red[32 + w];
+            }
+            red[0] = o;
+            red[32] = d;
+        }
+        __syncthreads();
+        const double o = red[0], d = red[32];
+        __syncthreads();
+        // quadratic convergence: once the off-diagonal mass is below 1e-13 relative, one more
+        // sweep leaves it at rounding level
+        if (o == 0.0 || polish) break;
+        if (o <= 1e-26 * (d + o)) polish = true;
+
+        for (int step = 0; step < np - 1; ++step) {
+            // schedule + rotation parameters
+            for (int k = tid; k < half; k += nt) {
+                int p = (k == 0) ? np - 1 : (step + k) % (np - 1);
+                int q = (step - k + (np - 1)) % (np - 1);
+                if (p > q) { int tmp = p; p = q; q = tmp; }
+                prs[2 * k] = p;
+                prs[2 * k + 1] = q;
+                const double a = A[p * lda + p].x, dd = A[q * lda + q].x;
+                const cplx b = A[p * lda + q];
+                const double ab = hypot(b.x, b.y);
+                double c = 1.0, s = 0.0, ex = 1.0, ey = 0.0;
+                if (ab > 0.0 && ab > 1e-19 * (fabs(a) + fabs(dd)) && p < n && q < n) {
+                    const double th = (dd - a) / (2.0 * ab);
+                    const double t = copysign(1.0, th) / (fabs(th) + sqrt(th * th + 1.0));
+                    c = 1.0 / sqrt(1.0 + t * t);
+                    s = t * c;
+                    ex = b.x / ab;
+                    ey = b.y / ab;
+                }
+                rot[4 * k] = c;
+                rot[4 * k + 1] = s;
+                rot[4 * k + 2] = ex;
+                rot[4 * k + 3] = ey;
+            }
+            __syncthreads();
+            // A <- J^H A J on 2x2 blocks (pair P of rows, pair Q of columns)
+            for (int blk = tid; blk < half * half; blk += nt) {
+                const int P = blk / half, Q = blk % half;
+                const int p = prs[2 * P], q = prs[2 * P + 1], pc = prs[2 * Q], qc = prs[2 * Q + 1];
+                const double cP = rot[4 * P], sP = rot[4 * P + 1];
+                const cplx eP = cmake(rot[4 * P + 2], rot[4 * P + 3]);
+                const double cQ = rot[4 * Q], sQ = rot[4 * Q + 1];
+                const cplx eQc = cmake(rot[4 * Q + 2], -rot[4 * Q + 3]);
+                const cplx a00 = A[p * lda + pc], a01 = A[p * lda + qc];
+                const cplx a10 = A[q * lda + pc], a11 = A[q * lda + qc];
+                // rows:  r0 = c a0 - s e a1 ;  r1 = s a0 + c e a1
+                const cplx ea10 = cmul(eP, a10), ea11 = cmul(eP, a11);
+                const cplx r00 = csub(cscale(cP, a00), cscale(sP, ea10));
+                const cplx r01 = csub(cscale(cP, a01), cscale(sP, ea11));
+                const cplx r10 = cadd(cscale(sP, a00), cscale(cP, ea10));
+                const cplx r11 = cadd(cscale(sP, a01), cscale(cP, ea11));
+                // cols:  o.0 = c r.0 - s conj(e) r.1 ;  o.1 = s r.0 + c conj(e) r.1
+                const cplx er01 = cmul(eQc, r01), er11 = cmul(eQc, r11);
+                cplx o00 = csub(cscale(cQ, r00), cscale(sQ, er01));
+                cplx o01 = cadd(cscale(sQ, r00), cscale(cQ, er01));
+                cplx o10 = csub(cscale(cQ, r10), cscale(sQ, er11));
+                cplx o11 = cadd(cscale(sQ, r10), cscale(cQ, er11));
+                if (P == Q) {
+                    o00.y = 0.0;
+                    o11.y = 0.0;
+                    if (sP != 0.0) {
+                        o01 = cmake(0.0, 0.0);
+                        o10 = cmake(0.0, 0.0);
+                    }
+                }
+                A[p * lda + pc] = o00;
+                A[p * lda + qc] = o01;
+                A[q * lda + pc] = o10;
+                A[q * lda + qc] = o11;
+            }
+            // Zt rows:  z_p <- c z_p - s conj(e) z_q ;  z_q <- s z_p + c conj(e) z_q
+            for (int e = tid; e < half * n; e += nt) {
+                const int P = e / n, i = e % n;
+                const double sP = rot[4 * P + 1];
+                if (sP == 0.0) continue;
+                const int p = prs[2 * P], q = prs[2 * P + 1];
+                const double cP = rot[4 * P];
+                const cplx ec = cmake(rot[4 * P + 2], -rot[4 * P + 3]);
+                const cplx zp = Zt[p * ldz + i], zq = cmul(ec, Zt[q * ldz + i]);
+                Zt[p * ldz + i] = csub(cscale(cP, zp), cscale(sP, zq));
+                Zt[q * ldz + i] = cadd(cscale(sP, zp), cscale(cP, zq));
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// batched heev
+// ---------------------------------------------------------------------------------------
+template <bool ZSMEM>
+__global__ void __launch_bounds__(JAC_THREADS)
+heev_kernel(const cplx* __restrict__ Ain, const int32_t* __restrict__ nArr, int n_fixed, int ld,
+            double* __restrict__ w, cplx* __restrict__ Zout, int np_max) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x;
+    const int n = nArr ? nArr[b] : n_fixed;
+    const int np = (n + 1) & ~1;
+    const int lda = np_max;
+    cplx* A = reinterpret_cast<cplx*>(smem);
+    cplx* Zs = A + (size_t)np_max * np_max;
+    double* rot = reinterpret_cast<double*>(ZSMEM ? Zs + (size_t)np_max * np_max : Zs);
+    double* red = rot + 2 * np_max;
+    int* prs = reinterpret_cast<int*>(red + 64);
+    int* rank = prs + np_max;
+    double* wv = reinterpret_cast<double*>(rank + np_max + (np_max & 1));
+    cplx* zglob = Zout + (int64_t)b * ld * ld;
+    const int tid = threadIdx.x;
+    double* wout = w + (int64_t)b * ld;
+    if (n <= 0) return;   // inactive sweep point: leave its previous results untouched
+    const cplx* a = Ain + (int64_t)b * ld * ld;
+    for (int e = tid; e < n * n; e += JAC_THREADS) {
+        const int r = e / n, c = e % n;
+        // Hermitian average of the two stored triangles
+        const cplx u = a[r * ld + c], v = a[c * ld + r];
+        A[r * lda + c] = cmake(0.5 * (u.x + v.x), 0.5 * (u.y - v.y));
+    }
+    __syncthreads();
+    cplx* Z = ZSMEM ? Zs : zglob;
+    const int ldz = ZSMEM ? np_max : ld;
+    jacobi_heev(A, n, np, lda, Z, ldz, rot, prs, red);
+    // sort ascending
+    for (int i = tid; i < n; i += JAC_THREADS) wv[i] = A[i * lda + i].x;
+    __syncthreads();
+    for (int i = tid; i < n; i += JAC_THREADS) {
+        const double wi = wv[i];
+        int r = 0;
+        for (int j = 0; j < n; ++j) r += (wv[j] < wi) || (wv[j] == wi && j < i);
+        rank[i] = r;
+    }
+    __syncthreads();
+    for (int i = tid; i < ld; i += JAC_THREADS) wout[i] = INFINITY;
+    __syncthreads();
+    for (int i = tid; i < n; i += JAC_THREADS) wout[rank[i]] = wv[i];
+    if (ZSMEM) {
+        for (int e = tid; e < n * n; e += JAC_THREADS) {
+            const int j = e / n, i = e % n;
+            zglob[rank[j] * ld + i] = Zs[j * ldz + i];
+        }
+    } else {
+        // in-place row permutation by cycle following (row buffer = A's first row area)
+        cplx* tmp = A;  // n entries; A is no longer needed except its diagonal (saved in wv)
+        for (int start = 0; start < n; ++start) {
+            // process the cycle containing `start` only from its smallest member
+            bool smallest = true;
+            int j = rank[start];
+            int guard = 0;
+            while (j != start && guard++ < n) {
+                if (j < start) { smallest = false; break; }
+                j = rank[j];
+            }
+            if (!smallest || rank[start] == start) continue;
+            // carry row `start` along the cycle: row r moves to rank[r]
+            for (int i = tid; i < n; i += JAC_THREADS) tmp[i] = zglob[start * ld + i];
+            __syncthreads();
+            int src = start;
+            do {
+                const int dst = rank[src];
+                for (int i = tid; i < n; i += JAC_THREADS) {
+                    const cplx keep = zglob[dst * ld + i];
+                    zglob[dst * ld + i] = tmp[i];
+                    tmp[i] = keep;
+                }
+                __syncthreads();
+                src = dst;
+            } while (src != start);
+        }
+    }
+}
+
+extern "C" int sqc_heev(const void* A, const int32_t* n, int32_t n_fixed, int32_t ld, double* w,
+                        void* Zt, int32_t B, void* stream) {
+    if (B <= 0 || ld <= 0 || ld > 112 || n_fixed > ld) return SQC_EINVAL;
+    const int np_max = (ld + 1) & ~1;
+    const bool zs = np_max <= 64;
+    size_t bytes = (size_t)np_max * np_max * sizeof(cplx) * (zs ? 2 : 1);
+    bytes += (2 * np_max + 64) * sizeof(double) + (2 * np_max + 2) * sizeof(int) + np_max * sizeof(double) + 16;
+    cudaError_t e;
+    if (zs) {
+        e = cudaFuncSetAttribute(heev_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        heev_kernel<true><<<B, JAC_THREADS, bytes, (cudaStream_t)stream>>>((const cplx*)A, n, n_fixed, ld, w, (cplx*)Zt, np_max);
+    } else {
+        e = cudaFuncSetAttribute(heev_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        heev_kernel<false><<<B, JAC_THREADS, bytes, (cudaStream_t)stream>>>((const cplx*)A, n, n_fixed, ld, w, (cplx*)Zt, np_max);
+    }
+    SQC_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// x-basis of a harmonic mode: eigen-decomposition of the truncated a + a^dag
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(JAC_THREADS)
+xbasis_kernel(int m, double* __restrict__ V, double* __restrict__ lam, cplx* __restrict__ zwork) {
+    extern __shared__ double smem[];
+    const int np = (m + 1) & ~1;
+    cplx* A = reinterpret_cast<cplx*>(smem);
+    double* rot = reinterpret_cast<double*>(A + (size_t)np * np);
+    double* red = rot + 2 * np;
+    int* prs = reinterpret_cast<int*>(red + 64);
+    int* rank = prs + np;
+    double* wv = reinterpret_cast<double*>(rank + np + (np & 1));
+    const int tid = threadIdx.x;
+    for (int e = tid; e < m * m; e += JAC_THREADS) {
+        const int r = e / m, c = e % m;
+        double v = 0.0;
+        if (c == r + 1) v = sqrt((double)(r + 1));
+        if (r == c + 1) v = sqrt((double)(c + 1));
+        A[r * np + c] = cmake(v, 0.0);
+    }
+    __syncthreads();
+    jacobi_heev(A, m, np, np, zwork, np, rot, prs, red);
+    for (int i = tid; i < m; i += JAC_THREADS) wv[i] = A[i * np + i].x;
+    __syncthreads();
+    for (int i = tid; i < m; i += JAC_THREADS) {
+        const double wi = wv[i];
+        int r = 0;
+        for (int j = 0; j < m; ++j) r += (wv[j] < wi) || (wv[j] == wi && j < i);
+        rank[i] = r;
+        lam[r] = wi;
+    }
+    __syncthreads();
+    // V[nf][i] = component nf of eigenvector i  (sign: first non-negligible component positive)
+    for (int j = tid; j < m; j += JAC_THREADS) {
+        double sg = 1.0;
+        for (int i = 0; i < m; ++i) {
+            const double v = zwork[j * np + i].x;
+            if (fabs(v) > 1e-8) { sg = v < 0.0 ? -1.0 : 1.0; break; }
+        }
+        for (int i = 0; i < m; ++i) V[i * m + rank[j]] = sg * zwork[j * np + i].x;
+    }
+}
+
+extern "C" int sqc_xbasis(int32_t m, double* V, double* lam, void* stream) {
+    if (m <= 0 || m > 112) return SQC_ELIMIT;
+    const int np = (m + 1) & ~1;
+    size_t bytes = (size_t)np * np * sizeof(cplx) + (2 * np + 64) * sizeof(double) +
+                   (2 * np + 2) * sizeof(int) + np * sizeof(double) + 16;
+    cplx* zwork = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&zwork, (size_t)np * np * sizeof(cplx), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(xbasis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    xbasis_kernel<<<1, JAC_THREADS, bytes, (cudaStream_t)stream>>>(m, V, lam, zwork);
+    ++g_sqc_launches;
+    e = cudaGetLastError();
+    cudaFreeAsync(zwork, (cudaStream_t)stream);
+    return (int)e;
+}
+
+// ---------------------------------------------------------------------------------------
+// SVQB coefficients for orthonormalising a block of <= 16 vectors from its Gram matrix
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+svqb_kernel(const cplx* __restrict__ S, int ld, int32_t* __restrict__ nact, double drop,
+            cplx* __restrict__ Cq, const int32_t* __restrict__ msz, int32_t* __restrict__ mtot) {
+    __shared__ cplx A[16 * 16];
+    __shared__ cplx Z[16 * 16];
+    __shared__ double rot[32], red[64], dsc[16], wv[16];
+    __shared__ int prs[16], order[16];
+    __shared__ int nkeep;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = min(nact[b], min(ld, 16));
+    cplx* cq = Cq + (int64_t)b * ld * ld;
+    for (int e = tid; e < ld * ld; e += 64) cq[e] = cmake(0.0, 0.0);
+    if (n <= 0) {
+        if (tid == 0 && mtot && msz) mtot[b] = msz[b];
+        return;
+    }
+    const cplx* s = S + (int64_t)b * ld * ld;
+    if (tid < n) {
+        const double dd = s[tid * ld + tid].x;
+        dsc[tid] = dd > 0.0 ? 1.0 / sqrt(dd) : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += 64) {
+        const int r = e / n, c = e % n;
+        const cplx u = s[r * ld + c], v = s[c * ld + r];
+        const double sc = dsc[r] * dsc[c];
+        A[r * 16 + c] = cmake(0.5 * (u.x + v.x) * sc, 0.5 * (u.y - v.y) * sc);
+    }
+    __syncthreads();
+    const int np = (n + 1) & ~1;
+    jacobi_heev(A, n, np, 16, Z, 16, rot, prs, red);
+    if (tid < n) wv[tid] = A[tid * 16 + tid].x;
+    __syncthreads();
+    if (tid == 0) {
+        double wmax = 0.0;
+        for (int i = 0; i < n; ++i) wmax = fmax(wmax, wv[i]);
+        // keep directions in DESCENDING sigma order
+        int cnt = 0;
+        bool used[16];
+        for (int i = 0; i < n; ++i) used[i] = false;
+        for (int r = 0; r < n; ++r) {
+            int best = -1;
+            for (int i = 0; i < n; ++i)
+                if (!used[i] && (best < 0 || wv[i] > wv[best])) best = i;
+            used[best] = true;
+            if (wv[best] > drop * wmax && wv[best] > 0.0) order[cnt++] = best;
+        }
+        nkeep = cnt;
+        nact[b] = cnt;
+        if (mtot && msz) mtot[b] = msz[b] + cnt;
+    }
+    __syncthreads();
+    // Cq[j][i] = D_i * U_i,src(j) / sqrt(sigma_src(j));  U column src = Z row src
+    for (int e = tid; e < nkeep * n; e += 64) {
+        const int j = e / n, i = e % n;
+        const int src = order[j];
+        const double f = dsc[i] / sqrt(wv[src]);
+        const cplx u = Z[src * 16 + i];
+        cq[j * ld + i] = cmake(u.x * f, u.y * f);
+    }
+}
+
+extern "C" int sqc_svqb_coeffs(const void* S, int32_t ld, int32_t* nact, double drop, void* Cq,
+                               const int32_t* msz, int32_t* mtot, int32_t B, void* stream) {
+    if (B <= 0 || ld <= 0 || ld > 16) return SQC_EINVAL;
+    svqb_kernel<<<B, 64, 0, (cudaStream_t)stream>>>((const cplx*)S, ld, nact, drop, (cplx*)Cq, msz, mtot);
+    SQC_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Davidson bookkeeping
+// ---------------------------------------------------------------------------------------
+__global__ void zero_counter_kernel(int32_t* c) { *c = 0; }
+
+__global__ void __launch_bounds__(64)
+davidson_decide_kernel(sqc_davidson_state_t st) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int p = st.p, k = st.k, ldg = st.ldg;
+    __shared__ int s_restart;
+    double* theta = st.theta + (int64_t)b * ldg;
+    if (st.done[b]) {
+        if (tid == 0) {
+            st.nact[b] = 0;
+            st.restart[b] = 0;
+        }
+        return;
+    }
+    if (tid == 0) {
+        const int msz = st.msz[b];
+        const int pe = min(p, msz);
+        double scale = st.tol_abs_floor;
+        for (int j = 0; j < min(k, pe); ++j) scale = fmax(scale, fabs(theta[j]));
+        double rmax = 0.0;
+        int n = 0;
+        for (int j = 0; j < pe; ++j) {
+            const double rel = sqrt(st.rn2[(int64_t)b * p + j]) / scale;
+            if (j < k) rmax = fmax(rmax, rel);
+            if (rel > 0.5 * st.tol_rel) st.act[(int64_t)b * p + n++] = j;
+        }
+        st.resmax[b] = rmax;
+        int restart = 0;
+        if (rmax <= st.tol_rel) {
+            st.done[b] = 1;
+            n = 0;
+        } else {
+            atomicAdd(st.n_not_done, 1);
+            if (msz + n > st.mmax) restart = 1;
+        }
+        st.nact[b] = n;
+        st.restart[b] = restart;
+        double fl = fmax(fabs(theta[0]), fabs(theta[pe - 1]));
+        fl = fmax(fl, theta[pe - 1] - theta[0]);
+        st.den_floor[b] = fmax(1e-3 * fl, 1e-300);
+        s_restart = restart;
+        if (restart) st.msz[b] = pe;
+    }
+    __syncthreads();
+    if (s_restart) {
+        cplx* G = reinterpret_cast<cplx*>(st.G) + (int64_t)b * ldg * ldg;
+        for (int e = tid; e < ldg * ldg; e += 64) {
+            const int r = e / ldg, c = e % ldg;
+            G[e] = (r == c && r < p) ? cmake(theta[r], 0.0) : cmake(0.0, 0.0);
+        }
+    }
+}
+
+extern "C" int sqc_davidson_decide(const sqc_davidson_state_t* st, int32_t B, void* stream) {
+    if (!st || B <= 0 || st->p <= 0 || st->p > 16 || st->k > st->p) return SQC_EINVAL;
+    zero_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(st->n_not_done);
+    SQC_LAUNCHED();
+    davidson_decide_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(*st);
+    SQC_LAUNCHED();
+    return 0;
+}
+
+__global__ void __launch_bounds__(128)
+davidson_insert_kernel(sqc_davidson_state_t st, const cplx* __restrict__ S, int ldr, int ldc) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int ldg = st.ldg;
+    const int msz = st.msz[b], na = st.nact[b];
+    if (na <= 0) return;
+    cplx* G = reinterpret_cast<cplx*>(st.G) + (int64_t)b * ldg * ldg;
+    const cplx* s = S + (int64_t)b * ldr * ldc;
+    const int rows = msz + na;
+    for (int e = tid; e < rows * na; e += 128) {
+        const int i = e / na, j = e % na;
+        cplx v = s[i * ldc + j];
+        if (i >= msz) {  // new diagonal block: Hermitian average
+            const cplx u = s[(msz + j) * ldc + (i - msz)];
+            v = cmake(0.5 * (v.x + u.x), 0.5 * (v.y - u.y));
+        }
+        G[i * ldg + msz + j] = v;
+        G[(msz + j) * ldg + i] = cconj(v);
+    }
+    __syncthreads();
+    if (tid == 0) st.msz[b] = rows;
+}
+
+extern "C" int sqc_davidson_insert(const sqc_davidson_state_t* st, const void* S, int32_t ldr,
+                                   int32_t ldc, int32_t B, void* stream) {
+    if (!st || B <= 0) return SQC_EINVAL;
+    davidson_insert_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(*st, (const cplx*)S, ldr, ldc);
+    SQC_LAUNCHED();
+    return 0;
+}

@@ -1,0 +1,154 @@
+"""Batched lowest-k Hermitian eigensolver over the points of a parameter sweep.
+
+Replaces ``scipy.sparse.linalg.eigs(H, k, which='SR')`` in ``Circuit._diag_np``
+(reference circuit.py:1938-1986), one call per sweep point in ``Sweep.sweepFlux``
+(sweep.py:71-108), by ONE lock-step batched solve on the GPU:
+
+* N <= DENSE_MAX : H(b) is materialised by applying the matrix-free operator to the identity
+  and handed to the batched Jacobi eigensolver (``sqc_heev``).
+* otherwise      : block Davidson with the LC diagonal as preconditioner.  Per iteration and
+  sweep point:  Rayleigh-Ritz on the projected matrix G = V^H H V (``sqc_heev``), Ritz
+  vectors / residuals (``sqc_block_update``, ``sqc_residual_norms``), preconditioned residuals
+  T = (d_LC - theta)^-1 r written into the free tail of the basis, two passes of block
+  Gram-Schmidt against V plus SVQB inside the block (``sqc_gram`` on the FP64 tensor cores,
+  ``sqc_svqb_coeffs``), W_new = H T (matrix-free) and the new columns of G.  Basis sizes are
+  per-point device counters; the host only reads one int per iteration (#unconverged points).
+
+All numerics run in the CUDA library; torch is used for allocation and trivial glue.
+"""
+from dataclasses import dataclass
+
+import torch
+
+from .kernels import BlockView
+
+DENSE_MAX = 112
+
+
+@dataclass
+class EigResult:
+    evals: torch.Tensor      # [B][k] float64 (rad/s)
+    evecs: torch.Tensor      # [B][k][N] complex128
+    iterations: int
+    resmax: torch.Tensor     # [B] final relative residual of the wanted pairs
+    converged: bool
+
+
+def solve_dense(kern, op, B, N, k):
+    dev = op.device
+    eye = torch.eye(N, dtype=torch.complex128, device=dev).unsqueeze(0).expand(B, N, N).contiguous()
+    HX = torch.empty_like(eye)
+    op.apply(BlockView(eye), BlockView(HX))
+    # HX[b][j][:] is column j of H, i.e. the array holds H^T = conj(H): eigenvectors come out
+    # conjugated.
+    w = torch.empty((B, N), dtype=torch.float64, device=dev)
+    Zt = torch.empty((B, N, N), dtype=torch.complex128, device=dev)
+    kern.heev(HX, N, w, Zt)
+    k = min(k, N)
+    return EigResult(w[:, :k].contiguous(), Zt[:, :k, :].conj().resolve_conj().contiguous(), 0,
+                     torch.zeros(B, dtype=torch.float64, device=dev), True)
+
+
+def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
+                   impl=0, stats=None):
+    """diag: [1 or B][N] real preconditioner diagonal (the LC part of H)."""
+    dev = op.device
+    if p is None:
+        p = min(16, max(k + 2, (k * 6 + 4) // 5))
+    p = min(p, 16, N)
+    k = min(k, p)
+    if mmax is None:
+        mmax = 4 * p
+    mmax = min(mmax, 64, N)
+    ld = mmax
+    c128, f64, i32 = torch.complex128, torch.float64, torch.int32
+
+    V = torch.zeros((B, mmax, N), dtype=c128, device=dev)
+    W = torch.zeros((B, mmax, N), dtype=c128, device=dev)
+    Xb = torch.zeros((B, p, N), dtype=c128, device=dev)
+    HXb = torch.zeros((B, p, N), dtype=c128, device=dev)
+    G = torch.zeros((B, ld, ld), dtype=c128, device=dev)
+    Zt = torch.zeros((B, ld, ld), dtype=c128, device=dev)
+    theta = torch.zeros((B, ld), dtype=f64, device=dev)
+    S1 = torch.zeros((B, mmax, 16), dtype=c128, device=dev)
+    S2 = torch.zeros((B, 16, 16), dtype=c128, device=dev)
+    Cq = torch.zeros((B, 16, 16), dtype=c128, device=dev)
+    msz = torch.full((B,), p, dtype=i32, device=dev)
+    mtot = torch.full((B,), p, dtype=i32, device=dev)
+    nact = torch.zeros((B,), dtype=i32, device=dev)
+    nin = torch.zeros((B,), dtype=i32, device=dev)     # block size before SVQB drops directions
+    act = torch.zeros((B, p), dtype=i32, device=dev)
+    restart = torch.zeros((B,), dtype=i32, device=dev)
+    done = torch.zeros((B,), dtype=i32, device=dev)
+    n_not_done = torch.zeros((1,), dtype=i32, device=dev)
+    rn2 = torch.zeros((B, p), dtype=f64, device=dev)
+    resmax = torch.zeros((B,), dtype=f64, device=dev)
+    den_floor = torch.zeros((B,), dtype=f64, device=dev)
+
+    # initial block: unit vectors on the p smallest entries of the preconditioner diagonal
+    if x0 is not None:
+        V[:, :p, :] = x0[:, :p, :]
+    else:
+        idx = torch.topk(diag, p, dim=1, largest=False).indices          # [1 or B][p]
+        idx = idx.expand(B, p)
+        V[:, :p, :].scatter_(2, idx.unsqueeze(2), torch.ones((B, p, 1), dtype=c128, device=dev))
+    Vp = BlockView(V, cnt_fixed=p)
+    Wp = BlockView(W, cnt_fixed=p)
+    if x0 is not None:
+        # orthonormalise the supplied block (SVQB twice)
+        for _ in range(2):
+            nact.fill_(p)
+            nin.fill_(p)
+            kern.gram(Vp, Vp, S2, impl)
+            kern.svqb_coeffs(S2, nact, 1e-14, Cq)
+            kern.block_rightmul(BlockView(V, cnt_fixed=p, cnt=nin), Cq, nact)
+    op.apply(Vp, Wp)
+    kern.gram(Vp, Wp, G, impl)
+
+    st = kern.davidson_state(p=p, k=k, mmax=mmax, ldg=ld, tol_rel=tol, tol_abs_floor=1e-300,
+                             msz=msz, nact=nact, act=act, restart=restart, done=done,
+                             n_not_done=n_not_done, theta=theta, rn2=rn2, resmax=resmax,
+                             den_floor=den_floor, G=G)
+    Xv = BlockView(Xb, cnt_fixed=p)
+    HXv = BlockView(HXb, cnt_fixed=p)
+    Tv = BlockView(V, cnt_fixed=p, off=msz, cnt=nact)      # free tail of the basis
+    Tin = BlockView(V, cnt_fixed=p, off=msz, cnt=nin)      # same window, pre-SVQB count
+    HTv = BlockView(W, cnt_fixed=p, off=msz, cnt=nact)
+    Vm = BlockView(V, cnt_fixed=mmax, cnt=msz)             # current basis
+    Wm = BlockView(W, cnt_fixed=mmax, cnt=msz)
+    Vt = BlockView(V, cnt_fixed=mmax, cnt=mtot)            # basis + new block
+
+    it = 0
+    converged = False
+    for it in range(1, maxit + 1):
+        live = 1 - done
+        nheev = msz * live
+        xcnt = (p * live).to(i32)
+        kern.heev(G, nheev, theta, Zt)
+        Xv.cnt = xcnt
+        HXv.cnt = xcnt
+        kern.block_update(Vm, Zt, Xv, op=0, trans=0)
+        kern.block_update(Wm, Zt, HXv, op=0, trans=0)
+        kern.residual_norms(Xv, HXv, theta, rn2)
+        kern.davidson_decide(st, B)
+        left = int(n_not_done.item())
+        if stats is not None:
+            stats.append((it, left))
+        if left == 0:
+            converged = True
+            break
+        Xv.cnt = None
+        HXv.cnt = None
+        kern.restart_copy(Xv, HXv, Vp, Wp, restart)
+        kern.precond_residual(Xv, HXv, Tv, theta, act, diag, den_floor)
+        for _ in range(2):
+            kern.gram(Vm, Tv, S1, impl)
+            kern.block_update(Vm, S1, Tv, op=1, trans=1)
+            kern.gram(Tv, Tv, S2, impl)
+            nin.copy_(nact)
+            kern.svqb_coeffs(S2, nact, 1e-12, Cq, msz, mtot)
+            kern.block_rightmul(Tin, Cq, nact)
+        op.apply(Tv, HTv)
+        kern.gram(Vt, HTv, S1, impl)
+        kern.davidson_insert(st, S1, B)
+    return EigResult(theta[:, :k].contiguous(), Xb[:, :k, :].contiguous(), it, resmax, converged)

@@ -1,0 +1,174 @@
+"""Thin torch-tensor wrappers over the C ABI (include/sqcircuit_b200.h).
+
+Tensors are only carriers of device memory: every call passes raw ``data_ptr()`` values
+and the current CUDA stream.  Nothing here computes on the host.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Block, DavidsonState, Potential, Space
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class BlockView:
+    """A [B][nvec][N] complex128 tensor (or a window of one) described as sqc_block_t."""
+
+    def __init__(self, tensor, cnt_fixed=None, off=None, cnt=None, first=0):
+        assert tensor.dtype == torch.complex128 and tensor.dim() == 3 and tensor.is_contiguous()
+        self.tensor = tensor
+        self.B, self.nvec, self.N = tensor.shape
+        self.first = first
+        self.off = off
+        self.cnt = cnt
+        self.cnt_fixed = int(cnt_fixed if cnt_fixed is not None else self.nvec - first)
+
+    def c(self):
+        base = self.tensor.data_ptr() + self.first * self.N * 16
+        return Block(C.c_void_p(base), self.nvec * self.N, _p(self.off), _p(self.cnt), self.cnt_fixed)
+
+
+def make_space(dims, harmonic):
+    sp = Space()
+    sp.n_modes = len(dims)
+    for i, (d, h) in enumerate(zip(dims, harmonic)):
+        sp.dims[i] = int(d)
+        sp.harmonic[i] = int(bool(h))
+    return sp
+
+
+class Kernels:
+    """CUDA backend (the only product backend)."""
+    name = 'cuda'
+
+    def __init__(self, device):
+        self.lib = _lib.load()
+        self.dev = torch.device(device)
+        if self.dev.type != 'cuda':
+            raise _lib.SqcLibraryError('sqcircuit_b200 kernels need a CUDA device')
+        self._gram_work = None
+
+    # ---- (1) operators ---------------------------------------------------
+    def xbasis(self, m):
+        V = torch.empty((m, m), dtype=torch.float64, device=self.dev)
+        lam = torch.empty((m,), dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.sqc_xbasis(m, _p(V), _p(lam), _stream(self.dev)), 'sqc_xbasis')
+        return V, lam
+
+    def phase_tables(self, sp, n_terms, lam, s, etab):
+        B = etab.shape[0]
+        sb = 0 if s.shape[0] == 1 else s.stride(0)
+        _lib.check(self.lib.sqc_phase_tables(C.byref(sp), n_terms, _p(lam), _p(s), sb, _p(etab),
+                                             etab.stride(0) if B > 1 else 0, B, _stream(self.dev)),
+                   'sqc_phase_tables')
+
+    def lc_diagonal(self, sp, omega, q, ng, out):
+        B = out.shape[0]
+        per_point = 1 if B > 1 else 0
+        _lib.check(self.lib.sqc_lc_diagonal(C.byref(sp), _p(omega), _p(q), _p(ng), per_point, _p(out), B,
+                                            _stream(self.dev)), 'sqc_lc_diagonal')
+
+    # ---- (2) operator application -----------------------------------------
+    def diag_mul(self, X, Y, diag, accumulate):
+        sb = 0 if diag.shape[0] == 1 else diag.stride(0)
+        _lib.check(self.lib.sqc_diag_mul(X.c(), Y.c(), _p(diag), sb, X.N, X.B, int(accumulate),
+                                         _stream(self.dev)), 'sqc_diag_mul')
+
+    def mode_transform(self, sp, mode, mat, transpose, X, Z, ediag=None, EX=None, impl=0):
+        msb = 0 if mat.dim() == 2 or mat.shape[0] == 1 else mat.stride(0)
+        if ediag is not None:
+            esb = 0 if ediag.shape[0] == 1 else ediag.stride(0)
+            exb = EX.c()
+        else:
+            esb = 0
+            exb = X.c()
+        _lib.check(self.lib.sqc_mode_transform(C.byref(sp), mode, _p(mat), msb, int(transpose), X.c(),
+                                               Z.c(), _p(ediag), esb, exb, X.B, impl, _stream(self.dev)),
+                   'sqc_mode_transform')
+
+    def potential_apply(self, sp, pot, X, Z):
+        _lib.check(self.lib.sqc_potential_apply(C.byref(sp), C.byref(pot), X.c(), Z.c(), X.B,
+                                                _stream(self.dev)), 'sqc_potential_apply')
+
+    def ladder_apply(self, sp, mode, c_dn, c_up, X, Y, accumulate):
+        _lib.check(self.lib.sqc_ladder_apply(C.byref(sp), mode, _p(c_dn), _p(c_up), X.c(), Y.c(), X.B,
+                                             int(accumulate), _stream(self.dev)), 'sqc_ladder_apply')
+
+    # ---- (3) eigensolver blocks --------------------------------------------
+    def gram(self, A, Bm, Cout, impl=0):
+        """Cout[b][i][j] = <A_i | Bm_j>; Cout: [B][ldr][ldc] complex128."""
+        B, ldr, ldc = Cout.shape
+        need = self.lib.sqc_gram_work_bytes(B, A.cnt_fixed, Bm.cnt_fixed, A.N)
+        if need and (self._gram_work is None or self._gram_work.numel() < need):
+            self._gram_work = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        _lib.check(self.lib.sqc_gram(A.c(), Bm.c(), A.N, B, _p(Cout), ldr, ldc,
+                                     _p(self._gram_work) if need else C.c_void_p(0), impl,
+                                     _stream(self.dev)), 'sqc_gram')
+
+    def block_update(self, A, Cf, Out, op=0, trans=0):
+        B, ldr, ldc = Cf.shape
+        _lib.check(self.lib.sqc_block_update(A.c(), _p(Cf), ldr, ldc, trans, Out.c(), A.N, B, op,
+                                             _stream(self.dev)), 'sqc_block_update')
+
+    def block_rightmul(self, T, Cq, nout):
+        B, ldr, ldc = Cq.shape
+        _lib.check(self.lib.sqc_block_rightmul(T.c(), _p(Cq), ldr, ldc, _p(nout), T.N, B,
+                                               _stream(self.dev)), 'sqc_block_rightmul')
+
+    def heev(self, A, n, w, Zt):
+        """A: [B][ld][ld]; n: int32[B] or int; w: [B][ld]; Zt: [B][ld][ld]."""
+        B, ld, _ = A.shape
+        if isinstance(n, int):
+            narr, nfix = None, n
+        else:
+            narr, nfix = n, ld
+        _lib.check(self.lib.sqc_heev(_p(A), _p(narr), nfix, ld, _p(w), _p(Zt), B, _stream(self.dev)),
+                   'sqc_heev')
+
+    def residual_norms(self, X, HX, theta, rn2):
+        _lib.check(self.lib.sqc_residual_norms(X.c(), HX.c(), _p(theta), theta.shape[1], X.N, X.B,
+                                               _p(rn2), _stream(self.dev)), 'sqc_residual_norms')
+
+    def davidson_state(self, **kw):
+        st = DavidsonState()
+        for key in ('p', 'k', 'mmax', 'ldg', 'tol_rel', 'tol_abs_floor'):
+            setattr(st, key, kw[key])
+        for key in ('msz', 'nact', 'act', 'restart', 'done', 'n_not_done', 'theta', 'rn2', 'resmax',
+                    'den_floor', 'G'):
+            setattr(st, key, kw[key].data_ptr())
+        st._keep = kw
+        return st
+
+    def davidson_decide(self, st, B):
+        _lib.check(self.lib.sqc_davidson_decide(C.byref(st), B, _stream(self.dev)), 'sqc_davidson_decide')
+
+    def restart_copy(self, X, HX, V, W, restart):
+        _lib.check(self.lib.sqc_restart_copy(X.c(), HX.c(), V.c(), W.c(), _p(restart), X.N, X.B,
+                                             _stream(self.dev)), 'sqc_restart_copy')
+
+    def precond_residual(self, X, HX, T, theta, act, d, den_floor):
+        dsb = 0 if d.shape[0] == 1 else d.stride(0)
+        _lib.check(self.lib.sqc_precond_residual(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act),
+                                                 act.shape[1], _p(d), dsb, _p(den_floor), X.N, X.B,
+                                                 _stream(self.dev)), 'sqc_precond_residual')
+
+    def svqb_coeffs(self, S, nact, drop, Cq, msz=None, mtot=None):
+        B, ld, _ = S.shape
+        _lib.check(self.lib.sqc_svqb_coeffs(_p(S), ld, _p(nact), drop, _p(Cq), _p(msz), _p(mtot), B,
+                                            _stream(self.dev)), 'sqc_svqb_coeffs')
+
+    def davidson_insert(self, st, S, B):
+        _, ldr, ldc = S.shape
+        _lib.check(self.lib.sqc_davidson_insert(C.byref(st), _p(S), ldr, ldc, B, _stream(self.dev)),
+                   'sqc_davidson_insert')
+
+    def launch_count(self):
+        return int(self.lib.sqc_launch_count())

@@ -1,0 +1,178 @@
+"""Batched transition matrix elements and decoherence rates on the eigenvectors of a sweep.
+
+Reference: Circuit.matrix_elements / dec_rate / _dec_rate_*_np / _get_partial_H
+(circuit.py:2397-2873).  Operators are applied matrix-free on the GPU to the two states of
+interest of every sweep point at once; the inner products use the tensor-core Gram kernel;
+the closed-form rate expressions (a handful of flops per sweep point) are evaluated on the host.
+"""
+import numpy as np
+import torch
+
+from . import units as unt
+from .elements import Capacitor
+from .kernels import BlockView
+from .noise import ENV
+
+
+class SweepNoise:
+    def __init__(self, kern, ops, hop, evals_rad, evecs, circuit):
+        self.kern, self.ops, self.hop = kern, ops, hop
+        self.evals = evals_rad            # [B][k] tensor
+        self.evecs = evecs                # [B][k][N] tensor
+        self.cr = circuit
+        self.B = evecs.shape[0]
+        self.dev = evecs.device
+
+    # ---- helpers ------------------------------------------------------------------------
+    def _pair(self, states):
+        idx = torch.as_tensor(list(states), device=self.dev)
+        return self.evecs.index_select(1, idx).contiguous()        # [B][2][N]
+
+    def _gram2(self, X, Y):
+        out = torch.empty((self.B, 2, 2), dtype=torch.complex128, device=self.dev)
+        self.kern.gram(BlockView(X), BlockView(Y), out)
+        return out.cpu().numpy()
+
+    def _phases(self, b_id, scale=1.0):
+        return np.exp(1j * scale * self.ops.ext_flux(self.hop.loop_vals, b_id))
+
+    def _zeros_a(self):
+        return np.zeros((self.B, max(self.ops.T, 1)), dtype=complex)
+
+    def _apply_pot(self, X, a, g, etab=None, shift=None):
+        ops = self.ops
+        Y = torch.empty_like(X)
+        g = np.broadcast_to(g, (self.B, 1 + ops.M))
+        ops.apply_potential_op(BlockView(X), BlockView(Y), ops.to_device(a, torch.complex128),
+                               ops.to_device(g, torch.float64), etab=etab, shift=shift)
+        return Y
+
+    def _apply_charge_comb(self, X, k):
+        """Y = (sum_i k_i Q_i) X  with Q_i of circuit.py:1471-1497 (normalised by sqrt(hbar))."""
+        ops = self.ops
+        Y = torch.zeros_like(X)
+        ng = self.hop.ng
+        Bn = ng.shape[0]
+        c = 2 * unt.e / np.sqrt(unt.hbar)
+        dvec = torch.zeros((Bn,) + tuple(ops.dims), dtype=torch.float64, device=self.dev)
+        any_charge = False
+        for i in range(ops.M):
+            if ops.harm[i] or k[i] == 0:
+                continue
+            any_charge = True
+            nmax = (ops.dims[i] - 1) // 2
+            vals = (np.arange(-nmax, nmax + 1)[None, :] - ng[:, i:i + 1]) * (k[i] * c)
+            shape = [Bn] + [1] * ops.M
+            shape[1 + i] = ops.dims[i]
+            dvec += torch.as_tensor(vals, dtype=torch.float64, device=self.dev).reshape(shape)
+        first = True
+        if any_charge:
+            self.kern.diag_mul(BlockView(X), BlockView(Y), dvec.reshape(Bn, ops.N).contiguous(), False)
+            first = False
+        for i in range(ops.M):
+            if not ops.harm[i] or ops.dims[i] == 1 or k[i] == 0:
+                continue
+            qzp = -1j * np.sqrt(0.5 / ops.Z[i]) * k[i]          # Q = qzp (a - a^dag)
+            cdn = torch.full((self.B,), qzp, dtype=torch.complex128, device=self.dev)
+            cup = torch.full((self.B,), -qzp, dtype=torch.complex128, device=self.dev)
+            self.kern.ladder_apply(ops.sp, i, cdn, cup, BlockView(X), BlockView(Y), not first)
+            first = False
+        return Y
+
+    # ---- operators of the reference ----------------------------------------------------------
+    def apply_coupling(self, X, ctype, nodes):
+        k = self.ops._kcoef(ctype, nodes)
+        if ctype == 'capacitive':
+            return self._apply_charge_comb(X, k)
+        return self._apply_pot(X, self._zeros_a(), self.ops._phi_lin(k))
+
+    def apply_junction_fn(self, X, kind, w_id, b_id, weight=1.0):
+        """cos / sin / sin_half operator of one junction (circuit.py:1809-1825)."""
+        a = self._zeros_a()
+        if kind == 'cos':
+            a[:, w_id] = weight * self._phases(b_id) / 2
+            return self._apply_pot(X, a, np.zeros(1 + self.ops.M))
+        if kind == 'sin':
+            a[:, w_id] = weight * self._phases(b_id) / 2j
+            return self._apply_pot(X, a, np.zeros(1 + self.ops.M))
+        if kind == 'sin_half':
+            a[:, w_id] = weight * self._phases(b_id, 0.5) / 2j
+            return self._apply_pot(X, a, np.zeros(1 + self.ops.M), etab=self.ops.etab_half(),
+                                   shift=np.zeros_like(self.ops.shift))
+        raise ValueError(kind)
+
+    def matrix_elements(self, ctype, nodes, states):
+        X = self._pair(states)
+        return self._gram2(X, self.apply_coupling(X, ctype, nodes))[:, 0, 1]
+
+    # ---- decoherence ----------------------------------------------------------------------------
+    @staticmethod
+    def _dephasing(A, p_omega):
+        return np.abs(p_omega * A) * np.sqrt(2 * np.abs(np.log(ENV['omega_low'] * ENV['t_exp'])))
+
+    def _partial_omega_loop(self, X, loop_idx):
+        """<m|dH/dphi_loop|m> - <n|...|n>  (circuit.py:2749-2763)."""
+        ops, t = self.ops, self.ops.topo
+        g = np.zeros(1 + ops.M)
+        for edge, el, b_id in t.ind_keys:
+            g += (t.B[b_id, loop_idx] / el.si() * unt.Phi0 / np.sqrt(unt.hbar) / 2 / np.pi
+                  * ops._phi_lin(ops._kcoef('inductive', edge)))
+        a = self._zeros_a()
+        for _, jj, b_id, w_id in t.jj_keys:
+            a[:, w_id] += t.B[b_id, loop_idx] * jj.si() * self._phases(b_id) / 2j
+        G = self._gram2(X, self._apply_pot(X, a, g))
+        return np.real(G[:, 0, 0] - G[:, 1, 1])
+
+    def dec_rate(self, dec_type, states, total=True):
+        cr, ops, t = self.cr, self.ops, self.ops.topo
+        w = self.evals.cpu().numpy()
+        omega = np.abs(w[:, states[1]] - w[:, states[0]])
+        X = self._pair(states)
+        alpha = unt.hbar * omega / (unt.k_B * ENV['T'])
+        big = alpha > 709
+        al = np.where(big, 1.0, alpha)
+        down = np.where(big, 2.0, 1 + 1 / np.tanh(al / 2))
+        up = np.where(big, 0.0, down * np.exp(-al))
+        if total:
+            tempS = down + up
+        else:
+            tempS = down if states[0] > states[1] else up
+        decay = np.zeros(self.B)
+        if dec_type == 'capacitive':
+            for edge, els in cr.elements.items():
+                for el in els:
+                    cap = el if isinstance(el, Capacitor) else el.cap
+                    if cap.Q:
+                        me = self._gram2(X, self.apply_coupling(X, 'capacitive', edge))[:, 0, 1]
+                        decay += tempS * cap.si() / cap.Q(omega) * np.abs(me) ** 2
+        elif dec_type == 'inductive':
+            for edge, el, b_id in t.ind_keys:
+                Q = np.asarray(el.Q(omega, ENV['T']), dtype=float) * np.ones(self.B)
+                me = self._gram2(X, self.apply_coupling(X, 'inductive', edge))[:, 0, 1]
+                term = tempS / Q / el.si() * np.abs(me) ** 2
+                decay += np.where(np.isnan(Q), 0.0, term)
+        elif dec_type == 'quasiparticle':
+            for _, el, b_id, w_id in t.jj_keys:
+                Y = np.asarray(el.Y(omega, ENV['T']), dtype=float) * np.ones(self.B)
+                me = self._gram2(X, self.apply_junction_fn(X, 'sin_half', w_id, b_id))[:, 0, 1]
+                term = tempS * Y * omega * el.si() * unt.hbar * np.abs(me) ** 2
+                decay += np.where(np.isnan(Y), 0.0, term)
+        elif dec_type == 'charge':
+            for i in range(ops.M):
+                if ops.harm[i]:
+                    continue
+                k = t.cInvTrans[i, :ops.M] / np.sqrt(unt.hbar)
+                G = self._gram2(X, self._apply_charge_comb(X, k))
+                p_omega = np.abs(G[:, 0, 0] - G[:, 1, 1])
+                decay += self._dephasing(cr.charge_islands[i].A * 2 * unt.e, p_omega)
+        elif dec_type == 'cc':
+            for _, el, b_id, w_id in t.jj_keys:
+                G = self._gram2(X, self.apply_junction_fn(X, 'cos', w_id, b_id, weight=-1.0))
+                p_omega = np.real(G[:, 0, 0] - G[:, 1, 1])
+                decay += self._dephasing(el.A * el.si(), p_omega)
+        elif dec_type == 'flux':
+            for li, lp in enumerate(t.loops):
+                decay += self._dephasing(lp.A, self._partial_omega_loop(X, li))
+        else:
+            raise ValueError(f'The decoherence type {dec_type} is not supported.')
+        return decay

@@ -17,3 +17,5 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+sys.path.insert(0, os.path.join(ROOT, 'tests'))

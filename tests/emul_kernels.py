@@ -1,0 +1,349 @@
+"""TEST-ONLY numpy emulation of the kernel contracts in include/sqcircuit_b200.h.
+
+The product has exactly one backend (the CUDA library).  This module restates what each C
+entry point is specified to compute so that the *host logic* (operator tables, block-Davidson
+orchestration, decoherence formulas) can be checked on a machine without a GPU
+(`pytest -m "not gpu"`).  It is injected through ``Circuit(..., kernels=EmulKernels())``; nothing
+under ``sqcircuit_b200/`` imports it.
+"""
+import numpy as np
+import torch
+
+
+def _cnt(blk, b):
+    return int(blk.cnt[b]) if blk.cnt is not None else blk.cnt_fixed
+
+
+def _off(blk, b):
+    return blk.first + (int(blk.off[b]) if blk.off is not None else 0)
+
+
+def _get(blk, b):
+    o, c = _off(blk, b), _cnt(blk, b)
+    return blk.tensor[b, o:o + c, :].numpy()
+
+
+def _set(blk, b, arr):
+    o = _off(blk, b)
+    blk.tensor[b, o:o + arr.shape[0], :] = torch.from_numpy(np.ascontiguousarray(arr))
+
+
+class EmulKernels:
+    name = 'emul'
+
+    def __init__(self):
+        self.dev = torch.device('cpu')
+        self.launches = 0
+
+    def launch_count(self):
+        return self.launches
+
+    # ---- (1) --------------------------------------------------------------------------
+    def xbasis(self, m):
+        x = np.diag(np.sqrt(np.arange(1, m)), 1)
+        x = x + x.T
+        lam, V = np.linalg.eigh(x)
+        for j in range(m):
+            nz = np.where(np.abs(V[:, j]) > 1e-8)[0][0]
+            if V[nz, j] < 0:
+                V[:, j] = -V[:, j]
+        return torch.from_numpy(V.copy()), torch.from_numpy(lam.copy())
+
+    def phase_tables(self, sp, n_terms, lam, s, etab):
+        dims = [sp.dims[i] for i in range(sp.n_modes)]
+        off = np.concatenate(([0], np.cumsum(dims)))
+        lamn = lam.numpy()
+        for b in range(etab.shape[0]):
+            sb = s[min(b, s.shape[0] - 1)].numpy()
+            for t in range(n_terms):
+                for m in range(sp.n_modes):
+                    seg = slice(off[m], off[m + 1])
+                    if sp.harmonic[m]:
+                        etab[b, t, seg] = torch.from_numpy(np.exp(1j * sb[t, m] * lamn[seg]))
+                    else:
+                        etab[b, t, seg] = 1.0
+
+    def lc_diagonal(self, sp, omega, q, ng, out):
+        M = sp.n_modes
+        dims = [sp.dims[i] for i in range(M)]
+        grids = np.meshgrid(*[np.arange(d) for d in dims], indexing='ij')
+        for b in range(out.shape[0]):
+            val = []
+            for m in range(M):
+                if sp.harmonic[m]:
+                    val.append(grids[m].astype(float))
+                else:
+                    val.append(grids[m] - (dims[m] - 1) // 2 - float(ng[b, m]))
+            acc = np.zeros(dims)
+            for m in range(M):
+                if sp.harmonic[m]:
+                    acc += float(omega[b, m]) * val[m]
+                else:
+                    for m2 in range(m, M):
+                        if not sp.harmonic[m2]:
+                            acc += float(q[b, m, m2]) * val[m] * val[m2]
+            out[b] = torch.from_numpy(acc.reshape(-1))
+
+    # ---- (2) --------------------------------------------------------------------------
+    def diag_mul(self, X, Y, diag, accumulate):
+        for b in range(X.B):
+            d = diag[min(b, diag.shape[0] - 1)].numpy()
+            r = _get(X, b) * d[None, :]
+            if accumulate:
+                r = r + _get(Y, b)[:r.shape[0]]
+            _set(Y, b, r)
+
+    def mode_transform(self, sp, mode, mat, transpose, X, Z, ediag=None, EX=None, impl=0):
+        dims = [sp.dims[i] for i in range(sp.n_modes)]
+        for b in range(X.B):
+            x = _get(X, b)
+            if x.shape[0] == 0:
+                continue
+            m = mat.numpy() if mat.dim() == 2 else mat[min(b, mat.shape[0] - 1)].numpy()
+            mm = m.T if transpose else m
+            t = x.reshape([x.shape[0]] + dims)
+            t = np.moveaxis(np.tensordot(mm, t, axes=([1], [1 + mode])), 0, 1 + mode)
+            r = t.reshape(x.shape[0], -1)
+            if ediag is not None:
+                r = r + ediag[min(b, ediag.shape[0] - 1)].numpy()[None, :] * _get(EX, b)
+            _set(Z, b, r)
+
+    def potential_apply(self, sp, pot, X, Z):
+        a, g, etab, diag = pot._keep
+        M = sp.n_modes
+        dims = [sp.dims[i] for i in range(M)]
+        off = np.concatenate(([0], np.cumsum(dims)))
+        lam = torch.frombuffer(bytearray(0), dtype=torch.float64) if False else None
+        lamn = self._lam_from_ptr(pot, off[-1])
+        for b in range(X.B):
+            x = _get(X, b)
+            nv = x.shape[0]
+            if nv == 0:
+                continue
+            t = x.reshape([nv] + dims)
+            gb = g[b].numpy()
+            lin = np.full(dims, gb[0])
+            for m in range(M):
+                if sp.harmonic[m]:
+                    shp = [1] * M
+                    shp[m] = dims[m]
+                    lin = lin + gb[1 + m] * lamn[off[m]:off[m + 1]].reshape(shp)
+            if diag is not None:
+                lin = lin + diag[min(b, diag.shape[0] - 1)].numpy().reshape(dims)
+            out = lin[None] * t
+            eb = etab[min(b, etab.shape[0] - 1)].numpy()
+            for tt in range(pot.n_terms):
+                ph = np.full(dims, complex(a[b, tt]))
+                sh = [0] * M
+                for m in range(M):
+                    if sp.harmonic[m]:
+                        shp = [1] * M
+                        shp[m] = dims[m]
+                        ph = ph * eb[tt, off[m]:off[m + 1]].reshape(shp)
+                    else:
+                        sh[m] = int(pot.shift[tt][m])
+                out = out + ph[None] * self._shifted(t, sh, +1) + np.conj(ph)[None] * self._shifted(t, sh, -1)
+            _set(Z, b, out.reshape(nv, -1))
+
+    @staticmethod
+    def _lam_from_ptr(pot, n):
+        import ctypes
+        arr = (ctypes.c_double * int(n)).from_address(pot.lam)
+        return np.frombuffer(arr, dtype=np.float64).copy()
+
+    @staticmethod
+    def _shifted(t, sh, sign):
+        """out(i) = t(i - sign*sh) with zero fill outside the truncated space."""
+        out = t
+        for m, s in enumerate(sh):
+            s = sign * s
+            if s == 0:
+                continue
+            ax = 1 + m
+            res = np.zeros_like(out)
+            n = out.shape[ax]
+            src = [slice(None)] * out.ndim
+            dst = [slice(None)] * out.ndim
+            if s > 0:
+                dst[ax], src[ax] = slice(s, n), slice(0, n - s)
+            else:
+                dst[ax], src[ax] = slice(0, n + s), slice(-s, n)
+            res[tuple(dst)] = out[tuple(src)]
+            out = res
+        return out
+
+    def ladder_apply(self, sp, mode, c_dn, c_up, X, Y, accumulate):
+        dims = [sp.dims[i] for i in range(sp.n_modes)]
+        m = dims[mode]
+        a = np.diag(np.sqrt(np.arange(1, m)), 1)
+        for b in range(X.B):
+            x = _get(X, b)
+            op = complex(c_dn[b]) * a + complex(c_up[b]) * a.T
+            t = x.reshape([x.shape[0]] + dims)
+            r = np.moveaxis(np.tensordot(op, t, axes=([1], [1 + mode])), 0, 1 + mode).reshape(x.shape[0], -1)
+            if accumulate:
+                r = r + _get(Y, b)[:r.shape[0]]
+            _set(Y, b, r)
+
+    # ---- (3) --------------------------------------------------------------------------
+    def gram(self, A, Bm, Cout, impl=0):
+        B, ldr, ldc = Cout.shape
+        rows, cols = min(A.cnt_fixed, ldr), min(Bm.cnt_fixed, ldc)
+        for b in range(B):
+            a, c = _get(A, b), _get(Bm, b)
+            Cout[b, :rows, :cols] = 0
+            if a.shape[0] and c.shape[0]:
+                Cout[b, :a.shape[0], :c.shape[0]] = torch.from_numpy(a.conj() @ c.T)
+
+    def block_update(self, A, Cf, Out, op=0, trans=0):
+        for b in range(A.B):
+            nb = _cnt(Out, b)
+            if nb == 0:
+                continue
+            a = _get(A, b)
+            na = a.shape[0]
+            if na == 0 and op == 1:
+                continue
+            cf = Cf[b].numpy()
+            co = cf[:na, :nb].T if trans else cf[:nb, :na]
+            r = co @ a
+            if op == 1:
+                r = _get(Out, b) - r
+            _set(Out, b, r)
+
+    def block_rightmul(self, T, Cq, nout):
+        for b in range(T.B):
+            nin = _cnt(T, b)
+            if nin == 0:
+                continue
+            t = _get(T, b)
+            no = int(nout[b])
+            r = np.zeros_like(t)
+            r[:no] = Cq[b].numpy()[:no, :nin] @ t
+            _set(T, b, r)
+
+    def heev(self, A, n, w, Zt):
+        B, ld, _ = A.shape
+        for b in range(B):
+            nb = n if isinstance(n, int) else int(n[b])
+            if nb <= 0:
+                continue
+            a = A[b, :nb, :nb].numpy()
+            ww, v = np.linalg.eigh((a + a.conj().T) / 2)
+            w[b] = float('inf')
+            w[b, :nb] = torch.from_numpy(ww)
+            Zt[b, :nb, :nb] = torch.from_numpy(np.ascontiguousarray(v.T))
+
+    def residual_norms(self, X, HX, theta, rn2):
+        p = X.cnt_fixed
+        for b in range(X.B):
+            x, hx = _get(X, b), _get(HX, b)
+            rn2[b] = 0
+            for j in range(x.shape[0]):
+                r = hx[j] - float(theta[b, j]) * x[j]
+                rn2[b, j] = float(np.vdot(r, r).real)
+
+    def davidson_state(self, **kw):
+        class S:
+            pass
+        st = S()
+        for k, v in kw.items():
+            setattr(st, k, v)
+        return st
+
+    def davidson_decide(self, st, B):
+        st.n_not_done[0] = 0
+        p, k = st.p, st.k
+        for b in range(B):
+            if int(st.done[b]):
+                st.nact[b] = 0
+                st.restart[b] = 0
+                continue
+            msz = int(st.msz[b])
+            pe = min(p, msz)
+            th = st.theta[b].numpy()
+            scale = max(st.tol_abs_floor, np.max(np.abs(th[:min(k, pe)])))
+            rmax, n = 0.0, 0
+            for j in range(pe):
+                rel = np.sqrt(float(st.rn2[b, j])) / scale
+                if j < k:
+                    rmax = max(rmax, rel)
+                if rel > 0.5 * st.tol_rel:
+                    st.act[b, n] = j
+                    n += 1
+            st.resmax[b] = rmax
+            restart = 0
+            if rmax <= st.tol_rel:
+                st.done[b] = 1
+                n = 0
+            else:
+                st.n_not_done[0] += 1
+                if msz + n > st.mmax:
+                    restart = 1
+            st.nact[b] = n
+            st.restart[b] = restart
+            fl = max(abs(th[0]), abs(th[pe - 1]), th[pe - 1] - th[0])
+            st.den_floor[b] = max(1e-3 * fl, 1e-300)
+            if restart:
+                st.msz[b] = pe
+                st.G[b] = 0
+                for r in range(p):
+                    st.G[b, r, r] = th[r]
+
+    def restart_copy(self, X, HX, V, W, restart):
+        for b in range(X.B):
+            if int(restart[b]):
+                _set(V, b, _get(X, b))
+                _set(W, b, _get(HX, b))
+
+    def precond_residual(self, X, HX, T, theta, act, d, den_floor):
+        for b in range(X.B):
+            n = _cnt(T, b)
+            if n == 0:
+                continue
+            x, hx = X.tensor[b].numpy(), HX.tensor[b].numpy()
+            dd = d[min(b, d.shape[0] - 1)].numpy()
+            fl = float(den_floor[b])
+            out = []
+            for jj in range(n):
+                a = int(act[b, jj])
+                th = float(theta[b, a])
+                den = dd - th
+                den = np.where(np.abs(den) < fl, np.where(den < 0, -fl, fl), den)
+                out.append((hx[a] - th * x[a]) / den)
+            _set(T, b, np.array(out))
+
+    def svqb_coeffs(self, S, nact, drop, Cq, msz=None, mtot=None):
+        B, ld, _ = S.shape
+        for b in range(B):
+            n = min(int(nact[b]), ld)
+            Cq[b] = 0
+            if n <= 0:
+                if mtot is not None:
+                    mtot[b] = msz[b]
+                continue
+            s = S[b, :n, :n].numpy()
+            dg = np.real(np.diag(s))
+            dsc = np.where(dg > 0, 1 / np.sqrt(np.where(dg > 0, dg, 1)), 0.0)
+            a = (s + s.conj().T) / 2 * np.outer(dsc, dsc)
+            w, u = np.linalg.eigh(a)
+            order = [i for i in np.argsort(-w) if w[i] > drop * w.max() and w[i] > 0]
+            for j, src in enumerate(order):
+                Cq[b, j, :n] = torch.from_numpy(dsc * u[:, src] / np.sqrt(w[src]))
+            nact[b] = len(order)
+            if mtot is not None:
+                mtot[b] = int(msz[b]) + len(order)
+
+    def davidson_insert(self, st, S, B):
+        for b in range(B):
+            na, msz = int(st.nact[b]), int(st.msz[b])
+            if na <= 0:
+                continue
+            s = S[b].numpy()
+            blk = s[:msz + na, :na].copy()
+            d = blk[msz:, :]
+            blk[msz:, :] = (d + d.conj().T) / 2
+            G = st.G[b].numpy()
+            G[:msz + na, msz:msz + na] = blk
+            G[msz:msz + na, :msz + na] = blk.conj().T
+            st.msz[b] = msz + na

@@ -1,0 +1,240 @@
+"""Kernel-level parity on the GPU: every C entry point against a torch/numpy restatement
+(the same contracts tests/emul_kernels.py states), through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from sqcircuit_b200.kernels import BlockView, Kernels, make_space  # noqa: E402
+from emul_kernels import EmulKernels  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def kern():
+    assert torch.cuda.is_available()
+    return Kernels('cuda:0')
+
+
+def rnd(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.complex(torch.randn(shape, dtype=torch.float64, generator=g),
+                         torch.randn(shape, dtype=torch.float64, generator=g))
+
+
+def relerr(a, b):
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-300))
+
+
+@pytest.mark.parametrize('B,na,nb,N', [(3, 48, 12, 10100), (5, 7, 3, 625), (2, 64, 16, 1000),
+                                       (300, 24, 12, 777), (1, 12, 12, 199), (4, 33, 9, 4096)])
+@pytest.mark.parametrize('impl', [0, 1])
+def test_gram(kern, B, na, nb, N, impl):
+    A = rnd((B, na, N), 1)
+    Bm = rnd((B, nb, N), 2)
+    ca = torch.randint(0, na + 1, (B,), dtype=torch.int32)
+    ca[0] = na
+    cb = torch.randint(0, nb + 1, (B,), dtype=torch.int32)
+    cb[0] = nb
+    ref = torch.zeros((B, na, 16), dtype=torch.complex128)
+    EmulKernels().gram(BlockView(A, cnt=ca), BlockView(Bm, cnt=cb), ref)
+    out = torch.full((B, na, 16), 7.0, dtype=torch.complex128, device='cuda')
+    kern.gram(BlockView(A.cuda(), cnt=ca.cuda()), BlockView(Bm.cuda(), cnt=cb.cuda()), out, impl)
+    assert relerr(out.cpu()[:, :na, :nb], ref[:, :na, :nb]) < 1e-13
+
+
+def test_gram_offsets(kern):
+    B, mm, N = 4, 40, 999
+    V = rnd((B, mm, N), 3)
+    off = torch.tensor([10, 20, 28, 5], dtype=torch.int32)
+    cnt = torch.tensor([12, 3, 12, 0], dtype=torch.int32)
+    msz = off.clone()
+    ref = torch.zeros((B, mm, 16), dtype=torch.complex128)
+    EmulKernels().gram(BlockView(V, cnt_fixed=mm, cnt=msz), BlockView(V, cnt_fixed=12, off=off, cnt=cnt), ref)
+    Vd = V.cuda()
+    out = torch.zeros((B, mm, 16), dtype=torch.complex128, device='cuda')
+    kern.gram(BlockView(Vd, cnt_fixed=mm, cnt=msz.cuda()),
+              BlockView(Vd, cnt_fixed=12, off=off.cuda(), cnt=cnt.cuda()), out)
+    assert relerr(out.cpu(), ref) < 1e-13
+
+
+@pytest.mark.parametrize('nb', [3, 8, 12, 16])
+@pytest.mark.parametrize('op,trans', [(0, 0), (1, 1)])
+def test_block_update(kern, nb, op, trans):
+    B, na, N = 3, 37, 2050
+    A = rnd((B, na, N), 4)
+    Out = rnd((B, nb, N), 5)
+    Cf = rnd((B, 48, 48), 6)
+    ca = torch.tensor([37, 20, 0], dtype=torch.int32)
+    cb = torch.tensor([nb, max(nb - 2, 1), nb], dtype=torch.int32)
+    ref = Out.clone()
+    EmulKernels().block_update(BlockView(A, cnt=ca), Cf, BlockView(ref, cnt=cb), op, trans)
+    o = Out.cuda()
+    kern.block_update(BlockView(A.cuda(), cnt=ca.cuda()), Cf.cuda(), BlockView(o, cnt=cb.cuda()), op, trans)
+    assert relerr(o.cpu(), ref) < 1e-13
+
+
+def test_block_rightmul(kern):
+    B, N = 3, 1500
+    T = rnd((B, 40, N), 7)
+    off = torch.tensor([5, 28, 0], dtype=torch.int32)
+    nin = torch.tensor([12, 7, 0], dtype=torch.int32)
+    nout = torch.tensor([9, 7, 0], dtype=torch.int32)
+    Cq = rnd((B, 16, 16), 8)
+    ref = T.clone()
+    EmulKernels().block_rightmul(BlockView(ref, cnt_fixed=12, off=off, cnt=nin), Cq, nout)
+    t = T.cuda()
+    kern.block_rightmul(BlockView(t, cnt_fixed=12, off=off.cuda(), cnt=nin.cuda()), Cq.cuda(), nout.cuda())
+    assert relerr(t.cpu(), ref) < 1e-13
+
+
+@pytest.mark.parametrize('ld,sizes', [(48, [48, 31, 12, 1, 0, 47]), (16, [16, 5]), (100, [100, 61]),
+                                      (112, [112]), (64, [64, 63])])
+def test_heev(kern, ld, sizes):
+    B = len(sizes)
+    A = rnd((B, ld, ld), 9)
+    A = A + A.conj().transpose(1, 2)
+    # a spectrum with clusters and a wide range, like a projected Hamiltonian
+    A[0] = A[0] * 1e10
+    n = torch.tensor(sizes, dtype=torch.int32)
+    w = torch.full((B, ld), -1.0, dtype=torch.float64, device='cuda')
+    Zt = torch.zeros((B, ld, ld), dtype=torch.complex128, device='cuda')
+    kern.heev(A.cuda(), n.cuda(), w, Zt)
+    w, Zt = w.cpu(), Zt.cpu()
+    for b, nb in enumerate(sizes):
+        if nb == 0:
+            assert float(w[b, 0]) == -1.0
+            continue
+        a = A[b, :nb, :nb].numpy()
+        wr = np.linalg.eigvalsh(a)
+        scale = np.abs(wr).max()
+        assert np.abs(w[b, :nb].numpy() - wr).max() < 1e-13 * scale
+        Z = Zt[b, :nb, :nb].numpy().T
+        assert np.abs(Z.conj().T @ Z - np.eye(nb)).max() < 1e-13
+        assert np.abs(a @ Z - Z * w[b, :nb].numpy()[None, :]).max() < 2e-13 * scale * np.sqrt(nb)
+
+
+@pytest.mark.parametrize('m', [2, 9, 25, 100, 101, 112])
+def test_xbasis(kern, m):
+    V, lam = kern.xbasis(m)
+    V, lam = V.cpu().numpy(), lam.cpu().numpy()
+    x = np.diag(np.sqrt(np.arange(1, m)), 1)
+    x = x + x.T
+    assert np.all(np.diff(lam) > 0)
+    assert np.abs(np.linalg.eigvalsh(x) - lam).max() < 1e-13 * np.sqrt(m) * 4
+    assert np.abs(V.T @ V - np.eye(m)).max() < 1e-13
+    assert np.abs(x @ V - V * lam[None, :]).max() < 1e-12
+    # displacement operator D(i s) == expm(i s (a + a^dag))  (what qt.displace computes)
+    import scipy.linalg
+    s = 0.37
+    D = (V * np.exp(1j * s * lam)[None, :]) @ V.T
+    assert np.abs(D - scipy.linalg.expm(1j * s * x)).max() < 1e-12
+
+
+def test_svqb(kern):
+    B, N, p = 4, 800, 12
+    T = rnd((B, p, N), 11)
+    T[1, 5] = T[1, 2] * (1 + 1e-9) + 1e-15 * T[1, 3]     # (numerically) dependent direction
+    T[2, 7] = 0                                           # zero vector
+    nact = torch.tensor([12, 12, 12, 0], dtype=torch.int32)
+    msz = torch.tensor([12, 24, 36, 12], dtype=torch.int32)
+    Td = T.cuda()
+    S = torch.zeros((B, 16, 16), dtype=torch.complex128, device='cuda')
+    nin = nact.clone().cuda()
+    na = nact.clone().cuda()
+    kern.gram(BlockView(Td, cnt=nin), BlockView(Td, cnt=nin), S)
+    Cq = torch.zeros((B, 16, 16), dtype=torch.complex128, device='cuda')
+    mtot = torch.zeros(B, dtype=torch.int32, device='cuda')
+    kern.svqb_coeffs(S, na, 1e-12, Cq, msz.cuda(), mtot)
+    kern.block_rightmul(BlockView(Td, cnt=nin), Cq, na)
+    na = na.cpu()
+    assert list(na) == [12, 11, 11, 0]
+    assert list(mtot.cpu()) == [24, 35, 47, 12]
+    for b in range(3):
+        q = Td[b, :int(na[b])].cpu().numpy()
+        assert np.abs(q.conj() @ q.T - np.eye(int(na[b]))).max() < 1e-6   # first SVQB pass
+        assert float(Td[b, int(na[b]):p].abs().max()) == 0.0 if int(na[b]) < p else True
+
+
+def _space_cases():
+    return [([25, 25], [1, 0]), ([100, 101], [1, 0]), ([6, 11, 11], [1, 0, 0]), ([100], [1]),
+            ([1, 9, 23], [1, 1, 1]), ([61], [0]), ([7, 5, 9], [0, 1, 0])]
+
+
+@pytest.mark.parametrize('dims,harm', _space_cases())
+@pytest.mark.parametrize('impl', [0, 1])
+def test_mode_transform(kern, dims, harm, impl):
+    N = int(np.prod(dims))
+    B, nv = 3, 5
+    sp = make_space(dims, harm)
+    X = rnd((B, nv, N), 12)
+    cnt = torch.tensor([5, 2, 0], dtype=torch.int32)
+    ed = torch.randn((B, N), dtype=torch.float64)
+    for mode, d in enumerate(dims):
+        if not harm[mode] or d == 1:
+            continue
+        mat = torch.randn((d, d), dtype=torch.float64)
+        for transpose in (0, 1):
+            for use_ep in (False, True):
+                ref = torch.zeros_like(X)
+                EmulKernels().mode_transform(sp, mode, mat, transpose, BlockView(X, cnt=cnt),
+                                             BlockView(ref, cnt=cnt), ed if use_ep else None,
+                                             BlockView(X, cnt=cnt) if use_ep else None)
+                Xd = X.cuda()
+                out = torch.zeros_like(Xd)
+                kern.mode_transform(sp, mode, mat.cuda(), transpose, BlockView(Xd, cnt=cnt.cuda()),
+                                    BlockView(out, cnt=cnt.cuda()), ed.cuda() if use_ep else None,
+                                    BlockView(Xd, cnt=cnt.cuda()) if use_ep else None, impl=impl)
+                assert relerr(out.cpu(), ref) < 1e-13, (mode, transpose, use_ep)
+                if not use_ep:  # in place
+                    kern.mode_transform(sp, mode, mat.cuda(), transpose, BlockView(Xd, cnt=cnt.cuda()),
+                                        BlockView(Xd, cnt=cnt.cuda()), impl=impl)
+                    assert relerr(Xd.cpu()[:2], ref[:2]) < 1e-13
+
+
+def test_small_elementwise_kernels(kern):
+    B, p, N = 3, 6, 1000
+    X, HX = rnd((B, p, N), 13), rnd((B, p, N), 14)
+    theta = torch.randn((B, 48), dtype=torch.float64)
+    E = EmulKernels()
+    ref = torch.zeros((B, p), dtype=torch.float64)
+    E.residual_norms(BlockView(X), BlockView(HX), theta, ref)
+    out = torch.zeros((B, p), dtype=torch.float64, device='cuda')
+    kern.residual_norms(BlockView(X.cuda()), BlockView(HX.cuda()), theta.cuda(), out)
+    assert float((out.cpu() - ref).abs().max() / ref.abs().max()) < 1e-13
+    # preconditioned residual into the tail of a basis
+    V = rnd((B, 30, N), 15)
+    msz = torch.tensor([6, 12, 20], dtype=torch.int32)
+    nact = torch.tensor([6, 3, 0], dtype=torch.int32)
+    act = torch.tensor([[0, 1, 2, 3, 4, 5], [5, 0, 2, 0, 0, 0], [0] * 6], dtype=torch.int32)
+    d = torch.randn((B, N), dtype=torch.float64) * 10
+    fl = torch.tensor([0.5, 0.1, 0.1], dtype=torch.float64)
+    refV = V.clone()
+    E.precond_residual(BlockView(X), BlockView(HX), BlockView(refV, cnt_fixed=p, off=msz, cnt=nact), theta, act, d, fl)
+    Vd = V.cuda()
+    kern.precond_residual(BlockView(X.cuda()), BlockView(HX.cuda()),
+                          BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()), theta.cuda(),
+                          act.cuda(), d.cuda(), fl.cuda())
+    assert relerr(Vd.cpu(), refV) < 1e-13
+    # restart copy
+    W = rnd((B, 30, N), 16)
+    rs = torch.tensor([1, 0, 1], dtype=torch.int32)
+    refV2, refW2 = V.clone(), W.clone()
+    E.restart_copy(BlockView(X), BlockView(HX), BlockView(refV2, cnt_fixed=p), BlockView(refW2, cnt_fixed=p), rs)
+    Vd, Wd = V.cuda(), W.cuda()
+    kern.restart_copy(BlockView(X.cuda()), BlockView(HX.cuda()), BlockView(Vd, cnt_fixed=p),
+                      BlockView(Wd, cnt_fixed=p), rs.cuda())
+    assert relerr(Vd.cpu(), refV2) == 0 and relerr(Wd.cpu(), refW2) == 0
+    # diag mul
+    Y = rnd((B, p, N), 17)
+    refY = Y.clone()
+    E.diag_mul(BlockView(X), BlockView(refY), d, True)
+    Yd = Y.cuda()
+    kern.diag_mul(BlockView(X.cuda()), BlockView(Yd), d.cuda(), True)
+    assert relerr(Yd.cpu(), refY) < 1e-14
+
+
+def test_launch_counter(kern):
+    n0 = kern.launch_count()
+    kern.xbasis(8)
+    assert kern.launch_count() == n0 + 1

@@ -1,0 +1,194 @@
+"""End-to-end parity on the GPU: the product path (C ABI, CUDA kernels) against the CPU oracle
+and the golden fixtures generated from the reference.
+
+Tolerances (BASELINE.json north_star): eigenfrequencies 1e-9 relative, eigenvectors by
+subspace overlap > 1 - 1e-10, |matrix elements| and decay rates 1e-8 relative (with an
+absolute floor of 1e-9 x the channel's scale over the sweep for symmetry-forbidden values)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import circuits as cs  # noqa: E402
+from oracle import sqc_oracle as o  # noqa: E402
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+DEC = ['capacitive', 'inductive', 'quasiparticle', 'charge', 'cc', 'flux']
+
+
+def _check(res, oc, setter, params, k, decs, mels=()):
+    ref_dec = {d: [] for d in decs}
+    for i, prm in enumerate(params):
+        setter(prm)
+        e, v = oc.diag(k + 1)
+        got = res.efreqs[i].cpu().numpy()
+        assert np.max(np.abs(got - e[:k]) / np.abs(e[:k])) < 1e-9, (i, got, e)
+        ov = o.subspace_overlap(v[:, :k], res.evecs[i].cpu().numpy().T, e[:k], w_next=e[k])
+        assert 1 - ov < 1e-10, (i, ov)
+        oc.diag(k)
+        for d in decs:
+            ref_dec[d].append(oc.dec_rate(d, (1, 0)))
+        for (ct, nodes, st) in mels:
+            a = abs(res.matrix_elements(ct, nodes, st)[i])
+            b = abs(oc.matrix_elements(ct, nodes, st))
+            assert abs(a - b) <= 1e-8 * b + 1e-14 * np.sqrt(abs(e[0]) + 1), (ct, nodes, a, b)
+    for d in decs:
+        got = np.asarray(res.dec_rate(d, (1, 0)))
+        ref = np.asarray(ref_dec[d])
+        assert np.all(np.abs(got - ref) <= 1e-8 * np.abs(ref) + 1e-9 * np.abs(ref).max() + 1e-5), (d, got, ref)
+
+
+def test_hamiltonian_matrix_matches_reference_golden():
+    g = np.load(os.path.join(G, 'zeropi_25_13.npz'))
+    cr, lp, _, _ = cs.zero_pi()
+    cr.set_trunc_nums([25, 13])
+    lp.set_flux(0.31)
+    H = cr.hamiltonian()
+    assert np.abs(H - g['H_at_0p31']).max() <= 1e-12 * np.abs(H).max()
+    g = np.load(os.path.join(G, 'fluxonium_100.npz'))
+    cr, lp, _, _ = cs.fluxonium()
+    cr.set_trunc_nums([100])
+    lp.set_flux(0.31)
+    H = cr.hamiltonian()
+    assert np.abs(H - g['H_at_0p31']).max() <= 1e-12 * np.abs(H).max()
+    g = np.load(os.path.join(G, 'transmon_ncut30.npz'))
+    cr, _ = cs.transmon_single()
+    cr.set_trunc_nums([30])
+    cr.set_charge_offset(1, 0.2)
+    H = cr.hamiltonian()
+    assert np.abs(H - g['H_at_ng0p2']).max() <= 1e-12 * np.abs(H).max()
+
+
+def test_config0_single_transmon_ncut30():
+    cr, oc = cs.transmon_single()
+    cr.set_trunc_nums([30])
+    oc.set_trunc_nums([30])
+    ngs = np.array([0.0, 0.2])
+    res = cr.sweep_diag(10, charge_offsets={1: ngs})
+    _check(res, oc, lambda x: oc.set_charge_offset(1, float(x)), ngs, 10, ['capacitive', 'cc', 'charge'],
+           mels=[('capacitive', (0, 1), (0, 1))])
+    g = np.load(os.path.join(G, 'transmon_ncut30.npz'))
+    assert np.max(np.abs(res.efreqs.cpu().numpy() - g['efreqs_exact']) / np.abs(g['efreqs_exact'])) < 1e-9
+    # the single-point API of the reference
+    cr.set_charge_offset(1, 0.2)
+    ef, ev = cr.diag(10)
+    assert np.max(np.abs(ef - g['efreqs_exact'][1]) / np.abs(ef)) < 1e-9
+    assert abs(cr.dec_rate('cc', (1, 0)) - g['dec_cc'][1]) <= 1e-8 * g['dec_cc'][1]
+
+
+def test_config1_fluxonium_flux_sweep():
+    cr, lp, oc, ol = cs.fluxonium()
+    cr.set_trunc_nums([100])
+    oc.set_trunc_nums([100])
+    g = np.load(os.path.join(G, 'fluxonium_100.npz'))
+    fl = g['params']
+    res = cr.sweep_diag(10, loop_fluxes={lp: fl})
+    ef = res.efreqs.cpu().numpy()
+    assert np.max(np.abs(ef - g['efreqs_exact']) / np.abs(g['efreqs_exact'])) < 1e-9
+    for d in ['capacitive', 'inductive', 'quasiparticle', 'cc', 'flux']:
+        got, ref = res.dec_rate(d, (1, 0)), g['dec_' + d]
+        assert np.all(np.abs(got - ref) <= 1e-8 * np.abs(ref) + 1e-9 * np.abs(ref).max() + 1e-5), d
+    for i in (0, 4, 8):
+        ov = o.subspace_overlap(g['evecs_%d' % i], res.evecs[i].cpu().numpy().T, g['efreqs_exact'][i])
+        assert 1 - ov < 1e-10
+    _check(res, oc, ol.set_flux, fl[:3], 10, ['capacitive', 'inductive', 'quasiparticle', 'cc', 'flux'],
+           mels=[('capacitive', (0, 1), (0, 1)), ('inductive', (0, 1), (0, 1))])
+
+
+def test_config2_zero_pi_flux_sweep_with_rates():
+    cr, lp, oc, ol = cs.zero_pi()
+    cr.set_trunc_nums([25, 13])
+    oc.set_trunc_nums([25, 13])
+    g = np.load(os.path.join(G, 'zeropi_25_13.npz'))
+    fl = g['params']
+    res = cr.sweep_diag(10, loop_fluxes={lp: fl})
+    ef = res.efreqs.cpu().numpy()
+    assert np.max(np.abs(ef - g['efreqs_exact']) / np.abs(g['efreqs_exact'])) < 1e-9
+    for d in DEC:
+        got, ref = res.dec_rate(d, (1, 0)), g['dec_' + d]
+        assert np.all(np.abs(got - ref) <= 1e-8 * np.abs(ref) + 1e-9 * np.abs(ref).max() + 1e-5), (d, got, ref)
+    for i in (0, 3, 8):
+        ov = o.subspace_overlap(g['evecs_%d' % i], res.evecs[i].cpu().numpy().T, g['efreqs_exact'][i])
+        assert 1 - ov < 1e-10
+    _check(res, oc, ol.set_flux, fl[[1, 5]], 10, [], mels=[('capacitive', (0, 1), (0, 1)),
+                                                           ('inductive', (0, 2), (0, 1)),
+                                                           ('capacitive', (2, 3), (1, 2))])
+
+
+def test_zero_pi_reference_known_answers():
+    """SQcircuit/tests/test_qubits.py::test_zero_pi through the Sweep class."""
+    import sqcircuit_b200 as sq
+    cr, lp, _, _ = cs.zero_pi()
+    cr.set_trunc_nums([25, 13])
+    ef, _ = sq.Sweep(cr, 2).sweepFlux([lp], [np.linspace(0, 0.5, 3)])
+    assert np.allclose(ef[1] - ef[0], [0.69721321, 0.45628775, 0.0239571], rtol=1e-6)
+
+
+def test_config2_zero_pi_bench_size_points():
+    """N = 10100 (the bench truncation): golden eigenvalues from the reference Hamiltonian."""
+    g = np.load(os.path.join(G, 'zeropi_100_51.npz'))
+    cr, lp, _, _ = cs.zero_pi()
+    cr.set_trunc_nums([100, 51])
+    st = []
+    res = cr.sweep_diag(10, loop_fluxes={lp: g['params']}, stats=st)
+    ef = res.efreqs.cpu().numpy()
+    assert np.max(np.abs(ef - g['efreqs_exact']) / np.abs(g['efreqs_exact'])) < 1e-9, (ef, st[-1])
+    # size-independent properties: orthonormal vectors, H x = theta x through the operator
+    X = res.evecs
+    gram = X.conj() @ X.transpose(1, 2)
+    assert float((gram - torch.eye(10, device=X.device)).abs().max()) < 1e-10
+    # flux -> -flux and flux -> flux + 1 leave the spectrum unchanged
+    res2 = cr.sweep_diag(10, loop_fluxes={lp: np.array([-0.37, 1.37])})
+    assert np.max(np.abs(res2.efreqs.cpu().numpy() - ef[1][None, :]) / np.abs(ef[1])) < 1e-9
+
+
+def test_config3_transmon_resonator_transmon():
+    cr, oc = cs.trt()
+    cr.set_trunc_nums([6, 6, 6])
+    oc.set_trunc_nums([6, 6, 6])
+    g = np.load(os.path.join(G, 'trt_6_6_6.npz'))
+    m1, m2 = [int(x) for x in g['charge_modes']]
+    ngs = g['params']
+    res = cr.sweep_diag(10, charge_offsets={m1: ngs[:, 0], m2: ngs[:, 1]})
+    ef = res.efreqs.cpu().numpy()
+    assert np.max(np.abs(ef - g['efreqs_exact']) / np.abs(g['efreqs_exact'])) < 1e-9
+
+    def setter(p):
+        oc.set_charge_offset(m1, float(p[0]))
+        oc.set_charge_offset(m2, float(p[1]))
+    _check(res, oc, setter, ngs, 10, ['capacitive', 'cc', 'charge'])
+
+
+def test_other_reference_circuits():
+    cr, lp, oc, ol = cs.coupled_fluxonium_transmon()
+    cr.set_trunc_nums([30, 10])
+    oc.set_trunc_nums([30, 10])
+    fl = np.array([0.0, 0.2, 0.5])
+    res = cr.sweep_diag(10, loop_fluxes={lp: fl})
+    _check(res, oc, ol.set_flux, fl, 10, DEC)
+    ef = res.efreqs[0].cpu().numpy()
+    assert np.allclose(ef - ef[0], [0., 2.07145177, 2.34187898, 3.09228726, 4.92917697, 5.19354651,
+                                    5.87412504, 7.49054673, 7.74403853, 8.2146904])
+    cr, lp, oc, ol = cs.inductively_shunted()
+    cr.set_trunc_nums([1, 9, 23])
+    oc.set_trunc_nums([1, 9, 23])
+    fl = np.array([0.0, 0.25, 0.5])
+    res = cr.sweep_diag(6, loop_fluxes={lp: fl})
+    _check(res, oc, ol.set_flux, fl, 6, ['capacitive', 'inductive', 'cc', 'flux'])
+    cr, oc = cs.transmon()
+    cr.set_trunc_nums([100])
+    oc.set_trunc_nums([100])
+    ngs = np.linspace(0, 0.5, 5)
+    res = cr.sweep_diag(10, charge_offsets={1: ngs})
+    _check(res, oc, lambda x: oc.set_charge_offset(1, float(x)), ngs, 10, ['capacitive', 'cc', 'charge'])
+
+
+def test_no_cpu_fallback_without_library(monkeypatch):
+    from sqcircuit_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libsqcircuit_b200.so')
+    with pytest.raises(_lib.SqcLibraryError):
+        _lib.load()

@@ -1,0 +1,178 @@
+"""CPU tests (no GPU): host-side logic of the product package checked against the oracle with
+the kernel contracts emulated in numpy (tests/emul_kernels.py), plus the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import circuits as cs
+import sqcircuit_b200 as sq
+from emul_kernels import EmulKernels
+from oracle import sqc_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, 'tests', 'golden')
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from sqcircuit_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'sqcircuit_b200.h')).read()
+    declared = set(re.findall(r'\b(sqc_[a-z0-9_]+)\s*\(', hdr))
+    declared = {d for d in declared if not d.endswith('_t')}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().sqc_abi_version() == 1
+    assert _lib.load().sqc_error_string(-1).decode().startswith('sqcircuit_b200')
+
+
+def test_struct_layouts_match_header():
+    from sqcircuit_b200 import _lib
+    assert ctypes.sizeof(_lib.Block) == 40
+    assert ctypes.sizeof(_lib.Space) == 4 + 32 + 32
+    assert _lib.Potential.shift.offset == 4 and _lib.Potential.lam.offset == 4 + 16 * 8 * 4 + 4
+
+
+def test_topology_matches_reference_goldens():
+    for name, builder in [('zeropi_25_13', cs.zero_pi), ('fluxonium_100', cs.fluxonium),
+                          ('fluxonium_transmon_30_10', cs.coupled_fluxonium_transmon),
+                          ('ind_shunted_1_9_23', cs.inductively_shunted)]:
+        g = np.load(os.path.join(G, name + '.npz'))
+        cr = builder(EmulKernels())[0]
+        for key in ('S', 'R', 'wTrans', 'cInvTrans', 'lTrans', 'omega', 'B'):
+            ref, got = g[key], getattr(cr, key)
+            assert np.allclose(got, ref, rtol=1e-12, atol=1e-12 * max(np.abs(ref).max(), 1e-300)), (name, key)
+    g = np.load(os.path.join(G, 'trt_6_6_6.npz'))
+    cr = cs.trt(EmulKernels())[0]
+    for key in ('wTrans', 'cInvTrans', 'omega'):
+        assert np.allclose(getattr(cr, key), g[key], rtol=1e-9, atol=1e-9 * np.abs(g[key]).max()), key
+
+
+@pytest.mark.parametrize('case', ['zeropi', 'fluxonium', 'transmon', 'trt', 'indsh', 'cft'])
+def test_matrix_free_hamiltonian_equals_reference_matrix(case):
+    K = EmulKernels()
+    if case == 'zeropi':
+        cr, lp, oc, ol = cs.zero_pi(K)
+        t = [25, 13]
+        lp.set_flux(0.31)
+        ol.set_flux(0.31)
+    elif case == 'fluxonium':
+        cr, lp, oc, ol = cs.fluxonium(K)
+        t = [100]
+        lp.set_flux(0.31)
+        ol.set_flux(0.31)
+    elif case == 'transmon':
+        cr, oc = cs.transmon(K)
+        t = [20]
+        cr.set_charge_offset(1, 0.2)
+        oc.set_charge_offset(1, 0.2)
+    elif case == 'trt':
+        cr, oc = cs.trt(K)
+        t = [6, 6, 6]
+        for m, v in ((2, 0.13), (3, 0.41)):
+            cr.set_charge_offset(m, v)
+            oc.set_charge_offset(m, v)
+    elif case == 'indsh':
+        cr, lp, oc, ol = cs.inductively_shunted(K)
+        t = [1, 9, 23]
+        lp.set_flux(0.2)
+        ol.set_flux(0.2)
+    else:
+        cr, lp, oc, ol = cs.coupled_fluxonium_transmon(K)
+        t = [30, 10]
+        lp.set_flux(0.2)
+        ol.set_flux(0.2)
+    cr.set_trunc_nums(t)
+    oc.set_trunc_nums(t)
+    H, Ho = cr.hamiltonian(), oc.hamiltonian().toarray()
+    assert np.abs(H - Ho).max() <= 1e-13 * np.abs(Ho).max()
+
+
+def _check(res, oc, setter, params, k, decs):
+    ref = {d: [] for d in decs}
+    for i, p in enumerate(params):
+        setter(p)
+        e, v = oc.diag(k + 1)
+        got = res.efreqs[i].numpy()
+        assert np.max(np.abs(got - e[:k]) / np.abs(e[:k])) < 1e-9
+        assert 1 - o.subspace_overlap(v[:, :k], res.evecs[i].numpy().T, e[:k], w_next=e[k]) < 1e-10
+        oc.diag(k)
+        for d in decs:
+            ref[d].append(oc.dec_rate(d, (1, 0)))
+    for d in decs:
+        got, r = np.asarray(res.dec_rate(d, (1, 0))), np.asarray(ref[d])
+        assert np.all(np.abs(got - r) <= 1e-8 * np.abs(r) + 1e-9 * np.abs(r).max() + 1e-5), (d, got, r)
+
+
+def test_davidson_orchestration_zero_pi():
+    K = EmulKernels()
+    cr, lp, oc, ol = cs.zero_pi(K)
+    cr.set_trunc_nums([25, 13])
+    oc.set_trunc_nums([25, 13])
+    fl = np.array([0.0, 0.3, 0.5])
+    res = cr.sweep_diag(10, loop_fluxes={lp: fl})
+    assert res.converged and res.iterations < 80
+    _check(res, oc, ol.set_flux, fl, 10, ['capacitive', 'inductive', 'quasiparticle', 'charge', 'cc', 'flux'])
+
+
+def test_dense_path_fluxonium():
+    K = EmulKernels()
+    cr, lp, oc, ol = cs.fluxonium(K)
+    cr.set_trunc_nums([100])
+    oc.set_trunc_nums([100])
+    fl = np.array([0.0, 0.25, 0.5])
+    res = cr.sweep_diag(10, loop_fluxes={lp: fl})
+    _check(res, oc, ol.set_flux, fl, 10, ['capacitive', 'inductive', 'quasiparticle', 'cc', 'flux'])
+
+
+def test_charge_sweep_transmon_and_three_modes():
+    K = EmulKernels()
+    cr, oc = cs.transmon(K)
+    cr.set_trunc_nums([100])
+    oc.set_trunc_nums([100])
+    ngs = np.array([0.0, 0.25, 0.5])
+    res = cr.sweep_diag(10, charge_offsets={1: ngs})
+    _check(res, oc, lambda g: oc.set_charge_offset(1, float(g)), ngs, 10, ['capacitive', 'cc', 'charge'])
+    cr, oc = cs.trt(K)
+    cr.set_trunc_nums([6, 6, 6])
+    oc.set_trunc_nums([6, 6, 6])
+    res = cr.sweep_diag(10, charge_offsets={2: np.array([0.0, 0.13]), 3: np.array([0.0, 0.41])})
+
+    def s(p):
+        oc.set_charge_offset(2, p[0])
+        oc.set_charge_offset(3, p[1])
+    _check(res, oc, s, [(0.0, 0.0), (0.13, 0.41)], 10, ['capacitive', 'cc', 'charge'])
+
+
+def test_sweep_class_and_single_point_api():
+    K = EmulKernels()
+    cr, lp, _, _ = cs.zero_pi(K)
+    cr.set_trunc_nums([25, 13])
+    ef, dec = sq.Sweep(cr, 2, properties=['efreq', 'loss']).sweepFlux([lp], [np.linspace(0, 0.5, 3)])
+    assert ef.shape == (2, 3)
+    assert np.allclose(ef[1] - ef[0], [0.69721321, 0.45628775, 0.0239571], rtol=1e-6)
+    assert set(dec) == {'capacitive', 'inductive', 'quasiparticle', 'charge', 'cc', 'flux'}
+    with pytest.raises(sq.CircuitStateError):
+        cs.zero_pi(K)[0].diag(2)
+    with pytest.raises(ValueError):
+        cr.diag(2.0)
+    efs, evs = cr.diag(3)
+    assert len(evs) == 3 and evs[0].full().shape == (625, 1)
+    assert np.allclose(cr.efreqs, efs)
+
+
+def test_elements_api_matches_reference_values():
+    cap = sq.Capacitor(10, 'GHz')
+    assert cap.get_value('GHz') == 10 and np.isclose(cap.get_value(), 2e-15, rtol=2e-2)
+    with pytest.raises(ValueError, match='The input unit is not valid'):
+        sq.Capacitor(10, 'H')
+    ind = sq.Inductor(10)
+    assert np.isclose(ind.get_value(), 1.6346e-8, rtol=1e-4)
+    assert np.isclose(sq.Inductor(10, 'GHz', Q='default').Q(100, 0.015), 559912673679772.0)
+    assert np.isclose(sq.Capacitor(3.4, 'GHz').Q(0.56e9), 19041456.468334354)
+    assert np.isclose(sq.Junction(0.142, 'GHz').Y(50e9, 0.015), 793439739057240.9)
+    with pytest.raises(sq.ModeError):
+        sq.Capacitor(10, requires_grad=True)
