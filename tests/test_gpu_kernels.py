@@ -189,7 +189,9 @@ def test_mode_transform(kern, dims, harm, impl):
                 if not use_ep:  # in place
                     kern.mode_transform(sp, mode, mat.cuda(), transpose, BlockView(Xd, cnt=cnt.cuda()),
                                         BlockView(Xd, cnt=cnt.cuda()), impl=impl)
-                    assert relerr(Xd.cpu()[:2], ref[:2]) < 1e-13
+                    got = Xd.cpu()
+                    assert relerr(got[0], ref[0]) < 1e-13 and relerr(got[1, :2], ref[1, :2]) < 1e-13
+                    assert relerr(got[1, 2:], X[1, 2:]) == 0 and relerr(got[2], X[2]) == 0
 
 
 def test_small_elementwise_kernels(kern):

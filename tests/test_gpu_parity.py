@@ -19,9 +19,11 @@ G = os.path.join(os.path.dirname(__file__), 'golden')
 DEC = ['capacitive', 'inductive', 'quasiparticle', 'charge', 'cc', 'flux']
 
 
-def _check(res, oc, setter, params, k, decs, mels=()):
+def _check(res, oc, setter, params, k, decs, mels=(), idx=None):
+    """Compare sweep points ``idx`` of ``res`` (default: all) with the oracle at ``params``."""
     ref_dec = {d: [] for d in decs}
-    for i, prm in enumerate(params):
+    idx = list(range(len(params))) if idx is None else list(idx)
+    for i, prm in zip(idx, params):
         setter(prm)
         e, v = oc.diag(k + 1)
         got = res.efreqs[i].cpu().numpy()
@@ -34,9 +36,11 @@ def _check(res, oc, setter, params, k, decs, mels=()):
         for (ct, nodes, st) in mels:
             a = abs(res.matrix_elements(ct, nodes, st)[i])
             b = abs(oc.matrix_elements(ct, nodes, st))
-            assert abs(a - b) <= 1e-8 * b + 1e-14 * np.sqrt(abs(e[0]) + 1), (ct, nodes, a, b)
+            # symmetry-forbidden elements are rounding noise: floor relative to ||O v||
+            scale = np.linalg.norm(oc.coupling_op(ct, nodes) @ oc.evecs[:, st[1]])
+            assert abs(a - b) <= 1e-8 * b + 1e-9 * scale, (ct, nodes, a, b, scale)
     for d in decs:
-        got = np.asarray(res.dec_rate(d, (1, 0)))
+        got = np.asarray(res.dec_rate(d, (1, 0)))[idx]
         ref = np.asarray(ref_dec[d])
         assert np.all(np.abs(got - ref) <= 1e-8 * np.abs(ref) + 1e-9 * np.abs(ref).max() + 1e-5), (d, got, ref)
 
@@ -95,7 +99,7 @@ def test_config1_fluxonium_flux_sweep():
         ov = o.subspace_overlap(g['evecs_%d' % i], res.evecs[i].cpu().numpy().T, g['efreqs_exact'][i])
         assert 1 - ov < 1e-10
     _check(res, oc, ol.set_flux, fl[:3], 10, ['capacitive', 'inductive', 'quasiparticle', 'cc', 'flux'],
-           mels=[('capacitive', (0, 1), (0, 1)), ('inductive', (0, 1), (0, 1))])
+           mels=[('capacitive', (0, 1), (0, 1)), ('inductive', (0, 1), (0, 1))], idx=[0, 1, 2])
 
 
 def test_config2_zero_pi_flux_sweep_with_rates():
@@ -113,9 +117,9 @@ def test_config2_zero_pi_flux_sweep_with_rates():
     for i in (0, 3, 8):
         ov = o.subspace_overlap(g['evecs_%d' % i], res.evecs[i].cpu().numpy().T, g['efreqs_exact'][i])
         assert 1 - ov < 1e-10
-    _check(res, oc, ol.set_flux, fl[[1, 5]], 10, [], mels=[('capacitive', (0, 1), (0, 1)),
-                                                           ('inductive', (0, 2), (0, 1)),
-                                                           ('capacitive', (2, 3), (1, 2))])
+    _check(res, oc, ol.set_flux, fl[[1, 5]], 10, DEC, mels=[('capacitive', (0, 1), (0, 1)),
+                                                            ('inductive', (0, 2), (0, 1)),
+                                                            ('capacitive', (2, 3), (1, 2))], idx=[1, 5])
 
 
 def test_zero_pi_reference_known_answers():
