@@ -119,6 +119,17 @@ int sqc_mode_transform(const sqc_space_t* sp, int32_t mode, const double* Mat,
                        const double* ediag, int64_t ediag_stride_b, sqc_block_t EX,
                        int32_t B, int32_t impl, void* stream);
 
+/* Fused Y = fdiag .* X + V [ P ( V^T X ) ] in one kernel for spaces with exactly one harmonic
+ * mode (mode 0) and one charge mode (mode 1) -- the 0-pi layout.  Uses the parity of the x
+ * basis: Ve[a][i] = V[2a][i] (ceil(m/2) square), Vo[a][i] = V[2a+1][i] (floor(m/2) square),
+ * i over the first half of the x points.  pot->diag must be NULL, shifts in {-1,0,1},
+ * n_terms <= 4.  fdiag may be NULL.  Returns SQC_ELIMIT when the layout is not supported
+ * (callers then use sqc_mode_transform + sqc_potential_apply).  Replaces the CSR mat-vec on
+ * the matrix of Circuit.hamiltonian() (circuit.py:2147-2164). */
+int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const double* Vo,
+                 const sqc_potential_t* pot, const double* fdiag, int64_t fdiag_stride_b,
+                 sqc_block_t X, sqc_block_t Y, int32_t B, void* stream);
+
 /* Z = P X with P as documented at sqc_potential_t (X, Z in the x/charge basis). */
 int sqc_potential_apply(const sqc_space_t* sp, const sqc_potential_t* pot, sqc_block_t X,
                         sqc_block_t Z, int32_t B, void* stream);
@@ -140,9 +151,10 @@ int sqc_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int32_t B, void* C, int32
 
 /* Out[b][j][n] (op)= sum_i Cf[b][j][i] A[b][i][n],  i < count(A), j < count(Out);
  * op: 0 assign, 1 subtract from Out.  Cf: device complex [B][ldr][ldc]; the coefficient of
- * A_i in Out_j is Cf[j][i] (trans = 0) or Cf[i][j] (trans = 1). */
+ * A_i in Out_j is Cf[j][i] (trans = 0) or Cf[i][j] (trans = 1).
+ * impl: 0 = FP64 tensor-core kernel, 1 = plain FP64 SIMT kernel. */
 int sqc_block_update(sqc_block_t A, const void* Cf, int32_t ldr, int32_t ldc, int32_t trans,
-                     sqc_block_t Out, int64_t N, int32_t B, int32_t op, void* stream);
+                     sqc_block_t Out, int64_t N, int32_t B, int32_t op, int32_t impl, void* stream);
 
 /* In-place T[b][j][n] <- sum_i Cq[b][j][i] T[b][i][n], i < count(T) (<= 16), j < nout[b]. */
 int sqc_block_rightmul(sqc_block_t T, const void* Cq, int32_t ldr, int32_t ldc,

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libsqcircuit_b200.so')
 MAX_MODES = 8
 MAX_TERMS = 16
+EINVAL, ELIMIT = -1, -2
 
 c_i32, c_i64, c_dbl, c_vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
 
@@ -56,7 +57,8 @@ SIGNATURES = {
     'sqc_ladder_apply': (c_i32, [C.POINTER(Space), c_i32, c_vp, c_vp, Block, Block, c_i32, c_i32, c_vp]),
     'sqc_gram_work_bytes': (c_i64, [c_i32, c_i32, c_i32, c_i64]),
     'sqc_gram': (c_i32, [Block, Block, c_i64, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_vp]),
-    'sqc_block_update': (c_i32, [Block, c_vp, c_i32, c_i32, c_i32, Block, c_i64, c_i32, c_i32, c_vp]),
+    'sqc_block_update': (c_i32, [Block, c_vp, c_i32, c_i32, c_i32, Block, c_i64, c_i32, c_i32, c_i32, c_vp]),
+    'sqc_hx_fused': (c_i32, [C.POINTER(Space), c_vp, c_vp, C.POINTER(Potential), c_vp, c_i64, Block, Block, c_i32, c_vp]),
     'sqc_block_rightmul': (c_i32, [Block, c_vp, c_i32, c_i32, c_vp, c_i64, c_i32, c_vp]),
     'sqc_heev': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     'sqc_residual_norms': (c_i32, [Block, Block, c_vp, c_i32, c_i64, c_i32, c_vp, c_vp]),

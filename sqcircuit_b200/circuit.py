@@ -171,8 +171,9 @@ class Circuit:
         return lv, ng
 
     def sweep_diag(self, n_eig, loop_fluxes: Optional[Dict] = None,
-                   charge_offsets: Optional[Dict[int, Sequence[float]]] = None, tol=1e-9,
-                   block_size=None, max_basis=None, maxit=300, stats=None) -> SweepResult:
+                   charge_offsets: Optional[Dict[int, Sequence[float]]] = None, tol=1e-8,
+                   block_size=None, max_basis=None, maxit=300, stats=None,
+                   warm_start=True, coarse_stride=8) -> SweepResult:
         """Diagonalise at every point of a sweep in one batched GPU solve.
 
         loop_fluxes: {Loop: array[B]} external fluxes in units of Phi0 (as Loop.set_flux);
@@ -202,16 +203,86 @@ class Circuit:
         kern = ops.kern
         if ops.N <= DENSE_MAX:
             res = solve_dense(kern, hop, B, ops.N, n_eig)
+        elif warm_start and B >= 4 * coarse_stride:
+            res = self._solve_continuation(ops, lv, ng, n_eig, tol, block_size, max_basis, maxit,
+                                           stats, coarse_stride)
         else:
             res = solve_davidson(kern, hop, B, ops.N, n_eig, hop.diag, p=block_size, mmax=max_basis,
                                  tol=tol, maxit=maxit, stats=stats)
-            if not res.converged:
-                raise RuntimeError(f'batched Davidson did not converge in {maxit} iterations '
-                                   f'(worst relative residual {float(res.resmax.max()):.2e})')
+        if not res.converged:
+            raise RuntimeError(f'batched Davidson did not converge in {maxit} iterations '
+                               f'(worst relative residual {float(res.resmax.max()):.2e})')
         out = SweepResult(res.evals / (2 * np.pi * unt.get_unit_freq()), res.evals, res.evecs,
                           res.iterations, res.converged, res.resmax)
         out.noise = SweepNoise(kern, ops, hop, res.evals, res.evecs, self)
         return out
+
+    def _solve_continuation(self, ops, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats, stride):
+        """Sweep continuation: eigenvectors vary smoothly along a sweep, so a coarse subset of the
+        points is solved from a cold start and every other point starts from the union of the Ritz
+        blocks of its two nearest solved neighbours (Rayleigh-Ritz in that subspace is second
+        order accurate in the parameter distance)."""
+        from .eigensolver import EigResult
+        kern = ops.kern
+        B = lv.shape[0]
+        ngb = np.broadcast_to(ng, (B, ng.shape[1]))
+        prm = np.concatenate([lv / (2 * np.pi), ngb], axis=1)
+        span = prm.max(axis=0) - prm.min(axis=0)
+        vary = span > 0
+        if not vary.any():
+            hop = HamiltonianOperator(ops, lv, ng)
+            return solve_davidson(kern, hop, B, ops.N, n_eig, hop.diag, p=block_size, mmax=max_basis,
+                                  tol=tol, maxit=maxit, stats=stats)
+        q = prm[:, vary] / span[vary]
+        order = np.lexsort(q.T[::-1])
+        coarse = order[::stride]
+        if order[-1] not in coarse:
+            coarse = np.append(coarse, order[-1])
+        is_coarse = np.zeros(B, dtype=bool)
+        is_coarse[coarse] = True
+        fine = np.where(~is_coarse)[0]
+
+        def sub(idx):
+            return HamiltonianOperator(ops, lv[idx], ng if ng.shape[0] == 1 else ng[idx])
+        hop_c = sub(coarse)
+        st_c = [] if stats is not None else None
+        rc = solve_davidson(kern, hop_c, len(coarse), ops.N, n_eig, hop_c.diag, p=block_size,
+                            mmax=max_basis, tol=tol, maxit=maxit, stats=st_c)
+        p = rc.ritz_block.shape[1]
+        k = rc.evals.shape[1]
+        dev = ops.device
+        evals = torch.empty((B, k), dtype=torch.float64, device=dev)
+        evecs = torch.empty((B, k, ops.N), dtype=torch.complex128, device=dev)
+        resmax = torch.empty((B,), dtype=torch.float64, device=dev)
+        ci = torch.as_tensor(coarse, device=dev)
+        evals[ci], evecs[ci], resmax[ci] = rc.evals, rc.evecs, rc.resmax
+        iters, conv = rc.iterations, rc.converged
+        if len(fine):
+            # two nearest coarse neighbours of every remaining point
+            d2 = ((q[fine][:, None, :] - q[coarse][None, :, :]) ** 2).sum(axis=2)
+            nb = np.argsort(d2, axis=1)[:, :2]
+            if nb.shape[1] == 1:
+                nb = np.repeat(nb, 2, axis=1)
+            hop_f = sub(fine)
+            st_f = [] if stats is not None else None
+            # process the fine points in chunks to bound the size of the warm-start buffer
+            chunk = max(1, min(len(fine), int(2e10 // (2 * p * ops.N * 16))))
+            fi = torch.as_tensor(fine, device=dev)
+            for c0 in range(0, len(fine), chunk):
+                sel = slice(c0, c0 + chunk)
+                x0 = torch.cat([rc.ritz_block[torch.as_tensor(nb[sel, 0], device=dev)],
+                                rc.ritz_block[torch.as_tensor(nb[sel, 1], device=dev)]], dim=1)
+                hop_s = sub(fine[sel]) if chunk < len(fine) else hop_f
+                rf = solve_davidson(kern, hop_s, x0.shape[0], ops.N, n_eig, hop_s.diag, p=block_size,
+                                    mmax=max_basis, tol=tol, maxit=maxit, x0=x0, stats=st_f)
+                del x0
+                evals[fi[sel]], evecs[fi[sel]], resmax[fi[sel]] = rf.evals, rf.evecs, rf.resmax
+                iters += rf.iterations
+                conv = conv and rf.converged
+            if stats is not None:
+                stats.append(('coarse', len(coarse), st_c))
+                stats.append(('fine', len(fine), st_f))
+        return EigResult(evals, evecs, iters, resmax, conv)
 
     # ---- single-point API of the reference -----------------------------------------------------------
     def diag(self, n_eig):

@@ -19,11 +19,13 @@ long long g_sqc_launches = 0;
 #define GRAM_CH 32                  // complex elements per staged chunk
 #define GRAM_LD (2 * GRAM_CH + 4)   // doubles per smem row: 68 == 4 (mod 16) -> conflict-free frags
 
-template <int NAT, int NBT>
+// NAT: max row tiles (8 vectors of A each); NCT: column tiles over the 2*nb packed real
+// columns (column 2j = Re C[.][j], column 2j+1 = Im C[.][j]).
+template <int NAT, int NCT>
 __global__ void __launch_bounds__(GRAM_THREADS)
 gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, int nsplit, cplx* __restrict__ C,
                  int ldr, int ldc, cplx* __restrict__ work) {
-    constexpr int NA = NAT * 8, NB = NBT * 8;
+    constexpr int NA = NAT * 8, NB = NCT * 4;
     extern __shared__ double smem[];
     double* sA[2] = {smem, smem + (NA + NB) * GRAM_LD};
     double* sB[2] = {sA[0] + NA * GRAM_LD, sA[1] + NA * GRAM_LD};
@@ -43,25 +45,26 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, int nsplit, cplx* __r
             out[(e / out_cols) * out_ld + (e % out_cols)] = cmake(0.0, 0.0);
         return;
     }
+    const int nat = (na + 7) >> 3;          // row tiles actually populated for this sweep point
     const cplx* a0 = blk_vec(A, b, 0, N);
     const cplx* b0 = blk_vec(Bm, b, 0, N);
 
     const int64_t nchunks = (N + GRAM_CH - 1) / GRAM_CH;
     const int64_t c_lo = nchunks * split / nsplit, c_hi = nchunks * (split + 1) / nsplit;
 
-    double acc[NAT][2 * NBT][2];
+    double acc[NAT][NCT][2];
 #pragma unroll
     for (int i = 0; i < NAT; ++i)
 #pragma unroll
-        for (int j = 0; j < 2 * NBT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NCT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto stage = [&](int buf, int64_t chunk) {
         const int64_t n0 = chunk * GRAM_CH;
-        // rows of A then rows of B; GRAM_CH complex (16 B) elements per row
-        for (int e = tid; e < (NA + NB) * GRAM_CH; e += GRAM_THREADS) {
+        const int rows = nat * 8 + NB;
+        for (int e = tid; e < rows * GRAM_CH; e += GRAM_THREADS) {
             const int r = e / GRAM_CH, c = e % GRAM_CH;
-            const bool isA = r < NA;
-            const int rr = isA ? r : r - NA;
+            const bool isA = r < nat * 8;
+            const int rr = isA ? r : r - nat * 8;
             double* dst = (isA ? sA[buf] : sB[buf]) + rr * GRAM_LD + 2 * c;
             const bool valid = (n0 + c < N) && (isA ? rr < na : rr < nb);
             if (valid) {
@@ -74,6 +77,12 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, int nsplit, cplx* __r
         cp_async_commit();
     };
 
+    // B fragment of packed column n = 8ct + g:  vector j = 4ct + (g>>1), part = g&1
+    //   part 0: B[j][k]        part 1: (k even) ? B[j][k+1] : -B[j][k-1]      (k = k0 + t)
+    const int bpart = g & 1;
+    const int bcol = t ^ bpart;
+    const double bsign = (bpart && (t & 1)) ? -1.0 : 1.0;
+
     if (c_lo < c_hi) stage(0, c_lo);
     for (int64_t ch = c_lo; ch < c_hi; ++ch) {
         const int buf = (int)((ch - c_lo) & 1);
@@ -84,39 +93,32 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, int nsplit, cplx* __r
             cp_async_wait<0>();
         }
         __syncthreads();
-        // 2*GRAM_CH doubles = 16 k-steps of 4; warp w takes k-steps w, w+4, ...
 #pragma unroll
         for (int ks = 0; ks < (2 * GRAM_CH / 4) / 4; ++ks) {
             const int k0 = 4 * (warp + 4 * ks);
-            double af[NAT];
+            double bf[NCT];
 #pragma unroll
-            for (int i = 0; i < NAT; ++i) af[i] = sA[buf][(8 * i + g) * GRAM_LD + k0 + t];
+            for (int j = 0; j < NCT; ++j)
+                bf[j] = bsign * sB[buf][(4 * j + (g >> 1)) * GRAM_LD + k0 + bcol];
 #pragma unroll
-            for (int j = 0; j < NBT; ++j) {
-                const double bf = sB[buf][(8 * j + g) * GRAM_LD + k0 + t];
-                // primed fragment: element t of B' is  (t even) ? B[t+1] : -B[t-1]
-                double bp = __shfl_xor_sync(0xffffffffu, bf, 1);
-                bp = (t & 1) ? -bp : bp;
+            for (int i = 0; i < NAT; ++i) {
+                if (i < nat) {
+                    const double af = sA[buf][(8 * i + g) * GRAM_LD + k0 + t];
 #pragma unroll
-                for (int i = 0; i < NAT; ++i) {
-                    dmma884(acc[i][j][0], acc[i][j][1], af[i], bf);
-                    dmma884(acc[i][NBT + j][0], acc[i][NBT + j][1], af[i], bp);
+                    for (int j = 0; j < NCT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
                 }
             }
         }
         __syncthreads();
     }
 
-    // cross-warp reduction through shared memory: red[warp][row][2*NB]
-    double* red = smem;  // 4 * NA * 2NB doubles  <= staging size (checked on the host)
+    // cross-warp reduction through shared memory: red[warp][row][NB] complex
+    cplx* red = reinterpret_cast<cplx*>(smem);
 #pragma unroll
     for (int i = 0; i < NAT; ++i)
 #pragma unroll
-        for (int j = 0; j < 2 * NBT; ++j) {
-            double* p = red + ((warp * NA + 8 * i + g) * (2 * NB)) + 8 * j + 2 * t;
-            p[0] = acc[i][j][0];
-            p[1] = acc[i][j][1];
-        }
+        for (int j = 0; j < NCT; ++j)
+            red[(warp * NA + 8 * i + g) * NB + 4 * j + t] = cmake(acc[i][j][0], acc[i][j][1]);
     __syncthreads();
     for (int e = tid; e < out_rows * out_cols; e += GRAM_THREADS) {
         const int r = e / out_cols, c = e % out_cols;
@@ -124,8 +126,9 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, int nsplit, cplx* __r
         if (r < NA && c < NB) {
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
-                re += red[(w * NA + r) * (2 * NB) + c];
-                im += red[(w * NA + r) * (2 * NB) + NB + c];
+                const cplx v = red[(w * NA + r) * NB + c];
+                re += v.x;
+                im += v.y;
             }
         }
         out[r * out_ld + c] = cmake(re, im);
@@ -193,38 +196,39 @@ static int gram_nsplit(int B, int64_t N) {
     if (want > 64) want = 64;
     return want;
 }
-static void gram_tiles(int na_max, int nb_max, int* nat, int* nbt) {
+static void gram_tiles(int na_max, int nb_max, int* nat, int* nct) {
     *nat = (na_max + 7) / 8;
     if (*nat < 1) *nat = 1;
     if (*nat > 2 && (*nat & 1)) ++*nat;  // instantiated: 1,2,4,6,8
     if (*nat == 3) *nat = 4;
-    *nbt = nb_max > 8 ? 2 : 1;
+    *nct = (2 * nb_max + 7) / 8;         // 1..4
+    if (*nct < 1) *nct = 1;
 }
 
 extern "C" int64_t sqc_gram_work_bytes(int32_t B, int32_t na_max, int32_t nb_max, int64_t N) {
-    int nat, nbt;
-    gram_tiles(na_max, nb_max, &nat, &nbt);
+    int nat, nct;
+    gram_tiles(na_max, nb_max, &nat, &nct);
     int ns = gram_nsplit(B, N);
     if (ns == 1) return 0;
-    return (int64_t)B * ns * (nat * 8) * (nbt * 8) * (int64_t)sizeof(cplx);
+    return (int64_t)B * ns * (nat * 8) * (nct * 4) * (int64_t)sizeof(cplx);
 }
 
-template <int NAT, int NBT>
+template <int NAT, int NCT>
 static int launch_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int B, cplx* C, int ldr, int ldc,
                        cplx* work, cudaStream_t st) {
     const int ns = gram_nsplit(B, N);
     if (ns > 1 && !work) return SQC_EINVAL;
-    size_t stage_bytes = 2 * (size_t)(NAT * 8 + NBT * 8) * GRAM_LD * sizeof(double);
-    size_t red_bytes = 4 * (size_t)(NAT * 8) * (2 * NBT * 8) * sizeof(double);
+    size_t stage_bytes = 2 * (size_t)(NAT * 8 + NCT * 4) * GRAM_LD * sizeof(double);
+    size_t red_bytes = 4 * (size_t)(NAT * 8) * (NCT * 4) * sizeof(cplx);
     size_t smem = stage_bytes > red_bytes ? stage_bytes : red_bytes;
-    auto kern = gram_dmma_kernel<NAT, NBT>;
+    auto kern = gram_dmma_kernel<NAT, NCT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<B * ns, GRAM_THREADS, smem, st>>>(A, Bm, N, ns, C, ldr, ldc, work);
     SQC_LAUNCHED();
     if (ns > 1) {
         int rows = A.cnt_fixed < ldr ? A.cnt_fixed : ldr, cols = Bm.cnt_fixed < ldc ? Bm.cnt_fixed : ldc;
-        gram_reduce_kernel<<<B, 128, 0, st>>>(work, ns, NAT * 8, NBT * 8, C, ldr, ldc, rows, cols);
+        gram_reduce_kernel<<<B, 128, 0, st>>>(work, ns, NAT * 8, NCT * 4, C, ldr, ldc, rows, cols);
         SQC_LAUNCHED();
     }
     return 0;
@@ -241,12 +245,14 @@ extern "C" int sqc_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int32_t B, voi
         return 0;
     }
     if (A.cnt_fixed > 64 || Bm.cnt_fixed > 16) return SQC_ELIMIT;
-    int nat, nbt;
-    gram_tiles(A.cnt_fixed, Bm.cnt_fixed, &nat, &nbt);
+    int nat, nct;
+    gram_tiles(A.cnt_fixed, Bm.cnt_fixed, &nat, &nct);
 #define GRAM_CASE(a, b_) \
-    if (nat == a && nbt == b_) return launch_gram<a, b_>(A, Bm, N, B, (cplx*)C, ldr, ldc, (cplx*)work, st)
+    if (nat == a && nct == b_) return launch_gram<a, b_>(A, Bm, N, B, (cplx*)C, ldr, ldc, (cplx*)work, st)
     GRAM_CASE(1, 1); GRAM_CASE(2, 1); GRAM_CASE(4, 1); GRAM_CASE(6, 1); GRAM_CASE(8, 1);
     GRAM_CASE(1, 2); GRAM_CASE(2, 2); GRAM_CASE(4, 2); GRAM_CASE(6, 2); GRAM_CASE(8, 2);
+    GRAM_CASE(1, 3); GRAM_CASE(2, 3); GRAM_CASE(4, 3); GRAM_CASE(6, 3); GRAM_CASE(8, 3);
+    GRAM_CASE(1, 4); GRAM_CASE(2, 4); GRAM_CASE(4, 4); GRAM_CASE(6, 4); GRAM_CASE(8, 4);
 #undef GRAM_CASE
     return SQC_ELIMIT;
 }
@@ -299,14 +305,121 @@ block_update_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, int ldc
     }
 }
 
+// Tensor-core version.  Real formulation (M = positions n, K = (vector i, re/im), N = packed
+// (output j, re/im)):   [Re Out, Im Out][n][j] = sum_i [Re A, Im A][i][n] . [[cre, cim], [-cim, cre]]
+// A warp owns 32 consecutive positions (4 M-tiles) and all outputs; A fragments are read straight
+// from global memory (per k-step two vectors x 512 contiguous bytes), the packed coefficient
+// matrix sits in shared memory.
+#define UPD2_THREADS 128
+#define UPD2_MT 4
+
+template <int NCT>
+__global__ void __launch_bounds__(UPD2_THREADS)
+block_update_dmma_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, int ldc, int trans,
+                         sqc_block_t Out, int64_t N, int nchunk, int op, int ldm) {
+    extern __shared__ double smem[];     // Mr[2*na][ldm]
+    const int b = blockIdx.x / nchunk;
+    const int na = blk_count(A, b), nb = min(blk_count(Out, b), NCT * 4);
+    if (nb == 0) return;
+    if (na == 0 && op == 1) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const cplx* cf = Cf + (int64_t)b * ldr * ldc;
+    const int kk = (2 * na + 3) & ~3;
+    for (int e = tid; e < kk * (NCT * 8); e += UPD2_THREADS) {
+        const int k = e / (NCT * 8), n = e % (NCT * 8);
+        const int i = k >> 1, pin = k & 1, j = n >> 1, pout = n & 1;
+        double v = 0.0;
+        if (i < na && j < nb) {
+            const cplx c = trans ? cf[i * ldc + j] : cf[j * ldc + i];
+            v = (pin == pout) ? c.x : (pin == 0 ? c.y : -c.y);
+        }
+        smem[k * ldm + n] = v;
+    }
+    __syncthreads();
+    const int64_t nbase = ((int64_t)(blockIdx.x % nchunk) * (UPD2_THREADS / 32) + warp) * (8 * UPD2_MT);
+    if (nbase >= N) return;
+    const double* a = reinterpret_cast<const double*>(blk_vec(A, b, 0, N));
+    double acc[UPD2_MT][NCT][2];
+#pragma unroll
+    for (int mt = 0; mt < UPD2_MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < NCT; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
+    // A fragment: row n = nbase + 8 mt + g, k = (i0 + (t>>1), t&1)  -> A_r[i][2n + (t&1)]
+    int64_t noff[UPD2_MT];
+    bool nok[UPD2_MT];
+#pragma unroll
+    for (int mt = 0; mt < UPD2_MT; ++mt) {
+        const int64_t n = nbase + 8 * mt + g;
+        nok[mt] = n < N;
+        noff[mt] = 2 * (nok[mt] ? n : 0) + (t & 1);
+    }
+#pragma unroll 2
+    for (int k0 = 0; k0 < kk; k0 += 4) {
+        const int i = (k0 >> 1) + (t >> 1);
+        const bool iok = i < na;
+        const double* ar = a + (int64_t)(iok ? i : 0) * 2 * N;
+        double af[UPD2_MT];
+#pragma unroll
+        for (int mt = 0; mt < UPD2_MT; ++mt) af[mt] = (iok && nok[mt]) ? ar[noff[mt]] : 0.0;
+#pragma unroll
+        for (int j = 0; j < NCT; ++j) {
+            const double bf = smem[(k0 + t) * ldm + 8 * j + g];
+#pragma unroll
+            for (int mt = 0; mt < UPD2_MT; ++mt) dmma884(acc[mt][j][0], acc[mt][j][1], af[mt], bf);
+        }
+    }
+    // C fragment: row n = nbase + 8 mt + g, packed cols 8j + 2t, +1  -> Out[4j + t][n] (re, im)
+    cplx* o = blk_vec(Out, b, 0, N);
+#pragma unroll
+    for (int mt = 0; mt < UPD2_MT; ++mt) {
+        const int64_t n = nbase + 8 * mt + g;
+        if (n < N) {
+#pragma unroll
+            for (int j = 0; j < NCT; ++j) {
+                const int jj = 4 * j + t;
+                if (jj < nb) {
+                    cplx* p = o + (int64_t)jj * N + n;
+                    cplx val = cmake(acc[mt][j][0], acc[mt][j][1]);
+                    if (op == 1) val = csub(*p, val);
+                    *p = val;
+                }
+            }
+        }
+    }
+}
+
 extern "C" int sqc_block_update(sqc_block_t A, const void* Cf, int32_t ldr, int32_t ldc, int32_t trans,
-                                sqc_block_t Out, int64_t N, int32_t B, int32_t op, void* stream) {
+                                sqc_block_t Out, int64_t N, int32_t B, int32_t op, int32_t impl,
+                                void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (B <= 0 || N <= 0 || Out.cnt_fixed <= 0 || Out.cnt_fixed > 16 || A.cnt_fixed > 128) return SQC_EINVAL;
+    const int nbm = Out.cnt_fixed;
+    if (impl == 0 && A.cnt_fixed <= 64) {
+        const int per_cta = (UPD2_THREADS / 32) * 8 * UPD2_MT;
+        const int nchunk = (int)((N + per_cta - 1) / per_cta);
+        const int64_t grid = (int64_t)B * nchunk;
+        if (grid > 0x7fffffffLL) return SQC_ELIMIT;
+        const int nct = (2 * nbm + 7) / 8;
+        int ldm = nct * 8;
+        while ((ldm & 15) != 4) ++ldm;
+        const int kk = (2 * (A.cnt_fixed > 0 ? A.cnt_fixed : 1) + 3) & ~3;
+        size_t smem = (size_t)kk * ldm * sizeof(double);
+#define UPD2_CASE(NCTv)                                                                               \
+    if (nct == NCTv) {                                                                                \
+        auto kern = block_update_dmma_kernel<NCTv>;                                                   \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return (int)e;                                                          \
+        kern<<<(unsigned)grid, UPD2_THREADS, smem, st>>>(A, (const cplx*)Cf, ldr, ldc, trans, Out, N, nchunk, op, ldm); \
+        SQC_LAUNCHED();                                                                               \
+        return 0;                                                                                     \
+    }
+        UPD2_CASE(1) UPD2_CASE(2) UPD2_CASE(3) UPD2_CASE(4)
+#undef UPD2_CASE
+        return SQC_ELIMIT;
+    }
     const int nchunk = (int)((N + UPD_THREADS - 1) / UPD_THREADS);
     const int64_t grid = (int64_t)B * nchunk;
     if (grid > 0x7fffffffLL) return SQC_ELIMIT;
-    const int nbm = Out.cnt_fixed;
 #define UPD_CASE(NBv)                                                                              \
     if (nbm <= NBv) {                                                                              \
         size_t smem = (size_t)(A.cnt_fixed > 0 ? A.cnt_fixed : 1) * NBv * sizeof(cplx);             \

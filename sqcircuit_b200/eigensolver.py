@@ -32,6 +32,7 @@ class EigResult:
     iterations: int
     resmax: torch.Tensor     # [B] final relative residual of the wanted pairs
     converged: bool
+    ritz_block: torch.Tensor = None   # [B][p][N] all Ritz vectors of the last iteration
 
 
 def solve_dense(kern, op, B, N, k):
@@ -49,7 +50,7 @@ def solve_dense(kern, op, B, N, k):
                      torch.zeros(B, dtype=torch.float64, device=dev), True)
 
 
-def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
+def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-8, maxit=300, x0=None,
                    impl=0, stats=None):
     """diag: [1 or B][N] real preconditioner diagonal (the LC part of H)."""
     dev = op.device
@@ -73,7 +74,7 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
     S1 = torch.zeros((B, mmax, 16), dtype=c128, device=dev)
     S2 = torch.zeros((B, 16, 16), dtype=c128, device=dev)
     Cq = torch.zeros((B, 16, 16), dtype=c128, device=dev)
-    msz = torch.full((B,), p, dtype=i32, device=dev)
+    msz = torch.full((B,), p, dtype=i32, device=dev)      # per-point basis size
     mtot = torch.full((B,), p, dtype=i32, device=dev)
     nact = torch.zeros((B,), dtype=i32, device=dev)
     nin = torch.zeros((B,), dtype=i32, device=dev)     # block size before SVQB drops directions
@@ -85,25 +86,50 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
     resmax = torch.zeros((B,), dtype=f64, device=dev)
     den_floor = torch.zeros((B,), dtype=f64, device=dev)
 
-    # initial block: unit vectors on the p smallest entries of the preconditioner diagonal
-    if x0 is not None:
-        V[:, :p, :] = x0[:, :p, :]
-    else:
+    Vp = BlockView(V, cnt_fixed=p)
+    Wp = BlockView(W, cnt_fixed=p)
+    if x0 is None:
+        # cold start: unit vectors on the p smallest entries of the preconditioner diagonal
         idx = torch.topk(diag, p, dim=1, largest=False).indices          # [1 or B][p]
         idx = idx.expand(B, p)
         V[:, :p, :].scatter_(2, idx.unsqueeze(2), torch.ones((B, p, 1), dtype=c128, device=dev))
-    Vp = BlockView(V, cnt_fixed=p)
-    Wp = BlockView(W, cnt_fixed=p)
-    if x0 is not None:
-        # orthonormalise the supplied block (SVQB twice)
-        for _ in range(2):
+        op.apply(Vp, Wp)
+        kern.gram(Vp, Wp, G, impl)
+    else:
+        # warm start: x0 holds one or two blocks of p vectors per point (Ritz vectors of solved
+        # neighbouring sweep points).  Block 0 is orthonormalised in place (SVQB x2); block 1 is
+        # orthogonalised against block 0 and itself exactly like a Davidson expansion block.
+        nblk = x0.shape[1] // p
+        V[:, :nblk * p, :] = x0[:, :nblk * p, :]
+        msz.zero_()
+        for blk in range(nblk):
+            Tb = BlockView(V, cnt_fixed=p, off=msz, cnt=nact)
+            Tbin = BlockView(V, cnt_fixed=p, off=msz, cnt=nin)
+            Vcur = BlockView(V, cnt_fixed=mmax, cnt=msz)
             nact.fill_(p)
-            nin.fill_(p)
-            kern.gram(Vp, Vp, S2, impl)
-            kern.svqb_coeffs(S2, nact, 1e-14, Cq)
-            kern.block_rightmul(BlockView(V, cnt_fixed=p, cnt=nin), Cq, nact)
-    op.apply(Vp, Wp)
-    kern.gram(Vp, Wp, G, impl)
+            for _ in range(2):
+                if blk > 0:
+                    kern.gram(Vcur, Tb, S1, impl)
+                    kern.block_update(Vcur, S1, Tb, op=1, trans=1)
+                kern.gram(Tb, Tb, S2, impl)
+                nin.copy_(nact)
+                kern.svqb_coeffs(S2, nact, 1e-10, Cq, msz, mtot)
+                kern.block_rightmul(Tbin, Cq, nact)
+            if blk > 0:
+                # compact: dropped directions leave zero vectors at the tail of the block, which
+                # the counters simply do not include
+                pass
+            msz.copy_(mtot)
+        Vinit = BlockView(V, cnt_fixed=mmax, cnt=msz)
+        Winit = BlockView(W, cnt_fixed=mmax, cnt=msz)
+        op.apply(Vinit, Winit)
+        # projected matrix of the initial basis, <= 16 columns at a time
+        for c0 in range(0, nblk * p, p):
+            ccnt = torch.clamp(msz - c0, min=0, max=p).to(i32)
+            coff = torch.full((B,), c0, dtype=i32, device=dev)
+            kern.gram(Vinit, BlockView(W, cnt_fixed=p, off=coff, cnt=ccnt), S1, impl)
+            G[:, :, c0:c0 + p] = S1[:, :, :p]
+        G.copy_(0.5 * (G + G.conj().transpose(1, 2)))
 
     st = kern.davidson_state(p=p, k=k, mmax=mmax, ldg=ld, tol_rel=tol, tol_abs_floor=1e-300,
                              msz=msz, nact=nact, act=act, restart=restart, done=done,
@@ -151,4 +177,5 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
         op.apply(Tv, HTv)
         kern.gram(Vt, HTv, S1, impl)
         kern.davidson_insert(st, S1, B)
-    return EigResult(theta[:, :k].contiguous(), Xb[:, :k, :].contiguous(), it, resmax, converged)
+    return EigResult(theta[:, :k].contiguous(), Xb[:, :k, :].contiguous(), it, resmax, converged,
+                     ritz_block=Xb)

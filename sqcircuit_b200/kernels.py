@@ -113,10 +113,20 @@ class Kernels:
                                      _p(self._gram_work) if need else C.c_void_p(0), impl,
                                      _stream(self.dev)), 'sqc_gram')
 
-    def block_update(self, A, Cf, Out, op=0, trans=0):
+    def block_update(self, A, Cf, Out, op=0, trans=0, impl=0):
         B, ldr, ldc = Cf.shape
-        _lib.check(self.lib.sqc_block_update(A.c(), _p(Cf), ldr, ldc, trans, Out.c(), A.N, B, op,
+        _lib.check(self.lib.sqc_block_update(A.c(), _p(Cf), ldr, ldc, trans, Out.c(), A.N, B, op, impl,
                                              _stream(self.dev)), 'sqc_block_update')
+
+    def hx_fused(self, sp, Ve, Vo, pot, fdiag, X, Y):
+        """Returns False when the fused kernel does not support the layout."""
+        fsb = 0 if fdiag is None or fdiag.shape[0] == 1 else fdiag.stride(0)
+        rc = self.lib.sqc_hx_fused(C.byref(sp), _p(Ve), _p(Vo), C.byref(pot), _p(fdiag), fsb, X.c(), Y.c(),
+                                   X.B, _stream(self.dev))
+        if rc == _lib.ELIMIT:
+            return False
+        _lib.check(rc, 'sqc_hx_fused')
+        return True
 
     def block_rightmul(self, T, Cq, nout):
         B, ldr, ldc = Cq.shape

@@ -32,6 +32,8 @@ def xbasis(kern, m):
 
 
 class CircuitOperators:
+    use_fused = True      # class-level switch (tests compare the fused and unfused paths)
+
     def __init__(self, kern, topo, dims, transform_impl=0):
         self.kern = kern
         self.device = kern.dev
@@ -73,6 +75,14 @@ class CircuitOperators:
                     self.shift[t, i] = int(np.sign(w))
         self.etab = self._tables(self.s)
         self._etab_half = None
+        # parity halves of the x basis for the fused kernel (one harmonic x one charge mode)
+        self.fused = (self.M == 2 and self.harm[0] and not self.harm[1] and self.dims[0] > 1
+                      and self.T <= 4)
+        if self.fused:
+            Vfull = self.V[0]
+            he, ho = (self.dims[0] + 1) // 2, self.dims[0] // 2
+            self.Ve = Vfull[0::2, :he].contiguous()
+            self.Vo = Vfull[1::2, :ho].contiguous()
         self._scratch = {}
         self._keep = []
 
@@ -204,6 +214,10 @@ class CircuitOperators:
         """Y = fock_diag .* X + back( P(a, g) fwd(X) )   (a: [B][T] complex, g: [B][1+M])."""
         etab = self.etab if etab is None else etab
         k = self.kern
+        if self.fused and self.use_fused:
+            pot = self.potential_struct(a, g, etab, shift, None)
+            if k.hx_fused(self.sp, self.Ve, self.Vo, pot, fock_diag, X, Y):
+                return
         if not self.tmodes:
             k.potential_apply(self.sp, self.potential_struct(a, g, etab, shift, fock_diag), X, Y)
             return

@@ -195,7 +195,10 @@ class EmulKernels:
             if a.shape[0] and c.shape[0]:
                 Cout[b, :a.shape[0], :c.shape[0]] = torch.from_numpy(a.conj() @ c.T)
 
-    def block_update(self, A, Cf, Out, op=0, trans=0):
+    def hx_fused(self, sp, Ve, Vo, pot, fdiag, X, Y):
+        return False      # not emulated: callers fall back to transform + potential + transform
+
+    def block_update(self, A, Cf, Out, op=0, trans=0, impl=0):
         for b in range(A.B):
             nb = _cnt(Out, b)
             if nb == 0:

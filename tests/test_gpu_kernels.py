@@ -58,19 +58,22 @@ def test_gram_offsets(kern):
     assert relerr(out.cpu(), ref) < 1e-13
 
 
-@pytest.mark.parametrize('nb', [3, 8, 12, 16])
+@pytest.mark.parametrize('nb', [1, 3, 8, 10, 12, 16])
 @pytest.mark.parametrize('op,trans', [(0, 0), (1, 1)])
-def test_block_update(kern, nb, op, trans):
-    B, na, N = 3, 37, 2050
+@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('na,N', [(37, 2050), (48, 10100), (5, 131)])
+def test_block_update(kern, nb, op, trans, impl, na, N):
+    B = 3
     A = rnd((B, na, N), 4)
     Out = rnd((B, nb, N), 5)
     Cf = rnd((B, 48, 48), 6)
-    ca = torch.tensor([37, 20, 0], dtype=torch.int32)
+    ca = torch.tensor([na, na // 2, 0], dtype=torch.int32)
     cb = torch.tensor([nb, max(nb - 2, 1), nb], dtype=torch.int32)
     ref = Out.clone()
     EmulKernels().block_update(BlockView(A, cnt=ca), Cf, BlockView(ref, cnt=cb), op, trans)
     o = Out.cuda()
-    kern.block_update(BlockView(A.cuda(), cnt=ca.cuda()), Cf.cuda(), BlockView(o, cnt=cb.cuda()), op, trans)
+    kern.block_update(BlockView(A.cuda(), cnt=ca.cuda()), Cf.cuda(), BlockView(o, cnt=cb.cuda()), op, trans,
+                      impl)
     assert relerr(o.cpu(), ref) < 1e-13
 
 
@@ -234,6 +237,54 @@ def test_small_elementwise_kernels(kern):
     Yd = Y.cuda()
     kern.diag_mul(BlockView(X.cuda()), BlockView(Yd), d.cuda(), True)
     assert relerr(Yd.cpu(), refY) < 1e-14
+
+
+@pytest.mark.parametrize('dims', [[100, 101], [25, 25], [30, 19], [7, 3], [2, 61], [101, 40]])
+def test_hx_fused_matches_unfused(kern, dims):
+    """Fused H.X kernel against the transform / potential / transform sequence."""
+    import ctypes as C
+    from sqcircuit_b200._lib import Potential
+    m, inner = dims
+    N = m * inner
+    B, nv, T = 3, 4, 2
+    sp = make_space(dims, [1, 0])
+    V, lam = kern.xbasis(m)
+    lamcat = torch.zeros(m + inner, dtype=torch.float64, device='cuda')
+    lamcat[:m] = lam
+    g = torch.Generator().manual_seed(5)
+    s = torch.tensor([[[0.61, 0.0], [-0.61, 0.0]]], dtype=torch.float64, device='cuda')
+    etab = torch.empty((1, T, m + inner), dtype=torch.complex128, device='cuda')
+    kern.phase_tables(sp, T, lamcat, s, etab)
+    a = rnd((B, T), 21).cuda()
+    gl = torch.randn((B, 3), dtype=torch.float64, generator=g).cuda()
+    fd = torch.randn((B, N), dtype=torch.float64, generator=g).cuda()
+    X = rnd((B, nv, N), 22).cuda()
+    cnt = torch.tensor([4, 1, 0], dtype=torch.int32, device='cuda')
+
+    def pot_struct():
+        pot = Potential()
+        pot.n_terms = T
+        pot.shift[0][1] = 1
+        pot.shift[1][1] = -1
+        pot.lam, pot.etab, pot.etab_stride_b = lamcat.data_ptr(), etab.data_ptr(), 0
+        pot.g, pot.a, pot.diag, pot.diag_stride_b = gl.data_ptr(), a.data_ptr(), None, 0
+        return pot
+    for use_fd in (True, False):
+        ref = torch.zeros_like(X)
+        s1, s2 = torch.zeros_like(X), torch.zeros_like(X)
+        kern.mode_transform(sp, 0, V, 1, BlockView(X, cnt=cnt), BlockView(s1, cnt=cnt), impl=1)
+        kern.potential_apply(sp, pot_struct(), BlockView(s1, cnt=cnt), BlockView(s2, cnt=cnt))
+        if use_fd:
+            kern.mode_transform(sp, 0, V, 0, BlockView(s2, cnt=cnt), BlockView(ref, cnt=cnt), ediag=fd,
+                                EX=BlockView(X, cnt=cnt), impl=1)
+        else:
+            kern.mode_transform(sp, 0, V, 0, BlockView(s2, cnt=cnt), BlockView(ref, cnt=cnt), impl=1)
+        out = torch.zeros_like(X)
+        he, ho = (m + 1) // 2, m // 2
+        ok = kern.hx_fused(sp, V[0::2, :he].contiguous(), V[1::2, :ho].contiguous(), pot_struct(),
+                           fd if use_fd else None, BlockView(X, cnt=cnt), BlockView(out, cnt=cnt))
+        assert ok
+        assert relerr(out.cpu(), ref.cpu()) < 2e-13, (dims, use_fd)
 
 
 def test_launch_counter(kern):
