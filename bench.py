@@ -40,6 +40,20 @@ def flux_grid(points, rank, world):
 # --------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: oracle port on host cores
 # --------------------------------------------------------------------------------------------
+def _ref_init():
+    # one BLAS/OpenMP thread per worker process: the workers already cover every core
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+
+
 def _ref_one(flux):
     import warnings
     warnings.filterwarnings('ignore')
@@ -65,7 +79,7 @@ def run_reference_sample(n_points, procs):
         for f in fl:
             _ref_one(f)
     else:
-        with mp.get_context('fork').Pool(procs) as pool:
+        with mp.get_context('fork').Pool(procs, initializer=_ref_init) as pool:
             pool.map(_ref_one, list(fl), chunksize=1)
     return time.perf_counter() - t0
 
@@ -74,8 +88,9 @@ def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    os.environ.setdefault('OMP_NUM_THREADS', '1')
-    cores = os.cpu_count() or 1
+    for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[var] = '1'
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     procs = max(1, min(cores, 64))
     n_points = procs          # one point per worker per step: ~10 s of wall clock per step
     for _ in range(args.warmup if args.warmup < 1 else 1):
@@ -218,6 +233,7 @@ def our_arm(args):
         dist.barrier()
     import sqcircuit_b200 as sq
     from sqcircuit_b200.kernels import Kernels
+    from sqcircuit_b200.sharding import gather_to_root
     sq.set_device(dev)
     kern = TimedKernels(Kernels(dev))
 
@@ -243,9 +259,7 @@ def our_arm(args):
         rates = [res.dec_rate(d, states=(1, 0)) for d in DEC_TYPES]
         if world > 1:
             # the only collective of the path: final gather of the per-point results to rank 0
-            ef = res.efreqs.contiguous()
-            out = [torch.empty_like(ef) for _ in range(world)] if rank == 0 else None
-            dist.gather(ef, out, dst=0)
+            gather_to_root(res.efreqs.contiguous(), points * world)
         if e2e:
             return res.efreqs.cpu(), rates, res
         return res.efreqs, rates, res
@@ -327,7 +341,9 @@ def our_arm(args):
     # ---- cpu baseline: bounded sample of the same workload on the host cores ----
     cpu = None
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+            os.environ[var] = '1'
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
         procs = max(1, min(cores, 64))
         t = run_reference_sample(procs, procs)
         cpu = {'value': procs / t, 'unit': 'diag/s', 'cores': procs, 'kind': 'port',
@@ -385,7 +401,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--points', type=int, default=POINTS, help='sweep points per GPU')
-    ap.add_argument('--tol', type=float, default=1e-8)
+    ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -171,7 +171,7 @@ class Circuit:
         return lv, ng
 
     def sweep_diag(self, n_eig, loop_fluxes: Optional[Dict] = None,
-                   charge_offsets: Optional[Dict[int, Sequence[float]]] = None, tol=1e-8,
+                   charge_offsets: Optional[Dict[int, Sequence[float]]] = None, tol=1e-9,
                    block_size=None, max_basis=None, maxit=300, stats=None,
                    warm_start=True, coarse_stride=8) -> SweepResult:
         """Diagonalise at every point of a sweep in one batched GPU solve.

@@ -314,7 +314,7 @@ block_update_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, int ldc
 #define UPD2_MT 4
 
 template <int NCT>
-__global__ void __launch_bounds__(UPD2_THREADS)
+__global__ void __launch_bounds__(UPD2_THREADS, 5)
 block_update_dmma_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, int ldc, int trans,
                          sqc_block_t Out, int64_t N, int nchunk, int op, int ldm) {
     extern __shared__ double smem[];     // Mr[2*na][ldm]
@@ -353,7 +353,7 @@ block_update_dmma_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, in
         nok[mt] = n < N;
         noff[mt] = 2 * (nok[mt] ? n : 0) + (t & 1);
     }
-#pragma unroll 2
+#pragma unroll 4
     for (int k0 = 0; k0 < kk; k0 += 4) {
         const int i = (k0 >> 1) + (t >> 1);
         const bool iok = i < na;

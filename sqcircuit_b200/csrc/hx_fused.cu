@@ -37,16 +37,18 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
                 const double* __restrict__ fdiag, long long fdiag_stride_b,
                 sqc_block_t X, sqc_block_t Y, int vmax, long long total_items) {
     extern __shared__ double smem[];
-    double* sVe = smem;                                   // [hep][vld]   Ve[a][i] = V[2a][i]
-    double* sVo = sVe + gm.hep * gm.vld;                  // [hep][vld]   Vo[a][i] = V[2a+1][i]
-    double* sP = sVo + gm.hep * gm.vld;                   // [2*hep][pld] panel
-    double* sLin = sP + 2 * gm.hep * gm.pld;              // [m]
+    // rows: kp (= he rounded up to the k-step) per half; row tiles that stick out past kp are
+    // masked when fragments are read / results written
+    double* sVe = smem;                                   // [kp][vld]   Ve[a][i] = V[2a][i]
+    double* sVo = sVe + gm.kp * gm.vld;                   // [kp][vld]   Vo[a][i] = V[2a+1][i]
+    double* sP = sVo + gm.kp * gm.vld;                    // [2*kp][pld] panel: S/even half, D/odd half
+    double* sLin = sP + 2 * gm.kp * gm.pld;               // [m]
     cplx* sPh = reinterpret_cast<cplx*>(sLin + ((gm.m + 1) & ~1));   // [n_terms][m]
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
     const int nwarp = nthr >> 5;
-    const int m = gm.m, he = gm.he, ho = gm.ho, hep = gm.hep, vld = gm.vld, pld = gm.pld;
+    const int m = gm.m, he = gm.he, ho = gm.ho, hep = gm.kp, vld = gm.vld, pld = gm.pld;
 
     // half matrices (zero padded), staged once per CTA
     for (int e = tid; e < hep * vld; e += nthr) {
@@ -106,8 +108,9 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
 #pragma unroll
                 for (int r = 0; r < HX_MAXRT; ++r) {
                     if (r < gm.nrt) {
-                        dmma884(aE[r][0], aE[r][1], ve[8 * r], bE);
-                        dmma884(aO[r][0], aO[r][1], vo[8 * r], bO);
+                        const bool in = 8 * r + gq < hep;
+                        dmma884(aE[r][0], aE[r][1], in ? ve[8 * r] : 0.0, bE);
+                        dmma884(aO[r][0], aO[r][1], in ? vo[8 * r] : 0.0, bO);
                     }
                 }
             }
@@ -115,8 +118,8 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
             const int cc = 8 * warp + 2 * tq;
 #pragma unroll
             for (int r = 0; r < HX_MAXRT; ++r) {
-                if (r < gm.nrt) {
-                    const int i = 8 * r + gq;
+                const int i = 8 * r + gq;
+                if (r < gm.nrt && i < hep) {
                     double2 zs = make_double2(aE[r][0] + aO[r][0], aE[r][1] + aO[r][1]);   // Z[i]
                     double2 zd = make_double2(aE[r][0] - aO[r][0], aE[r][1] - aO[r][1]);   // Z[m-1-i]
                     if (i >= ho) zd = make_double2(0.0, 0.0);
@@ -190,8 +193,9 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
 #pragma unroll
                 for (int r = 0; r < HX_MAXRT; ++r) {
                     if (r < gm.nrt) {
-                        dmma884(yE[r][0], yE[r][1], ve[8 * r * vld], bS);
-                        dmma884(yO[r][0], yO[r][1], vo[8 * r * vld], bD);
+                        const bool in = 8 * r + gq < hep;
+                        dmma884(yE[r][0], yE[r][1], in ? ve[8 * r * vld] : 0.0, bS);
+                        dmma884(yO[r][0], yO[r][1], in ? vo[8 * r * vld] : 0.0, bD);
                     }
                 }
             }
@@ -266,19 +270,20 @@ extern "C" int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const doubl
     gm.PC = best_pc;
     gm.TC = (gm.inner + gm.np - 1) / gm.np;
     gm.CT = gm.PC / 4;
-    gm.vld = gm.hep;
-    while ((gm.vld & 15) != 4) ++gm.vld;
+    // leading dims == 4 (mod 8) doubles keep both DMMA fragment patterns bank-conflict free
+    gm.vld = gm.kp;
+    while ((gm.vld & 7) != 4) ++gm.vld;
     gm.pld = 2 * gm.PC;
-    while ((gm.pld & 15) != 4) ++gm.pld;
+    while ((gm.pld & 7) != 4) ++gm.pld;
     int nwarp = gm.CT < 4 ? 4 : gm.CT;
-    size_t smem = ((size_t)2 * gm.hep * gm.vld + (size_t)2 * gm.hep * gm.pld + ((gm.m + 1) & ~1)) * sizeof(double) +
+    size_t smem = ((size_t)2 * gm.kp * gm.vld + (size_t)2 * gm.kp * gm.pld + ((gm.m + 1) & ~1)) * sizeof(double) +
                   (size_t)(gm.n_terms > 0 ? gm.n_terms : 1) * gm.m * sizeof(cplx);
     if (smem > 227 * 1024) return SQC_ELIMIT;
     cudaError_t e = cudaFuncSetAttribute(hx_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
-    const int per_sm = (smem <= 113 * 1024) ? 2 : 1;
+    const int per_sm = (smem <= 112 * 1024) ? 2 : 1;
     const long long total = (long long)B * X.cnt_fixed * gm.np;
     long long grid = (long long)nsm * per_sm;
     if (grid > total) grid = total;

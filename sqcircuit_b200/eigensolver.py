@@ -50,7 +50,7 @@ def solve_dense(kern, op, B, N, k):
                      torch.zeros(B, dtype=torch.float64, device=dev), True)
 
 
-def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-8, maxit=300, x0=None,
+def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
                    impl=0, stats=None):
     """diag: [1 or B][N] real preconditioner diagonal (the LC part of H)."""
     dev = op.device
