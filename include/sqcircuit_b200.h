@@ -203,6 +203,23 @@ int sqc_precond_residual(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const dou
                          const double* d, int64_t d_stride_b, const double* den_floor,
                          int64_t N, int32_t B, void* stream);
 
+/* Two-level preconditioner (harmonic x charge layouts): the ns basis states S[.] with the smallest
+ * LC energy get the exact inverse of (H_SS - sigma) instead of the diagonal one.
+ *  - assemble: out[b] (complex64 [ns][ns]) = (H_SS(b) - sigma[b] I) / unit, built analytically from
+ *    the Fock-basis displacement tables Dt[t] = V diag(etab_t) V^T (complex128 [n_terms][m][m]);
+ *  - inverse: in-place Gauss-Jordan in shared memory (ns <= 160);
+ *  - apply: T[b][jj][S[r]] = sum_q Ainv[b][r][q] (HX_a - theta_a X_a)[S[q]] / unit, a = act[b][jj]
+ *    (overwrites the diagonal-preconditioned entries written by sqc_precond_residual). */
+int sqc_lowblock_assemble(const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
+                          const void* Dt, const sqc_potential_t* pot, const double* d,
+                          int64_t d_stride_b, const double* sigma, double unit, void* out,
+                          int32_t B, void* stream);
+int sqc_hpd_inverse_c64(void* A, int32_t ns, int32_t B, void* stream);
+int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                       int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
+                       int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int64_t N,
+                       int32_t B, void* stream);
+
 /* SVQB coefficients from the Gram matrix S = T^H T of the new block:
  * Cq[j][i] = D_i U_ij sigma_j^-1/2 over directions with sigma_j > drop * sigma_max;
  * nact[b] <- number kept; mtot[b] <- msz[b] + nact[b] when both pointers are given.

@@ -173,7 +173,7 @@ class Circuit:
     def sweep_diag(self, n_eig, loop_fluxes: Optional[Dict] = None,
                    charge_offsets: Optional[Dict[int, Sequence[float]]] = None, tol=1e-9,
                    block_size=None, max_basis=None, maxit=300, stats=None,
-                   warm_start=True, coarse_stride=8) -> SweepResult:
+                   warm_start=True, coarse_stride=8, lowblock=160) -> SweepResult:
         """Diagonalise at every point of a sweep in one batched GPU solve.
 
         loop_fluxes: {Loop: array[B]} external fluxes in units of Phi0 (as Loop.set_flux);
@@ -205,7 +205,7 @@ class Circuit:
             res = solve_dense(kern, hop, B, ops.N, n_eig)
         elif warm_start and B >= 4 * coarse_stride:
             res = self._solve_continuation(ops, lv, ng, n_eig, tol, block_size, max_basis, maxit,
-                                           stats, coarse_stride)
+                                           stats, coarse_stride, lowblock)
         else:
             res = solve_davidson(kern, hop, B, ops.N, n_eig, hop.diag, p=block_size, mmax=max_basis,
                                  tol=tol, maxit=maxit, stats=stats)
@@ -217,11 +217,13 @@ class Circuit:
         out.noise = SweepNoise(kern, ops, hop, res.evals, res.evecs, self)
         return out
 
-    def _solve_continuation(self, ops, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats, stride):
+    def _solve_continuation(self, ops, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats, stride,
+                            lowblock=160):
         """Sweep continuation: eigenvectors vary smoothly along a sweep, so a coarse subset of the
         points is solved from a cold start and every other point starts from the union of the Ritz
-        blocks of its two nearest solved neighbours (Rayleigh-Ritz in that subspace is second
-        order accurate in the parameter distance)."""
+        blocks of its two nearest already-solved neighbours (Rayleigh-Ritz in that subspace is
+        second order accurate in the parameter distance).  Levels: every stride^2-th point cold,
+        then every stride-th point, then the rest."""
         from .eigensolver import EigResult
         kern = ops.kern
         B = lv.shape[0]
@@ -229,59 +231,85 @@ class Circuit:
         prm = np.concatenate([lv / (2 * np.pi), ngb], axis=1)
         span = prm.max(axis=0) - prm.min(axis=0)
         vary = span > 0
-        if not vary.any():
-            hop = HamiltonianOperator(ops, lv, ng)
-            return solve_davidson(kern, hop, B, ops.N, n_eig, hop.diag, p=block_size, mmax=max_basis,
-                                  tol=tol, maxit=maxit, stats=stats)
-        q = prm[:, vary] / span[vary]
-        order = np.lexsort(q.T[::-1])
-        coarse = order[::stride]
-        if order[-1] not in coarse:
-            coarse = np.append(coarse, order[-1])
-        is_coarse = np.zeros(B, dtype=bool)
-        is_coarse[coarse] = True
-        fine = np.where(~is_coarse)[0]
 
         def sub(idx):
             return HamiltonianOperator(ops, lv[idx], ng if ng.shape[0] == 1 else ng[idx])
-        hop_c = sub(coarse)
-        st_c = [] if stats is not None else None
-        rc = solve_davidson(kern, hop_c, len(coarse), ops.N, n_eig, hop_c.diag, p=block_size,
-                            mmax=max_basis, tol=tol, maxit=maxit, stats=st_c)
-        p = rc.ritz_block.shape[1]
-        k = rc.evals.shape[1]
+
+        def solve(idx, x0, st):
+            hop = sub(idx)
+            return solve_davidson(kern, hop, len(idx), ops.N, n_eig, hop.diag, p=block_size,
+                                  mmax=max_basis, tol=tol, maxit=maxit, x0=x0, stats=st,
+                                  lowblock_ns=lowblock if x0 is not None else 0)
+        if not vary.any():
+            return solve(np.arange(B), None, stats)
+        q = prm[:, vary] / span[vary]
+        order = np.lexsort(q.T[::-1])
+        # level sets: strides stride^2, stride, 1 over the sorted sweep (coarsest kept >= 32 points)
+        strides = [stride * stride, stride, 1]
+        while len(strides) > 1 and len(order[::strides[0]]) < 32:
+            strides.pop(0)
+        assigned = np.zeros(B, dtype=bool)
+        levels = []
+        for sd in strides:
+            idx = order[::sd]
+            if sd != 1 and order[-1] not in idx:
+                idx = np.append(idx, order[-1])
+            idx = idx[~assigned[idx]]
+            assigned[idx] = True
+            if len(idx):
+                levels.append(idx)
+
         dev = ops.device
-        evals = torch.empty((B, k), dtype=torch.float64, device=dev)
-        evecs = torch.empty((B, k, ops.N), dtype=torch.complex128, device=dev)
-        resmax = torch.empty((B,), dtype=torch.float64, device=dev)
-        ci = torch.as_tensor(coarse, device=dev)
-        evals[ci], evecs[ci], resmax[ci] = rc.evals, rc.evecs, rc.resmax
-        iters, conv = rc.iterations, rc.converged
-        if len(fine):
-            # two nearest coarse neighbours of every remaining point
-            d2 = ((q[fine][:, None, :] - q[coarse][None, :, :]) ** 2).sum(axis=2)
-            nb = np.argsort(d2, axis=1)[:, :2]
-            if nb.shape[1] == 1:
-                nb = np.repeat(nb, 2, axis=1)
-            hop_f = sub(fine)
-            st_f = [] if stats is not None else None
-            # process the fine points in chunks to bound the size of the warm-start buffer
-            chunk = max(1, min(len(fine), int(2e10 // (2 * p * ops.N * 16))))
-            fi = torch.as_tensor(fine, device=dev)
-            for c0 in range(0, len(fine), chunk):
-                sel = slice(c0, c0 + chunk)
-                x0 = torch.cat([rc.ritz_block[torch.as_tensor(nb[sel, 0], device=dev)],
-                                rc.ritz_block[torch.as_tensor(nb[sel, 1], device=dev)]], dim=1)
-                hop_s = sub(fine[sel]) if chunk < len(fine) else hop_f
-                rf = solve_davidson(kern, hop_s, x0.shape[0], ops.N, n_eig, hop_s.diag, p=block_size,
-                                    mmax=max_basis, tol=tol, maxit=maxit, x0=x0, stats=st_f)
-                del x0
-                evals[fi[sel]], evecs[fi[sel]], resmax[fi[sel]] = rf.evals, rf.evecs, rf.resmax
-                iters += rf.iterations
-                conv = conv and rf.converged
+        evals = evecs = resmax = ritz = None
+        solved = np.zeros(0, dtype=int)
+        iters, conv = 0, True
+        for li, idx in enumerate(levels):
+            st = [] if stats is not None else None
+            if li == 0:
+                r = solve(idx, None, st)
+                p = r.ritz_block.shape[1]
+                k = r.evals.shape[1]
+                evals = torch.empty((B, k), dtype=torch.float64, device=dev)
+                evecs = torch.empty((B, k, ops.N), dtype=torch.complex128, device=dev)
+                resmax = torch.empty((B,), dtype=torch.float64, device=dev)
+                # Ritz blocks (all p vectors) of solved points, kept until the last level starts
+                ritz = {int(i): j for j, i in enumerate(idx)}
+                ritz_store = [r.ritz_block]
+                ii = torch.as_tensor(idx, device=dev)
+                evals[ii], evecs[ii], resmax[ii] = r.evals, r.evecs, r.resmax
+                iters, conv = r.iterations, r.converged
+            else:
+                # two nearest solved neighbours of every point of this level
+                d2 = ((q[idx][:, None, :] - q[solved][None, :, :]) ** 2).sum(axis=2)
+                nb = np.argsort(d2, axis=1)[:, :2]
+                if nb.shape[1] == 1:
+                    nb = np.repeat(nb, 2, axis=1)
+                store = torch.cat(ritz_store, dim=0) if len(ritz_store) > 1 else ritz_store[0]
+                ritz_store = [store]
+                pos = np.array([ritz[int(i)] for i in solved])
+                chunk = max(1, min(len(idx), int(2.4e10 // (2 * p * ops.N * 16))))
+                last = li == len(levels) - 1
+                new_blocks = []
+                for c0 in range(0, len(idx), chunk):
+                    sel = slice(c0, c0 + chunk)
+                    x0 = torch.cat([store[torch.as_tensor(pos[nb[sel, 0]], device=dev)],
+                                    store[torch.as_tensor(pos[nb[sel, 1]], device=dev)]], dim=1)
+                    r = solve(idx[sel], x0, st)
+                    del x0
+                    ii = torch.as_tensor(idx[sel], device=dev)
+                    evals[ii], evecs[ii], resmax[ii] = r.evals, r.evecs, r.resmax
+                    iters += r.iterations
+                    conv = conv and r.converged
+                    if not last:
+                        new_blocks.append(r.ritz_block)
+                if not last:
+                    base = store.shape[0]
+                    for j, i in enumerate(idx):
+                        ritz[int(i)] = base + j
+                    ritz_store.extend(new_blocks)
+            solved = np.concatenate([solved, idx])
             if stats is not None:
-                stats.append(('coarse', len(coarse), st_c))
-                stats.append(('fine', len(fine), st_f))
+                stats.append(('level', li, len(idx), st))
         return EigResult(evals, evecs, iters, resmax, conv)
 
     # ---- single-point API of the reference -----------------------------------------------------------

@@ -51,7 +51,7 @@ def solve_dense(kern, op, B, N, k):
 
 
 def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
-                   impl=0, stats=None):
+                   impl=0, stats=None, lowblock_ns=0):
     """diag: [1 or B][N] real preconditioner diagonal (the LC part of H)."""
     dev = op.device
     if p is None:
@@ -146,11 +146,17 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
 
     it = 0
     converged = False
+    lowblock = None
     for it in range(1, maxit + 1):
         live = 1 - done
         nheev = msz * live
         xcnt = (p * live).to(i32)
         kern.heev(G, nheev, theta, Zt)
+        if it == 1 and lowblock_ns > 0 and getattr(op, 'supports_lowblock', lambda: False)():
+            # two-level preconditioner: exact (H_SS - sigma)^-1 on the lowest-energy basis states,
+            # sigma a little below the (already accurate, warm-started) lowest Ritz value
+            sigma = theta[:, 0] - 0.05 * theta[:, 0].abs()
+            lowblock = op.build_lowblock(sigma, lowblock_ns)
         Xv.cnt = xcnt
         HXv.cnt = xcnt
         kern.block_update(Vm, Zt, Xv, op=0, trans=0)
@@ -167,6 +173,8 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
         HXv.cnt = None
         kern.restart_copy(Xv, HXv, Vp, Wp, restart)
         kern.precond_residual(Xv, HXv, Tv, theta, act, diag, den_floor)
+        if lowblock is not None:
+            kern.lowblock_apply(Xv, HXv, Tv, theta, act, lowblock['S'], lowblock['Ainv'], lowblock['unit'])
         for _ in range(2):
             kern.gram(Vm, Tv, S1, impl)
             kern.block_update(Vm, S1, Tv, op=1, trans=1)

@@ -170,6 +170,24 @@ class Kernels:
                                                  act.shape[1], _p(d), dsb, _p(den_floor), X.N, X.B,
                                                  _stream(self.dev)), 'sqc_precond_residual')
 
+    def lowblock_assemble(self, sp, S, Dt, pot, d, sigma, unit, out):
+        B, ns, _ = out.shape
+        ssb = 0 if S.shape[0] == 1 else S.stride(0)
+        dsb = 0 if d.shape[0] == 1 else d.stride(0)
+        _lib.check(self.lib.sqc_lowblock_assemble(C.byref(sp), ns, _p(S), ssb, _p(Dt), C.byref(pot), _p(d), dsb,
+                                                  _p(sigma), unit, _p(out), B, _stream(self.dev)),
+                   'sqc_lowblock_assemble')
+
+    def hpd_inverse_c64(self, A):
+        B, ns, _ = A.shape
+        _lib.check(self.lib.sqc_hpd_inverse_c64(_p(A), ns, B, _stream(self.dev)), 'sqc_hpd_inverse_c64')
+
+    def lowblock_apply(self, X, HX, T, theta, act, S, Ainv, unit):
+        ssb = 0 if S.shape[0] == 1 else S.stride(0)
+        _lib.check(self.lib.sqc_lowblock_apply(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act),
+                                               act.shape[1], _p(S), ssb, _p(Ainv), Ainv.shape[1], unit, X.N, X.B,
+                                               _stream(self.dev)), 'sqc_lowblock_apply')
+
     def svqb_coeffs(self, S, nact, drop, Cq, msz=None, mtot=None):
         B, ld, _ = S.shape
         _lib.check(self.lib.sqc_svqb_coeffs(_p(S), ld, _p(nact), drop, _p(Cq), _p(msz), _p(mtot), B,

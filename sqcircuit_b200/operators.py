@@ -236,6 +236,16 @@ class CircuitOperators:
         else:
             k.mode_transform(self.sp, last, self.V[last], 0, s2, Y, impl=self.impl)
 
+    def displacement_tables(self):
+        """Dt[t] = V diag(etab_t) V^T: Fock-basis matrix of junction term t (the matrix the reference
+        gets from qt.displace), only needed to assemble the low-energy preconditioner block."""
+        if getattr(self, '_Dt', None) is None:
+            V = self.V[0].to(torch.complex128)
+            m = self.dims[0]
+            e = self.etab[0, :, :m]                              # [T][m]
+            self._Dt = torch.einsum('ni,ti,ki->tnk', V, e, V).contiguous()
+        return self._Dt
+
     def to_device(self, arr, dtype):
         return torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype, device=self.device).contiguous()
 
@@ -256,3 +266,19 @@ class HamiltonianOperator:
 
     def apply(self, X: BlockView, Y: BlockView):
         self.ops.apply_potential_op(X, Y, self.a, self.g, fock_diag=self.diag)
+
+    def supports_lowblock(self):
+        return bool(self.ops.fused and self.ops.T >= 1)
+
+    def build_lowblock(self, sigma, ns):
+        """Inverse of (H_SS - sigma)/unit on the ns basis states of smallest LC energy
+        (two-level preconditioner, see csrc/lowblock.cu).  sigma: [B] float64 (rad/s)."""
+        ops, kern = self.ops, self.ops.kern
+        ns = int(min(ns, 160, ops.N // 2))
+        S = torch.topk(self.diag, ns, dim=1, largest=False).indices.to(torch.int32).contiguous()
+        unit = 2 * np.pi * 1e9
+        Ainv = torch.empty((self.B, ns, ns), dtype=torch.complex64, device=self.device)
+        pot = ops.potential_struct(self.a, self.g, ops.etab)
+        kern.lowblock_assemble(ops.sp, S, ops.displacement_tables(), pot, self.diag, sigma.contiguous(), unit, Ainv)
+        kern.hpd_inverse_c64(Ainv)
+        return {'S': S, 'Ainv': Ainv, 'unit': unit, 'ns': ns}

@@ -316,6 +316,47 @@ class EmulKernels:
                 out.append((hx[a] - th * x[a]) / den)
             _set(T, b, np.array(out))
 
+    def lowblock_assemble(self, sp, S, Dt, pot, d, sigma, unit, out):
+        a, g, etab, diag = pot._keep
+        m, inner = sp.dims[0], sp.dims[1]
+        Dtn = Dt.numpy()
+        B, ns, _ = out.shape
+        for b in range(B):
+            s = S[min(b, S.shape[0] - 1)].numpy()
+            dd = d[min(b, d.shape[0] - 1)].numpy()
+            n, c = s // inner, s % inner
+            A = np.zeros((ns, ns), complex)
+            A[np.arange(ns), np.arange(ns)] = dd[s] - float(sigma[b])
+            same_c = c[:, None] == c[None, :]
+            g0, g1 = float(g[b, 0]), float(g[b, 1])
+            A += same_c * (g0 * (n[:, None] == n[None, :]) +
+                           g1 * (np.abs(n[:, None] - n[None, :]) == 1) * np.sqrt(np.maximum(n[:, None], n[None, :])))
+            for t in range(pot.n_terms):
+                sh = int(pot.shift[t][1])
+                at = complex(a[b, t])
+                A += (c[None, :] == c[:, None] - sh) * at * Dtn[t][n[:, None], n[None, :]]
+                A += (c[None, :] == c[:, None] + sh) * np.conj(at * Dtn[t][n[None, :], n[:, None]])
+            out[b] = torch.from_numpy((A / unit).astype(np.complex64))
+
+    def hpd_inverse_c64(self, A):
+        for b in range(A.shape[0]):
+            A[b] = torch.from_numpy(np.linalg.inv(A[b].numpy().astype(complex)).astype(np.complex64))
+
+    def lowblock_apply(self, X, HX, T, theta, act, S, Ainv, unit):
+        for b in range(X.B):
+            n = _cnt(T, b)
+            if n == 0:
+                continue
+            s = S[min(b, S.shape[0] - 1)].numpy()
+            x, hx = X.tensor[b].numpy(), HX.tensor[b].numpy()
+            t = _get(T, b).copy()
+            ai = Ainv[b].numpy().astype(complex)
+            for jj in range(n):
+                av = int(act[b, jj])
+                r = hx[av][s] - float(theta[b, av]) * x[av][s]
+                t[jj][s] = ai @ r / unit
+            _set(T, b, t)
+
     def svqb_coeffs(self, S, nact, drop, Cq, msz=None, mtot=None):
         B, ld, _ = S.shape
         for b in range(B):

@@ -287,6 +287,62 @@ def test_hx_fused_matches_unfused(kern, dims):
         assert relerr(out.cpu(), ref.cpu()) < 2e-13, (dims, use_fd)
 
 
+def test_lowblock_preconditioner_kernels(kern):
+    """assemble / inverse / apply of the two-level preconditioner against the numpy contracts."""
+    from sqcircuit_b200._lib import Potential
+    m, inner, ns, B, T = 25, 25, 96, 3, 2
+    N = m * inner
+    sp = make_space([m, inner], [1, 0])
+    V, lam = kern.xbasis(m)
+    lamcat = torch.zeros(m + inner, dtype=torch.float64, device='cuda')
+    lamcat[:m] = lam
+    s = torch.tensor([[[0.61, 0.0], [-0.61, 0.0]]], dtype=torch.float64, device='cuda')
+    etab = torch.empty((1, T, m + inner), dtype=torch.complex128, device='cuda')
+    kern.phase_tables(sp, T, lamcat, s, etab)
+    Dt = torch.einsum('ni,ti,ki->tnk', V.to(torch.complex128), etab[0, :, :m], V.to(torch.complex128)).contiguous()
+    a = rnd((B, T), 31).cuda()
+    gl = torch.randn((B, 3), dtype=torch.float64, generator=torch.Generator().manual_seed(3)).cuda()
+    d = (torch.rand((1, N), dtype=torch.float64, generator=torch.Generator().manual_seed(4)) * 50 + 20).cuda()
+    sigma = torch.tensor([-5.0, -6.0, -7.0], dtype=torch.float64, device='cuda')
+    S = torch.topk(d, ns, dim=1, largest=False).indices.to(torch.int32).contiguous()
+
+    def pot_struct(dev_a, dev_g, dev_e):
+        pot = Potential()
+        pot.n_terms = T
+        pot.shift[0][1] = 1
+        pot.shift[1][1] = -1
+        pot.lam, pot.etab, pot.etab_stride_b = lamcat.data_ptr(), dev_e.data_ptr(), 0
+        pot.g, pot.a, pot.diag, pot.diag_stride_b = dev_g.data_ptr(), dev_a.data_ptr(), None, 0
+        pot._keep = (dev_a, dev_g, dev_e, None)
+        return pot
+    out = torch.empty((B, ns, ns), dtype=torch.complex64, device='cuda')
+    kern.lowblock_assemble(sp, S, Dt, pot_struct(a, gl, etab), d, sigma, 1.0, out)
+    ref = torch.empty((B, ns, ns), dtype=torch.complex64)
+    E = EmulKernels()
+    E.lowblock_assemble(sp, S.cpu(), Dt.cpu(), pot_struct(a.cpu(), gl.cpu(), etab.cpu()), d.cpu(), sigma.cpu(), 1.0, ref)
+    assert relerr(out.cpu().to(torch.complex128), ref.to(torch.complex128)) < 1e-6
+    # Hermitian, diagonally dominant here -> positive definite; inverse in shared memory
+    inv = out.clone()
+    kern.hpd_inverse_c64(inv)
+    prod = inv.to(torch.complex128) @ out.to(torch.complex128)
+    assert float((prod - torch.eye(ns, device='cuda')).abs().max()) < 5e-4
+    # apply
+    p = 6
+    X, HX = rnd((B, p, N), 32).cuda(), rnd((B, p, N), 33).cuda()
+    Vb = rnd((B, 20, N), 34)
+    theta = torch.randn((B, 48), dtype=torch.float64)
+    msz = torch.tensor([6, 10, 14], dtype=torch.int32)
+    nact = torch.tensor([6, 2, 0], dtype=torch.int32)
+    act = torch.tensor([[0, 1, 2, 3, 4, 5], [4, 1, 0, 0, 0, 0], [0] * 6], dtype=torch.int32)
+    refV = Vb.clone()
+    E.lowblock_apply(BlockView(X.cpu()), BlockView(HX.cpu()), BlockView(refV, cnt_fixed=p, off=msz, cnt=nact),
+                     theta, act, S.cpu(), inv.cpu(), 2.0)
+    Vd = Vb.cuda()
+    kern.lowblock_apply(BlockView(X), BlockView(HX), BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()),
+                        theta.cuda(), act.cuda(), S, inv, 2.0)
+    assert relerr(Vd.cpu(), refV) < 1e-12
+
+
 def test_launch_counter(kern):
     n0 = kern.launch_count()
     kern.xbasis(8)
