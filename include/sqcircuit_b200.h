@@ -149,6 +149,12 @@ int64_t sqc_gram_work_bytes(int32_t B, int32_t na_max, int32_t nb_max, int64_t N
 int sqc_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int32_t B, void* C, int32_t ldr,
              int32_t ldc, void* work, int32_t impl, void* stream);
 
+/* One pass over A for two right-hand blocks: C = A^H Bm, C2 = A^H Bm2 (same leading dims;
+ * work sized by sqc_gram_work_bytes).  Used for the new columns of the basis Gram matrix and of
+ * the projected Hamiltonian in the non-orthogonalised Davidson iteration. */
+int sqc_gram_pair(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int32_t B, void* C,
+                  void* C2, int32_t ldr, int32_t ldc, void* work, void* stream);
+
 /* Out[b][j][n] (op)= sum_i Cf[b][j][i] A[b][i][n],  i < count(A), j < count(Out);
  * op: 0 assign, 1 subtract from Out.  Cf: device complex [B][ldr][ldc]; the coefficient of
  * A_i in Out_j is Cf[j][i] (trans = 0) or Cf[i][j] (trans = 1).
@@ -166,6 +172,12 @@ int sqc_block_rightmul(sqc_block_t T, const void* Cq, int32_t ldr, int32_t ldc,
  * Zt: device complex [B][ld][ld], Zt[j][i] = component i of eigenvector j.  ld <= 112. */
 int sqc_heev(const void* A, const int32_t* n, int32_t n_fixed, int32_t ld, double* w, void* Zt,
              int32_t B, void* stream);
+
+/* Generalised Rayleigh-Ritz GA c = theta GB c (GB = Gram matrix of a non-orthogonal basis):
+ * Cholesky of GB (vectors whose pivot falls below drop * GB_ii are removed), Jacobi on
+ * L^-1 GA L^-H, c = L^-H y.  w ascending, Zt[j][i] = coefficient i of Ritz vector j. ld <= 68. */
+int sqc_gen_rr(const void* GA, const void* GB, const int32_t* n, int32_t ld, double drop, double* w,
+               void* Zt, int32_t B, void* stream);
 
 /* rn2[b][j] = || HX_j - theta[b][j] X_j ||^2,  j < p. */
 int sqc_residual_norms(sqc_block_t X, sqc_block_t HX, const double* theta, int32_t ld_theta,
@@ -188,6 +200,9 @@ typedef struct {
     double*  resmax;            /* [B] max relative residual over the k wanted pairs */
     double*  den_floor;         /* [B] preconditioner denominator floor */
     void*    G;                 /* [B][ldg][ldg] projected Hamiltonian */
+    void*    GB;                /* [B][ldg][ldg] Gram matrix of the basis (non-orthogonalised
+                                   variant), or NULL */
+    int32_t* mtot;              /* [B] msz + nact after sqc_davidson_decide, or NULL */
 } sqc_davidson_state_t;
 
 int sqc_davidson_decide(const sqc_davidson_state_t* st, int32_t B, void* stream);
@@ -230,6 +245,10 @@ int sqc_svqb_coeffs(const void* S, int32_t ld, int32_t* nact, double drop, void*
 /* G[b][i][msz+j] = S[b][i][j], G[b][msz+j][i] = conj(.), i < msz+nact, j < nact; msz += nact. */
 int sqc_davidson_insert(const sqc_davidson_state_t* st, const void* S, int32_t ldr, int32_t ldc,
                         int32_t B, void* stream);
+
+/* as sqc_davidson_insert, for both G (from SA) and GB (from SB). */
+int sqc_davidson_insert2(const sqc_davidson_state_t* st, const void* SA, const void* SB, int32_t ldr,
+                         int32_t ldc, int32_t B, void* stream);
 
 #ifdef __cplusplus
 }

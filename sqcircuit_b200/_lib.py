@@ -39,7 +39,7 @@ class DavidsonState(C.Structure):
                 ('tol_rel', c_dbl), ('tol_abs_floor', c_dbl),
                 ('msz', c_vp), ('nact', c_vp), ('act', c_vp), ('restart', c_vp), ('done', c_vp),
                 ('n_not_done', c_vp), ('theta', c_vp), ('rn2', c_vp), ('resmax', c_vp),
-                ('den_floor', c_vp), ('G', c_vp)]
+                ('den_floor', c_vp), ('G', c_vp), ('GB', c_vp), ('mtot', c_vp)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/sqcircuit_b200.h
@@ -57,6 +57,9 @@ SIGNATURES = {
     'sqc_ladder_apply': (c_i32, [C.POINTER(Space), c_i32, c_vp, c_vp, Block, Block, c_i32, c_i32, c_vp]),
     'sqc_gram_work_bytes': (c_i64, [c_i32, c_i32, c_i32, c_i64]),
     'sqc_gram': (c_i32, [Block, Block, c_i64, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_vp]),
+    'sqc_gram_pair': (c_i32, [Block, Block, Block, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    'sqc_gen_rr': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_dbl, c_vp, c_vp, c_i32, c_vp]),
+    'sqc_davidson_insert2': (c_i32, [C.POINTER(DavidsonState), c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'sqc_block_update': (c_i32, [Block, c_vp, c_i32, c_i32, c_i32, Block, c_i64, c_i32, c_i32, c_i32, c_vp]),
     'sqc_hx_fused': (c_i32, [C.POINTER(Space), c_vp, c_vp, C.POINTER(Potential), c_vp, c_i64, Block, Block, c_i32, c_vp]),
     'sqc_block_rightmul': (c_i32, [Block, c_vp, c_i32, c_i32, c_vp, c_i64, c_i32, c_vp]),

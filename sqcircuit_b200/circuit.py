@@ -16,7 +16,18 @@ import numpy as np
 import torch
 
 from . import units as unt
-from .eigensolver import DENSE_MAX, solve_davidson, solve_dense
+from .eigensolver import DENSE_MAX, solve_davidson, solve_davidson_gen, solve_dense
+
+# iteration used by sweep_diag: 'gen' (non-orthogonalised basis, generalised Rayleigh-Ritz; 3 passes
+# over the basis per iteration) or 'orth' (CGS2 + SVQB; 7 passes)
+SOLVER = {'kind': 'gen'}
+
+
+def _davidson(*a, **kw):
+    if SOLVER['kind'] == 'gen':
+        kw.pop('impl', None)
+        return solve_davidson_gen(*a, **kw)
+    return solve_davidson(*a, **kw)
 from .elements import Capacitor, Charge, Inductor, Junction, Loop
 from .exceptions import CircuitStateError
 from .noise_ops import SweepNoise
@@ -207,8 +218,8 @@ class Circuit:
             res = self._solve_continuation(ops, lv, ng, n_eig, tol, block_size, max_basis, maxit,
                                            stats, coarse_stride, lowblock)
         else:
-            res = solve_davidson(kern, hop, B, ops.N, n_eig, hop.diag, p=block_size, mmax=max_basis,
-                                 tol=tol, maxit=maxit, stats=stats)
+            res = _davidson(kern, hop, B, ops.N, n_eig, hop.diag, p=block_size, mmax=max_basis,
+                            tol=tol, maxit=maxit, stats=stats)
         if not res.converged:
             raise RuntimeError(f'batched Davidson did not converge in {maxit} iterations '
                                f'(worst relative residual {float(res.resmax.max()):.2e})')
@@ -237,9 +248,9 @@ class Circuit:
 
         def solve(idx, x0, st):
             hop = sub(idx)
-            return solve_davidson(kern, hop, len(idx), ops.N, n_eig, hop.diag, p=block_size,
-                                  mmax=max_basis, tol=tol, maxit=maxit, x0=x0, stats=st,
-                                  lowblock_ns=lowblock if x0 is not None else 0)
+            return _davidson(kern, hop, len(idx), ops.N, n_eig, hop.diag, p=block_size,
+                             mmax=max_basis, tol=tol, maxit=maxit, x0=x0, stats=st,
+                             lowblock_ns=lowblock if x0 is not None else 0)
         if not vary.any():
             return solve(np.arange(B), None, stats)
         q = prm[:, vary] / span[vary]

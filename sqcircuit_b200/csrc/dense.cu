@@ -12,45 +12,89 @@ long long g_sqc_launches = 0;
 // Real formulation on the interleaved data (K index t runs over the 2N doubles of a vector):
 //   Re C = A_r . B_r^T           Im C = A_r . B'_r^T,   B'[2n] = Im b_n, B'[2n+1] = -Re b_n
 // so one DMMA B-fragment plus a lane-xor shuffle feeds both the real and the imaginary tile.
-// CTA = 4 warps; the warps split the K range of every staged chunk and each warp keeps all
-// (NAT x 2*NBT) 8x8 accumulator tiles; a final shared-memory reduction combines the warps.
+// CTA = 4 warps, two CTAs per SM, >= 3 cp.async stages sized by the rows the sweep point really
+// has (one block sync per chunk: the refill of the slot consumed one iteration earlier is issued
+// before the tensor-core work of the current chunk); the warps split the K range of every staged
+// chunk and each warp keeps all (NAT x NCT) 8x8 accumulator tiles; a final shared-memory
+// reduction combines them.
 // =====================================================================================
 #define GRAM_THREADS 128
+#define GRAM_WARPS (GRAM_THREADS / 32)
 #define GRAM_CH 32                  // complex elements per staged chunk
-#define GRAM_LD (2 * GRAM_CH + 4)   // doubles per smem row: 68 == 4 (mod 16) -> conflict-free frags
+#define GRAM_LD (2 * GRAM_CH + 4)   // doubles per smem row: 68 == 4 (mod 8) -> conflict-free frags
+
+// Tensor-core work of one staged chunk for exactly NATR populated row tiles.  The row-tile count
+// is a template parameter (dispatched by a warp-uniform switch) because a run-time guard is
+// compiled to PREDICATED DMMAs, and predicated-off DMMAs still occupy the FP64 tensor pipe.
+template <int NATR, int NAT, int NCT, int KW>
+__device__ __forceinline__ void gram_chunk(double (&acc)[NAT][NCT][2], const double* __restrict__ sAb,
+                                           const double* __restrict__ sBb, int warp, int g, int t,
+                                           int bcol, double bsign) {
+#pragma unroll
+    for (int ks = 0; ks < (2 * GRAM_CH / 4) / KW; ++ks) {
+        const int k0 = 4 * (warp + KW * ks);
+        double bf[NCT];
+#pragma unroll
+        for (int j = 0; j < NCT; ++j) bf[j] = bsign * sBb[(4 * j + (g >> 1)) * GRAM_LD + k0 + bcol];
+#pragma unroll
+        for (int i = 0; i < NATR; ++i) {
+            const double af = sAb[(8 * i + g) * GRAM_LD + k0 + t];
+#pragma unroll
+            for (int j = 0; j < NCT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+        }
+    }
+}
 
 // NAT: max row tiles (8 vectors of A each); NCT: column tiles over the 2*nb packed real
 // columns (column 2j = Re C[.][j], column 2j+1 = Im C[.][j]).
-template <int NAT, int NCT>
+// PAIR: two B blocks (Bm -> C, Bm2 -> C2) against the same A in ONE pass over A: warps 0,1 take
+// Bm, warps 2,3 take Bm2, each pair splitting K two ways.
+template <int NAT, int NCT, bool PAIR>
 __global__ void __launch_bounds__(GRAM_THREADS)
-gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, int nsplit, cplx* __restrict__ C,
-                 int ldr, int ldc, cplx* __restrict__ work) {
+gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int nsplit,
+                 cplx* __restrict__ C, cplx* __restrict__ C2, int ldr, int ldc, cplx* __restrict__ work,
+                 int smem_doubles) {
     constexpr int NA = NAT * 8, NB = NCT * 4;
+    constexpr int NBLK = PAIR ? 2 : 1;          // B blocks
+    constexpr int KW = GRAM_WARPS / NBLK;       // warps that split K for one B block
     extern __shared__ double smem[];
-    double* sA[2] = {smem, smem + (NA + NB) * GRAM_LD};
-    double* sB[2] = {sA[0] + NA * GRAM_LD, sA[1] + NA * GRAM_LD};
 
     const int b = blockIdx.x / nsplit, split = blockIdx.x % nsplit;
     const int na = min(blk_count(A, b), NA), nb = min(blk_count(Bm, b), NB);
+    const int nb2 = PAIR ? min(blk_count(Bm2, b), NB) : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int grp = PAIR ? (warp / KW) : 0, kw = warp % KW;
 
-    cplx* out = (nsplit == 1) ? C + (int64_t)b * ldr * ldc
-                              : work + ((int64_t)b * nsplit + split) * (NA * NB);
+    cplx* outs[2];
+    outs[0] = (nsplit == 1) ? C + (int64_t)b * ldr * ldc
+                            : work + (((int64_t)b * nsplit + split) * NBLK + 0) * (NA * NB);
+    outs[1] = !PAIR ? nullptr
+              : (nsplit == 1) ? C2 + (int64_t)b * ldr * ldc
+                              : work + (((int64_t)b * nsplit + split) * NBLK + 1) * (NA * NB);
     const int out_ld = (nsplit == 1) ? ldc : NB;
     const int out_rows = (nsplit == 1) ? min(A.cnt_fixed, ldr) : NA;
     const int out_cols = (nsplit == 1) ? min(Bm.cnt_fixed, ldc) : NB;
 
-    if (na == 0 || nb == 0) {
-        for (int e = tid; e < out_rows * out_cols; e += GRAM_THREADS)
-            out[(e / out_cols) * out_ld + (e % out_cols)] = cmake(0.0, 0.0);
+    if (na == 0 || (nb == 0 && nb2 == 0)) {
+        for (int o = 0; o < NBLK; ++o)
+            for (int e = tid; e < out_rows * out_cols; e += GRAM_THREADS)
+                outs[o][(e / out_cols) * out_ld + (e % out_cols)] = cmake(0.0, 0.0);
         return;
     }
     const int nat = (na + 7) >> 3;          // row tiles actually populated for this sweep point
+    // stages are sized by the rows this point really has, so small bases get a deeper pipeline
+    const int stage_doubles = (nat * 8 + NBLK * NB) * GRAM_LD;
+    int nstage = smem_doubles / stage_doubles;     // >= 3 by construction of the launch
+    nstage = nstage > 8 ? 8 : nstage;
     const cplx* a0 = blk_vec(A, b, 0, N);
     const cplx* b0 = blk_vec(Bm, b, 0, N);
+    const cplx* b1 = PAIR ? blk_vec(Bm2, b, 0, N) : b0;
 
+    // chunks are dealt round-robin to the nsplit CTAs of a sweep point: CTAs with adjacent
+    // blockIdx run concurrently and stream ADJACENT 512 B pieces of every vector, so DRAM sees
+    // multi-KB bursts per vector instead of isolated 512 B requests
     const int64_t nchunks = (N + GRAM_CH - 1) / GRAM_CH;
-    const int64_t c_lo = nchunks * split / nsplit, c_hi = nchunks * (split + 1) / nsplit;
+    const int64_t c_lo = 0, c_hi = (nchunks - split + nsplit - 1) / nsplit;   // local chunk indices
 
     double acc[NAT][NCT][2];
 #pragma unroll
@@ -58,23 +102,39 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, int nsplit, cplx* __r
 #pragma unroll
         for (int j = 0; j < NCT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    auto stage = [&](int buf, int64_t chunk) {
-        const int64_t n0 = chunk * GRAM_CH;
-        const int rows = nat * 8 + NB;
-        for (int e = tid; e < rows * GRAM_CH; e += GRAM_THREADS) {
-            const int r = e / GRAM_CH, c = e % GRAM_CH;
-            const bool isA = r < nat * 8;
-            const int rr = isA ? r : r - nat * 8;
-            double* dst = (isA ? sA[buf] : sB[buf]) + rr * GRAM_LD + 2 * c;
-            const bool valid = (n0 + c < N) && (isA ? rr < na : rr < nb);
-            if (valid) {
-                cp_async16(dst, (isA ? a0 : b0) + (int64_t)rr * N + n0 + c);
-            } else {
-                dst[0] = 0.0;
-                dst[1] = 0.0;
+    // one commit group per call, even when the chunk is past the end (keeps the group count uniform)
+    auto stage = [&](int64_t chunk) {
+        if (chunk < c_hi) {
+            double* base = smem + (int)((chunk - c_lo) % nstage) * stage_doubles;
+            const int64_t n0 = (split + chunk * nsplit) * GRAM_CH;
+            const int rows = nat * 8 + NBLK * NB;
+            for (int e = tid; e < rows * GRAM_CH; e += GRAM_THREADS) {
+                const int r = e / GRAM_CH, c = e % GRAM_CH;
+                const bool isA = r < nat * 8;
+                const bool isB2 = PAIR && r >= nat * 8 + NB;
+                const int rr = isA ? r : (isB2 ? r - nat * 8 - NB : r - nat * 8);
+                double* dst = base + r * GRAM_LD + 2 * c;
+                const bool valid = (n0 + c < N) && (isA ? rr < na : (isB2 ? rr < nb2 : rr < nb));
+                if (valid) {
+                    cp_async16(dst, (isA ? a0 : (isB2 ? b1 : b0)) + (int64_t)rr * N + n0 + c);
+                } else {
+                    dst[0] = 0.0;
+                    dst[1] = 0.0;
+                }
             }
         }
         cp_async_commit();
+    };
+    auto wait_oldest = [&]() {      // all but the newest (nstage - 2) groups complete
+        switch (nstage) {
+            case 2: cp_async_wait<0>(); break;
+            case 3: cp_async_wait<1>(); break;
+            case 4: cp_async_wait<2>(); break;
+            case 5: cp_async_wait<3>(); break;
+            case 6: cp_async_wait<4>(); break;
+            case 7: cp_async_wait<5>(); break;
+            default: cp_async_wait<6>(); break;
+        }
     };
 
     // B fragment of packed column n = 8ct + g:  vector j = 4ct + (g>>1), part = g&1
@@ -83,34 +143,26 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, int nsplit, cplx* __r
     const int bcol = t ^ bpart;
     const double bsign = (bpart && (t & 1)) ? -1.0 : 1.0;
 
-    if (c_lo < c_hi) stage(0, c_lo);
+    for (int pre = 0; pre < nstage - 1; ++pre) stage(c_lo + pre);
     for (int64_t ch = c_lo; ch < c_hi; ++ch) {
-        const int buf = (int)((ch - c_lo) & 1);
-        if (ch + 1 < c_hi) {
-            stage(buf ^ 1, ch + 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+        wait_oldest();
+        __syncthreads();            // chunk ch visible; everyone is done with chunk ch - 1
+        stage(ch + nstage - 1);     // refill the slot of chunk ch - 1 while computing chunk ch
+        const double* sAb = smem + (int)((ch - c_lo) % nstage) * stage_doubles;
+        const double* sBb = sAb + (nat * 8 + grp * NB) * GRAM_LD;
+        switch (nat) {
+            case 1: gram_chunk<1, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
+            case 2: if constexpr (NAT >= 2) gram_chunk<2, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
+            case 3: if constexpr (NAT >= 3) gram_chunk<3, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
+            case 4: if constexpr (NAT >= 4) gram_chunk<4, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
+            case 5: if constexpr (NAT >= 5) gram_chunk<5, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
+            case 6: if constexpr (NAT >= 6) gram_chunk<6, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
+            case 7: if constexpr (NAT >= 7) gram_chunk<7, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
+            default: if constexpr (NAT >= 8) gram_chunk<8, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
         }
-        __syncthreads();
-#pragma unroll
-        for (int ks = 0; ks < (2 * GRAM_CH / 4) / 4; ++ks) {
-            const int k0 = 4 * (warp + 4 * ks);
-            double bf[NCT];
-#pragma unroll
-            for (int j = 0; j < NCT; ++j)
-                bf[j] = bsign * sB[buf][(4 * j + (g >> 1)) * GRAM_LD + k0 + bcol];
-#pragma unroll
-            for (int i = 0; i < NAT; ++i) {
-                if (i < nat) {
-                    const double af = sA[buf][(8 * i + g) * GRAM_LD + k0 + t];
-#pragma unroll
-                    for (int j = 0; j < NCT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
-                }
-            }
-        }
-        __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();
 
     // cross-warp reduction through shared memory: red[warp][row][NB] complex
     cplx* red = reinterpret_cast<cplx*>(smem);
@@ -120,30 +172,32 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, int nsplit, cplx* __r
         for (int j = 0; j < NCT; ++j)
             red[(warp * NA + 8 * i + g) * NB + 4 * j + t] = cmake(acc[i][j][0], acc[i][j][1]);
     __syncthreads();
-    for (int e = tid; e < out_rows * out_cols; e += GRAM_THREADS) {
-        const int r = e / out_cols, c = e % out_cols;
-        double re = 0.0, im = 0.0;
-        if (r < NA && c < NB) {
+    for (int o = 0; o < NBLK; ++o) {
+        for (int e = tid; e < out_rows * out_cols; e += GRAM_THREADS) {
+            const int r = e / out_cols, c = e % out_cols;
+            double re = 0.0, im = 0.0;
+            if (r < NA && c < NB) {
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const cplx v = red[(w * NA + r) * NB + c];
-                re += v.x;
-                im += v.y;
+                for (int w = 0; w < KW; ++w) {
+                    const cplx v = red[((o * KW + w) * NA + r) * NB + c];
+                    re += v.x;
+                    im += v.y;
+                }
             }
+            outs[o][r * out_ld + c] = cmake(re, im);
         }
-        out[r * out_ld + c] = cmake(re, im);
     }
 }
 
-__global__ void gram_reduce_kernel(const cplx* __restrict__ work, int nsplit, int NA, int NB,
-                                   cplx* __restrict__ C, int ldr, int ldc, int rows, int cols) {
+__global__ void gram_reduce_kernel(const cplx* __restrict__ work, int nsplit, int NA, int NB, int nblk,
+                                   int blk, cplx* __restrict__ C, int ldr, int ldc, int rows, int cols) {
     const int b = blockIdx.x;
     for (int e = threadIdx.x; e < rows * cols; e += blockDim.x) {
         const int r = e / cols, c = e % cols;
         double re = 0.0, im = 0.0;
         if (r < NA && c < NB)
             for (int s = 0; s < nsplit; ++s) {
-                const cplx v = work[((int64_t)b * nsplit + s) * (NA * NB) + r * NB + c];
+                const cplx v = work[(((int64_t)b * nsplit + s) * nblk + blk) * (NA * NB) + r * NB + c];
                 re += v.x;
                 im += v.y;
             }
@@ -186,9 +240,12 @@ __global__ void gram_ref_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, cplx* 
     }
 }
 
+static int g_gram_split_min = 8;
 static int gram_nsplit(int B, int64_t N) {
-    // enough CTAs to fill 148 SMs x 3 resident CTAs, but never split below 8 chunks per CTA
-    int want = (148 * 3 + B - 1) / B;
+    // enough CTAs to fill 148 SMs x 2 resident CTAs, at least g_gram_split_min interleaved CTAs per
+    // sweep point (DRAM burst shaping), but never below 8 chunks per CTA
+    int want = (148 * 2 + B - 1) / B;
+    if (want < g_gram_split_min) want = g_gram_split_min;
     int64_t nchunks = (N + GRAM_CH - 1) / GRAM_CH;
     int64_t maxs = nchunks / 8 > 0 ? nchunks / 8 : 1;
     if (want > maxs) want = (int)maxs;
@@ -196,6 +253,7 @@ static int gram_nsplit(int B, int64_t N) {
     if (want > 64) want = 64;
     return want;
 }
+extern "C" void sqc_debug_set_gram_split(int v) { g_gram_split_min = v; }
 static void gram_tiles(int na_max, int nb_max, int* nat, int* nct) {
     *nat = (na_max + 7) / 8;
     if (*nat < 1) *nat = 1;
@@ -210,26 +268,35 @@ extern "C" int64_t sqc_gram_work_bytes(int32_t B, int32_t na_max, int32_t nb_max
     gram_tiles(na_max, nb_max, &nat, &nct);
     int ns = gram_nsplit(B, N);
     if (ns == 1) return 0;
-    return (int64_t)B * ns * (nat * 8) * (nct * 4) * (int64_t)sizeof(cplx);
+    return 2 * (int64_t)B * ns * (nat * 8) * (nct * 4) * (int64_t)sizeof(cplx);
 }
 
-template <int NAT, int NCT>
-static int launch_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int B, cplx* C, int ldr, int ldc,
-                       cplx* work, cudaStream_t st) {
+template <int NAT, int NCT, bool PAIR>
+static int launch_gram(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int B, cplx* C, cplx* C2,
+                       int ldr, int ldc, cplx* work, cudaStream_t st) {
     const int ns = gram_nsplit(B, N);
     if (ns > 1 && !work) return SQC_EINVAL;
-    size_t stage_bytes = 2 * (size_t)(NAT * 8 + NCT * 4) * GRAM_LD * sizeof(double);
-    size_t red_bytes = 4 * (size_t)(NAT * 8) * (NCT * 4) * sizeof(cplx);
-    size_t smem = stage_bytes > red_bytes ? stage_bytes : red_bytes;
-    auto kern = gram_dmma_kernel<NAT, NCT>;
+    // at least three full-size stages, as many as fit in ~108 KB (two CTAs per SM)
+    size_t stage_bytes = (size_t)(NAT * 8 + (PAIR ? 2 : 1) * NCT * 4) * GRAM_LD * sizeof(double);
+    size_t smem = 3 * stage_bytes;
+    if (smem < 108 * 1024) smem = (108 * 1024 / stage_bytes) * stage_bytes;
+    size_t red_bytes = GRAM_WARPS * (size_t)(NAT * 8) * (NCT * 4) * sizeof(cplx);
+    if (smem < red_bytes) smem = red_bytes;
+    if (smem > 227 * 1024) return SQC_ELIMIT;
+    auto kern = gram_dmma_kernel<NAT, NCT, PAIR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<B * ns, GRAM_THREADS, smem, st>>>(A, Bm, N, ns, C, ldr, ldc, work);
+    kern<<<B * ns, GRAM_THREADS, smem, st>>>(A, Bm, Bm2, N, ns, C, C2, ldr, ldc, work, (int)(smem / sizeof(double)));
     SQC_LAUNCHED();
     if (ns > 1) {
         int rows = A.cnt_fixed < ldr ? A.cnt_fixed : ldr, cols = Bm.cnt_fixed < ldc ? Bm.cnt_fixed : ldc;
-        gram_reduce_kernel<<<B, 128, 0, st>>>(work, ns, NAT * 8, NCT * 4, C, ldr, ldc, rows, cols);
+        const int nblk = PAIR ? 2 : 1;
+        gram_reduce_kernel<<<B, 128, 0, st>>>(work, ns, NAT * 8, NCT * 4, nblk, 0, C, ldr, ldc, rows, cols);
         SQC_LAUNCHED();
+        if (PAIR) {
+            gram_reduce_kernel<<<B, 128, 0, st>>>(work, ns, NAT * 8, NCT * 4, nblk, 1, C2, ldr, ldc, rows, cols);
+            SQC_LAUNCHED();
+        }
     }
     return 0;
 }
@@ -248,12 +315,31 @@ extern "C" int sqc_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int32_t B, voi
     int nat, nct;
     gram_tiles(A.cnt_fixed, Bm.cnt_fixed, &nat, &nct);
 #define GRAM_CASE(a, b_) \
-    if (nat == a && nct == b_) return launch_gram<a, b_>(A, Bm, N, B, (cplx*)C, ldr, ldc, (cplx*)work, st)
+    if (nat == a && nct == b_) return launch_gram<a, b_, false>(A, Bm, Bm, N, B, (cplx*)C, nullptr, ldr, ldc, (cplx*)work, st)
     GRAM_CASE(1, 1); GRAM_CASE(2, 1); GRAM_CASE(4, 1); GRAM_CASE(6, 1); GRAM_CASE(8, 1);
     GRAM_CASE(1, 2); GRAM_CASE(2, 2); GRAM_CASE(4, 2); GRAM_CASE(6, 2); GRAM_CASE(8, 2);
     GRAM_CASE(1, 3); GRAM_CASE(2, 3); GRAM_CASE(4, 3); GRAM_CASE(6, 3); GRAM_CASE(8, 3);
     GRAM_CASE(1, 4); GRAM_CASE(2, 4); GRAM_CASE(4, 4); GRAM_CASE(6, 4); GRAM_CASE(8, 4);
 #undef GRAM_CASE
+    return SQC_ELIMIT;
+}
+
+// One pass over A for two right-hand blocks: C = A^H Bm, C2 = A^H Bm2 (the new columns of the
+// basis Gram matrix and of the projected Hamiltonian in the non-orthogonalised Davidson).
+extern "C" int sqc_gram_pair(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int32_t B, void* C,
+                             void* C2, int32_t ldr, int32_t ldc, void* work, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || N <= 0 || A.cnt_fixed <= 0 || Bm.cnt_fixed <= 0 || Bm.cnt_fixed != Bm2.cnt_fixed) return SQC_EINVAL;
+    if (A.cnt_fixed > 64 || Bm.cnt_fixed > 16) return SQC_ELIMIT;
+    int nat, nct;
+    gram_tiles(A.cnt_fixed, Bm.cnt_fixed, &nat, &nct);
+#define GRAMP_CASE(a, b_) \
+    if (nat == a && nct == b_) return launch_gram<a, b_, true>(A, Bm, Bm2, N, B, (cplx*)C, (cplx*)C2, ldr, ldc, (cplx*)work, st)
+    GRAMP_CASE(1, 1); GRAMP_CASE(2, 1); GRAMP_CASE(4, 1); GRAMP_CASE(6, 1); GRAMP_CASE(8, 1);
+    GRAMP_CASE(1, 2); GRAMP_CASE(2, 2); GRAMP_CASE(4, 2); GRAMP_CASE(6, 2); GRAMP_CASE(8, 2);
+    GRAMP_CASE(1, 3); GRAMP_CASE(2, 3); GRAMP_CASE(4, 3); GRAMP_CASE(6, 3); GRAMP_CASE(8, 3);
+    GRAMP_CASE(1, 4); GRAMP_CASE(2, 4); GRAMP_CASE(4, 4); GRAMP_CASE(6, 4); GRAMP_CASE(8, 4);
+#undef GRAMP_CASE
     return SQC_ELIMIT;
 }
 
@@ -310,14 +396,16 @@ block_update_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, int ldc
 // A warp owns 32 consecutive positions (4 M-tiles) and all outputs; A fragments are read straight
 // from global memory (per k-step two vectors x 512 contiguous bytes), the packed coefficient
 // matrix sits in shared memory.
-#define UPD2_THREADS 128
+#define UPD2_THREADS 256
 #define UPD2_MT 4
+#define UPD2_DEPTH 10            // ring slots per warp (k-steps in flight = DEPTH - 1)
+#define UPD2_SLOT (2 * 32 * 2)   // doubles per slot: 2 vectors x 32 positions x (re, im)
 
 template <int NCT>
-__global__ void __launch_bounds__(UPD2_THREADS, 5)
+__global__ void __launch_bounds__(UPD2_THREADS, 2)
 block_update_dmma_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, int ldc, int trans,
-                         sqc_block_t Out, int64_t N, int nchunk, int op, int ldm) {
-    extern __shared__ double smem[];     // Mr[2*na][ldm]
+                         sqc_block_t Out, int64_t N, int nchunk, int op, int ldm, int kk_max) {
+    extern __shared__ double smem[];     // Mr[kk_max][ldm] | ring[warps][DEPTH][SLOT]
     const int b = blockIdx.x / nchunk;
     const int na = blk_count(A, b), nb = min(blk_count(Out, b), NCT * 4);
     if (nb == 0) return;
@@ -338,36 +426,52 @@ block_update_dmma_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, in
     __syncthreads();
     const int64_t nbase = ((int64_t)(blockIdx.x % nchunk) * (UPD2_THREADS / 32) + warp) * (8 * UPD2_MT);
     if (nbase >= N) return;
-    const double* a = reinterpret_cast<const double*>(blk_vec(A, b, 0, N));
+    double* ring = smem + kk_max * ldm + warp * (UPD2_DEPTH * UPD2_SLOT);
+    const cplx* a = blk_vec(A, b, 0, N);
+    const int nks = kk / 4;                 // k-steps; k-step s uses vectors 2s, 2s+1
+    // slot layout: [vector (2)][position (32)][re, im]; every lane copies its position of both vectors
+    auto issue = [&](int s) {
+        if (s < nks) {
+            double* dst = ring + (s % UPD2_DEPTH) * UPD2_SLOT + 2 * lane;
+            const int64_t n = nbase + lane;
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int i = 2 * s + v;
+                if (i < na && n < N) {
+                    cp_async16(dst + v * 64, a + (int64_t)i * N + n);
+                } else {
+                    dst[v * 64] = 0.0;
+                    dst[v * 64 + 1] = 0.0;
+                }
+            }
+        }
+        cp_async_commit();
+    };
     double acc[UPD2_MT][NCT][2];
 #pragma unroll
     for (int mt = 0; mt < UPD2_MT; ++mt)
 #pragma unroll
         for (int j = 0; j < NCT; ++j) acc[mt][j][0] = acc[mt][j][1] = 0.0;
-    // A fragment: row n = nbase + 8 mt + g, k = (i0 + (t>>1), t&1)  -> A_r[i][2n + (t&1)]
-    int64_t noff[UPD2_MT];
-    bool nok[UPD2_MT];
 #pragma unroll
-    for (int mt = 0; mt < UPD2_MT; ++mt) {
-        const int64_t n = nbase + 8 * mt + g;
-        nok[mt] = n < N;
-        noff[mt] = 2 * (nok[mt] ? n : 0) + (t & 1);
-    }
-#pragma unroll 4
-    for (int k0 = 0; k0 < kk; k0 += 4) {
-        const int i = (k0 >> 1) + (t >> 1);
-        const bool iok = i < na;
-        const double* ar = a + (int64_t)(iok ? i : 0) * 2 * N;
+    for (int s = 0; s < UPD2_DEPTH - 1; ++s) issue(s);
+    for (int s = 0; s < nks; ++s) {
+        cp_async_wait<UPD2_DEPTH - 2>();    // the group of k-step s has landed (for this lane)
+        __syncwarp();
+        const double* slot = ring + (s % UPD2_DEPTH) * UPD2_SLOT;
+        // A fragment: row n = 8 mt + g, k = (vector t>>1, part t&1)
         double af[UPD2_MT];
 #pragma unroll
-        for (int mt = 0; mt < UPD2_MT; ++mt) af[mt] = (iok && nok[mt]) ? ar[noff[mt]] : 0.0;
+        for (int mt = 0; mt < UPD2_MT; ++mt) af[mt] = slot[(t >> 1) * 64 + 2 * (8 * mt + g) + (t & 1)];
 #pragma unroll
         for (int j = 0; j < NCT; ++j) {
-            const double bf = smem[(k0 + t) * ldm + 8 * j + g];
+            const double bf = smem[(4 * s + t) * ldm + 8 * j + g];
 #pragma unroll
             for (int mt = 0; mt < UPD2_MT; ++mt) dmma884(acc[mt][j][0], acc[mt][j][1], af[mt], bf);
         }
+        __syncwarp();                       // slot may be overwritten by the next issue
+        issue(s + UPD2_DEPTH - 1);
     }
+    cp_async_wait<0>();
     // C fragment: row n = nbase + 8 mt + g, packed cols 8j + 2t, +1  -> Out[4j + t][n] (re, im)
     cplx* o = blk_vec(Out, b, 0, N);
 #pragma unroll
@@ -403,13 +507,13 @@ extern "C" int sqc_block_update(sqc_block_t A, const void* Cf, int32_t ldr, int3
         int ldm = nct * 8;
         while ((ldm & 15) != 4) ++ldm;
         const int kk = (2 * (A.cnt_fixed > 0 ? A.cnt_fixed : 1) + 3) & ~3;
-        size_t smem = (size_t)kk * ldm * sizeof(double);
+        size_t smem = ((size_t)kk * ldm + (size_t)(UPD2_THREADS / 32) * UPD2_DEPTH * UPD2_SLOT) * sizeof(double);
 #define UPD2_CASE(NCTv)                                                                               \
     if (nct == NCTv) {                                                                                \
         auto kern = block_update_dmma_kernel<NCTv>;                                                   \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return (int)e;                                                          \
-        kern<<<(unsigned)grid, UPD2_THREADS, smem, st>>>(A, (const cplx*)Cf, ldr, ldc, trans, Out, N, nchunk, op, ldm); \
+        kern<<<(unsigned)grid, UPD2_THREADS, smem, st>>>(A, (const cplx*)Cf, ldr, ldc, trans, Out, N, nchunk, op, ldm, kk); \
         SQC_LAUNCHED();                                                                               \
         return 0;                                                                                     \
     }

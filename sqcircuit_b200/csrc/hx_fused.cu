@@ -30,6 +30,7 @@ struct HxGeom {
     long long N;
 };
 
+template <int NRT>
 __global__ void __launch_bounds__(288, 2)
 hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restrict__ Vo,
                 const double* __restrict__ lam, const cplx* __restrict__ etab, long long etab_stride_b,
@@ -96,9 +97,9 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
 
         // ---- 2. forward transform (warp = column tile), in place ----
         if (warp < gm.CT) {
-            double aE[HX_MAXRT][2], aO[HX_MAXRT][2];
+            double aE[NRT][2], aO[NRT][2];
 #pragma unroll
-            for (int r = 0; r < HX_MAXRT; ++r) aE[r][0] = aE[r][1] = aO[r][0] = aO[r][1] = 0.0;
+            for (int r = 0; r < NRT; ++r) aE[r][0] = aE[r][1] = aO[r][0] = aO[r][1] = 0.0;
             const int cb = 8 * warp + gq;
             for (int k0 = 0; k0 < gm.kp; k0 += 4) {
                 const double bE = sP[(k0 + tq) * pld + cb];
@@ -106,20 +107,18 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
                 const double* ve = sVe + (k0 + tq) * vld + gq;     // A[i][a] = Ve[a][i]
                 const double* vo = sVo + (k0 + tq) * vld + gq;
 #pragma unroll
-                for (int r = 0; r < HX_MAXRT; ++r) {
-                    if (r < gm.nrt) {
-                        const bool in = 8 * r + gq < hep;
-                        dmma884(aE[r][0], aE[r][1], in ? ve[8 * r] : 0.0, bE);
-                        dmma884(aO[r][0], aO[r][1], in ? vo[8 * r] : 0.0, bO);
-                    }
+                for (int r = 0; r < NRT; ++r) {
+                    const bool in = 8 * r + gq < hep;
+                    dmma884(aE[r][0], aE[r][1], in ? ve[8 * r] : 0.0, bE);
+                    dmma884(aO[r][0], aO[r][1], in ? vo[8 * r] : 0.0, bO);
                 }
             }
             __syncwarp();
             const int cc = 8 * warp + 2 * tq;
 #pragma unroll
-            for (int r = 0; r < HX_MAXRT; ++r) {
+            for (int r = 0; r < NRT; ++r) {
                 const int i = 8 * r + gq;
-                if (r < gm.nrt && i < hep) {
+                if (i < hep) {
                     double2 zs = make_double2(aE[r][0] + aO[r][0], aE[r][1] + aO[r][1]);   // Z[i]
                     double2 zd = make_double2(aE[r][0] - aO[r][0], aE[r][1] - aO[r][1]);   // Z[m-1-i]
                     if (i >= ho) zd = make_double2(0.0, 0.0);
@@ -181,9 +180,9 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
 
         // ---- 4. backward transform + LC diagonal epilogue ----
         if (warp < gm.CT) {
-            double yE[HX_MAXRT][2], yO[HX_MAXRT][2];
+            double yE[NRT][2], yO[NRT][2];
 #pragma unroll
-            for (int r = 0; r < HX_MAXRT; ++r) yE[r][0] = yE[r][1] = yO[r][0] = yO[r][1] = 0.0;
+            for (int r = 0; r < NRT; ++r) yE[r][0] = yE[r][1] = yO[r][0] = yO[r][1] = 0.0;
             const int cb = 8 * warp + gq;
             for (int k0 = 0; k0 < gm.kp; k0 += 4) {
                 const double bS = sP[(k0 + tq) * pld + cb];
@@ -191,12 +190,10 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
                 const double* ve = sVe + gq * vld + k0 + tq;       // A[a][i] = Ve[a][i]
                 const double* vo = sVo + gq * vld + k0 + tq;
 #pragma unroll
-                for (int r = 0; r < HX_MAXRT; ++r) {
-                    if (r < gm.nrt) {
-                        const bool in = 8 * r + gq < hep;
-                        dmma884(yE[r][0], yE[r][1], in ? ve[8 * r * vld] : 0.0, bS);
-                        dmma884(yO[r][0], yO[r][1], in ? vo[8 * r * vld] : 0.0, bD);
-                    }
+                for (int r = 0; r < NRT; ++r) {
+                    const bool in = 8 * r + gq < hep;
+                    dmma884(yE[r][0], yE[r][1], in ? ve[8 * r * vld] : 0.0, bS);
+                    dmma884(yO[r][0], yO[r][1], in ? vo[8 * r * vld] : 0.0, bD);
                 }
             }
             const int pcc = 4 * warp + tq;              // complex panel column of this lane
@@ -205,8 +202,8 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
                 cplx* yv = blk_vec(Y, b, v, gm.N);
                 const double* fd = fdiag ? fdiag + b * fdiag_stride_b : nullptr;
 #pragma unroll
-                for (int r = 0; r < HX_MAXRT; ++r) {
-                    if (r < gm.nrt) {
+                for (int r = 0; r < NRT; ++r) {
+                    {
                         const int aidx = 8 * r + gq;
                         if (aidx < he) {
                             const long long idx = (long long)(2 * aidx) * gm.inner + c;
@@ -279,17 +276,27 @@ extern "C" int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const doubl
     size_t smem = ((size_t)2 * gm.kp * gm.vld + (size_t)2 * gm.kp * gm.pld + ((gm.m + 1) & ~1)) * sizeof(double) +
                   (size_t)(gm.n_terms > 0 ? gm.n_terms : 1) * gm.m * sizeof(cplx);
     if (smem > 227 * 1024) return SQC_ELIMIT;
-    cudaError_t e = cudaFuncSetAttribute(hx_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
     const int per_sm = (smem <= 112 * 1024) ? 2 : 1;
     const long long total = (long long)B * X.cnt_fixed * gm.np;
     long long grid = (long long)nsm * per_sm;
     if (grid > total) grid = total;
-    hx_fused_kernel<<<(unsigned)grid, 32 * nwarp, smem, (cudaStream_t)stream>>>(
-        gm, Ve, Vo, pot->lam, (const cplx*)pot->etab, pot->etab_stride_b, pot->g, (const cplx*)pot->a,
-        fdiag, fdiag_stride_b, X, Y, X.cnt_fixed, total);
+#define HX_CASE(R)                                                                                     \
+    case R: {                                                                                          \
+        cudaError_t e = cudaFuncSetAttribute(hx_fused_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem);                                               \
+        if (e != cudaSuccess) return (int)e;                                                           \
+        hx_fused_kernel<R><<<(unsigned)grid, 32 * nwarp, smem, (cudaStream_t)stream>>>(                \
+            gm, Ve, Vo, pot->lam, (const cplx*)pot->etab, pot->etab_stride_b, pot->g, (const cplx*)pot->a, \
+            fdiag, fdiag_stride_b, X, Y, X.cnt_fixed, total);                                          \
+        break;                                                                                         \
+    }
+    switch (gm.nrt) {
+        HX_CASE(1) HX_CASE(2) HX_CASE(3) HX_CASE(4) HX_CASE(5) HX_CASE(6) HX_CASE(7) HX_CASE(8)
+        default: return SQC_ELIMIT;
+    }
+#undef HX_CASE
     SQC_LAUNCHED();
     return 0;
 }

@@ -241,6 +241,183 @@ extern "C" int sqc_heev(const void* A, const int32_t* n, int32_t n_fixed, int32_
 }
 
 // ---------------------------------------------------------------------------------------
+// Generalised Rayleigh-Ritz  GA c = theta GB c  for a NON-orthogonal Davidson basis
+// (GB = basis Gram matrix).  Cholesky GB = L L^H with dead-column handling (pivot below
+// drop * original diagonal: the vector is numerically inside the span of the previous ones and
+// is removed from the problem), M = L^-1 GA L^-H, Jacobi on M, c = L^-H y.
+// ---------------------------------------------------------------------------------------
+#define RR_BIG 1.0e290
+
+__global__ void __launch_bounds__(JAC_THREADS)
+gen_rr_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
+              const int32_t* __restrict__ nArr, int ld, double drop, double* __restrict__ w,
+              cplx* __restrict__ Zout, int np_max) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x;
+    const int n = nArr[b];
+    if (n <= 0) return;
+    const int np = (n + 1) & ~1;
+    const int lda = np_max;
+    cplx* A = reinterpret_cast<cplx*>(smem);               // GA -> M -> eigenvalues on the diagonal
+    cplx* Lm = A + (size_t)np_max * np_max;                 // GB -> L -> tmp -> Jacobi vectors
+    cplx* Zs = Lm + (size_t)np_max * np_max;                // L^-1
+    double* rot = reinterpret_cast<double*>(Zs + (size_t)np_max * np_max);
+    double* red = rot + 2 * np_max;
+    double* gbd = red + 64;                                 // original diagonal of GB
+    double* wv = gbd + np_max;
+    int* prs = reinterpret_cast<int*>(wv + np_max);
+    int* rank = prs + np_max;
+    int* dead = rank + np_max;
+    const int tid = threadIdx.x;
+    const cplx* ga = GAin + (int64_t)b * ld * ld;
+    const cplx* gb = GBin + (int64_t)b * ld * ld;
+    for (int e = tid; e < n * n; e += JAC_THREADS) {
+        const int r = e / n, c = e % n;
+        const cplx u = ga[r * ld + c], v = ga[c * ld + r];
+        A[r * lda + c] = cmake(0.5 * (u.x + v.x), 0.5 * (u.y - v.y));
+        const cplx u2 = gb[r * ld + c], v2 = gb[c * ld + r];
+        Lm[r * lda + c] = cmake(0.5 * (u2.x + v2.x), 0.5 * (u2.y - v2.y));
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += JAC_THREADS) {
+        gbd[i] = Lm[i * lda + i].x;
+        dead[i] = 0;
+    }
+    __syncthreads();
+    // ---- Cholesky (lower), in place ----
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) {
+            const double d = Lm[j * lda + j].x;
+            if (!(d > drop * gbd[j]) || !(gbd[j] > 0.0)) {
+                dead[j] = 1;
+                Lm[j * lda + j] = cmake(1.0, 0.0);
+            } else {
+                Lm[j * lda + j] = cmake(sqrt(d), 0.0);
+            }
+        }
+        __syncthreads();
+        const bool dj = dead[j] != 0;
+        const double inv = 1.0 / Lm[j * lda + j].x;
+        for (int i = j + 1 + tid; i < n; i += JAC_THREADS)
+            Lm[i * lda + j] = dj ? cmake(0.0, 0.0) : cscale(inv, Lm[i * lda + j]);
+        if (dj)
+            for (int k = tid; k < j; k += JAC_THREADS) Lm[j * lda + k] = cmake(0.0, 0.0);
+        __syncthreads();
+        if (!dj) {
+            const int rem = n - j - 1;
+            for (int e = tid; e < rem * rem; e += JAC_THREADS) {
+                const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+                if (k <= i) {
+                    const cplx li = Lm[i * lda + j], lk = Lm[k * lda + j];
+                    cplx v = Lm[i * lda + k];                 // -= li * conj(lk)
+                    v.x -= li.x * lk.x + li.y * lk.y;
+                    v.y -= li.y * lk.x - li.x * lk.y;
+                    Lm[i * lda + k] = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // removed (dependent) vectors contribute nothing
+    for (int e = tid; e < n * n; e += JAC_THREADS) {
+        const int r = e / n, c = e % n;
+        if (dead[r] || dead[c]) A[r * lda + c] = cmake(0.0, 0.0);
+    }
+    // ---- Zs = L^-1 (lower triangular), one thread per column ----
+    for (int c = tid; c < n; c += JAC_THREADS) {
+        for (int i = 0; i < c; ++i) Zs[i * lda + c] = cmake(0.0, 0.0);
+        for (int i = c; i < n; ++i) {
+            cplx acc = (i == c) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+            for (int k = c; k < i; ++k) {
+                const cplx l = Lm[i * lda + k], x = Zs[k * lda + c];
+                acc.x -= l.x * x.x - l.y * x.y;
+                acc.y -= l.x * x.y + l.y * x.x;
+            }
+            Zs[i * lda + c] = cscale(1.0 / Lm[i * lda + i].x, acc);
+        }
+    }
+    __syncthreads();
+    // ---- Lm = Zs * A ;  A = Lm * Zs^H ----
+    for (int e = tid; e < n * n; e += JAC_THREADS) {
+        const int r = e / n, c = e % n;
+        cplx acc = cmake(0.0, 0.0);
+        for (int k = 0; k <= r; ++k) cfma(acc, Zs[r * lda + k], A[k * lda + c]);
+        Lm[r * lda + c] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += JAC_THREADS) {
+        const int r = e / n, c = e % n;
+        cplx acc = cmake(0.0, 0.0);
+        for (int k = 0; k <= c; ++k) cfma(acc, Lm[r * lda + k], cconj(Zs[c * lda + k]));
+        A[r * lda + c] = acc;
+    }
+    // alive index list (compaction of the removed vectors)
+    __shared__ int s_na;
+    if (tid == 0) {
+        int cnt = 0;
+        for (int i = 0; i < n; ++i)
+            if (!dead[i]) prs[cnt++] = i;       // prs is free until Jacobi starts
+        s_na = cnt;
+    }
+    __syncthreads();
+    const int na = s_na;
+    const int npa = (na + 1) & ~1;
+    // M restricted to the alive vectors -> Lm (Hermitian average); rank[] keeps the alive list
+    for (int i = tid; i < na; i += JAC_THREADS) rank[i] = prs[i];
+    __syncthreads();
+    for (int e = tid; e < na * na; e += JAC_THREADS) {
+        const int r = e / na, c = e % na;
+        const cplx u = A[rank[r] * lda + rank[c]], v = A[rank[c] * lda + rank[r]];
+        Lm[r * lda + c] = cmake(0.5 * (u.x + v.x), (r == c) ? 0.0 : 0.5 * (u.y - v.y));
+    }
+    __syncthreads();
+    // dead[] is reused as the alive list because rank[] / prs[] are scratch of the Jacobi + sort
+    for (int i = tid; i < na; i += JAC_THREADS) dead[i] = rank[i];
+    __syncthreads();
+    jacobi_heev(Lm, na, npa, lda, A, lda, rot, prs, red);     // eigenvectors: rows of A
+    for (int i = tid; i < na; i += JAC_THREADS) wv[i] = Lm[i * lda + i].x;
+    __syncthreads();
+    for (int i = tid; i < na; i += JAC_THREADS) {
+        const double wi = wv[i];
+        int r = 0;
+        for (int j = 0; j < na; ++j) r += (wv[j] < wi) || (wv[j] == wi && j < i);
+        rank[i] = r;
+    }
+    __syncthreads();
+    double* wout = w + (int64_t)b * ld;
+    for (int i = tid; i < ld; i += JAC_THREADS) wout[i] = INFINITY;
+    cplx* zg = Zout + (int64_t)b * ld * ld;
+    for (int e = tid; e < n * ld; e += JAC_THREADS) zg[e] = cmake(0.0, 0.0);
+    __syncthreads();
+    for (int i = tid; i < na; i += JAC_THREADS) wout[rank[i]] = wv[i];
+    // c_j = L^-H y_j :  Zout[rank j][i] = sum_k' conj(Zs[alive k'][i]) * y_j[k'],  y_j = row j of A
+    for (int e = tid; e < na * n; e += JAC_THREADS) {
+        const int j = e / n, i = e % n;
+        cplx acc = cmake(0.0, 0.0);
+        for (int kp = 0; kp < na; ++kp) {
+            const int kk = dead[kp];
+            if (kk >= i) cfma(acc, cconj(Zs[kk * lda + i]), A[j * lda + kp]);
+        }
+        zg[rank[j] * ld + i] = acc;
+    }
+}
+
+extern "C" int sqc_gen_rr(const void* GA, const void* GB, const int32_t* n, int32_t ld, double drop,
+                          double* w, void* Zt, int32_t B, void* stream) {
+    if (B <= 0 || ld <= 0 || ld > 68 || !n) return SQC_EINVAL;
+    const int np_max = (ld + 1) & ~1;
+    size_t bytes = 3 * (size_t)np_max * np_max * sizeof(cplx) + (4 * np_max + 64) * sizeof(double) +
+                   (3 * np_max + 4) * sizeof(int) + 16;
+    if (bytes > 227 * 1024) return SQC_ELIMIT;
+    cudaError_t e = cudaFuncSetAttribute(gen_rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    gen_rr_kernel<<<B, JAC_THREADS, bytes, (cudaStream_t)stream>>>((const cplx*)GA, (const cplx*)GB, n, ld, drop, w,
+                                                                   (cplx*)Zt, np_max);
+    SQC_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // x-basis of a harmonic mode: eigen-decomposition of the truncated a + a^dag
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(JAC_THREADS)
@@ -424,11 +601,14 @@ davidson_decide_kernel(sqc_davidson_state_t st) {
     __syncthreads();
     if (s_restart) {
         cplx* G = reinterpret_cast<cplx*>(st.G) + (int64_t)b * ldg * ldg;
+        cplx* GB = st.GB ? reinterpret_cast<cplx*>(st.GB) + (int64_t)b * ldg * ldg : nullptr;
         for (int e = tid; e < ldg * ldg; e += 64) {
             const int r = e / ldg, c = e % ldg;
             G[e] = (r == c && r < p) ? cmake(theta[r], 0.0) : cmake(0.0, 0.0);
+            if (GB) GB[e] = (r == c && r < p) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
         }
     }
+    if (tid == 0 && st.mtot) st.mtot[b] = st.msz[b] + st.nact[b];
 }
 
 extern "C" int sqc_davidson_decide(const sqc_davidson_state_t* st, int32_t B, void* stream) {
@@ -461,6 +641,45 @@ davidson_insert_kernel(sqc_davidson_state_t st, const cplx* __restrict__ S, int 
     }
     __syncthreads();
     if (tid == 0) st.msz[b] = rows;
+}
+
+// Non-orthogonalised variant: new columns of BOTH the projected Hamiltonian (SA = [V T]^H H T)
+// and the basis Gram matrix (SB = [V T]^H T).
+__global__ void __launch_bounds__(128)
+davidson_insert2_kernel(sqc_davidson_state_t st, const cplx* __restrict__ SA, const cplx* __restrict__ SB,
+                        int ldr, int ldc) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int ldg = st.ldg;
+    const int msz = st.msz[b], na = st.nact[b];
+    if (na <= 0) return;
+    cplx* G = reinterpret_cast<cplx*>(st.G) + (int64_t)b * ldg * ldg;
+    cplx* GB = reinterpret_cast<cplx*>(st.GB) + (int64_t)b * ldg * ldg;
+    const cplx* sa = SA + (int64_t)b * ldr * ldc;
+    const cplx* sb = SB + (int64_t)b * ldr * ldc;
+    const int rows = msz + na;
+    for (int e = tid; e < rows * na; e += 128) {
+        const int i = e / na, j = e % na;
+        cplx va = sa[i * ldc + j], vb = sb[i * ldc + j];
+        if (i >= msz) {
+            const cplx ua = sa[(msz + j) * ldc + (i - msz)], ub = sb[(msz + j) * ldc + (i - msz)];
+            va = cmake(0.5 * (va.x + ua.x), 0.5 * (va.y - ua.y));
+            vb = cmake(0.5 * (vb.x + ub.x), 0.5 * (vb.y - ub.y));
+        }
+        G[i * ldg + msz + j] = va;
+        G[(msz + j) * ldg + i] = cconj(va);
+        GB[i * ldg + msz + j] = vb;
+        GB[(msz + j) * ldg + i] = cconj(vb);
+    }
+    __syncthreads();
+    if (tid == 0) st.msz[b] = rows;
+}
+
+extern "C" int sqc_davidson_insert2(const sqc_davidson_state_t* st, const void* SA, const void* SB,
+                                    int32_t ldr, int32_t ldc, int32_t B, void* stream) {
+    if (!st || B <= 0 || !st->GB) return SQC_EINVAL;
+    davidson_insert2_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(*st, (const cplx*)SA, (const cplx*)SB, ldr, ldc);
+    SQC_LAUNCHED();
+    return 0;
 }
 
 extern "C" int sqc_davidson_insert(const sqc_davidson_state_t* st, const void* S, int32_t ldr,

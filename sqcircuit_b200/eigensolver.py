@@ -187,3 +187,114 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
         kern.davidson_insert(st, S1, B)
     return EigResult(theta[:, :k].contiguous(), Xb[:, :k, :].contiguous(), it, resmax, converged,
                      ritz_block=Xb)
+
+
+def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
+                       stats=None, lowblock_ns=0, drop=1e-8):
+    """Block Davidson WITHOUT orthogonalising the expansion block.
+
+    The basis V is allowed to be non-orthogonal inside a restart cycle; Rayleigh-Ritz is the
+    generalised problem GA c = theta GB c with GB = V^H V (``sqc_gen_rr``).  Per iteration the
+    basis is streamed three times instead of seven: X = V c, HX = W c (``sqc_block_update``) and ONE
+    paired Gram pass that produces the new columns of GA and GB together (``sqc_gram_pair``); the
+    CGS2 / SVQB passes of ``solve_davidson`` disappear.  Thick restarts (V <- Ritz vectors, which
+    are GB-orthonormal) put the basis back to an orthonormal one.  Same convergence and accuracy
+    as the orthogonalised iteration on every tested circuit (tools/proto_nonortho.py)."""
+    dev = op.device
+    if p is None:
+        p = min(16, max(k + 2, (k * 6 + 4) // 5))
+    p = min(p, 16, N)
+    k = min(k, p)
+    if mmax is None:
+        mmax = 4 * p
+    mmax = min(mmax, 64, N)
+    ld = mmax
+    c128, f64, i32 = torch.complex128, torch.float64, torch.int32
+    V = torch.zeros((B, mmax, N), dtype=c128, device=dev)
+    W = torch.zeros((B, mmax, N), dtype=c128, device=dev)
+    Xb = torch.zeros((B, p, N), dtype=c128, device=dev)
+    HXb = torch.zeros((B, p, N), dtype=c128, device=dev)
+    GA = torch.zeros((B, ld, ld), dtype=c128, device=dev)
+    GB = torch.zeros((B, ld, ld), dtype=c128, device=dev)
+    Zt = torch.zeros((B, ld, ld), dtype=c128, device=dev)
+    theta = torch.zeros((B, ld), dtype=f64, device=dev)
+    SA = torch.zeros((B, mmax, 16), dtype=c128, device=dev)
+    SB = torch.zeros((B, mmax, 16), dtype=c128, device=dev)
+    msz = torch.full((B,), p, dtype=i32, device=dev)
+    mtot = torch.full((B,), p, dtype=i32, device=dev)
+    nact = torch.zeros((B,), dtype=i32, device=dev)
+    act = torch.zeros((B, p), dtype=i32, device=dev)
+    restart = torch.zeros((B,), dtype=i32, device=dev)
+    done = torch.zeros((B,), dtype=i32, device=dev)
+    n_not_done = torch.zeros((1,), dtype=i32, device=dev)
+    rn2 = torch.zeros((B, p), dtype=f64, device=dev)
+    resmax = torch.zeros((B,), dtype=f64, device=dev)
+    den_floor = torch.zeros((B,), dtype=f64, device=dev)
+
+    Vp = BlockView(V, cnt_fixed=p)
+    Wp = BlockView(W, cnt_fixed=p)
+    if x0 is None:
+        idx = torch.topk(diag, p, dim=1, largest=False).indices.expand(B, p)
+        V[:, :p, :].scatter_(2, idx.unsqueeze(2), torch.ones((B, p, 1), dtype=c128, device=dev))
+        op.apply(Vp, Wp)
+        kern.gram(Vp, Wp, GA)
+        GB[:, :p, :p] = torch.eye(p, dtype=c128, device=dev)
+    else:
+        m0 = min(x0.shape[1], mmax)
+        V[:, :m0, :] = x0[:, :m0, :]
+        msz.fill_(m0)
+        Vi = BlockView(V, cnt_fixed=mmax, cnt=msz)
+        Wi = BlockView(W, cnt_fixed=mmax, cnt=msz)
+        op.apply(Vi, Wi)
+        for c0 in range(0, m0, p):
+            ccnt = torch.clamp(msz - c0, min=0, max=p).to(i32)
+            coff = torch.full((B,), c0, dtype=i32, device=dev)
+            kern.gram_pair(Vi, BlockView(V, cnt_fixed=p, off=coff, cnt=ccnt),
+                           BlockView(W, cnt_fixed=p, off=coff, cnt=ccnt), SB, SA)
+            GB[:, :, c0:c0 + p] = SB[:, :, :p]
+            GA[:, :, c0:c0 + p] = SA[:, :, :p]
+    st = kern.davidson_state(p=p, k=k, mmax=mmax, ldg=ld, tol_rel=tol, tol_abs_floor=1e-300,
+                             msz=msz, nact=nact, act=act, restart=restart, done=done,
+                             n_not_done=n_not_done, theta=theta, rn2=rn2, resmax=resmax,
+                             den_floor=den_floor, G=GA, GB=GB, mtot=mtot)
+    Xv = BlockView(Xb, cnt_fixed=p)
+    HXv = BlockView(HXb, cnt_fixed=p)
+    Tv = BlockView(V, cnt_fixed=p, off=msz, cnt=nact)
+    HTv = BlockView(W, cnt_fixed=p, off=msz, cnt=nact)
+    Vm = BlockView(V, cnt_fixed=mmax, cnt=msz)
+    Wm = BlockView(W, cnt_fixed=mmax, cnt=msz)
+    Vt = BlockView(V, cnt_fixed=mmax, cnt=mtot)
+    it = 0
+    converged = False
+    lowblock = None
+    for it in range(1, maxit + 1):
+        live = 1 - done
+        nrr = msz * live
+        xcnt = (p * live).to(i32)
+        kern.gen_rr(GA, GB, nrr, drop, theta, Zt)
+        if it == 1 and lowblock_ns > 0 and getattr(op, 'supports_lowblock', lambda: False)():
+            sigma = theta[:, 0] - 0.05 * theta[:, 0].abs()
+            lowblock = op.build_lowblock(sigma, lowblock_ns)
+        Xv.cnt = xcnt
+        HXv.cnt = xcnt
+        kern.block_update(Vm, Zt, Xv, op=0, trans=0)
+        kern.block_update(Wm, Zt, HXv, op=0, trans=0)
+        kern.residual_norms(Xv, HXv, theta, rn2)
+        kern.davidson_decide(st, B)
+        left = int(n_not_done.item())
+        if stats is not None:
+            stats.append((it, left))
+        if left == 0:
+            converged = True
+            break
+        Xv.cnt = None
+        HXv.cnt = None
+        kern.restart_copy(Xv, HXv, Vp, Wp, restart)
+        kern.precond_residual(Xv, HXv, Tv, theta, act, diag, den_floor)
+        if lowblock is not None:
+            kern.lowblock_apply(Xv, HXv, Tv, theta, act, lowblock['S'], lowblock['Ainv'], lowblock['unit'])
+        op.apply(Tv, HTv)
+        kern.gram_pair(Vt, Tv, HTv, SB, SA)
+        kern.davidson_insert2(st, SA, SB, B)
+    return EigResult(theta[:, :k].contiguous(), Xb[:, :k, :].contiguous(), it, resmax, converged,
+                     ritz_block=Xb)

@@ -113,6 +113,26 @@ class Kernels:
                                      _p(self._gram_work) if need else C.c_void_p(0), impl,
                                      _stream(self.dev)), 'sqc_gram')
 
+    def gram_pair(self, A, Bm, Bm2, C1, C2):
+        """C1 = A^H Bm, C2 = A^H Bm2 in one pass over A."""
+        B, ldr, ldc = C1.shape
+        need = self.lib.sqc_gram_work_bytes(B, A.cnt_fixed, Bm.cnt_fixed, A.N)
+        if need and (self._gram_work is None or self._gram_work.numel() < need):
+            self._gram_work = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        _lib.check(self.lib.sqc_gram_pair(A.c(), Bm.c(), Bm2.c(), A.N, B, _p(C1), _p(C2), ldr, ldc,
+                                          _p(self._gram_work) if need else C.c_void_p(0), _stream(self.dev)),
+                   'sqc_gram_pair')
+
+    def gen_rr(self, GA, GB, n, drop, w, Zt):
+        B, ld, _ = GA.shape
+        _lib.check(self.lib.sqc_gen_rr(_p(GA), _p(GB), _p(n), ld, drop, _p(w), _p(Zt), B, _stream(self.dev)),
+                   'sqc_gen_rr')
+
+    def davidson_insert2(self, st, SA, SB, B):
+        _, ldr, ldc = SA.shape
+        _lib.check(self.lib.sqc_davidson_insert2(C.byref(st), _p(SA), _p(SB), ldr, ldc, B, _stream(self.dev)),
+                   'sqc_davidson_insert2')
+
     def block_update(self, A, Cf, Out, op=0, trans=0, impl=0):
         B, ldr, ldc = Cf.shape
         _lib.check(self.lib.sqc_block_update(A.c(), _p(Cf), ldr, ldc, trans, Out.c(), A.N, B, op, impl,
@@ -154,6 +174,8 @@ class Kernels:
         for key in ('msz', 'nact', 'act', 'restart', 'done', 'n_not_done', 'theta', 'rn2', 'resmax',
                     'den_floor', 'G'):
             setattr(st, key, kw[key].data_ptr())
+        st.GB = kw['GB'].data_ptr() if kw.get('GB') is not None else None
+        st.mtot = kw['mtot'].data_ptr() if kw.get('mtot') is not None else None
         st._keep = kw
         return st
 

@@ -195,6 +195,61 @@ class EmulKernels:
             if a.shape[0] and c.shape[0]:
                 Cout[b, :a.shape[0], :c.shape[0]] = torch.from_numpy(a.conj() @ c.T)
 
+    def gram_pair(self, A, Bm, Bm2, C1, C2):
+        self.gram(A, Bm, C1)
+        self.gram(A, Bm2, C2)
+
+    def gen_rr(self, GA, GB, n, drop, w, Zt):
+        B, ld, _ = GA.shape
+        for b in range(B):
+            nb = int(n[b])
+            if nb <= 0:
+                continue
+            a = GA[b, :nb, :nb].numpy().copy()
+            g = GB[b, :nb, :nb].numpy().copy()
+            a = (a + a.conj().T) / 2
+            g = (g + g.conj().T) / 2
+            gd = np.real(np.diag(g)).copy()
+            # Cholesky with dead-column handling (same rule as the kernel)
+            L = np.zeros((nb, nb), complex)
+            dead = np.zeros(nb, bool)
+            for j in range(nb):
+                d = (g[j, j] - L[j, :j] @ L[j, :j].conj()).real
+                if not (d > drop * gd[j]) or not (gd[j] > 0):
+                    dead[j] = True
+                    L[j, :j] = 0
+                    L[j, j] = 1
+                    continue
+                L[j, j] = np.sqrt(d)
+                for i in range(j + 1, nb):
+                    L[i, j] = (g[i, j] - L[i, :j] @ L[j, :j].conj()) / L[j, j]
+            alive = np.where(~dead)[0]
+            La = L[np.ix_(alive, alive)]
+            Li = np.linalg.inv(La)
+            M = Li @ a[np.ix_(alive, alive)] @ Li.conj().T
+            ww, y = np.linalg.eigh((M + M.conj().T) / 2)
+            c = np.zeros((nb, len(alive)), complex)
+            c[alive, :] = Li.conj().T @ y
+            w[b] = float('inf')
+            w[b, :len(alive)] = torch.from_numpy(ww)
+            Zt[b, :nb, :nb] = 0
+            Zt[b, :len(alive), :nb] = torch.from_numpy(np.ascontiguousarray(c.T))
+
+    def davidson_insert2(self, st, SA, SB, B):
+        for b in range(B):
+            na, msz = int(st.nact[b]), int(st.msz[b])
+            if na <= 0:
+                continue
+            for S, G in ((SA, st.G), (SB, st.GB)):
+                s = S[b].numpy()
+                blk = s[:msz + na, :na].copy()
+                d = blk[msz:, :]
+                blk[msz:, :] = (d + d.conj().T) / 2
+                Gn = G[b].numpy()
+                Gn[:msz + na, msz:msz + na] = blk
+                Gn[msz:msz + na, :msz + na] = blk.conj().T
+            st.msz[b] = msz + na
+
     def hx_fused(self, sp, Ve, Vo, pot, fdiag, X, Y):
         return False      # not emulated: callers fall back to transform + potential + transform
 
@@ -292,6 +347,12 @@ class EmulKernels:
                 st.G[b] = 0
                 for r in range(p):
                     st.G[b, r, r] = th[r]
+                if getattr(st, 'GB', None) is not None:
+                    st.GB[b] = 0
+                    for r in range(p):
+                        st.GB[b, r, r] = 1.0
+            if getattr(st, 'mtot', None) is not None:
+                st.mtot[b] = int(st.msz[b]) + n
 
     def restart_copy(self, X, HX, V, W, restart):
         for b in range(X.B):

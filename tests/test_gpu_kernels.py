@@ -343,6 +343,58 @@ def test_lowblock_preconditioner_kernels(kern):
     assert relerr(Vd.cpu(), refV) < 1e-12
 
 
+def test_gram_pair_and_gen_rr(kern):
+    """Paired Gram pass and the generalised Rayleigh-Ritz kernel against the numpy contracts."""
+    E = EmulKernels()
+    B, mm, N, p = 5, 48, 3001, 12
+    V = rnd((B, mm, N), 41)
+    W = rnd((B, mm, N), 42)
+    msz = torch.tensor([12, 24, 36, 30, 0], dtype=torch.int32)
+    nact = torch.tensor([12, 7, 12, 1, 0], dtype=torch.int32)
+    mtot = msz + nact
+    r1, r2 = torch.zeros((B, mm, 16), dtype=torch.complex128), torch.zeros((B, mm, 16), dtype=torch.complex128)
+    E.gram_pair(BlockView(V, cnt_fixed=mm, cnt=mtot), BlockView(V, cnt_fixed=p, off=msz, cnt=nact),
+                BlockView(W, cnt_fixed=p, off=msz, cnt=nact), r1, r2)
+    Vd, Wd = V.cuda(), W.cuda()
+    o1 = torch.full((B, mm, 16), 3.0, dtype=torch.complex128, device='cuda')
+    o2 = torch.full((B, mm, 16), 3.0, dtype=torch.complex128, device='cuda')
+    kern.gram_pair(BlockView(Vd, cnt_fixed=mm, cnt=mtot.cuda()),
+                   BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()),
+                   BlockView(Wd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()), o1, o2)
+    assert relerr(o1.cpu()[:, :, :p], r1[:, :, :p]) < 1e-13 and relerr(o2.cpu()[:, :, :p], r2[:, :, :p]) < 1e-13
+    # generalised RR on a non-orthogonal basis with one exactly dependent vector
+    n = 40
+    Q = rnd((B, n, 200), 43)
+    Q[1, 7] = Q[1, 3] * (0.5 + 0.2j) + Q[1, 5]          # dependent -> must be removed
+    Hs = rnd((B, 200, 200), 44)
+    Hs = Hs + Hs.conj().transpose(1, 2)
+    GB = Q.conj() @ Q.transpose(1, 2)
+    GA = Q.conj() @ Hs @ Q.transpose(1, 2)
+    GBp = torch.zeros((B, mm, mm), dtype=torch.complex128)
+    GAp = torch.zeros((B, mm, mm), dtype=torch.complex128)
+    GBp[:, :n, :n], GAp[:, :n, :n] = GB, GA
+    nn = torch.tensor([n, n, 12, 1, 0], dtype=torch.int32)
+    w = torch.full((B, mm), -7.0, dtype=torch.float64, device='cuda')
+    Zt = torch.zeros((B, mm, mm), dtype=torch.complex128, device='cuda')
+    kern.gen_rr(GAp.cuda(), GBp.cuda(), nn.cuda(), 1e-8, w, Zt)
+    w, Zt = w.cpu(), Zt.cpu()
+    import scipy.linalg
+    for b in range(4):
+        nb = int(nn[b])
+        a, g = GA[b, :nb, :nb].numpy(), GB[b, :nb, :nb].numpy()
+        if b == 1:
+            keep = [i for i in range(nb) if i != 7]
+            wr = scipy.linalg.eigh(a[np.ix_(keep, keep)], g[np.ix_(keep, keep)], eigvals_only=True)
+        else:
+            wr = scipy.linalg.eigh(a, g, eigvals_only=True)
+        k = len(wr)
+        assert np.abs(w[b, :k].numpy() - wr).max() < 1e-10 * np.abs(wr).max()
+        c = Zt[b, :k, :nb].numpy().T                   # columns = coefficient vectors
+        assert np.abs(c.conj().T @ g @ c - np.eye(k)).max() < 1e-9
+        assert np.abs(a @ c - g @ c * w[b, :k].numpy()[None, :]).max() < 1e-9 * np.abs(wr).max() * np.abs(c).max()
+    assert float(w[4, 0]) == -7.0
+
+
 def test_launch_counter(kern):
     n0 = kern.launch_count()
     kern.xbasis(8)

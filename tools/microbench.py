@@ -31,8 +31,11 @@ def report(name, ms, bytes_, flops):
                       'TFLOPs': round(flops / ms / 1e9, 2)}))
 
 
-for msz in (12, 30, 48):
-    if only and 'gram' not in only: break
+import ctypes
+for split in ((1, 2, 4, 8, 16) if (only and 'gramsplit' in only) else (None,)):
+  if split: k.lib.sqc_debug_set_gram_split(split); print('gram split', split)
+  for msz in (12, 30, 48):
+    if only and 'gram' not in only and 'gramsplit' not in only: break
     cm = torch.full((B,), msz, dtype=torch.int32, device=dev)
     cn = torch.full((B,), p, dtype=torch.int32, device=dev)
     S = torch.zeros((B, mm, 16), dtype=torch.complex128, device=dev)
