@@ -172,7 +172,8 @@ class ClockSampler:
 class TimedKernels:
     """Wraps the CUDA backend: CUDA events on the launching stream around every C-ABI call,
     so per-kernel device time is measured live inside the timed region (no profiler)."""
-    TIMED = ['hx_fused', 'mode_transform', 'potential_apply', 'gram', 'block_update', 'block_rightmul', 'heev',
+    TIMED = ['hx_fused', 'mode_transform', 'potential_apply', 'gram', 'gram_pair', 'gen_rr', 'davidson_insert2',
+             'lowblock_assemble', 'hpd_inverse_c64', 'lowblock_apply', 'block_update', 'block_rightmul', 'heev',
              'residual_norms', 'precond_residual', 'restart_copy', 'svqb_coeffs', 'davidson_decide',
              'davidson_insert', 'diag_mul', 'ladder_apply']
 
@@ -223,6 +224,8 @@ def our_arm(args):
         args.gpus = world
     torch.cuda.set_device(local)
     dev = f'cuda:{local}'
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the single JSON line
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(dev))
 
@@ -255,7 +258,7 @@ def our_arm(args):
             fl = fluxes_host.to(dev, non_blocking=True).cpu().numpy()   # H2D of the step's inputs
         else:
             fl = fluxes_host.numpy()
-        res = cr.sweep_diag(N_EIG, loop_fluxes={loop: fl}, tol=args.tol)
+        res = cr.sweep_diag(N_EIG, loop_fluxes={loop: fl}, tol=args.tol, max_basis=args.mmax, lowblock=args.lowblock)
         rates = [res.dec_rate(d, states=(1, 0)) for d in DEC_TYPES]
         if world > 1:
             # the only collective of the path: final gather of the per-point results to rank 0
@@ -402,6 +405,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--points', type=int, default=POINTS, help='sweep points per GPU')
     ap.add_argument('--tol', type=float, default=1e-9)
+    ap.add_argument('--mmax', type=int, default=None, help='maximum Davidson basis size (default 4 x block)')
+    ap.add_argument('--lowblock', type=int, default=160)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

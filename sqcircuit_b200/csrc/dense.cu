@@ -240,12 +240,14 @@ __global__ void gram_ref_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, cplx* 
     }
 }
 
-static int g_gram_split_min = 8;
-static int gram_nsplit(int B, int64_t N) {
+static int g_gram_split_min = 1;
+static int gram_nsplit(int B, int64_t N, bool pair = false) {
     // enough CTAs to fill 148 SMs x 2 resident CTAs, at least g_gram_split_min interleaved CTAs per
-    // sweep point (DRAM burst shaping), but never below 8 chunks per CTA
+    // sweep point (measured: the paired kernel gains ~5% from 8 interleaved CTAs per point, the
+    // single-block kernel nothing), but never below 8 chunks per CTA
     int want = (148 * 2 + B - 1) / B;
     if (want < g_gram_split_min) want = g_gram_split_min;
+    if (pair && want < 8) want = 8;
     int64_t nchunks = (N + GRAM_CH - 1) / GRAM_CH;
     int64_t maxs = nchunks / 8 > 0 ? nchunks / 8 : 1;
     if (want > maxs) want = (int)maxs;
@@ -266,7 +268,7 @@ static void gram_tiles(int na_max, int nb_max, int* nat, int* nct) {
 extern "C" int64_t sqc_gram_work_bytes(int32_t B, int32_t na_max, int32_t nb_max, int64_t N) {
     int nat, nct;
     gram_tiles(na_max, nb_max, &nat, &nct);
-    int ns = gram_nsplit(B, N);
+    int ns = gram_nsplit(B, N, true);   // upper bound over both kernel flavours
     if (ns == 1) return 0;
     return 2 * (int64_t)B * ns * (nat * 8) * (nct * 4) * (int64_t)sizeof(cplx);
 }
@@ -274,7 +276,7 @@ extern "C" int64_t sqc_gram_work_bytes(int32_t B, int32_t na_max, int32_t nb_max
 template <int NAT, int NCT, bool PAIR>
 static int launch_gram(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int B, cplx* C, cplx* C2,
                        int ldr, int ldc, cplx* work, cudaStream_t st) {
-    const int ns = gram_nsplit(B, N);
+    const int ns = gram_nsplit(B, N, PAIR);
     if (ns > 1 && !work) return SQC_EINVAL;
     // at least three full-size stages, as many as fit in ~108 KB (two CTAs per SM)
     size_t stage_bytes = (size_t)(NAT * 8 + (PAIR ? 2 : 1) * NCT * 4) * GRAM_LD * sizeof(double);

@@ -4,7 +4,7 @@
 #include <math.h>
 #include "common.cuh"
 
-#define JAC_THREADS 256
+#define JAC_THREADS 512
 #define JAC_MAX_SWEEPS 30
 #define JAC_BIG 1.0e300
 
@@ -53,10 +53,10 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
         __syncthreads();
         const double o = red[0], d = red[32];
         __syncthreads();
-        // quadratic convergence: once the off-diagonal mass is below 1e-13 relative, one more
+        // quadratic convergence: once the off-diagonal mass is below 1e-11 relative, one more
         // sweep leaves it at rounding level
         if (o == 0.0 || polish) break;
-        if (o <= 1e-26 * (d + o)) polish = true;
+        if (o <= 1e-22 * (d + o)) polish = true;
 
         for (int step = 0; step < np - 1; ++step) {
             // schedule + rotation parameters
