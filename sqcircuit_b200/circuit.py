@@ -98,6 +98,48 @@ class Circuit:
         self._evecs = []
         self._last = None
 
+    # ---- optimisation parameters (circuit.py:498-591) ---------------------------------------------
+    def _collect_parameters(self):
+        from .exceptions import raise_optim_error_if_needed
+        self._parameters = OrderedDict()
+        if not get_optim_mode():
+            return
+
+        def add(el):
+            v = el.internal_value
+            if isinstance(v, torch.Tensor) and (v.requires_grad or not v.is_leaf) and el not in self._parameters:
+                self._parameters[el] = v
+        for edge, els in self.elements.items():
+            for el in els:
+                if hasattr(el, 'loops'):
+                    add(el.cap)
+                    for lp in el.loops:
+                        add(lp)
+                add(el)
+
+    @property
+    def parameters(self):
+        from .exceptions import raise_optim_error_if_needed
+        raise_optim_error_if_needed()
+        return list(self._parameters.values())
+
+    @property
+    def parameters_elems(self):
+        from .exceptions import raise_optim_error_if_needed
+        raise_optim_error_if_needed()
+        return list(self._parameters.keys())
+
+    @property
+    def parameters_grad(self):
+        grads = [v.grad for v in self.parameters]
+        if any(g is None for g in grads):
+            return grads
+        return torch.stack(grads).detach().clone()
+
+    def zero_grad(self):
+        for v in self.parameters:
+            v.grad = None
+
     # ---- topology ---------------------------------------------------------------------------
     def _analyse(self):
         top = assemble(self.elements, self.flux_dist)
@@ -112,6 +154,7 @@ class Circuit:
         self.num_jun_without_ind = top.n_jj_without_ind
         self.partial_mats = top.partial_mats
         self.elem_keys = {Inductor: top.ind_keys, Junction: top.jj_keys}
+        self._collect_parameters()
 
     def update(self):
         """Re-read element values after in-place changes (circuit.py:397-440)."""
@@ -330,13 +373,16 @@ class Circuit:
             raise CircuitStateError('Please specify the truncation number for each mode.')
         if not isinstance(n_eig, int):
             raise ValueError('n_eig (number of eigenvalues) should be an integer.')
+        if get_optim_mode():
+            from .autograd import EigenSolverFn
+            params = torch.stack(self.parameters) if self._parameters else torch.tensor([])
+            sol = EigenSolverFn.apply(params, self, n_eig)
+            self._efreqs = torch.real(sol[:, 0])
+            self._evecs = sol[:, 1:]
+            return self._efreqs / (2 * np.pi * unt.get_unit_freq()), self._evecs
         res = self.sweep_diag(n_eig)
         self._last = res
         ev = res.evecs[0]
-        if get_optim_mode():
-            self._efreqs = res.evals_rad[0]
-            self._evecs = ev
-            return res.efreqs[0], ev
         dims = [self.ms, len(self.ms) * [1]]
         self._efreqs = res.evals_rad[0].cpu().numpy()
         vecs = ev.cpu().numpy()
@@ -379,6 +425,41 @@ class Circuit:
         if self._last is None:
             raise CircuitStateError('Please diagonalize the circuit first.')
         return float(self._last.dec_rate(dec_type, states, total)[0])
+
+    def charge_op(self, mode, basis='original'):
+        """Charge operator of a mode as a dense matrix (circuit.py:1831-1875); host-side helper for
+        user expressions such as the paper's g_10 = |<1|Q|0>| / C.  Tensor in the PyTorch engine."""
+        if len(self.m) == 0:
+            raise CircuitStateError('Please specify the truncation number for each mode.')
+        if basis not in ('original', 'eig'):
+            raise ValueError(f"Invalid basis '{basis}' passed. Permitted bases are 'original' and 'eig'.")
+        i = mode - 1
+        ops = self._operators()
+        mats = []
+        for j in range(self.n):
+            mj = self.m[j]
+            if j != i:
+                mats.append(np.eye(mj))
+            elif self._is_charge_mode(j):
+                nmax = (mj - 1) // 2
+                ng = self.charge_islands[j].value()
+                mats.append((2 * unt.e / np.sqrt(unt.hbar)) * (np.diag(np.arange(-nmax, nmax + 1.0)) - ng * np.eye(mj)))
+            elif mj == 1:
+                mats.append(np.zeros((1, 1)))
+            else:
+                a = np.diag(np.sqrt(np.arange(1, mj)), 1)
+                mats.append(-1j * np.sqrt(0.5 / ops.Z[j]) * (a - a.T))
+        Q = mats[0]
+        for mt in mats[1:]:
+            Q = np.kron(Q, mt)
+        Q = Q.astype(complex)
+        if basis == 'eig':
+            if get_optim_mode():
+                V = self._evecs.detach().cpu().numpy().T
+            else:
+                V = np.concatenate([np.asarray(v) for v in self._evecs], axis=1)
+            Q = V.conj().T @ Q @ V
+        return torch.as_tensor(Q, dtype=torch.complex128) if get_optim_mode() else Q
 
     def check_convergence(self, eig_vec_idx=1, t=10, threshold=1e-5):
         """circuit.py:2090-2118."""
