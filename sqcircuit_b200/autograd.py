@@ -24,6 +24,21 @@ def set_max_eigenvector_grad(n):
     EIGENVECTOR_MAX_GRAD['n'] = n
 
 
+def gram_blocks(kern, A, Bm):
+    """<A_i | Bm_j> for [1][ka][N] x [1][kb][N] blocks of any size (the tensor-core Gram kernel takes
+    <= 64 left and <= 16 right vectors per call)."""
+    ka, kb = A.shape[1], Bm.shape[1]
+    out = torch.empty((1, ka, kb), dtype=torch.complex128, device=A.device)
+    for r0 in range(0, ka, 64):
+        ra = A[:, r0:r0 + 64].contiguous()
+        for c0 in range(0, kb, 16):
+            cb = Bm[:, c0:c0 + 16].contiguous()
+            tmp = torch.empty((1, ra.shape[1], cb.shape[1]), dtype=torch.complex128, device=A.device)
+            kern.gram(BlockView(ra), BlockView(cb), tmp)
+            out[:, r0:r0 + ra.shape[1], c0:c0 + cb.shape[1]] = tmp
+    return out
+
+
 class PartialH:
     """dH/dx applied to a block of state vectors [B=1][k][N] for one circuit at one point."""
 
@@ -121,16 +136,12 @@ class EigenSolverFn(torch.autograd.Function):
         w = res.evals_rad[0].cpu().numpy()
         nmax = EIGENVECTOR_MAX_GRAD['n'] if EIGENVECTOR_MAX_GRAD['n'] is not None else k
         # <g_m | psi_n>
-        ov = torch.empty((1, k, k), dtype=torch.complex128, device=dev)
-        nz.kern.gram(BlockView(g_vec), BlockView(psi), ov)
-        ov = ov[0].cpu().numpy()                                               # ov[m][n]
+        ov = gram_blocks(nz.kern, g_vec, psi)[0].cpu().numpy()                 # ov[m][n]
         ph = PartialH(cr, nz)
         grads = []
         for el in ctx.elems:
             Y = ph.apply(el, psi)
-            Mx = torch.empty((1, k, k), dtype=torch.complex128, device=dev)
-            nz.kern.gram(BlockView(psi), BlockView(Y), Mx)                     # Mx[n][m] = <n|dH|m>
-            Mx = Mx[0].cpu().numpy()
+            Mx = gram_blocks(nz.kern, psi, Y)[0].cpu().numpy()                 # Mx[n][m] = <n|dH|m>
             gval = np.sum(np.real(np.diag(Mx)) * np.conj(g_val.numpy()))
             gvec = 0.0
             for m in range(min(nmax, k)):

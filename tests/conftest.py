@@ -19,3 +19,12 @@ def golden_dir():
     return GOLDEN
 
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+
+@pytest.fixture(autouse=True)
+def _numpy_engine_by_default():
+    """Every test starts (and ends) in the NumPy engine, whatever a previous test did."""
+    import sqcircuit_b200 as sq
+    sq.set_engine('NumPy')
+    yield
+    sq.set_engine('NumPy')

@@ -166,6 +166,39 @@ def test_config3_transmon_resonator_transmon():
     _check(res, oc, setter, ngs, 10, ['capacitive', 'cc', 'charge'])
 
 
+def test_config3_full_size_dim_1e5():
+    """BASELINE configs[3] at its named size: transmon-resonator-transmon, N = 10 x 99 x 99 = 98010,
+    a 2-D gate-charge grid.  One grid point against the oracle (ARPACK on the CSR matrix), all
+    points through size-independent properties (orthonormality, residuals through the operator,
+    invariance of the spectrum under ng -> ng + 1 up to the truncation edge is NOT exact, so use
+    ng -> -ng with both offsets flipped: H(-ng) is the complex conjugate relabelling of H(ng))."""
+    from sqcircuit_b200.kernels import BlockView
+    cr, oc = cs.trt()
+    trunc = [10, 50, 50]
+    cr.set_trunc_nums(trunc)
+    g = np.load(os.path.join(G, 'trt_6_6_6.npz'))
+    m1, m2 = [int(x) for x in g['charge_modes']]
+    a, b = np.meshgrid(np.linspace(0.05, 0.45, 3), np.linspace(0.1, 0.4, 3), indexing='ij')
+    n1, n2 = a.ravel(), b.ravel()
+    n1 = np.concatenate([n1, -n1[:2]])
+    n2 = np.concatenate([n2, -n2[:2]])
+    res = cr.sweep_diag(10, charge_offsets={m1: n1, m2: n2})
+    X = res.evecs
+    N = X.shape[2]
+    assert N == 98010
+    gram = X.conj() @ X.transpose(1, 2)
+    assert float((gram - torch.eye(10, device=X.device)).abs().max()) < 1e-10
+    ef = res.efreqs.cpu().numpy()
+    assert np.max(np.abs(ef[9] - ef[0]) / np.abs(ef[0])) < 1e-9 and np.max(np.abs(ef[10] - ef[1]) / np.abs(ef[1])) < 1e-9
+    assert float(res.resmax.max()) < 1e-9
+    oc.set_trunc_nums(trunc)
+    oc.set_charge_offset(m1, float(n1[4]))
+    oc.set_charge_offset(m2, float(n2[4]))
+    e, v = oc.diag(11, dense=False)
+    assert np.max(np.abs(ef[4] - e[:10]) / np.abs(e[:10])) < 1e-9
+    assert 1 - o.subspace_overlap(v[:, :10], X[4].cpu().numpy().T, e[:10], w_next=e[10]) < 1e-10
+
+
 def test_other_reference_circuits():
     cr, lp, oc, ol = cs.coupled_fluxonium_transmon()
     cr.set_trunc_nums([30, 10])
