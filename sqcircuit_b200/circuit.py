@@ -293,7 +293,7 @@ class Circuit:
             hop = sub(idx)
             return _davidson(kern, hop, len(idx), ops.N, n_eig, hop.diag, p=block_size,
                              mmax=max_basis, tol=tol, maxit=maxit, x0=x0, stats=st,
-                             lowblock_ns=lowblock if x0 is not None else 0)
+                             lowblock_ns=lowblock)
         if not vary.any():
             return solve(np.arange(B), None, stats)
         q = prm[:, vary] / span[vary]

@@ -70,7 +70,7 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
                 const cplx b = A[p * lda + q];
                 const double ab = hypot(b.x, b.y);
                 double c = 1.0, s = 0.0, ex = 1.0, ey = 0.0;
-                if (ab > 0.0 && ab > 1e-19 * (fabs(a) + fabs(dd)) && p < n && q < n) {
+                if (ab > 0.0 && ab > 1e-17 * (fabs(a) + fabs(dd)) && p < n && q < n) {
                     const double th = (dd - a) / (2.0 * ab);
                     const double t = copysign(1.0, th) / (fabs(th) + sqrt(th * th + 1.0));
                     c = 1.0 / sqrt(1.0 + t * t);
@@ -91,6 +91,7 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
                 const double cP = rot[4 * P], sP = rot[4 * P + 1];
                 const cplx eP = cmake(rot[4 * P + 2], rot[4 * P + 3]);
                 const double cQ = rot[4 * Q], sQ = rot[4 * Q + 1];
+                if (sP == 0.0 && sQ == 0.0) continue;      // both rotations are the identity
                 const cplx eQc = cmake(rot[4 * Q + 2], -rot[4 * Q + 3]);
                 const cplx a00 = A[p * lda + pc], a01 = A[p * lda + qc];
                 const cplx a10 = A[q * lda + pc], a11 = A[q * lda + qc];

@@ -190,7 +190,7 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
 
 
 def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
-                       stats=None, lowblock_ns=0, drop=1e-8):
+                       stats=None, lowblock_ns=0, drop=1e-8, cold_gate=3e-3):
     """Block Davidson WITHOUT orthogonalising the expansion block.
 
     The basis V is allowed to be non-orthogonal inside a restart cycle; Rayleigh-Ritz is the
@@ -210,10 +210,11 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
     mmax = min(mmax, 64, N)
     ld = mmax
     c128, f64, i32 = torch.complex128, torch.float64, torch.int32
-    V = torch.zeros((B, mmax, N), dtype=c128, device=dev)
-    W = torch.zeros((B, mmax, N), dtype=c128, device=dev)
-    Xb = torch.zeros((B, p, N), dtype=c128, device=dev)
-    HXb = torch.zeros((B, p, N), dtype=c128, device=dev)
+    # basis buffers are never read beyond the per-point counters: no need to zero-fill tens of GB
+    V = torch.empty((B, mmax, N), dtype=c128, device=dev)
+    W = torch.empty((B, mmax, N), dtype=c128, device=dev)
+    Xb = torch.empty((B, p, N), dtype=c128, device=dev)
+    HXb = torch.empty((B, p, N), dtype=c128, device=dev)
     GA = torch.zeros((B, ld, ld), dtype=c128, device=dev)
     GB = torch.zeros((B, ld, ld), dtype=c128, device=dev)
     Zt = torch.zeros((B, ld, ld), dtype=c128, device=dev)
@@ -235,6 +236,7 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
     Wp = BlockView(W, cnt_fixed=p)
     if x0 is None:
         idx = torch.topk(diag, p, dim=1, largest=False).indices.expand(B, p)
+        V[:, :p, :] = 0
         V[:, :p, :].scatter_(2, idx.unsqueeze(2), torch.ones((B, p, 1), dtype=c128, device=dev))
         op.apply(Vp, Wp)
         kern.gram(Vp, Wp, GA)
@@ -272,9 +274,13 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
         nrr = msz * live
         xcnt = (p * live).to(i32)
         kern.gen_rr(GA, GB, nrr, drop, theta, Zt)
-        if it == 1 and lowblock_ns > 0 and getattr(op, 'supports_lowblock', lambda: False)():
-            sigma = theta[:, 0] - 0.05 * theta[:, 0].abs()
-            lowblock = op.build_lowblock(sigma, lowblock_ns)
+        if lowblock is None and lowblock_ns > 0 and getattr(op, 'supports_lowblock', lambda: False)():
+            # two-level preconditioner.  sigma must stay below the spectrum of H_SS (>= lambda_0): warm
+            # starts know lambda_0 to ~1e-6 at once; cold starts wait until every point's lowest Ritz
+            # value has settled (wanted residuals < cold_gate), then sigma = theta_0 - 5 %.
+            if x0 is not None or (it > 1 and float(resmax.max()) < cold_gate):
+                sigma = theta[:, 0] - 0.05 * theta[:, 0].abs()
+                lowblock = op.build_lowblock(sigma, lowblock_ns)
         Xv.cnt = xcnt
         HXv.cnt = xcnt
         kern.block_update(Vm, Zt, Xv, op=0, trans=0)
