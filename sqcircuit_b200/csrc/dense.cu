@@ -102,24 +102,35 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int 
 #pragma unroll
         for (int j = 0; j < NCT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // one commit group per call, even when the chunk is past the end (keeps the group count uniform)
+    // one commit group per call, even when the chunk is past the end (keeps the group count uniform).
+    // Every thread owns one column of the chunk and walks down the rows with plain pointer
+    // increments (the first version recomputed row/column/validity per 16-byte copy: three times
+    // the instructions of the tensor-core work).  Rows that do not exist for this sweep point are
+    // zeroed once (below) and never touched again.
+    const int scol = tid % GRAM_CH;            // column of this thread inside a chunk
+    const int srow0 = tid / GRAM_CH;           // first row, step GRAM_THREADS / GRAM_CH
+    constexpr int SROWSTEP = GRAM_THREADS / GRAM_CH;
     auto stage = [&](int64_t chunk) {
         if (chunk < c_hi) {
-            double* base = smem + (int)((chunk - c_lo) % nstage) * stage_doubles;
-            const int64_t n0 = (split + chunk * nsplit) * GRAM_CH;
-            const int rows = nat * 8 + NBLK * NB;
-            for (int e = tid; e < rows * GRAM_CH; e += GRAM_THREADS) {
-                const int r = e / GRAM_CH, c = e % GRAM_CH;
-                const bool isA = r < nat * 8;
-                const bool isB2 = PAIR && r >= nat * 8 + NB;
-                const int rr = isA ? r : (isB2 ? r - nat * 8 - NB : r - nat * 8);
-                double* dst = base + r * GRAM_LD + 2 * c;
-                const bool valid = (n0 + c < N) && (isA ? rr < na : (isB2 ? rr < nb2 : rr < nb));
-                if (valid) {
-                    cp_async16(dst, (isA ? a0 : (isB2 ? b1 : b0)) + (int64_t)rr * N + n0 + c);
-                } else {
-                    dst[0] = 0.0;
-                    dst[1] = 0.0;
+            double* base = smem + (int)((chunk - c_lo) % nstage) * stage_doubles + 2 * scol;
+            const int64_t n = (split + chunk * nsplit) * GRAM_CH + scol;
+            if (n < N) {
+                const cplx* src = a0 + n;
+                for (int r = srow0; r < na; r += SROWSTEP) cp_async16(base + r * GRAM_LD, src + (int64_t)r * N);
+                double* bb = base + nat * 8 * GRAM_LD;
+                src = b0 + n;
+                for (int r = srow0; r < nb; r += SROWSTEP) cp_async16(bb + r * GRAM_LD, src + (int64_t)r * N);
+                if (PAIR) {
+                    bb += NB * GRAM_LD;
+                    src = b1 + n;
+                    for (int r = srow0; r < nb2; r += SROWSTEP) cp_async16(bb + r * GRAM_LD, src + (int64_t)r * N);
+                }
+            } else {
+                // tail of the last chunk: this column is past the end of the vectors
+                const int rows = nat * 8 + NBLK * NB;
+                for (int r = srow0; r < rows; r += SROWSTEP) {
+                    base[r * GRAM_LD] = 0.0;
+                    base[r * GRAM_LD + 1] = 0.0;
                 }
             }
         }
@@ -143,6 +154,8 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int 
     const int bcol = t ^ bpart;
     const double bsign = (bpart && (t & 1)) ? -1.0 : 1.0;
 
+    for (int e = tid; e < nstage * stage_doubles; e += GRAM_THREADS) smem[e] = 0.0;
+    __syncthreads();
     for (int pre = 0; pre < nstage - 1; ++pre) stage(c_lo + pre);
     for (int64_t ch = c_lo; ch < c_hi; ++ch) {
         wait_oldest();

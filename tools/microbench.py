@@ -66,6 +66,22 @@ if not only or 'hx' in only:
     Ve, Vo = Vx[0::2, :50].contiguous(), Vx[1::2, :50].contiguous()
     ms = timeit(lambda: k.hx_fused(sp, Ve, Vo, pot, fd, BlockView(X), BlockView(Y)))
     report('hx_fused 12 vec/pt', ms, 32.0 * N * p * B, 2.0 * 2 * m * N * p * B)
+if not only or 'pair' in only:
+    W = torch.randn((B, mm, N), dtype=torch.complex128, device=dev)
+    for msz in (12, 24, 28):
+        cm = torch.full((B,), msz, dtype=torch.int32, device=dev)
+        ct = torch.full((B,), msz + p, dtype=torch.int32, device=dev)
+        cn = torch.full((B,), p, dtype=torch.int32, device=dev)
+        S1 = torch.zeros((B, mm, 16), dtype=torch.complex128, device=dev); S2 = torch.zeros_like(S1)
+        ms = timeit(lambda: k.gram_pair(BlockView(V, cnt=ct), BlockView(V, cnt_fixed=p, off=cm, cnt=cn), BlockView(W, cnt_fixed=p, off=cm, cnt=cn), S1, S2))
+        report(f'gram_pair rows={msz + p} nb=12+12', ms, 16.0 * (msz + p + 2 * p) * N * B, 8.0 * (msz + p) * 2 * p * N * B)
+    for n in (24, 32, 40):
+        GA = torch.randn((B, mm, mm), dtype=torch.complex128, device=dev); GA = GA + GA.conj().transpose(1, 2)
+        Q = torch.randn((B, mm, 80), dtype=torch.complex128, device=dev); GB = Q @ Q.conj().transpose(1, 2) / 80
+        w = torch.zeros((B, mm), dtype=torch.float64, device=dev); Zt = torch.zeros_like(GA)
+        nn = torch.full((B,), n, dtype=torch.int32, device=dev)
+        ms = timeit(lambda: k.gen_rr(GA, GB, nn, 1e-8, w, Zt))
+        report(f'gen_rr n={n}', ms, 0, 0)
 if not only or 'heev' in only:
     for n in (24, 36, 48):
         G = torch.randn((B, mm, mm), dtype=torch.complex128, device=dev); G = G + G.conj().transpose(1, 2)
