@@ -14,49 +14,65 @@
 // Replaces the CSR mat-vec on the Hamiltonian of Circuit.hamiltonian() (circuit.py:2147-2164).
 #include "common.cuh"
 
-#define HX_MAXRT 8       // row tiles per parity half  -> m <= 128
 #define HX_MAXT 4        // junction terms
+#ifndef HX_KUNROLL
+#define HX_KUNROLL 2
+#endif
+#ifndef HX_EB
+#define HX_EB 2
+#endif
 
 struct HxGeom {
     int m, he, ho;       // Fock dim, #even rows, #odd rows
-    int hep;             // he rounded up to 8 (rows of each half in shared memory)
-    int kp;              // he rounded up to 4 (contraction length)
-    int nrt;             // hep / 8
+    int kp;              // he rounded up to 4 (rows of each half / contraction length)
     int inner;           // charge-mode dimension (columns)
     int np, TC, PC, CT;  // panels per vector, useful cols per panel, cols incl. halo, col tiles
     int vld, pld;        // leading dims (doubles) of the half matrices and of the panel
+    int pg;              // row pairs per warp group in the potential pass
     int n_terms;
-    int shift[HX_MAXT];
+    int shpack;          // junction charge shifts (-1, 0, +1), 2 bits each, biased by one
     long long N;
 };
 
-template <int NRT>
+// KS = contraction steps (kp / 4) fixes every shared-memory extent of the half matrices at compile
+// time, so all A-fragment offsets in both transforms are immediates.
+template <int KS>
 __global__ void __launch_bounds__(288, 2)
 hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restrict__ Vo,
                 const double* __restrict__ lam, const cplx* __restrict__ etab, long long etab_stride_b,
                 const double* __restrict__ g, const cplx* __restrict__ a,
                 const double* __restrict__ fdiag, long long fdiag_stride_b,
                 sqc_block_t X, sqc_block_t Y, int vmax, long long total_items) {
+    constexpr int KP = 4 * KS;                            // rows of each parity half (he rounded to 4)
+    constexpr int NRT = (KS + 1) / 2;                     // 8-row tiles per half
+    constexpr int VLD = (KP % 8 == 4) ? KP : KP + 4;      // == 4 (mod 8): conflict-free fragments
+    constexpr int KU = HX_KUNROLL;
     extern __shared__ double smem[];
-    // rows: kp (= he rounded up to the k-step) per half; row tiles that stick out past kp are
-    // masked when fragments are read / results written
-    double* sVe = smem;                                   // [kp][vld]   Ve[a][i] = V[2a][i]
-    double* sVo = sVe + gm.kp * gm.vld;                   // [kp][vld]   Vo[a][i] = V[2a+1][i]
-    double* sP = sVo + gm.kp * gm.vld;                    // [2*kp][pld] panel: S/even half, D/odd half
-    double* sLin = sP + 2 * gm.kp * gm.pld;               // [m]
+    // row tiles that stick out past KP read finite neighbouring data and are never written back
+    double* sVe = smem;                                   // [KP][VLD]   Ve[a][i] = V[2a][i]
+    double* sVo = sVe + KP * VLD;                         // [KP][VLD]   Vo[a][i] = V[2a+1][i]
+    double* sP = sVo + KP * VLD;                          // [2*KP][pld] panel: S/even half, D/odd half
+    double* sLin = sP + 2 * KP * gm.pld;                  // [m]
     cplx* sPh = reinterpret_cast<cplx*>(sLin + ((gm.m + 1) & ~1));   // [n_terms][m]
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-    const int nwarp = nthr >> 5;
-    const int m = gm.m, he = gm.he, ho = gm.ho, hep = gm.kp, vld = gm.vld, pld = gm.pld;
+    const int m = gm.m, he = gm.he, ho = gm.ho, pld = gm.pld;
 
     // half matrices (zero padded), staged once per CTA
-    for (int e = tid; e < hep * vld; e += nthr) {
-        const int r = e / vld, c = e % vld;
+    for (int e = tid; e < KP * VLD; e += nthr) {
+        const int r = e / VLD, c = e % VLD;
         sVe[e] = (r < he && c < he) ? Ve[r * he + c] : 0.0;
         sVo[e] = (r < ho && c < ho) ? Vo[r * ho + c] : 0.0;
     }
+    for (int e = tid; e < 2 * KP * pld; e += nthr) sP[e] = 0.0;
+    __syncthreads();
+    // potential pass: the lane's (row in group, column) for the columns past 31
+    const int nwarp = nthr >> 5;
+    const int tw = gm.PC > 32 ? gm.PC - 32 : 1;
+    const int trow = lane / tw, tcol = 32 + lane % tw;
+    // DMMA warps: the lane's complex column inside the warp's 4-column tile
+    const int pcc = 4 * warp + tq;
     int loaded_b = -1;
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
         const long long vec = item / gm.np;
@@ -65,6 +81,7 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
         if (v >= blk_count(X, b)) continue;
         if (b != loaded_b) {
             // per-sweep-point tables: lin(i) = g0 + g1 lam_i ;  ph_t(i) = a_t etab_t[i]
+            // (only the potential pass reads them; it sits between CTA barriers)
             const double g0 = g[(long long)b * 3], g1 = g[(long long)b * 3 + 1];
             for (int i = tid; i < m; i += nthr) sLin[i] = fma(g1, lam[i], g0);
             for (int e = tid; e < gm.n_terms * m; e += nthr) {
@@ -76,162 +93,176 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
         }
         const cplx* xv = blk_vec(X, b, v, gm.N);
         const int c_first = panel * gm.TC - 1;          // global column of panel column 0
-        // ---- 1. stage the panel: Fock row n -> (n even ? n/2 : hep + n/2) ----
-        for (int e = tid; e < 2 * hep * gm.PC; e += nthr) {
-            const int r = e / gm.PC, pc = e % gm.PC;
-            const int n = (r < hep) ? 2 * r : 2 * (r - hep) + 1;
-            const int rr = (r < hep) ? r : r - hep;
-            const bool rowok = (r < hep) ? (rr < he) : (rr < ho);
-            const int c = c_first + pc;
-            double* dst = sP + r * pld + 2 * pc;
-            if (rowok && c >= 0 && c < gm.inner) {
-                cp_async16(dst, xv + (long long)n * gm.inner + c);
-            } else {
-                dst[0] = 0.0;
-                dst[1] = 0.0;
-            }
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
-
-        // ---- 2. forward transform (warp = column tile), in place ----
+        const int c = c_first + pcc;                    // this lane's global column (DMMA warps)
         if (warp < gm.CT) {
+            // ---- 1. warp-private staging of the warp's own 4-column tile (64 B per row) ----
+            // Fock row n -> (n even ? n/2 : KP + n/2); padding rows stay zero from the start
+            {
+                double* dcol = sP + 2 * pcc;
+                if (c >= 0 && c < gm.inner) {
+                    const cplx* src = xv + c;
+                    for (int a2 = gq; a2 < he; a2 += 8)
+                        cp_async16(dcol + a2 * pld, src + (long long)(2 * a2) * gm.inner);
+                    for (int a2 = gq; a2 < ho; a2 += 8)
+                        cp_async16(dcol + (KP + a2) * pld, src + (long long)(2 * a2 + 1) * gm.inner);
+                } else {
+                    for (int a2 = gq; a2 < he; a2 += 8)
+                        *reinterpret_cast<double2*>(dcol + a2 * pld) = make_double2(0.0, 0.0);
+                    for (int a2 = gq; a2 < ho; a2 += 8)
+                        *reinterpret_cast<double2*>(dcol + (KP + a2) * pld) = make_double2(0.0, 0.0);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncwarp();
+            }
+            // ---- 2. forward transform of the tile, in place ----
             double aE[NRT][2], aO[NRT][2];
 #pragma unroll
             for (int r = 0; r < NRT; ++r) aE[r][0] = aE[r][1] = aO[r][0] = aO[r][1] = 0.0;
-            const int cb = 8 * warp + gq;
-            for (int k0 = 0; k0 < gm.kp; k0 += 4) {
-                const double bE = sP[(k0 + tq) * pld + cb];
-                const double bO = sP[(hep + k0 + tq) * pld + cb];
-                const double* ve = sVe + (k0 + tq) * vld + gq;     // A[i][a] = Ve[a][i]
-                const double* vo = sVo + (k0 + tq) * vld + gq;
+            const double* bp = sP + tq * pld + 8 * warp + gq;
+            const double* ve = sVe + tq * VLD + gq;               // A[i][a] = Ve[a][i]
+            const double* vo = sVo + tq * VLD + gq;
+#pragma unroll KU
+            for (int k = 0; k < KS; ++k) {
+                const double bE = bp[(4 * k) * pld];
+                const double bO = bp[(KP + 4 * k) * pld];
 #pragma unroll
                 for (int r = 0; r < NRT; ++r) {
-                    const bool in = 8 * r + gq < hep;
-                    dmma884(aE[r][0], aE[r][1], in ? ve[8 * r] : 0.0, bE);
-                    dmma884(aO[r][0], aO[r][1], in ? vo[8 * r] : 0.0, bO);
+                    dmma884(aE[r][0], aE[r][1], ve[4 * k * VLD + 8 * r], bE);
+                    dmma884(aO[r][0], aO[r][1], vo[4 * k * VLD + 8 * r], bO);
                 }
             }
             __syncwarp();
-            const int cc = 8 * warp + 2 * tq;
+            double* zc = sP + 8 * warp + 2 * tq;
 #pragma unroll
             for (int r = 0; r < NRT; ++r) {
                 const int i = 8 * r + gq;
-                if (i < hep) {
+                if (i < KP) {
                     double2 zs = make_double2(aE[r][0] + aO[r][0], aE[r][1] + aO[r][1]);   // Z[i]
                     double2 zd = make_double2(aE[r][0] - aO[r][0], aE[r][1] - aO[r][1]);   // Z[m-1-i]
                     if (i >= ho) zd = make_double2(0.0, 0.0);
-                    *reinterpret_cast<double2*>(sP + i * pld + cc) = zs;
-                    *reinterpret_cast<double2*>(sP + (hep + i) * pld + cc) = zd;
+                    *reinterpret_cast<double2*>(zc + i * pld) = zs;
+                    *reinterpret_cast<double2*>(zc + (KP + i) * pld) = zd;
                 }
             }
         }
         __syncthreads();
 
-        // ---- 3. potential + mirror combination, in place (warp = mirrored row pair) ----
-        for (int i = warp; i < he; i += nwarp) {
-            const bool pair = i < ho;                 // centre row of an odd m has no mirror
-            const int im = m - 1 - i;
-            const double lin_i = sLin[i], lin_m = pair ? sLin[im] : 0.0;
-            cplx zi[2], zm[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int pc = lane + 32 * q;
-                zi[q] = cmake(0.0, 0.0);
-                zm[q] = cmake(0.0, 0.0);
-                if (pc < gm.PC) {
-                    const double* ri = sP + i * pld;
-                    const double* rm = sP + (hep + i) * pld;
-                    const cplx c0 = *reinterpret_cast<const cplx*>(ri + 2 * pc);
-                    const cplx m0 = *reinterpret_cast<const cplx*>(rm + 2 * pc);
-                    cplx oi = cmake(lin_i * c0.x, lin_i * c0.y);
-                    cplx om = cmake(lin_m * m0.x, lin_m * m0.y);
-                    for (int t = 0; t < gm.n_terms; ++t) {
-                        const int s = gm.shift[t];
-                        const cplx pi_ = sPh[t * m + i];
-                        const cplx pm_ = pair ? sPh[t * m + im] : cmake(0.0, 0.0);
-                        const int lo = pc - s, hi = pc + s;
-                        if (lo >= 0 && lo < gm.PC) {
-                            cfma(oi, pi_, *reinterpret_cast<const cplx*>(ri + 2 * lo));
-                            cfma(om, pm_, *reinterpret_cast<const cplx*>(rm + 2 * lo));
-                        }
-                        if (hi >= 0 && hi < gm.PC) {
-                            cfma(oi, cconj(pi_), *reinterpret_cast<const cplx*>(ri + 2 * hi));
-                            cfma(om, cconj(pm_), *reinterpret_cast<const cplx*>(rm + 2 * hi));
-                        }
+        // ---- 3. potential + mirror combination, in place ----
+        // a warp owns pg whole row pairs.  Columns 0..31 of a row are done by the 32 lanes (read,
+        // warp sync, write back); the columns past 31 of all its rows are evaluated first, in one
+        // pass, and written last, so every read sees original data and nothing waits on the CTA.
+        for (int i_base = warp * gm.pg; i_base < he; i_base += nwarp * gm.pg) {
+            const int i_end = min(i_base + gm.pg, he);
+            auto eval = [&](int i, int pc, cplx& S, cplx& D) {
+                const bool pair = i < ho;                 // centre row of an odd m has no mirror
+                const int im = m - 1 - i;
+                const double* ri = sP + i * pld;
+                const double* rm = sP + (KP + i) * pld;
+                const double lin_i = sLin[i], lin_m = pair ? sLin[im] : 0.0;
+                const cplx c0 = *reinterpret_cast<const cplx*>(ri + 2 * pc);
+                const cplx m0 = *reinterpret_cast<const cplx*>(rm + 2 * pc);
+                cplx oi = cmake(lin_i * c0.x, lin_i * c0.y);
+                cplx om = cmake(lin_m * m0.x, lin_m * m0.y);
+                for (int t = 0; t < gm.n_terms; ++t) {
+                    const int sh = ((gm.shpack >> (2 * t)) & 3) - 1;
+                    const cplx pi_ = sPh[t * m + i];
+                    const cplx pm_ = pair ? sPh[t * m + im] : cmake(0.0, 0.0);
+                    const int lo = pc - sh, hi = pc + sh;
+                    if (lo >= 0 && lo < gm.PC) {
+                        cfma(oi, pi_, *reinterpret_cast<const cplx*>(ri + 2 * lo));
+                        cfma(om, pm_, *reinterpret_cast<const cplx*>(rm + 2 * lo));
                     }
-                    zi[q] = oi;
-                    zm[q] = om;
+                    if (hi >= 0 && hi < gm.PC) {
+                        cfma(oi, cconj(pi_), *reinterpret_cast<const cplx*>(ri + 2 * hi));
+                        cfma(om, cconj(pm_), *reinterpret_cast<const cplx*>(rm + 2 * hi));
+                    }
+                }
+                S = cadd(oi, om);                                        // S_i
+                D = pair ? csub(oi, om) : cmake(0.0, 0.0);              // D_i
+            };
+            cplx ts, td;
+            const int ti = i_base + trow;
+            const bool tail = gm.PC > 32 && ti < i_end;
+            if (tail) eval(ti, tcol, ts, td);
+            for (int i = i_base; i < i_end; ++i) {
+                cplx s_, d_;
+                if (lane < gm.PC) eval(i, lane, s_, d_);
+                __syncwarp();
+                if (lane < gm.PC) {
+                    *reinterpret_cast<cplx*>(sP + i * pld + 2 * lane) = s_;
+                    *reinterpret_cast<cplx*>(sP + (KP + i) * pld + 2 * lane) = d_;
                 }
             }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int pc = lane + 32 * q;
-                if (pc < gm.PC) {
-                    *reinterpret_cast<cplx*>(sP + i * pld + 2 * pc) = cadd(zi[q], zm[q]);          // S_i
-                    *reinterpret_cast<cplx*>(sP + (hep + i) * pld + 2 * pc) =
-                        pair ? csub(zi[q], zm[q]) : cmake(0.0, 0.0);                               // D_i
-                }
+            if (tail) {
+                *reinterpret_cast<cplx*>(sP + ti * pld + 2 * tcol) = ts;
+                *reinterpret_cast<cplx*>(sP + (KP + ti) * pld + 2 * tcol) = td;
             }
         }
         __syncthreads();
 
-        // ---- 4. backward transform + LC diagonal epilogue ----
+        // ---- 4. backward transform of the warp's tile + LC diagonal epilogue (warp-private) ----
         if (warp < gm.CT) {
             double yE[NRT][2], yO[NRT][2];
 #pragma unroll
             for (int r = 0; r < NRT; ++r) yE[r][0] = yE[r][1] = yO[r][0] = yO[r][1] = 0.0;
-            const int cb = 8 * warp + gq;
-            for (int k0 = 0; k0 < gm.kp; k0 += 4) {
-                const double bS = sP[(k0 + tq) * pld + cb];
-                const double bD = sP[(hep + k0 + tq) * pld + cb];
-                const double* ve = sVe + gq * vld + k0 + tq;       // A[a][i] = Ve[a][i]
-                const double* vo = sVo + gq * vld + k0 + tq;
+            const double* bp = sP + tq * pld + 8 * warp + gq;
+            const double* ve = sVe + gq * VLD + tq;               // A[a][i] = Ve[a][i]
+            const double* vo = sVo + gq * VLD + tq;
+#pragma unroll KU
+            for (int k = 0; k < KS; ++k) {
+                const double bS = bp[(4 * k) * pld];
+                const double bD = bp[(KP + 4 * k) * pld];
 #pragma unroll
                 for (int r = 0; r < NRT; ++r) {
-                    const bool in = 8 * r + gq < hep;
-                    dmma884(yE[r][0], yE[r][1], in ? ve[8 * r * vld] : 0.0, bS);
-                    dmma884(yO[r][0], yO[r][1], in ? vo[8 * r * vld] : 0.0, bD);
+                    dmma884(yE[r][0], yE[r][1], ve[8 * r * VLD + 4 * k], bS);
+                    dmma884(yO[r][0], yO[r][1], vo[8 * r * VLD + 4 * k], bD);
                 }
             }
-            const int pcc = 4 * warp + tq;              // complex panel column of this lane
-            const int c = c_first + pcc;
+            // the lane holds complex column pcc of Fock rows 2(8r+gq) [yE] and 2(8r+gq)+1 [yO];
+            // all loads of a batch are issued before its first store (X, Y and fdiag may alias
+            // as far as the compiler knows)
             if (pcc >= 1 && pcc <= gm.TC && c < gm.inner) {
                 cplx* yv = blk_vec(Y, b, v, gm.N);
                 const double* fd = fdiag ? fdiag + b * fdiag_stride_b : nullptr;
+                constexpr int EB = HX_EB;                       // rows per batch
 #pragma unroll
-                for (int r = 0; r < NRT; ++r) {
-                    {
-                        const int aidx = 8 * r + gq;
-                        if (aidx < he) {
-                            const long long idx = (long long)(2 * aidx) * gm.inner + c;
-                            cplx o = cmake(yE[r][0], yE[r][1]);
-                            if (fd) {
-                                const double dv = fd[idx];
-                                const cplx x0 = xv[idx];
-                                o.x = fma(dv, x0.x, o.x);
-                                o.y = fma(dv, x0.y, o.y);
+                for (int r0 = 0; r0 < NRT; r0 += EB) {
+#pragma unroll
+                    for (int par = 0; par < 2; ++par) {
+                        const int hcnt = par ? ho : he;
+                        double dd[EB];
+                        cplx xx[EB];
+#pragma unroll
+                        for (int j = 0; j < EB; ++j) {
+                            const int aidx = 8 * (r0 + j) + gq;
+                            dd[j] = 0.0;
+                            xx[j] = cmake(0.0, 0.0);
+                            if (fd && r0 + j < NRT && aidx < hcnt) {
+                                const long long idx = (long long)(2 * aidx + par) * gm.inner + c;
+                                dd[j] = fd[idx];
+                                xx[j] = xv[idx];
                             }
-                            yv[idx] = o;
                         }
-                        if (aidx < ho) {
-                            const long long idx = (long long)(2 * aidx + 1) * gm.inner + c;
-                            cplx o = cmake(yO[r][0], yO[r][1]);
-                            if (fd) {
-                                const double dv = fd[idx];
-                                const cplx x0 = xv[idx];
-                                o.x = fma(dv, x0.x, o.x);
-                                o.y = fma(dv, x0.y, o.y);
+#pragma unroll
+                        for (int j = 0; j < EB; ++j) {
+                            const int aidx = 8 * (r0 + j) + gq;
+                            if (r0 + j < NRT && aidx < hcnt) {
+                                const long long idx = (long long)(2 * aidx + par) * gm.inner + c;
+                                const int rr = (r0 + j < NRT) ? r0 + j : 0;
+                                cplx o = par ? cmake(yO[rr][0], yO[rr][1]) : cmake(yE[rr][0], yE[rr][1]);
+                                o.x = fma(dd[j], xx[j].x, o.x);
+                                o.y = fma(dd[j], xx[j].y, o.y);
+                                yv[idx] = o;
                             }
-                            yv[idx] = o;
                         }
                     }
                 }
             }
+            __syncwarp();
         }
-        __syncthreads();
+        // no CTA barrier here: from the backward transform to the next forward transform a warp
+        // only touches its own column tile
     }
 }
 
@@ -247,14 +278,14 @@ extern "C" int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const doubl
     if (gm.m < 2 || gm.m > 128) return SQC_ELIMIT;
     gm.he = (gm.m + 1) / 2;
     gm.ho = gm.m / 2;
-    gm.hep = (gm.he + 7) & ~7;
     gm.kp = (gm.he + 3) & ~3;
-    gm.nrt = gm.hep / 8;
     gm.N = (long long)gm.m * gm.inner;
     gm.n_terms = pot->n_terms;
+    gm.shpack = 0;
     for (int t = 0; t < gm.n_terms; ++t) {
-        gm.shift[t] = pot->shift[t][1];
-        if (gm.shift[t] < -1 || gm.shift[t] > 1) return SQC_ELIMIT;
+        const int sh = pot->shift[t][1];
+        if (sh < -1 || sh > 1) return SQC_ELIMIT;
+        gm.shpack |= (sh + 1) << (2 * t);
     }
     // panels: PC = TC + 2 columns, PC a multiple of 4 (8 real columns per tile), PC <= 36 (9 warps)
     int best_np = 0, best_pc = 0;
@@ -268,11 +299,16 @@ extern "C" int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const doubl
     gm.TC = (gm.inner + gm.np - 1) / gm.np;
     gm.CT = gm.PC / 4;
     // leading dims == 4 (mod 8) doubles keep both DMMA fragment patterns bank-conflict free
-    gm.vld = gm.kp;
-    while ((gm.vld & 7) != 4) ++gm.vld;
+    gm.vld = (gm.kp % 8 == 4) ? gm.kp : gm.kp + 4;        // must match VLD in the kernel
     gm.pld = 2 * gm.PC;
     while ((gm.pld & 7) != 4) ++gm.pld;
     int nwarp = gm.CT < 4 ? 4 : gm.CT;
+    // potential pass: the fewest rounds whose groups of pg row pairs keep the columns past 31 of
+    // a whole group inside one warp pass
+    for (int rounds = 1;; ++rounds) {
+        gm.pg = (gm.he + nwarp * rounds - 1) / (nwarp * rounds);
+        if (gm.PC <= 32 || gm.pg * (gm.PC - 32) <= 32) break;
+    }
     size_t smem = ((size_t)2 * gm.kp * gm.vld + (size_t)2 * gm.kp * gm.pld + ((gm.m + 1) & ~1)) * sizeof(double) +
                   (size_t)(gm.n_terms > 0 ? gm.n_terms : 1) * gm.m * sizeof(cplx);
     if (smem > 227 * 1024) return SQC_ELIMIT;
@@ -292,8 +328,9 @@ extern "C" int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const doubl
             fdiag, fdiag_stride_b, X, Y, X.cnt_fixed, total);                                          \
         break;                                                                                         \
     }
-    switch (gm.nrt) {
+    switch (gm.kp / 4) {
         HX_CASE(1) HX_CASE(2) HX_CASE(3) HX_CASE(4) HX_CASE(5) HX_CASE(6) HX_CASE(7) HX_CASE(8)
+        HX_CASE(9) HX_CASE(10) HX_CASE(11) HX_CASE(12) HX_CASE(13) HX_CASE(14) HX_CASE(15) HX_CASE(16)
         default: return SQC_ELIMIT;
     }
 #undef HX_CASE
