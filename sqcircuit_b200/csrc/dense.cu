@@ -12,7 +12,7 @@ long long g_sqc_launches = 0;
 // Real formulation on the interleaved data (K index t runs over the 2N doubles of a vector):
 //   Re C = A_r . B_r^T           Im C = A_r . B'_r^T,   B'[2n] = Im b_n, B'[2n+1] = -Re b_n
 // so one DMMA B-fragment plus a lane-xor shuffle feeds both the real and the imaginary tile.
-// CTA = 4 warps, two CTAs per SM, >= 3 cp.async stages sized by the rows the sweep point really
+// CTA = 4 warps, 112 KB of stages so that two CTAs are always resident per SM, >= 3 cp.async stages sized by the rows the sweep point really
 // has (one block sync per chunk: the refill of the slot consumed one iteration earlier is issued
 // before the tensor-core work of the current chunk); the warps split the K range of every staged
 // chunk and each warp keeps all (NAT x NCT) 8x8 accumulator tiles; a final shared-memory
@@ -84,7 +84,7 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int 
     const int nat = (na + 7) >> 3;          // row tiles actually populated for this sweep point
     // stages are sized by the rows this point really has, so small bases get a deeper pipeline
     const int stage_doubles = (nat * 8 + NBLK * NB) * GRAM_LD;
-    int nstage = smem_doubles / stage_doubles;     // >= 3 by construction of the launch
+    int nstage = smem_doubles / stage_doubles;     // >= 2 by construction of the launch
     nstage = nstage > 8 ? 8 : nstage;
     const cplx* a0 = blk_vec(A, b, 0, N);
     const cplx* b0 = blk_vec(Bm, b, 0, N);
@@ -291,10 +291,12 @@ static int launch_gram(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N
                        int ldr, int ldc, cplx* work, cudaStream_t st) {
     const int ns = gram_nsplit(B, N, PAIR);
     if (ns > 1 && !work) return SQC_EINVAL;
-    // at least three full-size stages, as many as fit in ~108 KB (two CTAs per SM)
+    // always 112 KB so that TWO CTAs (8 warps) are resident per SM: one CTA alone cannot keep the
+    // FP64 tensor pipe busy.  The kernel cuts it into stages sized by the rows the sweep point
+    // really has (>= 2 stages even for a full 64-row basis, >= 3 up to 40 rows + a pair of blocks).
     size_t stage_bytes = (size_t)(NAT * 8 + (PAIR ? 2 : 1) * NCT * 4) * GRAM_LD * sizeof(double);
-    size_t smem = 3 * stage_bytes;
-    if (smem < 108 * 1024) smem = (108 * 1024 / stage_bytes) * stage_bytes;
+    size_t smem = 112 * 1024;
+    if (smem < 2 * stage_bytes) smem = 2 * stage_bytes;
     size_t red_bytes = GRAM_WARPS * (size_t)(NAT * 8) * (NCT * 4) * sizeof(cplx);
     if (smem < red_bytes) smem = red_bytes;
     if (smem > 227 * 1024) return SQC_ELIMIT;

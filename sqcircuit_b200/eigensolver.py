@@ -166,6 +166,10 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
         left = int(n_not_done.item())
         if stats is not None:
             stats.append((it, left))
+            if DETAIL_STATS is not None:      # dev instrumentation (tools/nact_stats.py): costs syncs
+                lv = (1 - done)
+                DETAIL_STATS.append((it, B, left, int((nact * lv).sum()), int((msz * lv).sum()),
+                                     int((((nact + 3) // 4) * lv).sum()), int(restart.sum())))
         if left == 0:
             converged = True
             break
@@ -187,6 +191,9 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
         kern.davidson_insert(st, S1, B)
     return EigResult(theta[:, :k].contiguous(), Xb[:, :k, :].contiguous(), it, resmax, converged,
                      ritz_block=Xb)
+
+
+DETAIL_STATS = None
 
 
 def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
@@ -290,6 +297,10 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
         left = int(n_not_done.item())
         if stats is not None:
             stats.append((it, left))
+            if DETAIL_STATS is not None:      # dev instrumentation (tools/nact_stats.py): costs syncs
+                lv = (1 - done)
+                DETAIL_STATS.append((it, B, left, int((nact * lv).sum()), int((msz * lv).sum()),
+                                     int((((nact + 3) // 4) * lv).sum()), int(restart.sum())))
         if left == 0:
             converged = True
             break

@@ -1,0 +1,24 @@
+"""Dev tool: per-iteration active-column statistics of the generalised Davidson on the bench sweep."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import sqcircuit_b200 as sq
+from sqcircuit_b200 import eigensolver
+
+points = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+sq.set_device('cuda:0')
+loop = sq.Loop()
+C, CJ = sq.Capacitor(0.15, 'GHz'), sq.Capacitor(10, 'GHz')
+JJ, L = sq.Junction(5, 'GHz', loops=[loop]), sq.Inductor(0.13, 'GHz', loops=[loop])
+cr = sq.Circuit({(0, 1): [CJ, JJ], (0, 2): [L], (0, 3): [C], (1, 2): [C], (1, 3): [L], (2, 3): [CJ, JJ]})
+cr.set_trunc_nums([100, 50])
+fl = np.linspace(0.0, 1.0, points)
+eigensolver.DETAIL_STATS = []
+stats = []
+res = cr.sweep_diag(10, loop_fluxes={loop: fl}, tol=1e-9, stats=stats, lowblock=160)
+tot = dict(cols=0, colmax=0, tiles=0, tilemax=0, rows=0)
+print('it B left nact_sum msz_sum tiles restarts')
+for (it, B, left, na, ms, tl, rs) in eigensolver.DETAIL_STATS:
+    print(it, B, left, na, ms, tl, rs)
+    tot['cols'] += na; tot['colmax'] += 12 * left; tot['tiles'] += tl; tot['tilemax'] += 3 * left
+print(tot, 'active col frac', tot['cols'] / tot['colmax'], 'tile frac', tot['tiles'] / tot['tilemax'])
