@@ -253,6 +253,58 @@ __global__ void gram_ref_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, cplx* 
     }
 }
 
+// Small Gram (at most 4 x 4, e.g. the 2 x 2 transition matrix elements of the decoherence rates):
+// the tensor-core pipeline above has nothing to amortise its staging over, so this is a plain
+// streaming kernel -- one CTA per sweep point, every vector read exactly once.
+template <int RA, int RB>
+__global__ void __launch_bounds__(256)
+gram_small_kernel(sqc_block_t A, sqc_block_t Bm, int64_t N, cplx* __restrict__ C, int ldr, int ldc) {
+    const int b = blockIdx.x;
+    const int na = min(blk_count(A, b), RA), nb = min(blk_count(Bm, b), RB);
+    const cplx* a0 = blk_vec(A, b, 0, N);
+    const cplx* b0 = blk_vec(Bm, b, 0, N);
+    cplx acc[RA][RB];
+#pragma unroll
+    for (int i = 0; i < RA; ++i)
+#pragma unroll
+        for (int j = 0; j < RB; ++j) acc[i][j] = cmake(0.0, 0.0);
+    for (int64_t n = threadIdx.x; n < N; n += blockDim.x) {
+        cplx av[RA], bv[RB];
+#pragma unroll
+        for (int i = 0; i < RA; ++i) av[i] = i < na ? a0[(int64_t)i * N + n] : cmake(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < RB; ++j) bv[j] = j < nb ? b0[(int64_t)j * N + n] : cmake(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < RA; ++i)
+#pragma unroll
+            for (int j = 0; j < RB; ++j) cfmac(acc[i][j], av[i], bv[j]);
+    }
+    __shared__ double red[8][RA * RB * 2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < RA; ++i)
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            const double re = warp_sum(acc[i][j].x), im = warp_sum(acc[i][j].y);
+            if (lane == 0) {
+                red[warp][2 * (i * RB + j)] = re;
+                red[warp][2 * (i * RB + j) + 1] = im;
+            }
+        }
+    __syncthreads();
+    const int rows = min(A.cnt_fixed, ldr), cols = min(Bm.cnt_fixed, ldc);
+    for (int e = threadIdx.x; e < rows * cols; e += blockDim.x) {
+        const int i = e / cols, j = e % cols;
+        double re = 0.0, im = 0.0;
+        if (i < RA && j < RB)
+            for (int w = 0; w < 8; ++w) {
+                re += red[w][2 * (i * RB + j)];
+                im += red[w][2 * (i * RB + j) + 1];
+            }
+        C[(int64_t)b * ldr * ldc + i * ldc + j] = cmake(re, im);
+    }
+}
+
 static int g_gram_split_min = 1;
 static int gram_nsplit(int B, int64_t N, bool pair = false) {
     // enough CTAs to fill 148 SMs x 2 resident CTAs, at least g_gram_split_min interleaved CTAs per
@@ -325,6 +377,16 @@ extern "C" int sqc_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int32_t B, voi
     if (impl == 1) {
         int rows = A.cnt_fixed < ldr ? A.cnt_fixed : ldr, cols = Bm.cnt_fixed < ldc ? Bm.cnt_fixed : ldc;
         gram_ref_kernel<<<B * rows * cols, 128, 0, st>>>(A, Bm, N, (cplx*)C, ldr, ldc);
+        SQC_LAUNCHED();
+        return 0;
+    }
+    if (A.cnt_fixed <= 4 && Bm.cnt_fixed <= 4) {
+        const int ra = A.cnt_fixed <= 1 ? 1 : A.cnt_fixed <= 2 ? 2 : 4, rb = Bm.cnt_fixed <= 1 ? 1 : Bm.cnt_fixed <= 2 ? 2 : 4;
+#define GRAMS_CASE(a, b_) \
+    if (ra == a && rb == b_) gram_small_kernel<a, b_><<<B, 256, 0, st>>>(A, Bm, N, (cplx*)C, ldr, ldc)
+        GRAMS_CASE(1, 1); GRAMS_CASE(1, 2); GRAMS_CASE(1, 4); GRAMS_CASE(2, 1); GRAMS_CASE(2, 2); GRAMS_CASE(2, 4);
+        GRAMS_CASE(4, 1); GRAMS_CASE(4, 2); GRAMS_CASE(4, 4);
+#undef GRAMS_CASE
         SQC_LAUNCHED();
         return 0;
     }

@@ -27,7 +27,8 @@ def relerr(a, b):
 
 
 @pytest.mark.parametrize('B,na,nb,N', [(3, 48, 12, 10100), (5, 7, 3, 625), (2, 64, 16, 1000),
-                                       (300, 24, 12, 777), (1, 12, 12, 199), (4, 33, 9, 4096)])
+                                       (300, 24, 12, 777), (1, 12, 12, 199), (4, 33, 9, 4096),
+                                       (7, 2, 2, 10100), (5, 1, 1, 333), (3, 4, 3, 1000), (6, 2, 1, 64), (2, 3, 4, 5)])
 @pytest.mark.parametrize('impl', [0, 1])
 def test_gram(kern, B, na, nb, N, impl):
     A = rnd((B, na, N), 1)

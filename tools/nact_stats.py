@@ -22,3 +22,23 @@ for (it, B, left, na, ms, tl, rs) in eigensolver.DETAIL_STATS:
     print(it, B, left, na, ms, tl, rs)
     tot['cols'] += na; tot['colmax'] += 12 * left; tot['tiles'] += tl; tot['tilemax'] += 3 * left
 print(tot, 'active col frac', tot['cols'] / tot['colmax'], 'tile frac', tot['tiles'] / tot['tilemax'])
+
+# ---- wall time per continuation level (no detail stats: no extra syncs) ----
+import time
+from sqcircuit_b200 import circuit as _c
+eigensolver.DETAIL_STATS = None
+orig = _c._davidson
+times = []
+def timed(kern, hop, B, *a, **k):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    r = orig(kern, hop, B, *a, **k)
+    torch.cuda.synchronize(); times.append((B, r.iterations, (time.perf_counter() - t0) * 1e3))
+    return r
+_c._davidson = timed
+for rep in range(2):
+    times.clear()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = cr.sweep_diag(10, loop_fluxes={loop: fl}, tol=1e-9, lowblock=160)
+    torch.cuda.synchronize(); tt = (time.perf_counter() - t0) * 1e3
+    print('sweep total ms', round(tt, 1), 'levels (B, its, ms):', [(b, i, round(t, 1)) for b, i, t in times],
+          'outside solver ms', round(tt - sum(t for _, _, t in times), 1))
