@@ -203,6 +203,19 @@ typedef struct {
     void*    GB;                /* [B][ldg][ldg] Gram matrix of the basis (non-orthogonalised
                                    variant), or NULL */
     int32_t* mtot;              /* [B] msz + nact after sqc_davidson_decide, or NULL */
+    int32_t  nexp;              /* only Ritz pairs j < nexp are expanded with a correction vector
+                                   (0 = all p; k = the wanted pairs only, the guard vectors ride along) */
+    /* Copy-free restarts (both NULL: the caller copies X, HX into the basis with sqc_restart_copy).
+     * The basis buffers have xrow + p rows; the Ritz block of an iteration is written either to
+     * rows [xrow, xrow + p) or, when this iteration restarts, straight into rows [0, p).  The
+     * restart of iteration i+1 is decided at iteration i (basis after the insert plus as many new
+     * vectors again would exceed mmax), so the row is known before the block is computed:
+     *   xoff[b]  (in/out) row for the NEXT Ritz block, restart[b] (in/out) the matching flag;
+     *   xlast[b] (out)    row of the Ritz block this call has judged (frozen once done[b]).
+     * The new-vector count is clipped to the free rows when no restart was scheduled. */
+    int32_t* xoff;
+    int32_t* xlast;
+    int32_t  xrow;
 } sqc_davidson_state_t;
 
 int sqc_davidson_decide(const sqc_davidson_state_t* st, int32_t B, void* stream);
@@ -224,7 +237,10 @@ int sqc_precond_residual(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const dou
  *    the Fock-basis displacement tables Dt[t] = V diag(etab_t) V^T (complex128 [n_terms][m][m]);
  *  - inverse: in-place Gauss-Jordan in shared memory (ns <= 160);
  *  - apply: T[b][jj][S[r]] = sum_q Ainv[b][r][q] (HX_a - theta_a X_a)[S[q]] / unit, a = act[b][jj]
- *    (overwrites the diagonal-preconditioned entries written by sqc_precond_residual). */
+ *    (overwrites the diagonal-preconditioned entries written by sqc_precond_residual).
+ *    group >= 1: sweep points b share the index set and inverse of slot b / group (S: [ceil(B/group)]
+ *    rows, Ainv: [ceil(B/group)][ns][ns]) -- neighbouring points of a sweep have nearly the same low
+ *    block, and a preconditioner only has to be approximate. */
 int sqc_lowblock_assemble(const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
                           const void* Dt, const sqc_potential_t* pot, const double* d,
                           int64_t d_stride_b, const double* sigma, double unit, void* out,
@@ -232,8 +248,8 @@ int sqc_lowblock_assemble(const sqc_space_t* sp, int32_t ns, const int32_t* S, i
 int sqc_hpd_inverse_c64(void* A, int32_t ns, int32_t B, void* stream);
 int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
                        int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
-                       int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int64_t N,
-                       int32_t B, void* stream);
+                       int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int32_t group,
+                       int64_t N, int32_t B, void* stream);
 
 /* SVQB coefficients from the Gram matrix S = T^H T of the new block:
  * Cq[j][i] = D_i U_ij sigma_j^-1/2 over directions with sigma_j > drop * sigma_max;

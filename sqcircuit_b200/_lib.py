@@ -39,7 +39,8 @@ class DavidsonState(C.Structure):
                 ('tol_rel', c_dbl), ('tol_abs_floor', c_dbl),
                 ('msz', c_vp), ('nact', c_vp), ('act', c_vp), ('restart', c_vp), ('done', c_vp),
                 ('n_not_done', c_vp), ('theta', c_vp), ('rn2', c_vp), ('resmax', c_vp),
-                ('den_floor', c_vp), ('G', c_vp), ('GB', c_vp), ('mtot', c_vp)]
+                ('den_floor', c_vp), ('G', c_vp), ('GB', c_vp), ('mtot', c_vp), ('nexp', c_i32),
+                ('xoff', c_vp), ('xlast', c_vp), ('xrow', c_i32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/sqcircuit_b200.h
@@ -73,7 +74,7 @@ SIGNATURES = {
                                       c_vp, c_dbl, c_vp, c_i32, c_vp]),
     'sqc_hpd_inverse_c64': (c_i32, [c_vp, c_i32, c_i32, c_vp]),
     'sqc_lowblock_apply': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32, c_dbl,
-                                   c_i64, c_i32, c_vp]),
+                                   c_i32, c_i64, c_i32, c_vp]),
     'sqc_svqb_coeffs': (c_i32, [c_vp, c_i32, c_vp, c_dbl, c_vp, c_vp, c_vp, c_i32, c_vp]),
     'sqc_davidson_insert': (c_i32, [C.POINTER(DavidsonState), c_vp, c_i32, c_i32, c_i32, c_vp]),
 }
@@ -102,7 +103,7 @@ def load():
             raise SqcLibraryError(f'{LIB_PATH} does not export {name}') from e
         fn.restype = res
         fn.argtypes = args
-    if lib.sqc_abi_version() != 1:
+    if lib.sqc_abi_version() != 2:
         raise SqcLibraryError('sqcircuit_b200 ABI version mismatch')
     _lib = lib
     return lib

@@ -266,9 +266,10 @@ class Circuit:
         if not res.converged:
             raise RuntimeError(f'batched Davidson did not converge in {maxit} iterations '
                                f'(worst relative residual {float(res.resmax.max()):.2e})')
-        out = SweepResult(res.evals / (2 * np.pi * unt.get_unit_freq()), res.evals, res.evecs,
+        evecs = res.evecs if res.evecs.is_contiguous() else res.evecs.contiguous()
+        out = SweepResult(res.evals / (2 * np.pi * unt.get_unit_freq()), res.evals, evecs,
                           res.iterations, res.converged, res.resmax)
-        out.noise = SweepNoise(kern, ops, hop, res.evals, res.evecs, self)
+        out.noise = SweepNoise(kern, ops, hop, res.evals, evecs, self)
         return out
 
     def _solve_continuation(self, ops, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats, stride,
@@ -335,9 +336,12 @@ class Circuit:
             else:
                 # two nearest solved neighbours of every point of this level
                 d2 = ((q[idx][:, None, :] - q[solved][None, :, :]) ** 2).sum(axis=2)
-                nb = np.argsort(d2, axis=1)[:, :2]
-                if nb.shape[1] == 1:
-                    nb = np.repeat(nb, 2, axis=1)
+                if d2.shape[1] == 1:
+                    nb = np.zeros((len(idx), 2), dtype=int)
+                else:
+                    nb = np.argpartition(d2, 1, axis=1)[:, :2]          # O(n) instead of a full sort
+                    swap = d2[np.arange(len(idx)), nb[:, 0]] > d2[np.arange(len(idx)), nb[:, 1]]
+                    nb[swap] = nb[swap][:, ::-1]
                 store = torch.cat(ritz_store, dim=0) if len(ritz_store) > 1 else ritz_store[0]
                 ritz_store = [store]
                 pos = np.array([ritz[int(i)] for i in solved])

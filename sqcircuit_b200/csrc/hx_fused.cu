@@ -15,6 +15,19 @@
 #include "common.cuh"
 
 #define HX_MAXT 4        // junction terms
+// timing ablations for tools/hx_variants.sh (wrong results when set)
+#ifndef HX_ABL_NOPOT
+#define HX_ABL_NOPOT 0
+#endif
+#ifndef HX_ABL_NOSTAGE
+#define HX_ABL_NOSTAGE 0
+#endif
+#ifndef HX_ABL_NOEPI
+#define HX_ABL_NOEPI 0
+#endif
+#ifndef HX_ABL_NODMMA
+#define HX_ABL_NODMMA 0
+#endif
 #ifndef HX_KUNROLL
 #define HX_KUNROLL 2
 #endif
@@ -27,6 +40,7 @@ struct HxGeom {
     int kp;              // he rounded up to 4 (rows of each half / contraction length)
     int inner;           // charge-mode dimension (columns)
     int np, TC, PC, CT;  // panels per vector, useful cols per panel, cols incl. halo, col tiles
+    int CT_last;         // column tiles of the last (narrower) panel of a vector
     int vld, pld;        // leading dims (doubles) of the half matrices and of the panel
     int pg;              // row pairs per warp group in the potential pass
     int n_terms;
@@ -37,7 +51,7 @@ struct HxGeom {
 // KS = contraction steps (kp / 4) fixes every shared-memory extent of the half matrices at compile
 // time, so all A-fragment offsets in both transforms are immediates.
 template <int KS>
-__global__ void __launch_bounds__(288, 2)
+__global__ void __launch_bounds__(256, 2)
 hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restrict__ Vo,
                 const double* __restrict__ lam, const cplx* __restrict__ etab, long long etab_stride_b,
                 const double* __restrict__ g, const cplx* __restrict__ a,
@@ -67,16 +81,16 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
     }
     for (int e = tid; e < 2 * KP * pld; e += nthr) sP[e] = 0.0;
     __syncthreads();
-    // potential pass: the lane's (row in group, column) for the columns past 31
     const int nwarp = nthr >> 5;
-    const int tw = gm.PC > 32 ? gm.PC - 32 : 1;
-    const int trow = lane / tw, tcol = 32 + lane % tw;
     // DMMA warps: the lane's complex column inside the warp's 4-column tile
     const int pcc = 4 * warp + tq;
     int loaded_b = -1;
-    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+    // the grid is a multiple of np, so all panels of a vector are dealt in the same round; the panel
+    // index is rotated by the round so that every CTA sees wide and narrow panels alike
+    int round = 0;
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++round) {
         const long long vec = item / gm.np;
-        const int panel = (int)(item % gm.np);
+        const int panel = (int)((item % gm.np + round) % gm.np);
         const int b = (int)(vec / vmax), v = (int)(vec % vmax);
         if (v >= blk_count(X, b)) continue;
         if (b != loaded_b) {
@@ -93,13 +107,17 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
         }
         const cplx* xv = blk_vec(X, b, v, gm.N);
         const int c_first = panel * gm.TC - 1;          // global column of panel column 0
+        // the last panel of a vector is narrower: fewer column tiles (still a multiple of four,
+        // so that the tensor-core work stays evenly spread over the four SM sub-partitions)
+        const int ct = (panel == gm.np - 1) ? gm.CT_last : gm.CT;
+        const int pcn = 4 * ct;
         const int c = c_first + pcc;                    // this lane's global column (DMMA warps)
-        if (warp < gm.CT) {
+        if (warp < ct) {
             // ---- 1. warp-private staging of the warp's own 4-column tile (64 B per row) ----
             // Fock row n -> (n even ? n/2 : KP + n/2); padding rows stay zero from the start
             {
                 double* dcol = sP + 2 * pcc;
-                if (c >= 0 && c < gm.inner) {
+                if (!HX_ABL_NOSTAGE && c >= 0 && c < gm.inner) {
                     const cplx* src = xv + c;
                     for (int a2 = gq; a2 < he; a2 += 8)
                         cp_async16(dcol + a2 * pld, src + (long long)(2 * a2) * gm.inner);
@@ -123,7 +141,7 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
             const double* ve = sVe + tq * VLD + gq;               // A[i][a] = Ve[a][i]
             const double* vo = sVo + tq * VLD + gq;
 #pragma unroll KU
-            for (int k = 0; k < KS; ++k) {
+            for (int k = 0; k < (HX_ABL_NODMMA ? 1 : KS); ++k) {
                 const double bE = bp[(4 * k) * pld];
                 const double bO = bp[(KP + 4 * k) * pld];
 #pragma unroll
@@ -149,10 +167,9 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
         __syncthreads();
 
         // ---- 3. potential + mirror combination, in place ----
-        // a warp owns pg whole row pairs.  Columns 0..31 of a row are done by the 32 lanes (read,
-        // warp sync, write back); the columns past 31 of all its rows are evaluated first, in one
-        // pass, and written last, so every read sees original data and nothing waits on the CTA.
-        for (int i_base = warp * gm.pg; i_base < he; i_base += nwarp * gm.pg) {
+        // a warp owns pg whole row pairs; the (at most 32) columns of a row are done by its lanes:
+        // read, warp sync, write back -- nothing waits on the CTA inside the pass.
+        for (int i_base = warp * gm.pg; i_base < (HX_ABL_NOPOT ? 0 : he); i_base += nwarp * gm.pg) {
             const int i_end = min(i_base + gm.pg, he);
             auto eval = [&](int i, int pc, cplx& S, cplx& D) {
                 const bool pair = i < ho;                 // centre row of an odd m has no mirror
@@ -169,11 +186,11 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
                     const cplx pi_ = sPh[t * m + i];
                     const cplx pm_ = pair ? sPh[t * m + im] : cmake(0.0, 0.0);
                     const int lo = pc - sh, hi = pc + sh;
-                    if (lo >= 0 && lo < gm.PC) {
+                    if (lo >= 0 && lo < pcn) {
                         cfma(oi, pi_, *reinterpret_cast<const cplx*>(ri + 2 * lo));
                         cfma(om, pm_, *reinterpret_cast<const cplx*>(rm + 2 * lo));
                     }
-                    if (hi >= 0 && hi < gm.PC) {
+                    if (hi >= 0 && hi < pcn) {
                         cfma(oi, cconj(pi_), *reinterpret_cast<const cplx*>(ri + 2 * hi));
                         cfma(om, cconj(pm_), *reinterpret_cast<const cplx*>(rm + 2 * hi));
                     }
@@ -181,28 +198,20 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
                 S = cadd(oi, om);                                        // S_i
                 D = pair ? csub(oi, om) : cmake(0.0, 0.0);              // D_i
             };
-            cplx ts, td;
-            const int ti = i_base + trow;
-            const bool tail = gm.PC > 32 && ti < i_end;
-            if (tail) eval(ti, tcol, ts, td);
             for (int i = i_base; i < i_end; ++i) {
                 cplx s_, d_;
-                if (lane < gm.PC) eval(i, lane, s_, d_);
+                if (lane < pcn) eval(i, lane, s_, d_);
                 __syncwarp();
-                if (lane < gm.PC) {
+                if (lane < pcn) {
                     *reinterpret_cast<cplx*>(sP + i * pld + 2 * lane) = s_;
                     *reinterpret_cast<cplx*>(sP + (KP + i) * pld + 2 * lane) = d_;
                 }
-            }
-            if (tail) {
-                *reinterpret_cast<cplx*>(sP + ti * pld + 2 * tcol) = ts;
-                *reinterpret_cast<cplx*>(sP + (KP + ti) * pld + 2 * tcol) = td;
             }
         }
         __syncthreads();
 
         // ---- 4. backward transform of the warp's tile + LC diagonal epilogue (warp-private) ----
-        if (warp < gm.CT) {
+        if (warp < ct) {
             double yE[NRT][2], yO[NRT][2];
 #pragma unroll
             for (int r = 0; r < NRT; ++r) yE[r][0] = yE[r][1] = yO[r][0] = yO[r][1] = 0.0;
@@ -210,7 +219,7 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
             const double* ve = sVe + gq * VLD + tq;               // A[a][i] = Ve[a][i]
             const double* vo = sVo + gq * VLD + tq;
 #pragma unroll KU
-            for (int k = 0; k < KS; ++k) {
+            for (int k = 0; k < (HX_ABL_NODMMA ? 1 : KS); ++k) {
                 const double bS = bp[(4 * k) * pld];
                 const double bD = bp[(KP + 4 * k) * pld];
 #pragma unroll
@@ -224,7 +233,7 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
             // as far as the compiler knows)
             if (pcc >= 1 && pcc <= gm.TC && c < gm.inner) {
                 cplx* yv = blk_vec(Y, b, v, gm.N);
-                const double* fd = fdiag ? fdiag + b * fdiag_stride_b : nullptr;
+                const double* fd = (fdiag && !HX_ABL_NOEPI) ? fdiag + b * fdiag_stride_b : nullptr;
                 constexpr int EB = HX_EB;                       // rows per batch
 #pragma unroll
                 for (int r0 = 0; r0 < NRT; r0 += EB) {
@@ -287,28 +296,31 @@ extern "C" int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const doubl
         if (sh < -1 || sh > 1) return SQC_ELIMIT;
         gm.shpack |= (sh + 1) << (2 * t);
     }
-    // panels: PC = TC + 2 columns, PC a multiple of 4 (8 real columns per tile), PC <= 36 (9 warps)
-    int best_np = 0, best_pc = 0;
-    for (int np = 1; np <= gm.inner; ++np) {
-        int tc = (gm.inner + np - 1) / np;
-        int pc = ((tc + 2) + 3) & ~3;
-        if (pc <= 36) { best_np = np; best_pc = pc; break; }
+    // panels: PC = TC + 2 columns (one halo column each side), 4 complex columns per warp tile.
+    // The tile count is kept a multiple of four wherever possible: a CTA's warps are dealt
+    // round-robin to the four SM sub-partitions, each with its own FP64 tensor pipe, and e.g. nine
+    // equal tiles put 3+3 warps of two resident CTAs on one sub-partition (measured: 6.2 instead of
+    // 4.0 cycles per DMMA).  Wide modes use 30 + 2 column panels; the last panel takes the remainder.
+    if (gm.inner + 2 <= 32) {
+        gm.np = 1;
+        gm.TC = gm.inner;
+        gm.PC = (gm.inner + 2 + 3) & ~3;
+        gm.CT = gm.CT_last = gm.PC / 4;
+    } else {
+        gm.TC = 30;
+        gm.PC = 32;
+        gm.CT = 8;
+        gm.np = (gm.inner + gm.TC - 1) / gm.TC;
+        const int tl = gm.inner - gm.TC * (gm.np - 1);
+        gm.CT_last = ((tl + 2 + 3) / 4 + 3) & ~3;
+        if (gm.CT_last > 8) gm.CT_last = 8;
     }
-    gm.np = best_np;
-    gm.PC = best_pc;
-    gm.TC = (gm.inner + gm.np - 1) / gm.np;
-    gm.CT = gm.PC / 4;
     // leading dims == 4 (mod 8) doubles keep both DMMA fragment patterns bank-conflict free
     gm.vld = (gm.kp % 8 == 4) ? gm.kp : gm.kp + 4;        // must match VLD in the kernel
     gm.pld = 2 * gm.PC;
     while ((gm.pld & 7) != 4) ++gm.pld;
     int nwarp = gm.CT < 4 ? 4 : gm.CT;
-    // potential pass: the fewest rounds whose groups of pg row pairs keep the columns past 31 of
-    // a whole group inside one warp pass
-    for (int rounds = 1;; ++rounds) {
-        gm.pg = (gm.he + nwarp * rounds - 1) / (nwarp * rounds);
-        if (gm.PC <= 32 || gm.pg * (gm.PC - 32) <= 32) break;
-    }
+    gm.pg = (gm.he + nwarp - 1) / nwarp;      // row pairs per warp in the potential pass
     size_t smem = ((size_t)2 * gm.kp * gm.vld + (size_t)2 * gm.kp * gm.pld + ((gm.m + 1) & ~1)) * sizeof(double) +
                   (size_t)(gm.n_terms > 0 ? gm.n_terms : 1) * gm.m * sizeof(cplx);
     if (smem > 227 * 1024) return SQC_ELIMIT;
@@ -318,6 +330,7 @@ extern "C" int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const doubl
     const long long total = (long long)B * X.cnt_fixed * gm.np;
     long long grid = (long long)nsm * per_sm;
     if (grid > total) grid = total;
+    grid -= grid % gm.np;                 // see the panel rotation in the kernel (total is a multiple of np)
 #define HX_CASE(R)                                                                                     \
     case R: {                                                                                          \
         cudaError_t e = cudaFuncSetAttribute(hx_fused_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

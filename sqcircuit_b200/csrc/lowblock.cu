@@ -133,13 +133,14 @@ __global__ void __launch_bounds__(256)
 lowblock_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* __restrict__ theta,
                       int ld_theta, const int32_t* __restrict__ act, int ld_act,
                       const int32_t* __restrict__ S, long long s_stride_b, const float2* __restrict__ Ainv,
-                      int ns, double inv_unit, long long N) {
+                      int ns, double inv_unit, int group, long long N) {
     extern __shared__ double smd[];
     cplx* rS = reinterpret_cast<cplx*>(smd);        // [na][ns]
     const int b = blockIdx.x;
     const int na = blk_count(T, b);
     if (na <= 0) return;
-    const int32_t* s = S + b * s_stride_b;
+    const int slot = b / group;
+    const int32_t* s = S + slot * s_stride_b;
     const int tid = threadIdx.x;
     for (int e = tid; e < na * ns; e += 256) {
         const int jj = e / ns, q = e % ns;
@@ -150,7 +151,7 @@ lowblock_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
-    const float2* ai = Ainv + (long long)b * ns * ns;
+    const float2* ai = Ainv + (long long)slot * ns * ns;
     for (int r = warp; r < ns; r += 8) {
         const float2* row = ai + (long long)r * ns;
         for (int jj = 0; jj < na; ++jj) {
@@ -170,14 +171,14 @@ lowblock_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double
 
 extern "C" int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
                                   int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
-                                  int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int64_t N,
-                                  int32_t B, void* stream) {
-    if (B <= 0 || ns <= 0 || T.cnt_fixed <= 0) return SQC_EINVAL;
+                                  int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int32_t group,
+                                  int64_t N, int32_t B, void* stream) {
+    if (B <= 0 || ns <= 0 || T.cnt_fixed <= 0 || group < 1) return SQC_EINVAL;
     size_t smem = (size_t)T.cnt_fixed * ns * sizeof(cplx);
     cudaError_t e = cudaFuncSetAttribute(lowblock_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     lowblock_apply_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(X, HX, T, theta, ld_theta, act, ld_act, S,
-                                                                 s_stride_b, (const float2*)Ainv, ns, 1.0 / unit, N);
+                                                                 s_stride_b, (const float2*)Ainv, ns, 1.0 / unit, group, N);
     SQC_LAUNCHED();
     return 0;
 }

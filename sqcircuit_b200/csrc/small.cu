@@ -561,6 +561,7 @@ __global__ void __launch_bounds__(64)
 davidson_decide_kernel(sqc_davidson_state_t st) {
     const int b = blockIdx.x, tid = threadIdx.x;
     const int p = st.p, k = st.k, ldg = st.ldg;
+    const int nexp = st.nexp > 0 ? st.nexp : p;
     __shared__ int s_restart;
     double* theta = st.theta + (int64_t)b * ldg;
     if (st.done[b]) {
@@ -580,19 +581,36 @@ davidson_decide_kernel(sqc_davidson_state_t st) {
         for (int j = 0; j < pe; ++j) {
             const double rel = sqrt(st.rn2[(int64_t)b * p + j]) / scale;
             if (j < k) rmax = fmax(rmax, rel);
-            if (rel > 0.5 * st.tol_rel) st.act[(int64_t)b * p + n++] = j;
+            if (rel > 0.5 * st.tol_rel && j < nexp) st.act[(int64_t)b * p + n++] = j;
         }
         st.resmax[b] = rmax;
         int restart = 0;
+        const bool planned = st.xoff != nullptr;      // copy-free restarts, see the header
+        if (planned) st.xlast[b] = st.xoff[b];
         if (rmax <= st.tol_rel) {
             st.done[b] = 1;
             n = 0;
         } else {
             atomicAdd(st.n_not_done, 1);
-            if (msz + n > st.mmax) restart = 1;
+            if (planned) {
+                restart = st.restart[b];
+                const int mcur = restart ? pe : msz;
+                if (mcur + n > st.mmax) n = st.mmax - mcur;
+            } else if (msz + n > st.mmax) {
+                restart = 1;
+            }
         }
         st.nact[b] = n;
-        st.restart[b] = restart;
+        if (!planned) {
+            st.restart[b] = restart;
+        } else if (!st.done[b]) {
+            // next iteration: the basis will hold (restart ? pe : msz) + n vectors; it restarts if
+            // another n new ones would not fit
+            const int mnext = (restart ? pe : msz) + n;
+            const int rnext = mnext + n > st.mmax;
+            st.restart[b] = rnext;
+            st.xoff[b] = rnext ? 0 : st.xrow;
+        }
         double fl = fmax(fabs(theta[0]), fabs(theta[pe - 1]));
         fl = fmax(fl, theta[pe - 1] - theta[0]);
         st.den_floor[b] = fmax(1e-3 * fl, 1e-300);

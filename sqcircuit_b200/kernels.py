@@ -176,6 +176,10 @@ class Kernels:
             setattr(st, key, kw[key].data_ptr())
         st.GB = kw['GB'].data_ptr() if kw.get('GB') is not None else None
         st.mtot = kw['mtot'].data_ptr() if kw.get('mtot') is not None else None
+        st.nexp = int(kw.get('nexp') or 0)
+        st.xoff = kw['xoff'].data_ptr() if kw.get('xoff') is not None else None
+        st.xlast = kw['xlast'].data_ptr() if kw.get('xlast') is not None else None
+        st.xrow = int(kw.get('xrow') or 0)
         st._keep = kw
         return st
 
@@ -204,11 +208,13 @@ class Kernels:
         B, ns, _ = A.shape
         _lib.check(self.lib.sqc_hpd_inverse_c64(_p(A), ns, B, _stream(self.dev)), 'sqc_hpd_inverse_c64')
 
-    def lowblock_apply(self, X, HX, T, theta, act, S, Ainv, unit):
+    def lowblock_apply(self, X, HX, T, theta, act, S, Ainv, unit, group=1):
         ssb = 0 if S.shape[0] == 1 else S.stride(0)
+        if Ainv.shape[0] * group < X.B:
+            raise ValueError('lowblock_apply: not enough inverse slots for this group size')
         _lib.check(self.lib.sqc_lowblock_apply(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act),
-                                               act.shape[1], _p(S), ssb, _p(Ainv), Ainv.shape[1], unit, X.N, X.B,
-                                               _stream(self.dev)), 'sqc_lowblock_apply')
+                                               act.shape[1], _p(S), ssb, _p(Ainv), Ainv.shape[1], unit, group,
+                                               X.N, X.B, _stream(self.dev)), 'sqc_lowblock_apply')
 
     def svqb_coeffs(self, S, nact, drop, Cq, msz=None, mtot=None):
         B, ld, _ = S.shape

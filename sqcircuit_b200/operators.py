@@ -14,6 +14,7 @@ coupling operators needed for matrix elements and decoherence rates.
 """
 import ctypes as C
 
+import os
 import numpy as np
 import torch
 
@@ -250,6 +251,10 @@ class CircuitOperators:
         return torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype, device=self.device).contiguous()
 
 
+# sweep points per shared low-block inverse of the two-level preconditioner (see build_lowblock)
+LOWBLOCK_GROUP = int(os.environ.get('SQC_LOWBLOCK_GROUP', '0'))     # 0 = choose from the sweep spacing
+
+
 class HamiltonianOperator:
     """H(b) for a batch of sweep points: loop values [B][nloops] (radians), ng [B or 1][M]."""
 
@@ -270,15 +275,51 @@ class HamiltonianOperator:
     def supports_lowblock(self):
         return bool(self.ops.fused and self.ops.T >= 1)
 
-    def build_lowblock(self, sigma, ns):
+    def _auto_lowblock_group(self, max_group=8, budget=0.05):
+        """Largest power-of-two group whose members differ by less than ``budget`` (relative) in the
+        junction phase factors and the LC diagonal between first and last member: consecutive
+        points of a sorted sweep qualify, points in arbitrary order do not."""
+        if self.B < 2:
+            return 1
+        step = 0.0
+        if self.a.numel():
+            da = (self.a[1:] - self.a[:-1]).abs().amax(dim=0)
+            step = float((da / self.a.abs().amax(dim=0).clamp_min(1e-300)).max())
+        if self.g.numel():
+            dg = (self.g[1:] - self.g[:-1]).abs().amax(dim=0)
+            step = max(step, float((dg / self.g.abs().amax(dim=0).clamp_min(1e-300)).max()))
+        if self.diag.shape[0] > 1:
+            dd = (self.diag[1:] - self.diag[:-1]).abs().amax()
+            step = max(step, float(dd / self.diag.abs().amax().clamp_min(1e-300)))
+        group = max_group
+        while group > 1 and step * group > budget:
+            group //= 2
+        return group
+
+    def build_lowblock(self, sigma, ns, group=None):
         """Inverse of (H_SS - sigma)/unit on the ns basis states of smallest LC energy
-        (two-level preconditioner, see csrc/lowblock.cu).  sigma: [B] float64 (rad/s)."""
+        (two-level preconditioner, see csrc/lowblock.cu).  sigma: [B] float64 (rad/s).
+
+        ``group`` consecutive sweep points (they are neighbours along the sweep) share the block of
+        the middle point of the group: the low block varies slowly along a sweep and only has to
+        precondition, so one inversion per ``group`` points is enough."""
         ops, kern = self.ops, self.ops.kern
         ns = int(min(ns, 160, ops.N // 2))
-        S = torch.topk(self.diag, ns, dim=1, largest=False).indices.to(torch.int32).contiguous()
+        if group is None:
+            group = LOWBLOCK_GROUP or self._auto_lowblock_group()
+        group = int(max(1, min(group, self.B)))
         unit = 2 * np.pi * 1e9
-        Ainv = torch.empty((self.B, ns, ns), dtype=torch.complex64, device=self.device)
-        pot = ops.potential_struct(self.a, self.g, ops.etab)
-        kern.lowblock_assemble(ops.sp, S, ops.displacement_tables(), pot, self.diag, sigma.contiguous(), unit, Ainv)
+        if group == 1:
+            a, g, diag, sig, nslot = self.a, self.g, self.diag, sigma.contiguous(), self.B
+        else:
+            nslot = (self.B + group - 1) // group
+            rep = torch.clamp(torch.arange(nslot, device=self.device) * group + group // 2, max=self.B - 1)
+            a, g = self.a[rep].contiguous(), self.g[rep].contiguous()
+            diag = self.diag if self.diag.shape[0] == 1 else self.diag[rep].contiguous()
+            sig = sigma[rep].contiguous()
+        S = torch.topk(diag, ns, dim=1, largest=False).indices.to(torch.int32).contiguous()
+        Ainv = torch.empty((nslot, ns, ns), dtype=torch.complex64, device=self.device)
+        pot = ops.potential_struct(a, g, ops.etab)
+        kern.lowblock_assemble(ops.sp, S, ops.displacement_tables(), pot, diag, sig, unit, Ainv)
         kern.hpd_inverse_c64(Ainv)
-        return {'S': S, 'Ainv': Ainv, 'unit': unit, 'ns': ns}
+        return {'S': S, 'Ainv': Ainv, 'unit': unit, 'ns': ns, 'group': group}

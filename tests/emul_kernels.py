@@ -23,6 +23,12 @@ def _get(blk, b):
     return blk.tensor[b, o:o + c, :].numpy()
 
 
+def _rows(blk, b):
+    """all cnt_fixed rows of the block of sweep point b (Ritz index addressing)"""
+    o = _off(blk, b)
+    return blk.tensor[b, o:o + blk.cnt_fixed, :].numpy()
+
+
 def _set(blk, b, arr):
     o = _off(blk, b)
     blk.tensor[b, o:o + arr.shape[0], :] = torch.from_numpy(np.ascontiguousarray(arr))
@@ -326,20 +332,34 @@ class EmulKernels:
                 rel = np.sqrt(float(st.rn2[b, j])) / scale
                 if j < k:
                     rmax = max(rmax, rel)
-                if rel > 0.5 * st.tol_rel:
+                if rel > 0.5 * st.tol_rel and j < (getattr(st, 'nexp', 0) or p):
                     st.act[b, n] = j
                     n += 1
             st.resmax[b] = rmax
             restart = 0
+            planned = getattr(st, 'xoff', None) is not None
+            if planned:
+                st.xlast[b] = st.xoff[b]
             if rmax <= st.tol_rel:
                 st.done[b] = 1
                 n = 0
             else:
                 st.n_not_done[0] += 1
-                if msz + n > st.mmax:
+                if planned:
+                    restart = int(st.restart[b])
+                    mcur = pe if restart else msz
+                    if mcur + n > st.mmax:
+                        n = st.mmax - mcur
+                elif msz + n > st.mmax:
                     restart = 1
             st.nact[b] = n
-            st.restart[b] = restart
+            if not planned:
+                st.restart[b] = restart
+            elif not int(st.done[b]):
+                mnext = (pe if restart else msz) + n
+                rnext = int(mnext + n > st.mmax)
+                st.restart[b] = rnext
+                st.xoff[b] = 0 if rnext else st.xrow
             fl = max(abs(th[0]), abs(th[pe - 1]), th[pe - 1] - th[0])
             st.den_floor[b] = max(1e-3 * fl, 1e-300)
             if restart:
@@ -365,7 +385,7 @@ class EmulKernels:
             n = _cnt(T, b)
             if n == 0:
                 continue
-            x, hx = X.tensor[b].numpy(), HX.tensor[b].numpy()
+            x, hx = _rows(X, b), _rows(HX, b)
             dd = d[min(b, d.shape[0] - 1)].numpy()
             fl = float(den_floor[b])
             out = []
@@ -403,15 +423,15 @@ class EmulKernels:
         for b in range(A.shape[0]):
             A[b] = torch.from_numpy(np.linalg.inv(A[b].numpy().astype(complex)).astype(np.complex64))
 
-    def lowblock_apply(self, X, HX, T, theta, act, S, Ainv, unit):
+    def lowblock_apply(self, X, HX, T, theta, act, S, Ainv, unit, group=1):
         for b in range(X.B):
             n = _cnt(T, b)
             if n == 0:
                 continue
-            s = S[min(b, S.shape[0] - 1)].numpy()
-            x, hx = X.tensor[b].numpy(), HX.tensor[b].numpy()
+            s = S[min(b // group, S.shape[0] - 1)].numpy()
+            x, hx = _rows(X, b), _rows(HX, b)
             t = _get(T, b).copy()
-            ai = Ainv[b].numpy().astype(complex)
+            ai = Ainv[b // group].numpy().astype(complex)
             for jj in range(n):
                 av = int(act[b, jj])
                 r = hx[av][s] - float(theta[b, av]) * x[av][s]

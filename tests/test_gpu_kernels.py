@@ -342,6 +342,14 @@ def test_lowblock_preconditioner_kernels(kern):
     kern.lowblock_apply(BlockView(X), BlockView(HX), BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()),
                         theta.cuda(), act.cuda(), S, inv, 2.0)
     assert relerr(Vd.cpu(), refV) < 1e-12
+    # grouped: sweep points b share the inverse of slot b // group
+    refV = Vb.clone()
+    E.lowblock_apply(BlockView(X.cpu()), BlockView(HX.cpu()), BlockView(refV, cnt_fixed=p, off=msz, cnt=nact),
+                     theta, act, S.cpu(), inv.cpu()[:2], 2.0, group=2)
+    Vd = Vb.cuda()
+    kern.lowblock_apply(BlockView(X), BlockView(HX), BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()),
+                        theta.cuda(), act.cuda(), S, inv[:2].contiguous(), 2.0, group=2)
+    assert relerr(Vd.cpu(), refV) < 1e-12
 
 
 def test_gram_pair_and_gen_rr(kern):
@@ -400,3 +408,51 @@ def test_launch_counter(kern):
     n0 = kern.launch_count()
     kern.xbasis(8)
     assert kern.launch_count() == n0 + 1
+
+
+@pytest.mark.parametrize('planned', [False, True])
+def test_davidson_decide_matches_emulation(kern, planned):
+    """Bookkeeping kernel against the emulation, legacy and copy-free (planned) restart modes,
+    over a few chained calls so that the planned flags of one call drive the next."""
+    B, p, k, mmax, ld = 40, 6, 4, 20, 20
+    gen = torch.Generator().manual_seed(5)
+
+    def fresh(dev):
+        t = dict(msz=torch.randint(p, mmax + 1, (B,), generator=torch.Generator().manual_seed(1)).to(torch.int32),
+                 nact=torch.zeros(B, dtype=torch.int32), act=torch.zeros((B, p), dtype=torch.int32),
+                 restart=torch.zeros(B, dtype=torch.int32), done=torch.zeros(B, dtype=torch.int32),
+                 n_not_done=torch.zeros(1, dtype=torch.int32),
+                 theta=torch.sort(torch.randn((B, ld), dtype=torch.float64, generator=torch.Generator().manual_seed(2)), dim=1).values,
+                 rn2=torch.zeros((B, p), dtype=torch.float64), resmax=torch.zeros(B, dtype=torch.float64),
+                 den_floor=torch.zeros(B, dtype=torch.float64),
+                 G=torch.zeros((B, ld, ld), dtype=torch.complex128), GB=torch.zeros((B, ld, ld), dtype=torch.complex128),
+                 mtot=torch.zeros(B, dtype=torch.int32))
+        if planned:
+            t['xoff'] = torch.full((B,), mmax, dtype=torch.int32)
+            t['xlast'] = torch.full((B,), mmax, dtype=torch.int32)
+        return {kk: v.to(dev) for kk, v in t.items()}
+    tc, tg = fresh('cpu'), fresh('cuda')
+    E = EmulKernels()
+    extra = dict(xrow=mmax) if planned else {}
+    sc = E.davidson_state(p=p, k=k, mmax=mmax, ldg=ld, tol_rel=1e-3, tol_abs_floor=1e-300, **tc, **extra)
+    sg = kern.davidson_state(p=p, k=k, mmax=mmax, ldg=ld, tol_rel=1e-3, tol_abs_floor=1e-300, **tg, **extra)
+    for it in range(4):
+        rn = (10.0 ** (-torch.rand((B, p), dtype=torch.float64, generator=gen) * (3 + 2 * it))) ** 2
+        tc['rn2'].copy_(rn)
+        tg['rn2'].copy_(rn.cuda())
+        E.davidson_decide(sc, B)
+        kern.davidson_decide(sg, B)
+        for name in tc:
+            a, b_ = tc[name], tg[name].cpu()
+            if name == 'act':       # entries past nact are unspecified
+                for b in range(B):
+                    n = int(tc['nact'][b])
+                    assert torch.equal(a[b, :n], b_[b, :n])
+            elif a.dtype.is_floating_point or a.dtype.is_complex:
+                assert relerr(b_, a) < 1e-14, name
+            else:
+                assert torch.equal(a, b_), name
+        # emulate the insert: the basis grows by nact
+        tc['msz'] += tc['nact']
+        tg['msz'] += tg['nact']
+        assert int(tc['msz'].max()) <= mmax
