@@ -173,7 +173,7 @@ class TimedKernels:
     """Wraps the CUDA backend: CUDA events on the launching stream around every C-ABI call,
     so per-kernel device time is measured live inside the timed region (no profiler)."""
     TIMED = ['hx_fused', 'mode_transform', 'potential_apply', 'gram', 'gram_pair', 'gen_rr', 'davidson_insert2',
-             'lowblock_assemble', 'hpd_inverse_c64', 'lowblock_apply', 'block_update', 'block_rightmul', 'heev',
+             'lowblock_assemble', 'hpd_inverse_c64', 'lowblock_apply', 'block_update', 'ritz_update', 'block_rightmul', 'heev',
              'residual_norms', 'precond_residual', 'restart_copy', 'svqb_coeffs', 'davidson_decide',
              'davidson_insert', 'diag_mul', 'ladder_apply']
 
@@ -182,6 +182,7 @@ class TimedKernels:
         self._k = kern
         self._torch = torch
         self.enabled = False
+        self.only = None       # restrict the instrumentation to these entry points
         self.records = []      # (name, start_event, stop_event, meta)
         for name in self.TIMED:
             setattr(self, name, self._wrap(name))
@@ -194,7 +195,7 @@ class TimedKernels:
         torch = self._torch
 
         def call(*a, **kw):
-            if not self.enabled:
+            if not self.enabled or (self.only is not None and name not in self.only):
                 return fn(*a, **kw)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
@@ -279,7 +280,17 @@ def our_arm(args):
         t0.record()
         last = None
         for _ in range(nsteps):
+            if DEBUG:
+                torch.cuda.synchronize()
+                ts = time.perf_counter()
             last = step(e2e)
+            if DEBUG:
+                torch.cuda.synchronize()
+                st_ = torch.cuda.memory_stats()
+                print(f'[debug] step e2e={e2e} {1e3 * (time.perf_counter() - ts):.1f} ms  cudaMalloc segments '
+                      f'{st_["segment.all.allocated"]} retries {st_["num_alloc_retries"]} reserved '
+                      f'{st_["reserved_bytes.all.current"] / 2**30:.1f} GiB peak-alloc '
+                      f'{st_["allocated_bytes.all.peak"] / 2**30:.1f} GiB', file=sys.stderr)
         t1.record()
         sync()
         ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
@@ -292,15 +303,27 @@ def our_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # timed region: only the dominant kernel (the fused H.X) carries CUDA events -- bracketing all
+    # ~900 C-ABI calls of a step costs ~60 ms of host time per step (measured), which would be
+    # charged to `value`.  The full per-kernel breakdown comes from one extra, untimed step below.
+    kern.only = {'hx_fused', 'mode_transform', 'potential_apply'}
     kern.enabled = True
     l0 = kern.launch_count()
     ms_dev, last = timed(args.steps, False)
     launches = kern.launch_count() - l0
     kern.enabled = False
-    per_kernel = kern.summary()
+    hx_kernel = kern.summary()
+    nvec = HX_COUNTER['vectors'] + (int(HX_COUNTER['dev'].item()) if 'dev' in HX_COUNTER else 0)
     ms_e2e, last_e2e = timed(args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
     iters = last[2].iterations
+    kern.records = []
+    kern.only = None
+    kern.enabled = True
+    step(False)
+    sync()
+    kern.enabled = False
+    per_kernel = kern.summary()
 
     if rank != 0:
         if world > 1:
@@ -318,8 +341,8 @@ def our_arm(args):
         peaks = json.load(open(pk))
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'MEASURED_PEAKS.json (sustained copy)' if peaks else 'fallback 6.65 TB/s'
-    hx_ms = sum(per_kernel.get(k, [0, 0])[0] for k in ('hx_fused', 'mode_transform', 'potential_apply'))
-    hx_calls = per_kernel.get('hx_fused', per_kernel.get('potential_apply', [0, 1]))[1]
+    hx_ms = sum(hx_kernel.get(k, [0, 0])[0] for k in ('hx_fused', 'mode_transform', 'potential_apply'))
+    hx_calls = hx_kernel.get('hx_fused', hx_kernel.get('potential_apply', [0, 1]))[1]
     # algorithmic bytes of one H.X: read X once + write Y once, 16 B per complex amplitude
     total_ms = sum(v[0] for v in per_kernel.values())
     shares = {k: {'ms': round(v[0], 3), 'calls': v[1], 'share': round(v[0] / total_ms, 4)}
@@ -327,7 +350,6 @@ def our_arm(args):
     roof = {'bound': 'hbm', 'kernel': 'H.X apply (sqc_hx_fused: transform + potential + transform in one kernel)',
             'unit': 'GB/s', 'peak': hbm_peak, 'peak_source': peak_src, 'traffic': None,
             'achieved': None, 'frac': None}
-    nvec = HX_COUNTER['vectors'] + (int(HX_COUNTER['dev'].item()) if 'dev' in HX_COUNTER else 0)
     if hx_ms > 0 and nvec > 0:
         alg_bytes = 32.0 * N * nvec
         roof['achieved'] = alg_bytes / (hx_ms / 1e3) / 1e9
@@ -370,6 +392,7 @@ def our_arm(args):
         'gpu_launches': int(launches),
         'roofline': roof,
         'kernel_time_breakdown': shares,
+        'kernel_time_breakdown_note': 'ms of ONE extra fully instrumented step run after the timed region',
         'cpu_baseline': cpu,
         'clocks': clocks,
     }
@@ -379,6 +402,7 @@ def our_arm(args):
 
 
 HX_COUNTER = {'vectors': 0}
+DEBUG = bool(os.environ.get('SQC_BENCH_DEBUG'))
 
 
 def _install_hx_counter():

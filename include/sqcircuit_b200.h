@@ -179,6 +179,18 @@ int sqc_heev(const void* A, const int32_t* n, int32_t n_fixed, int32_t ld, doubl
 int sqc_gen_rr(const void* GA, const void* GB, const int32_t* n, int32_t ld, double drop, double* w,
                void* Zt, int32_t B, void* stream);
 
+/* Ritz block in one pass over the basis A and its image A2 (same counts):
+ *   Out[b][j] = sum_i Cf[b][j][i] A[b][i],  Out2[b][j] = sum_i Cf[b][j][i] A2[b][i],
+ *   rn2[b][j] = || Out2_j - theta[b][j] Out_j ||^2,   j < count(Out, b)   (row stride Out.cnt_fixed).
+ * Equivalent to two sqc_block_update(op = 0, trans = 0) calls plus sqc_residual_norms without reading
+ * the Ritz vectors back.  Out may alias the leading rows of A (and Out2 of A2): every position reads all
+ * its inputs before it is written.  Sweep points with count(Out, b) == 0 are left untouched (rn2 too).
+ * work: sqc_ritz_update_work_bytes(B, N) bytes of device scratch. */
+int64_t sqc_ritz_update_work_bytes(int32_t B, int64_t N);
+int sqc_ritz_update(sqc_block_t A, sqc_block_t A2, const void* Cf, int32_t ldr, int32_t ldc,
+                    sqc_block_t Out, sqc_block_t Out2, const double* theta, int32_t ld_theta,
+                    double* rn2, void* work, int64_t N, int32_t B, void* stream);
+
 /* rn2[b][j] = || HX_j - theta[b][j] X_j ||^2,  j < p. */
 int sqc_residual_norms(sqc_block_t X, sqc_block_t HX, const double* theta, int32_t ld_theta,
                        int64_t N, int32_t B, double* rn2, void* stream);

@@ -61,6 +61,9 @@ SIGNATURES = {
     'sqc_gram_pair': (c_i32, [Block, Block, Block, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     'sqc_gen_rr': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_dbl, c_vp, c_vp, c_i32, c_vp]),
     'sqc_davidson_insert2': (c_i32, [C.POINTER(DavidsonState), c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'sqc_ritz_update_work_bytes': (c_i64, [c_i32, c_i64]),
+    'sqc_ritz_update': (c_i32, [Block, Block, c_vp, c_i32, c_i32, Block, Block, c_vp, c_i32, c_vp, c_vp, c_i64, c_i32,
+                                c_vp]),
     'sqc_block_update': (c_i32, [Block, c_vp, c_i32, c_i32, c_i32, Block, c_i64, c_i32, c_i32, c_i32, c_vp]),
     'sqc_hx_fused': (c_i32, [C.POINTER(Space), c_vp, c_vp, C.POINTER(Potential), c_vp, c_i64, Block, Block, c_i32, c_vp]),
     'sqc_block_rightmul': (c_i32, [Block, c_vp, c_i32, c_i32, c_vp, c_i64, c_i32, c_vp]),

@@ -279,7 +279,7 @@ class Circuit:
         blocks of its two nearest already-solved neighbours (Rayleigh-Ritz in that subspace is
         second order accurate in the parameter distance).  Levels: every stride^2-th point cold,
         then every stride-th point, then the rest."""
-        from .eigensolver import EigResult
+        from .eigensolver import EigResult, RitzPairStart
         kern = ops.kern
         B = lv.shape[0]
         ngb = np.broadcast_to(ng, (B, ng.shape[1]))
@@ -350,8 +350,8 @@ class Circuit:
                 new_blocks = []
                 for c0 in range(0, len(idx), chunk):
                     sel = slice(c0, c0 + chunk)
-                    x0 = torch.cat([store[torch.as_tensor(pos[nb[sel, 0]], device=dev)],
-                                    store[torch.as_tensor(pos[nb[sel, 1]], device=dev)]], dim=1)
+                    x0 = RitzPairStart(store, torch.as_tensor(pos[nb[sel, 0]], device=dev),
+                                       torch.as_tensor(pos[nb[sel, 1]], device=dev))
                     r = solve(idx[sel], x0, st)
                     del x0
                     ii = torch.as_tensor(idx[sel], device=dev)

@@ -618,6 +618,200 @@ extern "C" int sqc_block_update(sqc_block_t A, const void* Cf, int32_t ldr, int3
     return SQC_ELIMIT;
 }
 
+// ---------------------------------------------------------------------------------------
+// Ritz block in ONE pass over the basis and its image:  X = Cf . V,  HX = Cf . W  and the squared
+// residual norms rn2[j] = || HX_j - theta_j X_j ||^2 (replaces two sqc_block_update calls and
+// sqc_residual_norms: the Ritz vectors are not read back from HBM for their residuals).
+// Same real DMMA formulation as block_update_dmma_kernel; a warp owns 32 positions and streams its
+// piece of the basis first and of the image second, keeping both accumulator sets in registers.
+// Residuals: per-CTA partial sums -> work[b][chunk][16], summed by a second tiny kernel in a fixed
+// order (no atomics: the convergence decisions stay reproducible run to run).
+// ---------------------------------------------------------------------------------------
+#define UPD3_THREADS 256
+#define UPD3_MT 4
+#define UPD3_DEPTH 10
+#define UPD3_SLOT (2 * 32 * 2)   // doubles per slot: 2 vectors x 32 positions x (re, im)
+
+template <int NCT>
+__global__ void __launch_bounds__(UPD3_THREADS, 2)
+ritz_update_dmma_kernel(sqc_block_t A, sqc_block_t A2, const cplx* __restrict__ Cf, int ldr, int ldc,
+                        sqc_block_t Out, sqc_block_t Out2, const double* __restrict__ theta, int ld_theta,
+                        double* __restrict__ work, int64_t N, int nchunk, int ldm, int kk_max) {
+    extern __shared__ double smem[];     // Mr[kk_max][ldm] | ring[warps][DEPTH][SLOT] | red[warps][16]
+    const int b = blockIdx.x / nchunk, chunk = blockIdx.x % nchunk;
+    const int na = blk_count(A, b), nb = min(blk_count(Out, b), NCT * 4);
+    if (nb == 0) return;                 // inactive sweep point: nothing is written, not even partials
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const cplx* cf = Cf + (int64_t)b * ldr * ldc;
+    const int kk = (2 * na + 3) & ~3;
+    for (int e = tid; e < kk * (NCT * 8); e += UPD3_THREADS) {
+        const int k = e / (NCT * 8), n = e % (NCT * 8);
+        const int i = k >> 1, pin = k & 1, j = n >> 1, pout = n & 1;
+        double v = 0.0;
+        if (i < na && j < nb) {
+            const cplx c = cf[j * ldc + i];
+            v = (pin == pout) ? c.x : (pin == 0 ? c.y : -c.y);
+        }
+        smem[k * ldm + n] = v;
+    }
+    double* red = smem + kk_max * ldm + (UPD3_THREADS / 32) * (UPD3_DEPTH * UPD3_SLOT);
+    __syncthreads();
+    const int64_t nbase = ((int64_t)chunk * (UPD3_THREADS / 32) + warp) * (8 * UPD3_MT);
+    double part[NCT];
+#pragma unroll
+    for (int j = 0; j < NCT; ++j) part[j] = 0.0;
+    if (nbase < N) {
+        double* ring = smem + kk_max * ldm + warp * (UPD3_DEPTH * UPD3_SLOT);
+        // the warp streams its 32 positions of the basis first, then of the image: one long
+        // cp.async ring over 2 * nks k-steps (k-step s of a matrix uses its vectors 2s, 2s+1)
+        const cplx* a0 = blk_vec(A, b, 0, N);
+        const cplx* a1 = blk_vec(A2, b, 0, N);
+        const int nks = kk / 4;
+        auto issue = [&](int s) {
+            if (s < 2 * nks) {
+                const cplx* a = s < nks ? a0 : a1;
+                const int sl = s < nks ? s : s - nks;
+                double* dst = ring + (s % UPD3_DEPTH) * UPD3_SLOT + 2 * lane;
+                const int64_t n = nbase + lane;
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const int i = 2 * sl + v;
+                    if (i < na && n < N) {
+                        cp_async16(dst + v * 64, a + (int64_t)i * N + n);
+                    } else {
+                        dst[v * 64] = 0.0;
+                        dst[v * 64 + 1] = 0.0;
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+        double acc[2][UPD3_MT][NCT][2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+            for (int mt = 0; mt < UPD3_MT; ++mt)
+#pragma unroll
+                for (int j = 0; j < NCT; ++j) acc[w][mt][j][0] = acc[w][mt][j][1] = 0.0;
+#pragma unroll
+        for (int s = 0; s < UPD3_DEPTH - 1; ++s) issue(s);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            for (int sl = 0; sl < nks; ++sl) {
+                const int s = w * nks + sl;
+                cp_async_wait<UPD3_DEPTH - 2>();
+                __syncwarp();
+                const double* slot = ring + (s % UPD3_DEPTH) * UPD3_SLOT;
+                // A fragment: row n = 8 mt + g, k = (vector t>>1, part t&1)
+                double af[UPD3_MT];
+#pragma unroll
+                for (int mt = 0; mt < UPD3_MT; ++mt) af[mt] = slot[(t >> 1) * 64 + 2 * (8 * mt + g) + (t & 1)];
+#pragma unroll
+                for (int j = 0; j < NCT; ++j) {
+                    const double bf = smem[(4 * sl + t) * ldm + 8 * j + g];
+#pragma unroll
+                    for (int mt = 0; mt < UPD3_MT; ++mt) dmma884(acc[w][mt][j][0], acc[w][mt][j][1], af[mt], bf);
+                }
+                __syncwarp();
+                issue(s + UPD3_DEPTH - 1);
+            }
+        }
+        cp_async_wait<0>();
+        // C fragment: row n = nbase + 8 mt + g, packed cols 8j + 2t, +1  -> vector 4j + t (re, im)
+        cplx* o = blk_vec(Out, b, 0, N);
+        cplx* o2 = blk_vec(Out2, b, 0, N);
+#pragma unroll
+        for (int j = 0; j < NCT; ++j) {
+            const int jj = 4 * j + t;
+            if (jj < nb) {
+                const double th = theta[(int64_t)b * ld_theta + jj];
+#pragma unroll
+                for (int mt = 0; mt < UPD3_MT; ++mt) {
+                    const int64_t n = nbase + 8 * mt + g;
+                    if (n < N) {
+                        const cplx x = cmake(acc[0][mt][j][0], acc[0][mt][j][1]);
+                        const cplx h = cmake(acc[1][mt][j][0], acc[1][mt][j][1]);
+                        o[(int64_t)jj * N + n] = x;
+                        o2[(int64_t)jj * N + n] = h;
+                        const double rr = h.x - th * x.x, ri = h.y - th * x.y;
+                        part[j] = fma(rr, rr, part[j]);
+                        part[j] = fma(ri, ri, part[j]);
+                    }
+                }
+            }
+        }
+    }
+    // sum over the 8 row groups g of the warp (lanes with equal t), then over the warps of the CTA
+#pragma unroll
+    for (int j = 0; j < NCT; ++j) {
+        part[j] += __shfl_xor_sync(0xffffffffu, part[j], 4);
+        part[j] += __shfl_xor_sync(0xffffffffu, part[j], 8);
+        part[j] += __shfl_xor_sync(0xffffffffu, part[j], 16);
+        if (g == 0) red[warp * 16 + 4 * j + t] = part[j];
+    }
+    __syncthreads();
+    if (tid < NCT * 4) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < UPD3_THREADS / 32; ++w) sacc += red[w * 16 + tid];
+        work[((int64_t)b * nchunk + chunk) * 16 + tid] = sacc;
+    }
+}
+
+__global__ void ritz_rn2_reduce_kernel(const double* __restrict__ work, int nchunk, sqc_block_t Out, int p,
+                                       double* __restrict__ rn2) {
+    const int b = blockIdx.x, j = threadIdx.x;
+    if (j >= p) return;
+    const int nb = blk_count(Out, b);
+    if (nb == 0) return;                 // inactive point: rn2 keeps its last values
+    double sacc = 0.0;
+    if (j < nb)
+        for (int c = 0; c < nchunk; ++c) sacc += work[((int64_t)b * nchunk + c) * 16 + j];
+    rn2[(int64_t)b * p + j] = sacc;
+}
+
+static int ritz_nchunk(int64_t N) {
+    const int per_cta = (UPD3_THREADS / 32) * 8 * UPD3_MT;
+    return (int)((N + per_cta - 1) / per_cta);
+}
+
+extern "C" int64_t sqc_ritz_update_work_bytes(int32_t B, int64_t N) {
+    return (int64_t)B * ritz_nchunk(N) * 16 * (int64_t)sizeof(double);
+}
+
+extern "C" int sqc_ritz_update(sqc_block_t A, sqc_block_t A2, const void* Cf, int32_t ldr, int32_t ldc,
+                               sqc_block_t Out, sqc_block_t Out2, const double* theta, int32_t ld_theta,
+                               double* rn2, void* work, int64_t N, int32_t B, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || N <= 0 || Out.cnt_fixed <= 0 || Out.cnt_fixed > 16 || A.cnt_fixed > 64 || !work || !rn2 || !theta)
+        return SQC_EINVAL;
+    if (A.cnt_fixed != A2.cnt_fixed || Out.cnt_fixed != Out2.cnt_fixed) return SQC_EINVAL;
+    const int nchunk = ritz_nchunk(N);
+    const int64_t grid = (int64_t)B * nchunk;
+    if (grid > 0x7fffffffLL) return SQC_ELIMIT;
+    const int nct = (2 * Out.cnt_fixed + 7) / 8;
+    int ldm = nct * 8;
+    while ((ldm & 15) != 4) ++ldm;
+    const int kk = (2 * (A.cnt_fixed > 0 ? A.cnt_fixed : 1) + 3) & ~3;
+    size_t smem = ((size_t)kk * ldm + (size_t)(UPD3_THREADS / 32) * UPD3_DEPTH * UPD3_SLOT + (UPD3_THREADS / 32) * 16) *
+                  sizeof(double);
+#define UPD3_CASE(NCTv)                                                                               \
+    if (nct == NCTv) {                                                                                \
+        auto kern = ritz_update_dmma_kernel<NCTv>;                                                    \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return (int)e;                                                          \
+        kern<<<(unsigned)grid, UPD3_THREADS, smem, st>>>(A, A2, (const cplx*)Cf, ldr, ldc, Out, Out2, theta, ld_theta, \
+                                                         (double*)work, N, nchunk, ldm, kk);          \
+        SQC_LAUNCHED();                                                                               \
+        ritz_rn2_reduce_kernel<<<B, 32, 0, st>>>((const double*)work, nchunk, Out, Out.cnt_fixed, rn2); \
+        SQC_LAUNCHED();                                                                               \
+        return 0;                                                                                     \
+    }
+    UPD3_CASE(1) UPD3_CASE(2) UPD3_CASE(3) UPD3_CASE(4)
+#undef UPD3_CASE
+    return SQC_ELIMIT;
+}
+
 // In-place right multiplication of a (<=16 vector) block by a small matrix.
 __global__ void __launch_bounds__(UPD_THREADS)
 block_rightmul_kernel(sqc_block_t T, const cplx* __restrict__ Cq, int ldr, int ldc,

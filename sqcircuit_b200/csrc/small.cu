@@ -85,8 +85,14 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
             }
             __syncthreads();
             // A <- J^H A J on 2x2 blocks (pair P of rows, pair Q of columns)
-            for (int blk = tid; blk < half * half; blk += nt) {
-                const int P = blk / half, Q = blk % half;
+            // Hermitian: only the blocks P <= Q are rotated (block (Q, P) is written as the mirror).
+            // The upper triangle is enumerated densely so that whole warps drop out: FP64 issue
+            // slots, not threads, are what this kernel runs out of.
+            for (int u = tid; u < half * (half + 1) / 2; u += nt) {
+                int P = (int)((2 * half + 1 - sqrtf((float)((2 * half + 1) * (2 * half + 1) - 8 * u))) * 0.5f);
+                while (P > 0 && P * half - P * (P - 1) / 2 > u) --P;
+                while ((P + 1) * half - (P + 1) * P / 2 <= u) ++P;
+                const int Q = P + (u - (P * half - P * (P - 1) / 2));
                 const int p = prs[2 * P], q = prs[2 * P + 1], pc = prs[2 * Q], qc = prs[2 * Q + 1];
                 const double cP = rot[4 * P], sP = rot[4 * P + 1];
                 const cplx eP = cmake(rot[4 * P + 2], rot[4 * P + 3]);
@@ -119,6 +125,12 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
                 A[p * lda + qc] = o01;
                 A[q * lda + pc] = o10;
                 A[q * lda + qc] = o11;
+                if (P != Q) {
+                    A[pc * lda + p] = cconj(o00);
+                    A[qc * lda + p] = cconj(o01);
+                    A[pc * lda + q] = cconj(o10);
+                    A[qc * lda + q] = cconj(o11);
+                }
             }
             // Zt rows:  z_p <- c z_p - s conj(e) z_q ;  z_q <- s z_p + c conj(e) z_q
             for (int e = tid; e < half * n; e += nt) {

@@ -101,7 +101,10 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
         # neighbouring sweep points).  Block 0 is orthonormalised in place (SVQB x2); block 1 is
         # orthogonalised against block 0 and itself exactly like a Davidson expansion block.
         nblk = x0.shape[1] // p
-        V[:, :nblk * p, :] = x0[:, :nblk * p, :]
+        if hasattr(x0, 'write_into'):
+            x0.write_into(kern, V)
+        else:
+            V[:, :nblk * p, :] = x0[:, :nblk * p, :]
         msz.zero_()
         for blk in range(nblk):
             Tb = BlockView(V, cnt_fixed=p, off=msz, cnt=nact)
@@ -195,6 +198,26 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
                      ritz_block=Xb)
 
 
+class RitzPairStart:
+    """Warm start = union of the Ritz blocks of two solved sweep points per point, gathered from a
+    pool ``store`` [S][p][N] straight into the basis buffer (one kernel, no [B][2p][N] staging)."""
+
+    def __init__(self, store, ia, ib):
+        self.store, self.ia, self.ib = store, ia, ib
+        self.p = store.shape[1]
+        self.shape = (ia.shape[0], 2 * self.p, store.shape[2])
+
+    def write_into(self, kern, V):
+        p, dev = self.p, V.device
+        pool = self.store.reshape(1, -1, self.store.shape[2])
+        oa = (self.ia.to(device=dev, dtype=torch.int64) * p).to(torch.int32)
+        ob = (self.ib.to(device=dev, dtype=torch.int64) * p).to(torch.int32)
+        ones = torch.ones((V.shape[0],), dtype=torch.int32, device=dev)
+        kern.restart_copy(BlockView(pool, cnt_fixed=p, off=oa, stride_b=0),
+                          BlockView(pool, cnt_fixed=p, off=ob, stride_b=0),
+                          BlockView(V, cnt_fixed=p), BlockView(V, cnt_fixed=p, first=p), ones)
+
+
 DETAIL_STATS = None
 
 
@@ -211,7 +234,7 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
 
     The basis V is allowed to be non-orthogonal inside a restart cycle; Rayleigh-Ritz is the
     generalised problem GA c = theta GB c with GB = V^H V (``sqc_gen_rr``).  Per iteration the
-    basis is streamed three times instead of seven: X = V c, HX = W c (``sqc_block_update``) and ONE
+    basis is streamed three times instead of seven: X = V c, HX = W c (``sqc_ritz_update``) and ONE
     paired Gram pass that produces the new columns of GA and GB together (``sqc_gram_pair``); the
     CGS2 / SVQB passes of ``solve_davidson`` disappear.  Thick restarts (V <- Ritz vectors, which
     are GB-orthonormal) put the basis back to an orthonormal one.  Same convergence and accuracy
@@ -231,8 +254,8 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
     # restart.  An iteration that restarts writes its Ritz block straight into rows [0, p) (the
     # update kernel reads every basis row of a position before it writes that position), so there
     # is no restart copy; sqc_davidson_decide plans the restart one iteration ahead (xoff / xlast).
-    V = torch.empty((B, mmax + p, N), dtype=c128, device=dev)
-    W = torch.empty((B, mmax + p, N), dtype=c128, device=dev)
+    V = kern.workspace('davidson_V', (B, mmax + p, N), c128)
+    W = kern.workspace('davidson_W', (B, mmax + p, N), c128)
     GA = torch.zeros((B, ld, ld), dtype=c128, device=dev)
     GB = torch.zeros((B, ld, ld), dtype=c128, device=dev)
     Zt = torch.zeros((B, ld, ld), dtype=c128, device=dev)
@@ -263,7 +286,10 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
         GB[:, :p, :p] = torch.eye(p, dtype=c128, device=dev)
     else:
         m0 = min(x0.shape[1], mmax)
-        V[:, :m0, :] = x0[:, :m0, :]
+        if hasattr(x0, 'write_into'):
+            x0.write_into(kern, V)         # gather straight into the basis (no staging copy)
+        else:
+            V[:, :m0, :] = x0[:, :m0, :]
         msz.fill_(m0)
         Vi = BlockView(V, cnt_fixed=mmax, cnt=msz)
         Wi = BlockView(W, cnt_fixed=mmax, cnt=msz)
@@ -307,9 +333,7 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
                 lowblock = op.build_lowblock(sigma, lowblock_ns)
         Xv.cnt = xcnt
         HXv.cnt = xcnt
-        kern.block_update(Vm, Zt, Xv, op=0, trans=0)
-        kern.block_update(Wm, Zt, HXv, op=0, trans=0)
-        kern.residual_norms(Xv, HXv, theta, rn2)
+        kern.ritz_update(Vm, Wm, Zt, Xv, HXv, theta, rn2)       # X = V c, HX = W c, ||HX - theta X||^2
         kern.davidson_decide(st, B)
         left = int(n_not_done.item())
         if stats is not None:

@@ -18,20 +18,25 @@ def _off(blk, b):
     return blk.first + (int(blk.off[b]) if blk.off is not None else 0)
 
 
+def _bi(blk, b):
+    """index of sweep point b in the tensor (0 for a shared pool, stride_b == 0)"""
+    return 0 if getattr(blk, 'stride_b', None) == 0 else b
+
+
 def _get(blk, b):
     o, c = _off(blk, b), _cnt(blk, b)
-    return blk.tensor[b, o:o + c, :].numpy()
+    return blk.tensor[_bi(blk, b), o:o + c, :].numpy()
 
 
 def _rows(blk, b):
     """all cnt_fixed rows of the block of sweep point b (Ritz index addressing)"""
     o = _off(blk, b)
-    return blk.tensor[b, o:o + blk.cnt_fixed, :].numpy()
+    return blk.tensor[_bi(blk, b), o:o + blk.cnt_fixed, :].numpy()
 
 
 def _set(blk, b, arr):
     o = _off(blk, b)
-    blk.tensor[b, o:o + arr.shape[0], :] = torch.from_numpy(np.ascontiguousarray(arr))
+    blk.tensor[_bi(blk, b), o:o + arr.shape[0], :] = torch.from_numpy(np.ascontiguousarray(arr))
 
 
 class EmulKernels:
@@ -40,6 +45,9 @@ class EmulKernels:
     def __init__(self):
         self.dev = torch.device('cpu')
         self.launches = 0
+
+    def workspace(self, key, shape, dtype):
+        return torch.empty(tuple(int(d) for d in shape), dtype=dtype)
 
     def launch_count(self):
         return self.launches
@@ -275,6 +283,21 @@ class EmulKernels:
                 r = _get(Out, b) - r
             _set(Out, b, r)
 
+    def ritz_update(self, A, A2, Cf, Out, Out2, theta, rn2):
+        for b in range(A.B):
+            nb = _cnt(Out, b)
+            if nb == 0:
+                continue
+            a, a2 = _get(A, b).copy(), _get(A2, b).copy()
+            co = Cf[b].numpy()[:nb, :a.shape[0]]
+            x, hx = co @ a, co @ a2
+            _set(Out, b, x)
+            _set(Out2, b, hx)
+            rn2[b] = 0
+            for j in range(nb):
+                r = hx[j] - float(theta[b, j]) * x[j]
+                rn2[b, j] = float(np.vdot(r, r).real)
+
     def block_rightmul(self, T, Cq, nout):
         for b in range(T.B):
             nin = _cnt(T, b)
@@ -375,7 +398,7 @@ class EmulKernels:
                 st.mtot[b] = int(st.msz[b]) + n
 
     def restart_copy(self, X, HX, V, W, restart):
-        for b in range(X.B):
+        for b in range(V.B):
             if int(restart[b]):
                 _set(V, b, _get(X, b))
                 _set(W, b, _get(HX, b))

@@ -456,3 +456,32 @@ def test_davidson_decide_matches_emulation(kern, planned):
         tc['msz'] += tc['nact']
         tg['msz'] += tg['nact']
         assert int(tc['msz'].max()) <= mmax
+
+
+@pytest.mark.parametrize('B,mm,p,N', [(3, 40, 12, 10100), (5, 20, 6, 777), (2, 64, 16, 1000), (4, 12, 4, 130)])
+def test_ritz_update(kern, B, mm, p, N):
+    """Fused X = C V, HX = C W, ||HX - theta X||^2 against the emulation, with per-point basis
+    sizes, an inactive point, and the Ritz block aliasing the leading basis rows (planned restart)."""
+    V, W = rnd((B, mm + p, N), 41), rnd((B, mm + p, N), 42)
+    Cf = rnd((B, mm, mm), 43)
+    theta = torch.randn((B, mm), dtype=torch.float64, generator=torch.Generator().manual_seed(44))
+    msz = torch.randint(p, mm + 1, (B,), generator=torch.Generator().manual_seed(45)).to(torch.int32)
+    msz[0] = mm
+    xcnt = torch.full((B,), p, dtype=torch.int32)
+    xcnt[-1] = 0                                     # inactive sweep point
+    xoff = torch.full((B,), mm, dtype=torch.int32)
+    xoff[0] = 0                                      # in place over the first p basis vectors
+    rv, rw = V.clone(), W.clone()
+    rn_ref = torch.full((B, p), 3.0, dtype=torch.float64)
+    EmulKernels().ritz_update(BlockView(rv, cnt_fixed=mm, cnt=msz), BlockView(rw, cnt_fixed=mm, cnt=msz), Cf,
+                              BlockView(rv, cnt_fixed=p, off=xoff, cnt=xcnt),
+                              BlockView(rw, cnt_fixed=p, off=xoff, cnt=xcnt), theta, rn_ref)
+    Vd, Wd = V.cuda(), W.cuda()
+    rn = torch.full((B, p), 3.0, dtype=torch.float64, device='cuda')
+    mszd, xcd, xod = msz.cuda(), xcnt.cuda(), xoff.cuda()
+    kern.ritz_update(BlockView(Vd, cnt_fixed=mm, cnt=mszd), BlockView(Wd, cnt_fixed=mm, cnt=mszd), Cf.cuda(),
+                     BlockView(Vd, cnt_fixed=p, off=xod, cnt=xcd), BlockView(Wd, cnt_fixed=p, off=xod, cnt=xcd),
+                     theta.cuda(), rn)
+    assert relerr(Vd.cpu(), rv) < 1e-13 and relerr(Wd.cpu(), rw) < 1e-13
+    assert float((rn.cpu() - rn_ref).abs().max() / rn_ref.abs().max()) < 1e-12
+    assert torch.equal(rn.cpu()[-1], torch.full((p,), 3.0, dtype=torch.float64))
