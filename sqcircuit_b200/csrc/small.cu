@@ -3,10 +3,21 @@
 // block-Davidson bookkeeping.  One CTA per sweep point.
 #include <math.h>
 #include "common.cuh"
+#ifdef RR_PROFILE
+#include <cstdio>
+#endif
 
 #define JAC_THREADS 512
 #define JAC_MAX_SWEEPS 30
 #define JAC_BIG 1.0e300
+
+// u-th block (P <= Q) of the upper triangle of a half x half block grid, row by row
+__device__ __forceinline__ void tri_index(int u, int half, int& P, int& Q) {
+    P = (int)((2 * half + 1 - sqrtf((float)((2 * half + 1) * (2 * half + 1) - 8 * u))) * 0.5f);
+    while (P > 0 && P * half - P * (P - 1) / 2 > u) --P;
+    while ((P + 1) * half - (P + 1) * P / 2 <= u) ++P;
+    Q = P + (u - (P * half - P * (P - 1) / 2));
+}
 
 // Parallel cyclic (round-robin) two-sided Jacobi for an n x n Hermitian matrix.
 //   A  : np x np complex, leading dim lda (shared memory), np even, rows/cols >= n are padding
@@ -24,8 +35,22 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
         Zt[r * ldz + c] = (r == c) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
     }
     __syncthreads();
+    // thread teams of the rotation phase: the first na_thr threads rotate the 2x2 blocks of the upper
+    // triangle of A (one block each for n <= 62), the others the eigenvector rows -- side by side
+    // instead of one after the other, the phase is latency bound
+    const int ntri = half * (half + 1) / 2;
+    int na_thr = (ntri + 31) & ~31;
+    if (na_thr > nt - 128) na_thr = nt / 2;
+    int P0 = 0, Q0 = 0;
+    if (tid < ntri) tri_index(tid, half, P0, Q0);
+#ifdef RR_PROFILE
+    long long tpa = 0, tpb = 0, tpc = 0, t0p;
+#endif
     bool polish = false;
     for (int sweep = 0; sweep < JAC_MAX_SWEEPS; ++sweep) {
+#ifdef RR_PROFILE
+        t0p = clock64();
+#endif
         // convergence test: off-diagonal vs diagonal Frobenius mass (real rows only)
         double off = 0.0, dg = 0.0;
         for (int e = tid; e < n * n; e += nt) {
@@ -55,10 +80,22 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
         __syncthreads();
         // quadratic convergence: once the off-diagonal mass is below 1e-11 relative, one more
         // sweep leaves it at rounding level
+#ifdef RR_PROFILE
+        if ((o == 0.0 || polish) && blockIdx.x == 0 && tid == 0) printf("  jacobi n=%d sweeps %d  cycles: params %lld apply %lld conv-test %lld\n", n, sweep, tpa, tpb, tpc);
+#endif
         if (o == 0.0 || polish) break;
+#ifdef RR_PROFILE
+        tpc += clock64() - t0p;
+#endif
         if (o <= 1e-22 * (d + o)) polish = true;
+        // single-precision rotation angles only while the off-diagonal mass is large: their 1e-7
+        // remnants would break the quadratic end game the polish rule relies on
+        const bool fast_angle = o > 1e-8 * (d + o);
 
         for (int step = 0; step < np - 1; ++step) {
+#ifdef RR_PROFILE
+            t0p = clock64();
+#endif
             // schedule + rotation parameters
             for (int k = tid; k < half; k += nt) {
                 int p = (k == 0) ? np - 1 : (step + k) % (np - 1);
@@ -68,15 +105,30 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
                 prs[2 * k + 1] = q;
                 const double a = A[p * lda + p].x, dd = A[q * lda + q].x;
                 const cplx b = A[p * lda + q];
-                const double ab = hypot(b.x, b.y);
+                // this scalar chain is the critical path of a Jacobi step (every other thread waits
+                // for it at the barrier): reciprocal square roots instead of hypot / sqrt / divisions
+                const double ab2 = b.x * b.x + b.y * b.y;
                 double c = 1.0, s = 0.0, ex = 1.0, ey = 0.0;
-                if (ab > 0.0 && ab > 1e-17 * (fabs(a) + fabs(dd)) && p < n && q < n) {
-                    const double th = (dd - a) / (2.0 * ab);
-                    const double t = copysign(1.0, th) / (fabs(th) + sqrt(th * th + 1.0));
-                    c = 1.0 / sqrt(1.0 + t * t);
+                const double lim = 1e-17 * (fabs(a) + fabs(dd));
+                if (ab2 > 0.0 && ab2 > lim * lim && p < n && q < n) {
+                    // phase of the pivot: exact to double precision (unitarity), off the angle's path
+                    const double iab = rsqrt(ab2);
+                    ex = b.x * iab;
+                    ey = b.y * iab;
+                    // tangent of the rotation angle in SINGLE precision: its error only leaves a
+                    // 1e-7-relative remnant of the pivot for the next sweep, while (c, s) below are
+                    // normalised in double, so the transformation stays unitary to rounding
+                    const float ab2f = (float)ab2;
+                    double t;
+                    if (fast_angle && ab2f > 1e-30f && ab2f < 1e30f) {
+                        const float thf = 0.5f * (float)(dd - a) * rsqrtf(ab2f);
+                        t = (double)(copysignf(1.0f, thf) / (fabsf(thf) + sqrtf(fmaf(thf, thf, 1.0f))));
+                    } else {                    // outside the single-precision range: all in double
+                        const double th = 0.5 * (dd - a) * iab;
+                        t = copysign(1.0, th) / (fabs(th) + sqrt(th * th + 1.0));
+                    }
+                    c = rsqrt(fma(t, t, 1.0));
                     s = t * c;
-                    ex = b.x / ab;
-                    ey = b.y / ab;
                 }
                 rot[4 * k] = c;
                 rot[4 * k + 1] = s;
@@ -84,15 +136,17 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
                 rot[4 * k + 3] = ey;
             }
             __syncthreads();
+#ifdef RR_PROFILE
+            tpa += clock64() - t0p;
+            t0p = clock64();
+#endif
             // A <- J^H A J on 2x2 blocks (pair P of rows, pair Q of columns)
             // Hermitian: only the blocks P <= Q are rotated (block (Q, P) is written as the mirror).
             // The upper triangle is enumerated densely so that whole warps drop out: FP64 issue
             // slots, not threads, are what this kernel runs out of.
-            for (int u = tid; u < half * (half + 1) / 2; u += nt) {
-                int P = (int)((2 * half + 1 - sqrtf((float)((2 * half + 1) * (2 * half + 1) - 8 * u))) * 0.5f);
-                while (P > 0 && P * half - P * (P - 1) / 2 > u) --P;
-                while ((P + 1) * half - (P + 1) * P / 2 <= u) ++P;
-                const int Q = P + (u - (P * half - P * (P - 1) / 2));
+            for (int u = tid; u < ntri && tid < na_thr; u += na_thr) {
+                int P = P0, Q = Q0;
+                if (u != tid) tri_index(u, half, P, Q);
                 const int p = prs[2 * P], q = prs[2 * P + 1], pc = prs[2 * Q], qc = prs[2 * Q + 1];
                 const double cP = rot[4 * P], sP = rot[4 * P + 1];
                 const cplx eP = cmake(rot[4 * P + 2], rot[4 * P + 3]);
@@ -117,8 +171,10 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
                     o00.y = 0.0;
                     o11.y = 0.0;
                     if (sP != 0.0) {
-                        o01 = cmake(0.0, 0.0);
-                        o10 = cmake(0.0, 0.0);
+                        // exact angle: the pivot is annihilated (set it to a clean zero); single-
+                        // precision angle: keep the true remnant, or the similarity would be off by it
+                        o01 = fast_angle ? o01 : cmake(0.0, 0.0);
+                        o10 = cconj(o01);
                     }
                 }
                 A[p * lda + pc] = o00;
@@ -133,7 +189,7 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
                 }
             }
             // Zt rows:  z_p <- c z_p - s conj(e) z_q ;  z_q <- s z_p + c conj(e) z_q
-            for (int e = tid; e < half * n; e += nt) {
+            for (int e = tid - na_thr; e < half * n && e >= 0; e += nt - na_thr) {
                 const int P = e / n, i = e % n;
                 const double sP = rot[4 * P + 1];
                 if (sP == 0.0) continue;
@@ -145,6 +201,9 @@ __device__ void jacobi_heev(cplx* A, int n, int np, int lda, cplx* Zt, int ldz, 
                 Zt[q * ldz + i] = cadd(cscale(sP, zp), cscale(cP, zq));
             }
             __syncthreads();
+#ifdef RR_PROFILE
+            tpb += clock64() - t0p;
+#endif
         }
     }
 }
@@ -160,10 +219,10 @@ heev_kernel(const cplx* __restrict__ Ain, const int32_t* __restrict__ nArr, int 
     const int b = blockIdx.x;
     const int n = nArr ? nArr[b] : n_fixed;
     const int np = (n + 1) & ~1;
-    const int lda = np_max;
+    const int lda = np_max | 1;   // odd (complex elements): a column walk touches every bank
     cplx* A = reinterpret_cast<cplx*>(smem);
-    cplx* Zs = A + (size_t)np_max * np_max;
-    double* rot = reinterpret_cast<double*>(ZSMEM ? Zs + (size_t)np_max * np_max : Zs);
+    cplx* Zs = A + (size_t)np_max * lda;
+    double* rot = reinterpret_cast<double*>(ZSMEM ? Zs + (size_t)np_max * lda : Zs);
     double* red = rot + 2 * np_max;
     int* prs = reinterpret_cast<int*>(red + 64);
     int* rank = prs + np_max;
@@ -181,7 +240,7 @@ heev_kernel(const cplx* __restrict__ Ain, const int32_t* __restrict__ nArr, int 
     }
     __syncthreads();
     cplx* Z = ZSMEM ? Zs : zglob;
-    const int ldz = ZSMEM ? np_max : ld;
+    const int ldz = ZSMEM ? lda : ld;
     jacobi_heev(A, n, np, lda, Z, ldz, rot, prs, red);
     // sort ascending
     for (int i = tid; i < n; i += JAC_THREADS) wv[i] = A[i * lda + i].x;
@@ -237,7 +296,7 @@ extern "C" int sqc_heev(const void* A, const int32_t* n, int32_t n_fixed, int32_
     if (B <= 0 || ld <= 0 || ld > 112 || n_fixed > ld) return SQC_EINVAL;
     const int np_max = (ld + 1) & ~1;
     const bool zs = np_max <= 64;
-    size_t bytes = (size_t)np_max * np_max * sizeof(cplx) * (zs ? 2 : 1);
+    size_t bytes = (size_t)np_max * (np_max | 1) * sizeof(cplx) * (zs ? 2 : 1);
     bytes += (2 * np_max + 64) * sizeof(double) + (2 * np_max + 2) * sizeof(int) + np_max * sizeof(double) + 16;
     cudaError_t e;
     if (zs) {
@@ -270,11 +329,11 @@ gen_rr_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
     const int n = nArr[b];
     if (n <= 0) return;
     const int np = (n + 1) & ~1;
-    const int lda = np_max;
+    const int lda = np_max | 1;   // odd (complex elements): a column walk touches every bank
     cplx* A = reinterpret_cast<cplx*>(smem);               // GA -> M -> eigenvalues on the diagonal
-    cplx* Lm = A + (size_t)np_max * np_max;                 // GB -> L -> tmp -> Jacobi vectors
-    cplx* Zs = Lm + (size_t)np_max * np_max;                // L^-1
-    double* rot = reinterpret_cast<double*>(Zs + (size_t)np_max * np_max);
+    cplx* Lm = A + (size_t)np_max * lda;                    // GB -> L -> tmp -> Jacobi vectors
+    cplx* Zs = Lm + (size_t)np_max * lda;                   // L^-1
+    double* rot = reinterpret_cast<double*>(Zs + (size_t)np_max * lda);
     double* red = rot + 2 * np_max;
     double* gbd = red + 64;                                 // original diagonal of GB
     double* wv = gbd + np_max;
@@ -282,6 +341,13 @@ gen_rr_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
     int* rank = prs + np_max;
     int* dead = rank + np_max;
     const int tid = threadIdx.x;
+#ifdef RR_PROFILE
+    long long tp[8]; int tpi = 0;
+#define RR_MARK() do { __syncthreads(); tp[tpi++] = clock64(); } while (0)
+#else
+#define RR_MARK() do {} while (0)
+#endif
+    RR_MARK();
     const cplx* ga = GAin + (int64_t)b * ld * ld;
     const cplx* gb = GBin + (int64_t)b * ld * ld;
     for (int e = tid; e < n * n; e += JAC_THREADS) {
@@ -298,6 +364,7 @@ gen_rr_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
     }
     __syncthreads();
     // ---- Cholesky (lower), in place ----
+    RR_MARK();
     for (int j = 0; j < n; ++j) {
         if (tid == 0) {
             const double d = Lm[j * lda + j].x;
@@ -332,6 +399,7 @@ gen_rr_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
         __syncthreads();
     }
     // removed (dependent) vectors contribute nothing
+    RR_MARK();
     for (int e = tid; e < n * n; e += JAC_THREADS) {
         const int r = e / n, c = e % n;
         if (dead[r] || dead[c]) A[r * lda + c] = cmake(0.0, 0.0);
@@ -351,6 +419,7 @@ gen_rr_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
     }
     __syncthreads();
     // ---- Lm = Zs * A ;  A = Lm * Zs^H ----
+    RR_MARK();
     for (int e = tid; e < n * n; e += JAC_THREADS) {
         const int r = e / n, c = e % n;
         cplx acc = cmake(0.0, 0.0);
@@ -365,6 +434,7 @@ gen_rr_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
         A[r * lda + c] = acc;
     }
     // alive index list (compaction of the removed vectors)
+    RR_MARK();
     __shared__ int s_na;
     if (tid == 0) {
         int cnt = 0;
@@ -387,7 +457,9 @@ gen_rr_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
     // dead[] is reused as the alive list because rank[] / prs[] are scratch of the Jacobi + sort
     for (int i = tid; i < na; i += JAC_THREADS) dead[i] = rank[i];
     __syncthreads();
+    RR_MARK();
     jacobi_heev(Lm, na, npa, lda, A, lda, rot, prs, red);     // eigenvectors: rows of A
+    RR_MARK();
     for (int i = tid; i < na; i += JAC_THREADS) wv[i] = Lm[i * lda + i].x;
     __syncthreads();
     for (int i = tid; i < na; i += JAC_THREADS) {
@@ -413,13 +485,19 @@ gen_rr_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
         }
         zg[rank[j] * ld + i] = acc;
     }
+#ifdef RR_PROFILE
+    RR_MARK();
+    if (b == 0 && tid == 0)
+        printf("gen_rr n=%d na=%d cycles: load %lld chol %lld inv %lld mm %lld compact %lld jacobi %lld back %lld\n", n, na,
+               tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4], tp[6] - tp[5], tp[7] - tp[6]);
+#endif
 }
 
 extern "C" int sqc_gen_rr(const void* GA, const void* GB, const int32_t* n, int32_t ld, double drop,
                           double* w, void* Zt, int32_t B, void* stream) {
     if (B <= 0 || ld <= 0 || ld > 68 || !n) return SQC_EINVAL;
     const int np_max = (ld + 1) & ~1;
-    size_t bytes = 3 * (size_t)np_max * np_max * sizeof(cplx) + (4 * np_max + 64) * sizeof(double) +
+    size_t bytes = 3 * (size_t)np_max * (np_max | 1) * sizeof(cplx) + (4 * np_max + 64) * sizeof(double) +
                    (3 * np_max + 4) * sizeof(int) + 16;
     if (bytes > 227 * 1024) return SQC_ELIMIT;
     cudaError_t e = cudaFuncSetAttribute(gen_rr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
