@@ -173,7 +173,7 @@ class TimedKernels:
     """Wraps the CUDA backend: CUDA events on the launching stream around every C-ABI call,
     so per-kernel device time is measured live inside the timed region (no profiler)."""
     TIMED = ['hx_fused', 'mode_transform', 'potential_apply', 'gram', 'gram_pair', 'gen_rr', 'davidson_insert2',
-             'lowblock_assemble', 'hpd_inverse_c64', 'lowblock_apply', 'block_update', 'ritz_update', 'block_rightmul', 'heev',
+             'lowblock_assemble', 'hpd_inverse_c64', 'lowblock_apply', 'lowband_factor', 'lowband_apply', 'block_update', 'ritz_update', 'block_rightmul', 'heev',
              'residual_norms', 'precond_residual', 'restart_copy', 'svqb_coeffs', 'davidson_decide',
              'davidson_insert', 'diag_mul', 'ladder_apply']
 
@@ -430,7 +430,7 @@ def main():
     ap.add_argument('--points', type=int, default=POINTS, help='sweep points per GPU')
     ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--mmax', type=int, default=None, help='maximum Davidson basis size (default 4 x block)')
-    ap.add_argument('--lowblock', type=int, default=160)
+    ap.add_argument('--lowblock', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

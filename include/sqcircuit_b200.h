@@ -263,6 +263,22 @@ int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const doubl
                        int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int32_t group,
                        int64_t N, int32_t B, void* stream);
 
+/* Banded form of the two-level preconditioner for LARGE low-energy blocks (ns up to 1024).
+ * With the index set ordered charge-major (all kept Fock states of charge q form block q, index
+ * range [blk_off[q], blk_off[q+1])), H_SS is block tridiagonal (junction charge shifts in {-1,0,1}).
+ *  - factor: A ([B][ns][ns] complex64 from sqc_lowblock_assemble with that ordering) gets its diagonal
+ *    blocks overwritten by the inverses P_q of the block-LDL^H Schur complements; blocks (q, q+1) stay.
+ *    blk_off: [B][ld_off] int32, nblk: [B], nbmax: largest block (<= 96).
+ *  - apply: same contract as sqc_lowblock_apply, via forward / backward block substitution
+ *    (cost ~ 3 sum_q n_q^2 per right-hand side instead of ns^2). */
+int sqc_lowband_factor(void* A, int32_t ns, const int32_t* blk_off, int32_t ld_off, const int32_t* nblk,
+                       int32_t nbmax, int32_t B, void* stream);
+int sqc_lowband_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                      int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
+                      int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
+                      int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit, int32_t group,
+                      int64_t N, int32_t B, void* stream);
+
 /* SVQB coefficients from the Gram matrix S = T^H T of the new block:
  * Cq[j][i] = D_i U_ij sigma_j^-1/2 over directions with sigma_j > drop * sigma_max;
  * nact[b] <- number kept; mtot[b] <- msz[b] + nact[b] when both pointers are given.

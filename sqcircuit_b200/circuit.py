@@ -227,7 +227,7 @@ class Circuit:
     def sweep_diag(self, n_eig, loop_fluxes: Optional[Dict] = None,
                    charge_offsets: Optional[Dict[int, Sequence[float]]] = None, tol=1e-9,
                    block_size=None, max_basis=None, maxit=300, stats=None,
-                   warm_start=True, coarse_stride=8, lowblock=160) -> SweepResult:
+                   warm_start=True, coarse_stride=8, lowblock=512) -> SweepResult:
         """Diagonalise at every point of a sweep in one batched GPU solve.
 
         loop_fluxes: {Loop: array[B]} external fluxes in units of Phi0 (as Loop.set_flux);
@@ -273,7 +273,7 @@ class Circuit:
         return out
 
     def _solve_continuation(self, ops, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats, stride,
-                            lowblock=160):
+                            lowblock=512):
         """Sweep continuation: eigenvectors vary smoothly along a sweep, so a coarse subset of the
         points is solved from a cold start and every other point starts from the union of the Ritz
         blocks of its two nearest already-solved neighbours (Rayleigh-Ritz in that subspace is

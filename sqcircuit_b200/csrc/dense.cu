@@ -18,7 +18,9 @@ long long g_sqc_launches = 0;
 // chunk and each warp keeps all (NAT x NCT) 8x8 accumulator tiles; a final shared-memory
 // reduction combines them.
 // =====================================================================================
+#ifndef GRAM_THREADS
 #define GRAM_THREADS 128
+#endif
 #define GRAM_WARPS (GRAM_THREADS / 32)
 #define GRAM_CH 32                  // complex elements per staged chunk
 #define GRAM_LD (2 * GRAM_CH + 4)   // doubles per smem row: 68 == 4 (mod 8) -> conflict-free frags

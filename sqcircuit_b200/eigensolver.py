@@ -346,7 +346,11 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
             converged = True
             break
         kern.precond_residual(Xl, HXl, Tv, theta, act, diag, den_floor)
-        if lowblock is not None:
+        if lowblock is not None and lowblock.get('band') is not None:
+            off, nblk, nbmax = lowblock['band']
+            kern.lowband_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], off, nblk, nbmax,
+                               lowblock['unit'], lowblock.get('group', 1))
+        elif lowblock is not None:
             kern.lowblock_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], lowblock['unit'],
                                 lowblock.get('group', 1))
         op.apply(Tv, HTv)

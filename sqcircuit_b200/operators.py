@@ -304,7 +304,7 @@ class HamiltonianOperator:
         the middle point of the group: the low block varies slowly along a sweep and only has to
         precondition, so one inversion per ``group`` points is enough."""
         ops, kern = self.ops, self.ops.kern
-        ns = int(min(ns, 160, ops.N // 2))
+        ns = int(min(ns, 1024, ops.N // 2))
         if group is None:
             group = LOWBLOCK_GROUP or self._auto_lowblock_group()
         group = int(max(1, min(group, self.B)))
@@ -317,9 +317,35 @@ class HamiltonianOperator:
             a, g = self.a[rep].contiguous(), self.g[rep].contiguous()
             diag = self.diag if self.diag.shape[0] == 1 else self.diag[rep].contiguous()
             sig = sigma[rep].contiguous()
-        S = torch.topk(diag, ns, dim=1, largest=False).indices.to(torch.int32).contiguous()
-        Ainv = torch.empty((nslot, ns, ns), dtype=torch.complex64, device=self.device)
         pot = ops.potential_struct(a, g, ops.etab)
+        band = None
+        if ns > 160:
+            # large block: charge-major ordering makes H_SS block tridiagonal (csrc/lowblock.cu)
+            m, inner = ops.dims
+            S = torch.topk(diag, ns, dim=1, largest=False).indices
+            key = torch.sort((S % inner) * m + S // inner, dim=1).values
+            S = ((key % m) * inner + key // m).to(torch.int32).contiguous()
+            qv = (key // m).cpu().numpy()
+            rows = qv.shape[0]
+            starts = [np.concatenate(([0], np.nonzero(np.diff(r))[0] + 1, [ns])) for r in qv]
+            nblk = np.array([len(st) - 1 for st in starts], dtype=np.int32)
+            nbmax = int(max(np.diff(st).max() for st in starts))
+            if nbmax <= 64:
+                off = np.zeros((rows, int(nblk.max()) + 1), dtype=np.int32)
+                for r, st in enumerate(starts):
+                    off[r, :len(st)] = st
+                if rows == 1 and nslot > 1:      # LC diagonal shared by all sweep points (flux sweeps)
+                    off, nblk = np.repeat(off, nslot, axis=0), np.repeat(nblk, nslot)
+                band = (torch.as_tensor(off, device=self.device), torch.as_tensor(nblk, device=self.device), nbmax)
+            else:
+                ns = 160          # blocks too large for the banded kernels: dense 160 x 160 instead
+        if band is None:
+            ns = min(ns, 160)
+            S = torch.topk(diag, ns, dim=1, largest=False).indices.to(torch.int32).contiguous()
+        Ainv = torch.empty((nslot, ns, ns), dtype=torch.complex64, device=self.device)
         kern.lowblock_assemble(ops.sp, S, ops.displacement_tables(), pot, diag, sig, unit, Ainv)
-        kern.hpd_inverse_c64(Ainv)
-        return {'S': S, 'Ainv': Ainv, 'unit': unit, 'ns': ns, 'group': group}
+        if band is None:
+            kern.hpd_inverse_c64(Ainv)
+        else:
+            kern.lowband_factor(Ainv, band[0], band[1], band[2])
+        return {'S': S, 'Ainv': Ainv, 'unit': unit, 'ns': ns, 'group': group, 'band': band}

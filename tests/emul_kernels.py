@@ -461,6 +461,51 @@ class EmulKernels:
                 t[jj][s] = ai @ r / unit
             _set(T, b, t)
 
+    def lowband_factor(self, A, blk_off, nblk, nbmax):
+        """block LDL^H of the block-tridiagonal matrix: diagonal blocks <- inverse Schur complements"""
+        for b in range(A.shape[0]):
+            a = A[b].numpy().astype(complex)
+            off = blk_off[b].numpy()
+            pprev = None
+            for q in range(int(nblk[b])):
+                o, o1 = int(off[q]), int(off[q + 1])
+                m = a[o:o1, o:o1].copy()
+                if q > 0:
+                    op = int(off[q - 1])
+                    e = a[op:o, o:o1]
+                    m = m - e.conj().T @ pprev @ e
+                pprev = np.linalg.inv(m)
+                a[o:o1, o:o1] = pprev
+            A[b] = torch.from_numpy(a.astype(np.complex64))
+
+    def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1):
+        for b in range(X.B):
+            n = _cnt(T, b)
+            if n == 0:
+                continue
+            sl = b // group
+            s = S[min(sl, S.shape[0] - 1)].numpy()
+            a = Afac[sl].numpy().astype(complex)
+            off = blk_off[sl].numpy()
+            nb = int(nblk[sl])
+            x, hx = _rows(X, b), _rows(HX, b)
+            t = _get(T, b).copy()
+            for jj in range(n):
+                av = int(act[b, jj])
+                v = (hx[av][s] - float(theta[b, av]) * x[av][s]) / unit
+                for q in range(nb):
+                    o, o1 = int(off[q]), int(off[q + 1])
+                    y = v[o:o1].copy()
+                    if q > 0:
+                        op = int(off[q - 1])
+                        y = y - a[op:o, o:o1].conj().T @ v[op:o]
+                    v[o:o1] = a[o:o1, o:o1] @ y
+                for q in range(nb - 2, -1, -1):
+                    o, o1, o2 = int(off[q]), int(off[q + 1]), int(off[q + 2])
+                    v[o:o1] = v[o:o1] - a[o:o1, o:o1] @ (a[o:o1, o1:o2] @ v[o1:o2])
+                t[jj][s] = v
+            _set(T, b, t)
+
     def svqb_coeffs(self, S, nact, drop, Cq, msz=None, mtot=None):
         B, ld, _ = S.shape
         for b in range(B):

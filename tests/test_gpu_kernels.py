@@ -485,3 +485,57 @@ def test_ritz_update(kern, B, mm, p, N):
     assert relerr(Vd.cpu(), rv) < 1e-13 and relerr(Wd.cpu(), rw) < 1e-13
     assert float((rn.cpu() - rn_ref).abs().max() / rn_ref.abs().max()) < 1e-12
     assert torch.equal(rn.cpu()[-1], torch.full((p,), 3.0, dtype=torch.float64))
+
+
+def test_lowband_factor_and_apply(kern):
+    """Banded two-level preconditioner: block-LDL^H factor and substitution against the emulation and
+    against a dense solve of the same block-tridiagonal Hermitian positive definite matrices."""
+    rng = np.random.default_rng(7)
+    sizes = [[3, 7, 12, 17, 12, 6, 3], [5, 5, 20, 20, 10], [60]]
+    B, ns, N, p = 5, 60, 500, 6
+    nslot, group = 3, 2
+    off = np.zeros((nslot, 8), dtype=np.int32)
+    nblk = np.zeros(nslot, dtype=np.int32)
+    A = np.zeros((nslot, ns, ns), dtype=complex)
+    for sl, sz in enumerate(sizes):
+        o = np.concatenate(([0], np.cumsum(sz)))
+        off[sl, :len(o)] = o
+        nblk[sl] = len(sz)
+        for q in range(len(sz)):
+            a, b_ = o[q], o[q + 1]
+            d = rng.standard_normal((sz[q], sz[q])) + 1j * rng.standard_normal((sz[q], sz[q]))
+            A[sl, a:b_, a:b_] = d @ d.conj().T / sz[q] + 4 * np.eye(sz[q])
+            if q + 1 < len(sz):
+                c = o[q + 2]
+                e = 0.5 * (rng.standard_normal((sz[q], sz[q + 1])) + 1j * rng.standard_normal((sz[q], sz[q + 1])))
+                A[sl, a:b_, b_:c] = e
+                A[sl, b_:c, a:b_] = e.conj().T
+    A64 = torch.from_numpy(A.astype(np.complex64))
+    offt, nbt = torch.from_numpy(off), torch.from_numpy(nblk)
+    E = EmulKernels()
+    fref = A64.clone()
+    E.lowband_factor(fref, offt, nbt, 60)
+    fac = A64.clone().cuda()
+    kern.lowband_factor(fac, offt.cuda(), nbt.cuda(), 60)
+    assert relerr(fac.cpu().to(torch.complex128), fref.to(torch.complex128)) < 2e-5
+    S = torch.stack([torch.randperm(N, generator=torch.Generator().manual_seed(s))[:ns] for s in range(nslot)]).to(torch.int32)
+    X, HX = rnd((B, p, N), 51), rnd((B, p, N), 52)
+    Vb = rnd((B, 20, N), 53)
+    theta = torch.randn((B, 48), dtype=torch.float64, generator=torch.Generator().manual_seed(54))
+    msz = torch.tensor([6, 10, 14, 3, 8], dtype=torch.int32)
+    nact = torch.tensor([6, 2, 0, 4, 1], dtype=torch.int32)
+    act = torch.tensor([[0, 1, 2, 3, 4, 5], [4, 1, 0, 0, 0, 0], [0] * 6, [5, 3, 2, 0, 0, 0], [2, 0, 0, 0, 0, 0]], dtype=torch.int32)
+    refV = Vb.clone()
+    E.lowband_apply(BlockView(X), BlockView(HX), BlockView(refV, cnt_fixed=p, off=msz, cnt=nact), theta, act, S,
+                    fref, offt, nbt, 60, 2.0, group=group)
+    Vd = Vb.cuda()
+    kern.lowband_apply(BlockView(X.cuda()), BlockView(HX.cuda()), BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()),
+                       theta.cuda(), act.cuda(), S.cuda(), fac, offt.cuda(), nbt.cuda(), 60, 2.0, group=group)
+    assert relerr(Vd.cpu(), refV) < 2e-5
+    # the substitution really solves the block-tridiagonal system
+    b, jj = 0, 1
+    s = S[0].long().numpy()
+    r = (HX[b, jj].numpy()[s] - float(theta[b, jj]) * X[b, jj].numpy()[s]) / 2.0
+    sol = np.linalg.solve(A[0], r)
+    got = Vd.cpu()[b, int(msz[b]) + jj].numpy()[s]
+    assert np.abs(got - sol).max() / np.abs(sol).max() < 1e-4

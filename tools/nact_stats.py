@@ -15,7 +15,8 @@ cr.set_trunc_nums([100, 50])
 fl = np.linspace(0.0, 1.0, points)
 eigensolver.DETAIL_STATS = []
 stats = []
-res = cr.sweep_diag(10, loop_fluxes={loop: fl}, tol=1e-9, stats=stats, lowblock=160)
+LB = int(sys.argv[2]) if len(sys.argv) > 2 else 160
+res = cr.sweep_diag(10, loop_fluxes={loop: fl}, tol=1e-9, stats=stats, lowblock=LB)
 tot = dict(cols=0, colmax=0, tiles=0, tilemax=0, rows=0)
 print('it B left nact_sum msz_sum tiles restarts')
 for (it, B, left, na, ms, tl, rs) in eigensolver.DETAIL_STATS:
@@ -38,7 +39,7 @@ _c._davidson = timed
 for rep in range(2):
     times.clear()
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    res = cr.sweep_diag(10, loop_fluxes={loop: fl}, tol=1e-9, lowblock=160)
+    res = cr.sweep_diag(10, loop_fluxes={loop: fl}, tol=1e-9, lowblock=LB)
     torch.cuda.synchronize(); tt = (time.perf_counter() - t0) * 1e3
     print('sweep total ms', round(tt, 1), 'levels (B, its, ms):', [(b, i, round(t, 1)) for b, i, t in times],
           'outside solver ms', round(tt - sum(t for _, _, t in times), 1))

@@ -17,7 +17,7 @@ DEC = ['capacitive', 'inductive', 'quasiparticle', 'charge', 'cc', 'flux']
 
 
 def step():
-    res = cr.sweep_diag(10, loop_fluxes={loop: fl}, tol=1e-9, lowblock=160)
+    res = cr.sweep_diag(10, loop_fluxes={loop: fl}, tol=1e-9, lowblock=512)
     t0 = time.perf_counter(); torch.cuda.synchronize(); t1 = time.perf_counter()
     rates = [res.dec_rate(d, states=(1, 0)) for d in DEC]
     torch.cuda.synchronize()
