@@ -28,6 +28,11 @@
 #ifndef HX_ABL_NODMMA
 #define HX_ABL_NODMMA 0
 #endif
+#ifndef HX_TEAMS
+#define HX_TEAMS 1      // 1: a single 8-warp team (30 + 2 column panels); 2: two independent 4-warp teams per
+                        // CTA (14 + 2 column panels) -- measured slower (7.5 vs 6.7 ms at 2048 x 12 vectors): the extra
+                        // halo work costs more than the additional stream overlaps
+#endif
 #ifndef HX_KUNROLL
 #define HX_KUNROLL 2
 #endif
@@ -42,7 +47,10 @@ struct HxGeom {
     int np, TC, PC, CT;  // panels per vector, useful cols per panel, cols incl. halo, col tiles
     int CT_last;         // column tiles of the last (narrower) panel of a vector
     int vld, pld;        // leading dims (doubles) of the half matrices and of the panel
-    int pg;              // row pairs per warp group in the potential pass
+    int pg;              // row pairs per warp in the potential pass
+    int rotate;          // panel index rotated by the round (needs grid x teams to be a multiple of np)
+    int ng;              // independent warp teams per CTA (each works on its own panel; they share Ve / Vo)
+    int team_doubles;    // shared-memory doubles of one team (panel + per-point tables)
     int n_terms;
     int shpack;          // junction charge shifts (-1, 0, +1), 2 bits each, biased by one
     long long N;
@@ -65,32 +73,42 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
     // row tiles that stick out past KP read finite neighbouring data and are never written back
     double* sVe = smem;                                   // [KP][VLD]   Ve[a][i] = V[2a][i]
     double* sVo = sVe + KP * VLD;                         // [KP][VLD]   Vo[a][i] = V[2a+1][i]
-    double* sP = sVo + KP * VLD;                          // [2*KP][pld] panel: S/even half, D/odd half
-    double* sLin = sP + 2 * KP * gm.pld;                  // [m]
-    cplx* sPh = reinterpret_cast<cplx*>(sLin + ((gm.m + 1) & ~1));   // [n_terms][m]
-
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    // Teams: the warps of a CTA are split into gm.ng independent teams.  A team streams its own panels
+    // (own panel buffer, own per-point tables, own named barrier); the teams only share the half
+    // matrices.  More independent panel streams per SM = better overlap of the tensor-core phases
+    // of one stream with the staging / potential / epilogue phases of the others.
+    const int tid_cta = threadIdx.x;
+    const int nwarp = (blockDim.x >> 5) / gm.ng;          // warps per team
+    const int team = (tid_cta >> 5) / nwarp;
+    const int tid = tid_cta - team * nwarp * 32, nthr = nwarp * 32;      // thread index / count inside the team
     const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
     const int m = gm.m, he = gm.he, ho = gm.ho, pld = gm.pld;
+    double* sP = sVo + KP * VLD + team * gm.team_doubles; // [2*KP][pld] panel: S/even half, D/odd half
+    double* sLin = sP + 2 * KP * pld;                     // [m]
+    cplx* sPh = reinterpret_cast<cplx*>(sLin + ((m + 1) & ~1));   // [n_terms][m]
+    auto team_sync = [&]() {
+        if (gm.ng == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(nthr) : "memory");
+    };
 
     // half matrices (zero padded), staged once per CTA
-    for (int e = tid; e < KP * VLD; e += nthr) {
+    for (int e = tid_cta; e < KP * VLD; e += blockDim.x) {
         const int r = e / VLD, c = e % VLD;
         sVe[e] = (r < he && c < he) ? Ve[r * he + c] : 0.0;
         sVo[e] = (r < ho && c < ho) ? Vo[r * ho + c] : 0.0;
     }
     for (int e = tid; e < 2 * KP * pld; e += nthr) sP[e] = 0.0;
     __syncthreads();
-    const int nwarp = nthr >> 5;
     // DMMA warps: the lane's complex column inside the warp's 4-column tile
     const int pcc = 4 * warp + tq;
     int loaded_b = -1;
-    // the grid is a multiple of np, so all panels of a vector are dealt in the same round; the panel
+    // grid x teams is a multiple of np, so all panels of a vector are dealt in the same round; the panel
     // index is rotated by the round so that every CTA sees wide and narrow panels alike
     int round = 0;
-    for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++round) {
+    for (long long item = (long long)blockIdx.x * gm.ng + team; item < total_items;
+         item += (long long)gridDim.x * gm.ng, ++round) {
         const long long vec = item / gm.np;
-        const int panel = (int)((item % gm.np + round) % gm.np);
+        const int panel = (int)((item % gm.np + (gm.rotate ? round : 0)) % gm.np);
         const int b = (int)(vec / vmax), v = (int)(vec % vmax);
         if (v >= blk_count(X, b)) continue;
         if (b != loaded_b) {
@@ -164,7 +182,7 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
                 }
             }
         }
-        __syncthreads();
+        team_sync();
 
         // ---- 3. potential + mirror combination, in place ----
         // a warp owns pg whole row pairs; the (at most 32) columns of a row are done by its lanes:
@@ -198,17 +216,28 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
                 S = cadd(oi, om);                                        // S_i
                 D = pair ? csub(oi, om) : cmake(0.0, 0.0);              // D_i
             };
-            for (int i = i_base; i < i_end; ++i) {
-                cplx s_, d_;
-                if (lane < pcn) eval(i, lane, s_, d_);
+            // two evaluations per trip: their loads and FP64 chains are independent (the pass is
+            // latency bound); with <= 16 panel columns the lanes of one evaluation cover two rows
+            const int cw = pcn <= 16 ? 16 : 32, rpl = 32 / cw;
+            const int pcol = lane % cw, prow = lane / cw;
+            for (int i = i_base; i < i_end; i += 2 * rpl) {
+                const int r0 = i + prow, r1 = i + rpl + prow;
+                const bool ok0 = pcol < pcn && r0 < i_end, ok1 = pcol < pcn && r1 < i_end;
+                cplx s0, d0, s1, d1;
+                if (ok0) eval(r0, pcol, s0, d0);
+                if (ok1) eval(r1, pcol, s1, d1);
                 __syncwarp();
-                if (lane < pcn) {
-                    *reinterpret_cast<cplx*>(sP + i * pld + 2 * lane) = s_;
-                    *reinterpret_cast<cplx*>(sP + (KP + i) * pld + 2 * lane) = d_;
+                if (ok0) {
+                    *reinterpret_cast<cplx*>(sP + r0 * pld + 2 * pcol) = s0;
+                    *reinterpret_cast<cplx*>(sP + (KP + r0) * pld + 2 * pcol) = d0;
+                }
+                if (ok1) {
+                    *reinterpret_cast<cplx*>(sP + r1 * pld + 2 * pcol) = s1;
+                    *reinterpret_cast<cplx*>(sP + (KP + r1) * pld + 2 * pcol) = d1;
                 }
             }
         }
-        __syncthreads();
+        team_sync();
 
         // ---- 4. backward transform of the warp's tile + LC diagonal epilogue (warp-private) ----
         if (warp < ct) {
@@ -301,42 +330,50 @@ extern "C" int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const doubl
     // round-robin to the four SM sub-partitions, each with its own FP64 tensor pipe, and e.g. nine
     // equal tiles put 3+3 warps of two resident CTAs on one sub-partition (measured: 6.2 instead of
     // 4.0 cycles per DMMA).  Wide modes use 30 + 2 column panels; the last panel takes the remainder.
-    if (gm.inner + 2 <= 32) {
+    // HX_TEAMS teams of 4 warps (14 + 2 column panels) or one team of 8 warps (30 + 2 column panels)
+    const int teams = HX_TEAMS;
+    const int tcw = teams == 2 ? 14 : 30, ctw = teams == 2 ? 4 : 8;
+    if (gm.inner + 2 <= 4 * ctw) {
         gm.np = 1;
         gm.TC = gm.inner;
         gm.PC = (gm.inner + 2 + 3) & ~3;
         gm.CT = gm.CT_last = gm.PC / 4;
     } else {
-        gm.TC = 30;
-        gm.PC = 32;
-        gm.CT = 8;
+        gm.TC = tcw;
+        gm.PC = 4 * ctw;
+        gm.CT = ctw;
         gm.np = (gm.inner + gm.TC - 1) / gm.TC;
         const int tl = gm.inner - gm.TC * (gm.np - 1);
         gm.CT_last = ((tl + 2 + 3) / 4 + 3) & ~3;
-        if (gm.CT_last > 8) gm.CT_last = 8;
+        if (gm.CT_last > ctw) gm.CT_last = ctw;
     }
+    gm.ng = teams;
     // leading dims == 4 (mod 8) doubles keep both DMMA fragment patterns bank-conflict free
     gm.vld = (gm.kp % 8 == 4) ? gm.kp : gm.kp + 4;        // must match VLD in the kernel
     gm.pld = 2 * gm.PC;
     while ((gm.pld & 7) != 4) ++gm.pld;
-    int nwarp = gm.CT < 4 ? 4 : gm.CT;
+    int nwarp = gm.CT < 4 ? 4 : gm.CT;       // warps per team
     gm.pg = (gm.he + nwarp - 1) / nwarp;      // row pairs per warp in the potential pass
-    size_t smem = ((size_t)2 * gm.kp * gm.vld + (size_t)2 * gm.kp * gm.pld + ((gm.m + 1) & ~1)) * sizeof(double) +
-                  (size_t)(gm.n_terms > 0 ? gm.n_terms : 1) * gm.m * sizeof(cplx);
+    gm.team_doubles = 2 * gm.kp * gm.pld + ((gm.m + 1) & ~1) + 2 * (gm.n_terms > 0 ? gm.n_terms : 1) * gm.m;
+    size_t smem = ((size_t)2 * gm.kp * gm.vld + (size_t)gm.ng * gm.team_doubles) * sizeof(double);
     if (smem > 227 * 1024) return SQC_ELIMIT;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
     const int per_sm = (smem <= 112 * 1024) ? 2 : 1;
     const long long total = (long long)B * X.cnt_fixed * gm.np;
     long long grid = (long long)nsm * per_sm;
-    if (grid > total) grid = total;
-    grid -= grid % gm.np;                 // see the panel rotation in the kernel (total is a multiple of np)
+    if (grid * gm.ng > total) grid = (total + gm.ng - 1) / gm.ng;
+    // panel rotation (see the kernel) needs grid x teams to be a multiple of np; tiny launches go without
+    long long gr = grid;
+    while ((gr * gm.ng) % gm.np != 0 && gr > 1) --gr;
+    gm.rotate = (gr * gm.ng) % gm.np == 0;
+    if (gm.rotate) grid = gr;
 #define HX_CASE(R)                                                                                     \
     case R: {                                                                                          \
         cudaError_t e = cudaFuncSetAttribute(hx_fused_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)smem);                                               \
         if (e != cudaSuccess) return (int)e;                                                           \
-        hx_fused_kernel<R><<<(unsigned)grid, 32 * nwarp, smem, (cudaStream_t)stream>>>(                \
+        hx_fused_kernel<R><<<(unsigned)grid, 32 * nwarp * gm.ng, smem, (cudaStream_t)stream>>>(                \
             gm, Ve, Vo, pot->lam, (const cplx*)pot->etab, pot->etab_stride_b, pot->g, (const cplx*)pot->a, \
             fdiag, fdiag_stride_b, X, Y, X.cnt_fixed, total);                                          \
         break;                                                                                         \
