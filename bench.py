@@ -355,6 +355,12 @@ def our_arm(args):
         roof['achieved'] = alg_bytes / (hx_ms / 1e3) / 1e9
         roof['frac'] = roof['achieved'] / hbm_peak
         roof['algorithmic_bytes_per_vector'] = 32 * N
+        # DRAM bytes of the kernel from the ncu --set full capture (profiles/r01_ncu_full_v28_hx_fused.txt):
+        # 331.4 MB read + 283.0 MB written for a launch of 1751 vectors = 1.0855 x its algorithmic bytes
+        # (halo columns + LC diagonal).  Reported per launch, scaled to this run's average launch.
+        roof['traffic'] = NCU_HX_TRAFFIC_RATIO * alg_bytes / max(hx_calls, 1)
+        roof['algorithmic_bytes_per_launch'] = alg_bytes / max(hx_calls, 1)
+        roof['traffic_source'] = 'ncu dram__bytes_read+write / algorithmic = 1.0855 (profiles/r01_ncu_full_v28_hx_fused.txt)'
         roof['vectors'] = nvec
         roof['ms'] = hx_ms
         # FP64 work of the same apply with the parity-split transforms: two real (m/2 x m/2)
@@ -401,6 +407,7 @@ def our_arm(args):
         dist.destroy_process_group()
 
 
+NCU_HX_TRAFFIC_RATIO = 1.0855
 HX_COUNTER = {'vectors': 0}
 DEBUG = bool(os.environ.get('SQC_BENCH_DEBUG'))
 
