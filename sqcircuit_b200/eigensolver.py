@@ -51,6 +51,33 @@ def solve_dense(kern, op, B, N, k):
                      torch.zeros(B, dtype=torch.float64, device=dev), True)
 
 
+def cold_start_block(diag, B, p, N, dev, k=None):
+    """Start block of a cold solve: unit vectors on the p smallest entries of the LC diagonal plus a
+    small deterministic perturbation on the 8p smallest.  The perturbation matters at symmetric
+    operating points (e.g. the 0-pi qubit at zero flux): H then commutes with a parity, every
+    Davidson vector stays inside the symmetry sectors of the start block, and a wanted eigenstate
+    whose sector is not represented is never found (the iteration "converges" to the wrong set)."""
+    c128 = torch.complex128
+    nl = min(8 * p, N)
+    dlow, low = torch.topk(diag, nl, dim=1, largest=False)               # [1 or B][nl], ascending energy
+    # damped with the LC energy above the start block, so that the Rayleigh quotients of the start
+    # vectors are not swamped by high-energy basis states (charge-dominated circuits)
+    spread = (dlow[:, p - 1:p] - dlow[:, :1]).clamp_min(1e-300)
+    damp = spread / (spread + (dlow - dlow[:, :1]))                      # [1 or B][nl]
+    V0 = torch.zeros((B, p, N), dtype=c128, device=dev)
+    V0.scatter_(2, low[:, :p].expand(B, p).unsqueeze(2), torch.ones((B, p, 1), dtype=c128, device=dev))
+    i = torch.arange(nl, device=dev, dtype=torch.float64).unsqueeze(0)
+    j = torch.arange(p, device=dev, dtype=torch.float64).unsqueeze(1)
+    xi = float(os.environ.get("SQC_START_NOISE", "0.03")) * torch.cos(2.399963229728653 * (i + 1.0) * (j + 1.0) + 0.5 * j)      # [p][nl]
+    if k is not None and k < p:
+        # only the guard vectors carry the perturbation: the k wanted start vectors stay clean (they
+        # are already eigenvectors of charge-dominated circuits), the guards seed the other sectors
+        xi = xi * (torch.arange(p, device=dev) >= k).to(xi.dtype).unsqueeze(1)
+    pert = (xi.unsqueeze(0) * damp.unsqueeze(1)).to(c128).expand(B, p, nl).contiguous()
+    V0.scatter_add_(2, low.unsqueeze(1).expand(B, p, nl), pert)
+    return V0
+
+
 def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
                    impl=0, stats=None, lowblock_ns=0):
     """diag: [1 or B][N] real preconditioner diagonal (the LC part of H)."""
@@ -89,14 +116,10 @@ def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=3
 
     Vp = BlockView(V, cnt_fixed=p)
     Wp = BlockView(W, cnt_fixed=p)
+    warm = x0 is not None
     if x0 is None:
-        # cold start: unit vectors on the p smallest entries of the preconditioner diagonal
-        idx = torch.topk(diag, p, dim=1, largest=False).indices          # [1 or B][p]
-        idx = idx.expand(B, p)
-        V[:, :p, :].scatter_(2, idx.unsqueeze(2), torch.ones((B, p, 1), dtype=c128, device=dev))
-        op.apply(Vp, Wp)
-        kern.gram(Vp, Wp, G, impl)
-    else:
+        x0 = cold_start_block(diag, B, p, N, dev, k)    # orthonormalised below like a warm start
+    if True:
         # warm start: x0 holds one or two blocks of p vectors per point (Ritz vectors of solved
         # neighbouring sweep points).  Block 0 is orthonormalised in place (SVQB x2); block 1 is
         # orthogonalised against block 0 and itself exactly like a Davidson expansion block.
@@ -229,7 +252,7 @@ def EXPAND_DEFAULT(k, p):
 
 
 def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
-                       stats=None, lowblock_ns=0, drop=1e-8, cold_gate=3e-3, expand=None):
+                       stats=None, lowblock_ns=0, drop=float(os.environ.get("SQC_DROP", "1e-8")), cold_gate=3e-3, expand=None):
     """Block Davidson WITHOUT orthogonalising the expansion block.
 
     The basis V is allowed to be non-orthogonal inside a restart cycle; Rayleigh-Ritz is the
@@ -277,14 +300,10 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
 
     Vp = BlockView(V, cnt_fixed=p)
     Wp = BlockView(W, cnt_fixed=p)
+    warm = x0 is not None
     if x0 is None:
-        idx = torch.topk(diag, p, dim=1, largest=False).indices.expand(B, p)
-        V[:, :p, :] = 0
-        V[:, :p, :].scatter_(2, idx.unsqueeze(2), torch.ones((B, p, 1), dtype=c128, device=dev))
-        op.apply(Vp, Wp)
-        kern.gram(Vp, Wp, GA)
-        GB[:, :p, :p] = torch.eye(p, dtype=c128, device=dev)
-    else:
+        x0 = cold_start_block(diag, B, p, N, dev, k)    # not orthonormal: goes through the general start
+    if True:
         m0 = min(x0.shape[1], mmax)
         if hasattr(x0, 'write_into'):
             x0.write_into(kern, V)         # gather straight into the basis (no staging copy)
@@ -319,6 +338,7 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
     it = 0
     converged = False
     lowblock = None
+    best_left, best_it = B + 1, 0
     for it in range(1, maxit + 1):
         live = 1 - done
         nrr = msz * live
@@ -328,7 +348,7 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
             # two-level preconditioner.  sigma must stay below the spectrum of H_SS (>= lambda_0): warm
             # starts know lambda_0 to ~1e-6 at once; cold starts wait until every point's lowest Ritz
             # value has settled (wanted residuals < cold_gate), then sigma = theta_0 - 5 %.
-            if x0 is not None or (it > 1 and float(resmax.max()) < cold_gate):
+            if warm or (it > 1 and float(resmax.max()) < cold_gate):
                 sigma = theta[:, 0] - 0.05 * theta[:, 0].abs()
                 lowblock = op.build_lowblock(sigma, lowblock_ns)
         Xv.cnt = xcnt
@@ -344,6 +364,12 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
                                      int((((nact + 3) // 4) * lv).sum()), int(restart.sum())))
         if left == 0:
             converged = True
+            break
+        # stagnation guard: no sweep point has finished for 30 iterations (a healthy solve finishes
+        # points every iteration once the first ones converge, and a cold start needs ~35)
+        if left < best_left:
+            best_left, best_it = left, it
+        elif it - best_it >= 30 and it >= 60:
             break
         kern.precond_residual(Xl, HXl, Tv, theta, act, diag, den_floor)
         if lowblock is not None and lowblock.get('band') is not None:

@@ -25,8 +25,12 @@ class SweepNoise:
 
     # ---- helpers ------------------------------------------------------------------------
     def _pair(self, states):
-        idx = torch.as_tensor(list(states), device=self.dev)
-        return self.evecs.index_select(1, idx).contiguous()        # [B][2][N]
+        key = tuple(int(x) for x in states)
+        if getattr(self, '_pair_key', None) != key:      # the six channels of a T1 / Tphi query share it
+            idx = torch.as_tensor(list(key), device=self.dev)
+            self._pair_val = self.evecs.index_select(1, idx).contiguous()        # [B][2][N]
+            self._pair_key = key
+        return self._pair_val
 
     def _gram2(self, X, Y):
         out = torch.empty((self.B, 2, 2), dtype=torch.complex128, device=self.dev)

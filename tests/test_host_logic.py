@@ -176,3 +176,18 @@ def test_elements_api_matches_reference_values():
     assert np.isclose(sq.Junction(0.142, 'GHz').Y(50e9, 0.015), 793439739057240.9)
     with pytest.raises(sq.ModeError):
         sq.Capacitor(10, requires_grad=True)
+
+
+def test_cold_start_finds_every_symmetry_sector():
+    """0-pi at zero external flux has an exact parity: a start block of bare basis states spans only
+    some of its sectors and the Davidson iteration would 'converge' while skipping the 4th level
+    (this is the scenario of __graft_entry__.smoke()).  The perturbed guard vectors must seed it."""
+    K = EmulKernels()
+    cr, lp, oc, ol = cs.zero_pi(K)
+    cr.set_trunc_nums([25, 13])
+    oc.set_trunc_nums([25, 13])
+    res = cr.sweep_diag(4, loop_fluxes={lp: np.array([0.0, 0.5])})
+    for i, f in enumerate((0.0, 0.5)):
+        ol.set_flux(f)
+        e, _ = oc.diag(4)
+        assert np.max(np.abs(res.efreqs[i].numpy() - e) / np.abs(e)) < 1e-9, (f, res.efreqs[i], e)
