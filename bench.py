@@ -367,6 +367,10 @@ def our_arm(args):
         # contractions per parity half and direction on complex data = 2*2*m flops per amplitude
         flops = 2.0 * (2 * cr.m[0]) * N * nvec
         roof['fp64_tflops'] = flops / (hx_ms / 1e3) / 1e12
+        # the kernel is FP64-tensor-bound (12.5 flop/B): context for the HBM fraction above.  Peak =
+        # measured DMMA issue rate (tools/cu/dmma_peak.cu, profiles/r01_dmma_peak.txt): 37.1 TFLOP/s
+        roof['fp64_tensor_peak_tflops'] = 37.1
+        roof['fp64_tensor_frac'] = roof['fp64_tflops'] / 37.1
     roof['calls'] = hx_calls
 
     # ---- cpu baseline: bounded sample of the same workload on the host cores ----

@@ -28,22 +28,35 @@ long long g_sqc_launches = 0;
 // Tensor-core work of one staged chunk for exactly NATR populated row tiles.  The row-tile count
 // is a template parameter (dispatched by a warp-uniform switch) because a run-time guard is
 // compiled to PREDICATED DMMAs, and predicated-off DMMAs still occupy the FP64 tensor pipe.
-template <int NATR, int NAT, int NCT, int KW>
+template <int NATR, int NCTR, int NAT, int NCT, int KW>
 __device__ __forceinline__ void gram_chunk(double (&acc)[NAT][NCT][2], const double* __restrict__ sAb,
                                            const double* __restrict__ sBb, int warp, int g, int t,
                                            int bcol, double bsign) {
 #pragma unroll
     for (int ks = 0; ks < (2 * GRAM_CH / 4) / KW; ++ks) {
         const int k0 = 4 * (warp + KW * ks);
-        double bf[NCT];
+        double bf[NCTR];
 #pragma unroll
-        for (int j = 0; j < NCT; ++j) bf[j] = bsign * sBb[(4 * j + (g >> 1)) * GRAM_LD + k0 + bcol];
+        for (int j = 0; j < NCTR; ++j) bf[j] = bsign * sBb[(4 * j + (g >> 1)) * GRAM_LD + k0 + bcol];
 #pragma unroll
         for (int i = 0; i < NATR; ++i) {
             const double af = sAb[(8 * i + g) * GRAM_LD + k0 + t];
 #pragma unroll
-            for (int j = 0; j < NCT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+            for (int j = 0; j < NCTR; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
         }
+    }
+}
+
+// column tiles actually populated (the active right-hand vectors of the sweep point), then row tiles
+template <int NATR, int NAT, int NCT, int KW>
+__device__ __forceinline__ void gram_chunk_cols(double (&acc)[NAT][NCT][2], const double* __restrict__ sAb,
+                                                const double* __restrict__ sBb, int warp, int g, int t,
+                                                int bcol, double bsign, int nctr) {
+    switch (nctr) {
+        case 1: gram_chunk<NATR, 1, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign); break;
+        case 2: if constexpr (NCT >= 2) gram_chunk<NATR, 2, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign); break;
+        case 3: if constexpr (NCT >= 3) gram_chunk<NATR, 3, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign); break;
+        default: if constexpr (NCT >= 4) gram_chunk<NATR, 4, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign); break;
     }
 }
 
@@ -84,6 +97,8 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int 
         return;
     }
     const int nat = (na + 7) >> 3;          // row tiles actually populated for this sweep point
+    // column tiles (4 vectors each) populated in this warp's right-hand block
+    const int nctr = max(1, ((PAIR && grp == 1 ? nb2 : nb) + 3) >> 2);
     // stages are sized by the rows this point really has, so small bases get a deeper pipeline
     const int stage_doubles = (nat * 8 + NBLK * NB) * GRAM_LD;
     int nstage = smem_doubles / stage_doubles;     // >= 2 by construction of the launch
@@ -166,14 +181,14 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int 
         const double* sAb = smem + (int)((ch - c_lo) % nstage) * stage_doubles;
         const double* sBb = sAb + (nat * 8 + grp * NB) * GRAM_LD;
         switch (nat) {
-            case 1: gram_chunk<1, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
-            case 2: if constexpr (NAT >= 2) gram_chunk<2, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
-            case 3: if constexpr (NAT >= 3) gram_chunk<3, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
-            case 4: if constexpr (NAT >= 4) gram_chunk<4, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
-            case 5: if constexpr (NAT >= 5) gram_chunk<5, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
-            case 6: if constexpr (NAT >= 6) gram_chunk<6, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
-            case 7: if constexpr (NAT >= 7) gram_chunk<7, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
-            default: if constexpr (NAT >= 8) gram_chunk<8, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign); break;
+            case 1: gram_chunk_cols<1, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
+            case 2: if constexpr (NAT >= 2) gram_chunk_cols<2, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
+            case 3: if constexpr (NAT >= 3) gram_chunk_cols<3, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
+            case 4: if constexpr (NAT >= 4) gram_chunk_cols<4, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
+            case 5: if constexpr (NAT >= 5) gram_chunk_cols<5, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
+            case 6: if constexpr (NAT >= 6) gram_chunk_cols<6, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
+            case 7: if constexpr (NAT >= 7) gram_chunk_cols<7, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
+            default: if constexpr (NAT >= 8) gram_chunk_cols<8, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
         }
     }
     cp_async_wait<0>();
