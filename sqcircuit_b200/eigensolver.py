@@ -252,7 +252,8 @@ def EXPAND_DEFAULT(k, p):
 
 
 def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
-                       stats=None, lowblock_ns=0, drop=float(os.environ.get("SQC_DROP", "1e-8")), cold_gate=3e-3, expand=None):
+                       stats=None, lowblock_ns=0, drop=float(os.environ.get("SQC_DROP", "1e-8")),
+                       cold_gate=float(os.environ.get("SQC_COLD_GATE", "0.25")), expand=None):
     """Block Davidson WITHOUT orthogonalising the expansion block.
 
     The basis V is allowed to be non-orthogonal inside a restart cycle; Rayleigh-Ritz is the
@@ -347,10 +348,19 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
         if lowblock is None and lowblock_ns > 0 and getattr(op, 'supports_lowblock', lambda: False)():
             # two-level preconditioner.  sigma must stay below the spectrum of H_SS (>= lambda_0): warm
             # starts know lambda_0 to ~1e-6 at once; cold starts wait until every point's lowest Ritz
-            # value has settled (wanted residuals < cold_gate), then sigma = theta_0 - 5 %.
-            if warm or (it > 1 and float(resmax.max()) < cold_gate):
+            # value has settled, then sigma = theta_0 - 5 %.
+            if warm:
                 sigma = theta[:, 0] - 0.05 * theta[:, 0].abs()
                 lowblock = op.build_lowblock(sigma, lowblock_ns)
+            elif it > 1:
+                # cold: the lowest Ritz pair converges first; once its own residual is below
+                # cold_gate x |theta_0| there is an eigenvalue within ||r_0|| of theta_0, and the shift
+                # keeps that distance plus the 5 % margin
+                r0 = rn2[:, 0].sqrt()
+                scale = torch.maximum(theta[:, 0].abs(), theta[:, p - 1] - theta[:, 0])
+                if bool((r0 < cold_gate * scale).all()):
+                    sigma = theta[:, 0] - 0.05 * theta[:, 0].abs() - r0
+                    lowblock = op.build_lowblock(sigma, lowblock_ns)
         Xv.cnt = xcnt
         HXv.cnt = xcnt
         kern.ritz_update(Vm, Wm, Zt, Xv, HXv, theta, rn2)       # X = V c, HX = W c, ||HX - theta X||^2
