@@ -34,6 +34,7 @@ def _davidson(*a, **kw):
         # charge-dominated Hamiltonians with ||H|| >> the wanted eigenvalues).  The orthogonalised
         # iteration (CGS2 + SVQB: seven basis passes instead of three) does not have that floor.
         kw = {k: v for k, v in kw.items() if k not in ('drop', 'cold_gate', 'expand')}
+        kw['lowblock_ns'] = 0          # plain diagonal preconditioner: slower, nothing to go wrong
     return solve_davidson(*a, **kw)
 from .elements import Capacitor, Charge, Inductor, Junction, Loop
 from .exceptions import CircuitStateError
