@@ -328,6 +328,19 @@ class HamiltonianOperator:
             qv = (key // m).cpu().numpy()
             rows = qv.shape[0]
             starts = [np.concatenate(([0], np.nonzero(np.diff(r))[0] + 1, [ns])) for r in qv]
+            # neighbouring small blocks (the thin ends of the low-energy ellipse) are merged up to one
+            # warp's width: still block tridiagonal, fewer sequential substitution steps
+            cap = max(32, int(max(np.diff(st).max() for st in starts)))
+            merged = []
+            for st in starts:
+                out = [0]
+                for e in st[1:]:
+                    if len(out) >= 2 and e - out[-2] <= cap:
+                        out[-1] = e
+                    else:
+                        out.append(e)
+                merged.append(np.array(out))
+            starts = merged
             nblk = np.array([len(st) - 1 for st in starts], dtype=np.int32)
             nbmax = int(max(np.diff(st).max() for st in starts))
             if nbmax <= 64:
