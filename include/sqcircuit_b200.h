@@ -270,14 +270,16 @@ int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const doubl
  *    blocks overwritten by the inverses P_q of the block-LDL^H Schur complements; blocks (q, q+1) stay.
  *    blk_off: [B][ld_off] int32, nblk: [B], nbmax: largest block (<= 96).
  *  - apply: same contract as sqc_lowblock_apply, via forward / backward block substitution
- *    (cost ~ 3 sum_q n_q^2 per right-hand side instead of ns^2). */
+ *    (cost ~ 3 sum_q n_q^2 per right-hand side instead of ns^2).  perm (same shape and stride as S, or
+ *    NULL): a permutation that sorts each index set by address; gather and scatter then walk memory
+ *    in ascending order (coalesced runs) instead of the charge-major block order. */
 int sqc_lowband_factor(void* A, int32_t ns, const int32_t* blk_off, int32_t ld_off, const int32_t* nblk,
                        int32_t nbmax, int32_t B, void* stream);
 int sqc_lowband_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
                       int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
                       int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
                       int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit, int32_t group,
-                      int64_t N, int32_t B, void* stream);
+                      const int32_t* perm, int64_t N, int32_t B, void* stream);
 
 /* SVQB coefficients from the Gram matrix S = T^H T of the new block:
  * Cq[j][i] = D_i U_ij sigma_j^-1/2 over directions with sigma_j > drop * sigma_max;

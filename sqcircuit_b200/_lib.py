@@ -78,7 +78,7 @@ SIGNATURES = {
     'sqc_hpd_inverse_c64': (c_i32, [c_vp, c_i32, c_i32, c_vp]),
     'sqc_lowband_factor': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp]),
     'sqc_lowband_apply': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32,
-                                  c_vp, c_i32, c_dbl, c_i32, c_i64, c_i32, c_vp]),
+                                  c_vp, c_i32, c_dbl, c_i32, c_vp, c_i64, c_i32, c_vp]),
     'sqc_lowblock_apply': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32, c_dbl,
                                    c_i32, c_i64, c_i32, c_vp]),
     'sqc_svqb_coeffs': (c_i32, [c_vp, c_i32, c_vp, c_dbl, c_vp, c_vp, c_vp, c_i32, c_vp]),

@@ -349,7 +349,7 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
                      int ld_theta, const int32_t* __restrict__ act, int ld_act,
                      const int32_t* __restrict__ S, long long s_stride_b, const float2* __restrict__ Afac,
                      int ns, const int32_t* __restrict__ blk_off, int ld_off, const int32_t* __restrict__ nblk,
-                     int nbmax, double inv_unit, int group, long long N) {
+                     int nbmax, double inv_unit, int group, long long N, const int32_t* __restrict__ perm) {
     extern __shared__ float2 smf[];
     const int b = blockIdx.x;
     const int na = blk_count(T, b);
@@ -362,6 +362,7 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
     float2* tmp = vec + (size_t)nwarp * ns;    // [nwarp][nbmax]
     const int slot = b / group;
     const int32_t* s = S + slot * s_stride_b;
+    const int32_t* pm = perm ? perm + slot * s_stride_b : nullptr;
     const float2* A = Afac + (long long)slot * ns * ns;
     const int32_t* off = blk_off + (long long)slot * ld_off;
     const int nb = nblk[slot];
@@ -398,7 +399,10 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
         const double th = theta[(long long)b * ld_theta + av];
         const cplx* x = blk_vec(X, b, av, N);
         const cplx* h = blk_vec(HX, b, av, N);
-        for (int i = lane; i < ns; i += 32) {
+        // gather in ascending-address order (perm sorts the index set by address): the set is made of
+        // runs of consecutive charge states, so neighbouring lanes read neighbouring amplitudes
+        for (int j = lane; j < ns; j += 32) {
+            const int i = pm ? pm[j] : j;
             const int idx = s[i];
             const cplx xv = x[idx], hv = h[idx];
             v[i] = make_float2((float)((hv.x - th * xv.x) * inv_unit), (float)((hv.y - th * xv.y) * inv_unit));
@@ -440,7 +444,10 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
     cp_async_wait<0>();
     if (mine) {
         cplx* t = blk_vec(T, b, warp, N);
-        for (int i = lane; i < ns; i += 32) t[s[i]] = cmake((double)v[i].x, (double)v[i].y);
+        for (int j = lane; j < ns; j += 32) {
+            const int i = pm ? pm[j] : j;
+            t[s[i]] = cmake((double)v[i].x, (double)v[i].y);
+        }
     }
 }
 
@@ -448,7 +455,7 @@ extern "C" int sqc_lowband_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, c
                                  int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
                                  int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
                                  int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit, int32_t group,
-                                 int64_t N, int32_t B, void* stream) {
+                                 const int32_t* perm, int64_t N, int32_t B, void* stream) {
     if (B <= 0 || ns <= 0 || T.cnt_fixed <= 0 || T.cnt_fixed > 16 || group < 1 || nbmax <= 0) return SQC_EINVAL;
     const int nwarp = T.cnt_fixed;
     const size_t smem = ((size_t)4 * nbmax * (nbmax | 1) + (size_t)nwarp * ns + (size_t)nwarp * nbmax) * sizeof(float2);
@@ -457,7 +464,7 @@ extern "C" int sqc_lowband_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, c
     if (e != cudaSuccess) return (int)e;
     lowband_apply_kernel<<<B, 32 * nwarp, smem, (cudaStream_t)stream>>>(
         X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, (const float2*)Afac, ns, blk_off, ld_off, nblk, nbmax,
-        1.0 / unit, group, N);
+        1.0 / unit, group, N, perm);
     SQC_LAUNCHED();
     return 0;
 }

@@ -383,9 +383,9 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
             break
         kern.precond_residual(Xl, HXl, Tv, theta, act, diag, den_floor)
         if lowblock is not None and lowblock.get('band') is not None:
-            off, nblk, nbmax = lowblock['band']
+            off, nblk, nbmax, perm = lowblock['band']
             kern.lowband_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], off, nblk, nbmax,
-                               lowblock['unit'], lowblock.get('group', 1))
+                               lowblock['unit'], lowblock.get('group', 1), perm)
         elif lowblock is not None:
             kern.lowblock_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], lowblock['unit'],
                                 lowblock.get('group', 1))

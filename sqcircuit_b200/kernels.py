@@ -254,13 +254,13 @@ class Kernels:
         _lib.check(self.lib.sqc_lowband_factor(_p(A), ns, _p(blk_off), blk_off.shape[1], _p(nblk), int(nbmax), B,
                                                _stream(self.dev)), 'sqc_lowband_factor')
 
-    def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1):
+    def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1, perm=None):
         ssb = 0 if S.shape[0] == 1 else S.stride(0)
         if Afac.shape[0] * group < X.B:
             raise ValueError('lowband_apply: not enough factor slots for this group size')
         _lib.check(self.lib.sqc_lowband_apply(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act),
                                               act.shape[1], _p(S), ssb, _p(Afac), Afac.shape[1], _p(blk_off),
-                                              blk_off.shape[1], _p(nblk), int(nbmax), unit, group, X.N, X.B,
+                                              blk_off.shape[1], _p(nblk), int(nbmax), unit, group, _p(perm), X.N, X.B,
                                               _stream(self.dev)), 'sqc_lowband_apply')
 
     def svqb_coeffs(self, S, nact, drop, Cq, msz=None, mtot=None):

@@ -349,7 +349,8 @@ class HamiltonianOperator:
                     off[r, :len(st)] = st
                 if rows == 1 and nslot > 1:      # LC diagonal shared by all sweep points (flux sweeps)
                     off, nblk = np.repeat(off, nslot, axis=0), np.repeat(nblk, nslot)
-                band = (torch.as_tensor(off, device=self.device), torch.as_tensor(nblk, device=self.device), nbmax)
+                band = (torch.as_tensor(off, device=self.device), torch.as_tensor(nblk, device=self.device), nbmax,
+                        torch.argsort(S, dim=1).to(torch.int32).contiguous())
             else:
                 ns = 160          # blocks too large for the banded kernels: dense 160 x 160 instead
         if band is None:

@@ -478,7 +478,7 @@ class EmulKernels:
                 a[o:o1, o:o1] = pprev
             A[b] = torch.from_numpy(a.astype(np.complex64))
 
-    def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1):
+    def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1, perm=None):
         for b in range(X.B):
             n = _cnt(T, b)
             if n == 0:

@@ -532,6 +532,12 @@ def test_lowband_factor_and_apply(kern):
     kern.lowband_apply(BlockView(X.cuda()), BlockView(HX.cuda()), BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()),
                        theta.cuda(), act.cuda(), S.cuda(), fac, offt.cuda(), nbt.cuda(), 60, 2.0, group=group)
     assert relerr(Vd.cpu(), refV) < 2e-5
+    # address-ordered gather / scatter gives the same result
+    Vd2 = Vb.cuda()
+    kern.lowband_apply(BlockView(X.cuda()), BlockView(HX.cuda()), BlockView(Vd2, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()),
+                       theta.cuda(), act.cuda(), S.cuda(), fac, offt.cuda(), nbt.cuda(), 60, 2.0, group=group,
+                       perm=torch.argsort(S, dim=1).to(torch.int32).cuda())
+    assert torch.equal(Vd2, Vd)
     # the substitution really solves the block-tridiagonal system
     b, jj = 0, 1
     s = S[0].long().numpy()
