@@ -340,6 +340,10 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
     converged = False
     lowblock = None
     best_left, best_it = B + 1, 0
+    async_count = dev.type == 'cuda'
+    if async_count:
+        host_count = torch.zeros((1,), dtype=i32).pin_memory()
+        count_ready = torch.cuda.Event()
     for it in range(1, maxit + 1):
         live = 1 - done
         nrr = msz * live
@@ -365,13 +369,38 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
         HXv.cnt = xcnt
         kern.ritz_update(Vm, Wm, Zt, Xv, HXv, theta, rn2)       # X = V c, HX = W c, ||HX - theta X||^2
         kern.davidson_decide(st, B)
-        left = int(n_not_done.item())
-        if stats is not None:
-            stats.append((it, left))
-            if DETAIL_STATS is not None:      # dev instrumentation (tools/nact_stats.py): costs syncs
+        # The host needs the number of unfinished points to stop the loop.  Reading it right here would
+        # drain the GPU once per iteration; instead the counter is copied to pinned memory
+        # asynchronously, the rest of the iteration is enqueued (all of it is a no-op for finished
+        # points), and only then does the host wait for the copy.
+        detail = stats is not None and DETAIL_STATS is not None
+        if async_count and not detail:
+            host_count.copy_(n_not_done, non_blocking=True)
+            count_ready.record()
+            left = None
+        else:
+            left = int(n_not_done.item())
+            if detail:      # dev instrumentation (tools/nact_stats.py): costs syncs
                 lv = (1 - done)
                 DETAIL_STATS.append((it, B, left, int((nact * lv).sum()), int((msz * lv).sum()),
                                      int((((nact + 3) // 4) * lv).sum()), int(restart.sum())))
+        if left != 0:
+            kern.precond_residual(Xl, HXl, Tv, theta, act, diag, den_floor)
+            if lowblock is not None and lowblock.get('band') is not None:
+                off, nblk, nbmax, perm = lowblock['band']
+                kern.lowband_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], off, nblk, nbmax,
+                                   lowblock['unit'], lowblock.get('group', 1), perm)
+            elif lowblock is not None:
+                kern.lowblock_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], lowblock['unit'],
+                                    lowblock.get('group', 1))
+            op.apply(Tv, HTv)
+            kern.gram_pair(Vt, Tv, HTv, SB, SA)
+            kern.davidson_insert2(st, SA, SB, B)
+        if left is None:
+            count_ready.synchronize()
+            left = int(host_count[0])
+        if stats is not None:
+            stats.append((it, left))
         if left == 0:
             converged = True
             break
@@ -381,17 +410,6 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
             best_left, best_it = left, it
         elif it - best_it >= 30 and it >= 60:
             break
-        kern.precond_residual(Xl, HXl, Tv, theta, act, diag, den_floor)
-        if lowblock is not None and lowblock.get('band') is not None:
-            off, nblk, nbmax, perm = lowblock['band']
-            kern.lowband_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], off, nblk, nbmax,
-                               lowblock['unit'], lowblock.get('group', 1), perm)
-        elif lowblock is not None:
-            kern.lowblock_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], lowblock['unit'],
-                                lowblock.get('group', 1))
-        op.apply(Tv, HTv)
-        kern.gram_pair(Vt, Tv, HTv, SB, SA)
-        kern.davidson_insert2(st, SA, SB, B)
     # the Ritz block of every point sits at the row its last judged iteration wrote it to
     rows = xlast.long().unsqueeze(1) + torch.arange(p, device=dev).unsqueeze(0)
     ritz = V[torch.arange(B, device=dev).unsqueeze(1), rows]
