@@ -305,46 +305,75 @@ extern "C" int sqc_lowband_factor(void* A, int32_t ns, const int32_t* blk_off, i
     return 0;
 }
 
-// dot helpers with four independent partial sums (the loops are latency bound)
-__device__ __forceinline__ float2 dot_conj_col(const float2* __restrict__ Mcol, int ld, const float2* __restrict__ x, int n) {
-    // sum_k conj(M[k][i]) x[k]   (Mcol = &M[0][i])
-    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-    int k = 0;
-    for (; k + 3 < n; k += 4) {
-        const float2 m0 = Mcol[k * ld], m1 = Mcol[(k + 1) * ld], m2 = Mcol[(k + 2) * ld], m3 = Mcol[(k + 3) * ld];
-        const float2 x0 = x[k], x1 = x[k + 1], x2 = x[k + 2], x3 = x[k + 3];
-        a0.x += m0.x * x0.x + m0.y * x0.y; a0.y += m0.x * x0.y - m0.y * x0.x;
-        a1.x += m1.x * x1.x + m1.y * x1.y; a1.y += m1.x * x1.y - m1.y * x1.x;
-        a2.x += m2.x * x2.x + m2.y * x2.y; a2.y += m2.x * x2.y - m2.y * x2.x;
-        a3.x += m3.x * x3.x + m3.y * x3.y; a3.y += m3.x * x3.y - m3.y * x3.x;
+// Apply: T[b][jj][S[i]] = ((H_SS - sigma)^-1 (HX_a - theta_a X_a)[S])_i,  a = act[b][jj], through the block
+// factorisation above.  One CTA per sweep point; a warp owns LBC right-hand sides (stored
+// interleaved, [row][LBC]) and a lane one row of the current block, so a factor entry is fetched from
+// shared memory once per four multiply-adds and the four vector entries arrive as two broadcast
+// 16-byte loads -- the kernel is shared-memory-bandwidth bound (ncu: one RHS per warp issued
+// 3 wavefronts per multiply-add).  The factor blocks of a step are staged once for all warps,
+// one step ahead (cp.async, two buffers).
+#ifndef LBC
+#define LBC 2
+#endif
+
+struct f2x4 { float2 c[LBC]; };
+
+// acc[c] (+/-)= sum_k conj(M[k][i]) x[k][c]    (Mcol = &M[0][i];  x: [n][LBC])
+template <bool SUB>
+__device__ __forceinline__ void dot4_conj_col(f2x4& acc, const float2* __restrict__ Mcol, int ld,
+                                              const float2* __restrict__ x, int n) {
+    for (int k = 0; k < n; ++k) {
+        const float2 m = Mcol[k * ld];
+        float2 xs[LBC];
+#pragma unroll
+        for (int h = 0; h < LBC / 2; ++h) {
+            const float4 xa = *reinterpret_cast<const float4*>(x + k * LBC + 2 * h);
+            xs[2 * h] = make_float2(xa.x, xa.y);
+            xs[2 * h + 1] = make_float2(xa.z, xa.w);
+        }
+#pragma unroll
+        for (int c = 0; c < LBC; ++c) {
+            const float re = m.x * xs[c].x + m.y * xs[c].y, im = m.x * xs[c].y - m.y * xs[c].x;
+            acc.c[c].x += SUB ? -re : re;
+            acc.c[c].y += SUB ? -im : im;
+        }
     }
-    for (; k < n; ++k) {
-        const float2 m0 = Mcol[k * ld], x0 = x[k];
-        a0.x += m0.x * x0.x + m0.y * x0.y; a0.y += m0.x * x0.y - m0.y * x0.x;
-    }
-    return make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
 }
-__device__ __forceinline__ float2 dot_row(const float2* __restrict__ Mrow, const float2* __restrict__ x, int n) {
-    // sum_k M[i][k] x[k]   (Mrow = &M[i][0])
-    float2 a0 = make_float2(0.f, 0.f), a1 = a0;
-    int k = 0;
-    for (; k + 1 < n; k += 2) {
-        const float2 w0 = cmulf(Mrow[k], x[k]), w1 = cmulf(Mrow[k + 1], x[k + 1]);
-        a0.x += w0.x; a0.y += w0.y;
-        a1.x += w1.x; a1.y += w1.y;
+// acc[c] = sum_k M[i][k] x[k][c]    (Mrow = &M[i][0])
+__device__ __forceinline__ void dot4_row(f2x4& acc, const float2* __restrict__ Mrow, const float2* __restrict__ x, int n) {
+    for (int k = 0; k < n; ++k) {
+        const float2 m = Mrow[k];
+        float2 xs[LBC];
+#pragma unroll
+        for (int h = 0; h < LBC / 2; ++h) {
+            const float4 xa = *reinterpret_cast<const float4*>(x + k * LBC + 2 * h);
+            xs[2 * h] = make_float2(xa.x, xa.y);
+            xs[2 * h + 1] = make_float2(xa.z, xa.w);
+        }
+#pragma unroll
+        for (int c = 0; c < LBC; ++c) {
+            acc.c[c].x += m.x * xs[c].x - m.y * xs[c].y;
+            acc.c[c].y += m.x * xs[c].y + m.y * xs[c].x;
+        }
     }
-    if (k < n) {
-        const float2 w0 = cmulf(Mrow[k], x[k]);
-        a0.x += w0.x; a0.y += w0.y;
+}
+__device__ __forceinline__ void st4(float2* dst, const f2x4& v) {
+#pragma unroll
+    for (int h = 0; h < LBC / 2; ++h)
+        *reinterpret_cast<float4*>(dst + 2 * h) = make_float4(v.c[2 * h].x, v.c[2 * h].y, v.c[2 * h + 1].x, v.c[2 * h + 1].y);
+}
+__device__ __forceinline__ f2x4 ld4(const float2* src) {
+    f2x4 v;
+#pragma unroll
+    for (int h = 0; h < LBC / 2; ++h) {
+        const float4 a = *reinterpret_cast<const float4*>(src + 2 * h);
+        v.c[2 * h] = make_float2(a.x, a.y);
+        v.c[2 * h + 1] = make_float2(a.z, a.w);
     }
-    return make_float2(a0.x + a1.x, a0.y + a1.y);
+    return v;
 }
 
-// Apply: T[b][jj][S[i]] = ((H_SS - sigma)^-1 (HX_a - theta_a X_a)[S])_i,  a = act[b][jj], through the block
-// factorisation above.  One CTA per sweep point, one warp per right-hand side; the factor blocks
-// of a step are staged in shared memory once for all the warps, one step ahead (cp.async, two
-// buffers), so the L2 latency of a step hides behind the substitution of the previous one.
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(32 * (16 / LBC))
 lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* __restrict__ theta,
                      int ld_theta, const int32_t* __restrict__ act, int ld_act,
                      const int32_t* __restrict__ S, long long s_stride_b, const float2* __restrict__ Afac,
@@ -358,8 +387,8 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
     const int nwarp = blockDim.x >> 5;
     const int bufsz = 2 * nbmax * ld;          // P block + E block
     float2* buf = smf;                         // two buffers of (P, E)
-    float2* vec = buf + 2 * bufsz;             // [nwarp][ns]  r -> z -> x   (per right-hand side)
-    float2* tmp = vec + (size_t)nwarp * ns;    // [nwarp][nbmax]
+    float2* vec = buf + 2 * bufsz + (2 * bufsz & 1);      // 16-byte aligned: [nwarp][ns][LBC]  r -> z -> x
+    float2* tmp = vec + (size_t)nwarp * ns * LBC;         // [nwarp][nbmax][LBC]
     const int slot = b / group;
     const int32_t* s = S + slot * s_stride_b;
     const int32_t* pm = perm ? perm + slot * s_stride_b : nullptr;
@@ -367,9 +396,10 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
     const int32_t* off = blk_off + (long long)slot * ld_off;
     const int nb = nblk[slot];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool mine = warp < na;
-    float2* v = vec + (size_t)warp * ns;
-    float2* u = tmp + (size_t)warp * nbmax;
+    const int c0 = warp * LBC;                 // first right-hand side of this warp
+    const bool mine = c0 < na;
+    float2* v = vec + (size_t)warp * ns * LBC;
+    float2* u = tmp + (size_t)warp * nbmax * LBC;
     // stage step `st` (0 .. 2 nb - 2: forward steps q = st, then backward steps q = 2 nb - 2 - st)
     // into buffer st & 1:  P_q, and E_{q-1} (forward) or E_q (backward).  8-byte cp.async.
     auto stage = [&](int st) {
@@ -395,17 +425,24 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
     };
     stage(0);
     if (mine) {
-        const int av = act[(long long)b * ld_act + warp];
-        const double th = theta[(long long)b * ld_theta + av];
-        const cplx* x = blk_vec(X, b, av, N);
-        const cplx* h = blk_vec(HX, b, av, N);
-        // gather in ascending-address order (perm sorts the index set by address): the set is made of
-        // runs of consecutive charge states, so neighbouring lanes read neighbouring amplitudes
-        for (int j = lane; j < ns; j += 32) {
-            const int i = pm ? pm[j] : j;
-            const int idx = s[i];
-            const cplx xv = x[idx], hv = h[idx];
-            v[i] = make_float2((float)((hv.x - th * xv.x) * inv_unit), (float)((hv.y - th * xv.y) * inv_unit));
+        // gather in ascending-address order (perm sorts the index set by address)
+#pragma unroll
+        for (int c = 0; c < LBC; ++c) {
+            if (c0 + c < na) {
+                const int av = act[(long long)b * ld_act + c0 + c];
+                const double th = theta[(long long)b * ld_theta + av];
+                const cplx* x = blk_vec(X, b, av, N);
+                const cplx* h = blk_vec(HX, b, av, N);
+                for (int j = lane; j < ns; j += 32) {
+                    const int i = pm ? pm[j] : j;
+                    const int idx = s[i];
+                    const cplx xv = x[idx], hv = h[idx];
+                    v[i * LBC + c] = make_float2((float)((hv.x - th * xv.x) * inv_unit),
+                                                 (float)((hv.y - th * xv.y) * inv_unit));
+                }
+            } else {
+                for (int j = lane; j < ns; j += 32) v[j * LBC + c] = make_float2(0.0f, 0.0f);
+            }
         }
     }
     for (int st = 0; st <= 2 * nb - 2; ++st) {
@@ -421,32 +458,52 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
             const int q = st, o = off[q], n = off[q + 1] - o;
             const int op = q > 0 ? off[q - 1] : 0, np_ = q > 0 ? o - op : 0;
             for (int i = lane; i < n; i += 32) {
-                const float2 d = dot_conj_col(E + i, ld, v + op, np_);
-                u[i] = make_float2(v[o + i].x - d.x, v[o + i].y - d.y);
+                f2x4 acc = ld4(v + (o + i) * LBC);
+                dot4_conj_col<true>(acc, E + i, ld, v + op * LBC, np_);
+                st4(u + i * LBC, acc);
             }
             __syncwarp();
             // P Hermitian: P[i][k] = conj(P[k][i]) -> lanes read consecutive addresses
-            for (int i = lane; i < n; i += 32) v[o + i] = dot_conj_col(P + i, ld, u, n);
+            for (int i = lane; i < n; i += 32) {
+                f2x4 acc;
+#pragma unroll
+                for (int c = 0; c < LBC; ++c) acc.c[c] = make_float2(0.0f, 0.0f);
+                dot4_conj_col<false>(acc, P + i, ld, u, n);
+                st4(v + (o + i) * LBC, acc);
+            }
             __syncwarp();
         } else {
             // ---- backward:  x_q = z_q - P_q (E_q x_{q+1}) ----
             const int q = 2 * nb - 2 - st, o = off[q], n = off[q + 1] - o;
             const int on = off[q + 1], nn = off[q + 2] - on;
-            for (int i = lane; i < n; i += 32) u[i] = dot_row(E + i * ld, v + on, nn);
+            for (int i = lane; i < n; i += 32) {
+                f2x4 acc;
+#pragma unroll
+                for (int c = 0; c < LBC; ++c) acc.c[c] = make_float2(0.0f, 0.0f);
+                dot4_row(acc, E + i * ld, v + on * LBC, nn);
+                st4(u + i * LBC, acc);
+            }
             __syncwarp();
             for (int i = lane; i < n; i += 32) {
-                const float2 d = dot_conj_col(P + i, ld, u, n);
-                v[o + i] = make_float2(v[o + i].x - d.x, v[o + i].y - d.y);
+                f2x4 acc = ld4(v + (o + i) * LBC);
+                dot4_conj_col<true>(acc, P + i, ld, u, n);
+                st4(v + (o + i) * LBC, acc);
             }
             __syncwarp();
         }
     }
     cp_async_wait<0>();
     if (mine) {
-        cplx* t = blk_vec(T, b, warp, N);
-        for (int j = lane; j < ns; j += 32) {
-            const int i = pm ? pm[j] : j;
-            t[s[i]] = cmake((double)v[i].x, (double)v[i].y);
+#pragma unroll
+        for (int c = 0; c < LBC; ++c) {
+            if (c0 + c < na) {
+                cplx* t = blk_vec(T, b, c0 + c, N);
+                for (int j = lane; j < ns; j += 32) {
+                    const int i = pm ? pm[j] : j;
+                    const float2 w = v[i * LBC + c];
+                    t[s[i]] = cmake((double)w.x, (double)w.y);
+                }
+            }
         }
     }
 }
@@ -457,8 +514,9 @@ extern "C" int sqc_lowband_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, c
                                  int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit, int32_t group,
                                  const int32_t* perm, int64_t N, int32_t B, void* stream) {
     if (B <= 0 || ns <= 0 || T.cnt_fixed <= 0 || T.cnt_fixed > 16 || group < 1 || nbmax <= 0) return SQC_EINVAL;
-    const int nwarp = T.cnt_fixed;
-    const size_t smem = ((size_t)4 * nbmax * (nbmax | 1) + (size_t)nwarp * ns + (size_t)nwarp * nbmax) * sizeof(float2);
+    const int nwarp = (T.cnt_fixed + LBC - 1) / LBC;
+    const size_t smem = ((size_t)4 * nbmax * (nbmax | 1) + 1 + (size_t)nwarp * ns * LBC + (size_t)nwarp * nbmax * LBC) *
+                        sizeof(float2);
     if (smem > 227 * 1024) return SQC_ELIMIT;
     cudaError_t e = cudaFuncSetAttribute(lowband_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
