@@ -149,6 +149,30 @@ def test_config2_zero_pi_bench_size_points():
     assert np.max(np.abs(res2.efreqs.cpu().numpy() - ef[1][None, :]) / np.abs(ef[1])) < 1e-9
 
 
+def test_config2_bench_path_continuation_at_full_size():
+    """The bench path itself: N = 10100, a flux sweep long enough for the four-level continuation
+    (cold level, warm starts gathered from solved neighbours, banded two-level preconditioner with
+    shared factorisations, planned restarts), symmetric end points included.  Sampled points against
+    the oracle: eigenfrequencies 1e-9, subspace overlap 1 - 1e-10, the six decay rates 1e-8; every
+    point through size-independent properties."""
+    cr, lp, oc, ol = cs.zero_pi()
+    cr.set_trunc_nums([100, 51])
+    oc.set_trunc_nums([100, 51])
+    fl = np.linspace(0.0, 0.5, 2049)
+    st = []
+    res = cr.sweep_diag(10, loop_fluxes={lp: fl}, stats=st)
+    levels = [s_ for s_ in st if isinstance(s_, tuple) and s_[0] == 'level']
+    assert len(levels) == 4, levels                      # 64 / 8 / 2 / 1 strides all populated
+    idx = [0, 77, 1024, 1555, 2048]
+    _check(res, oc, ol.set_flux, fl[idx], 10, DEC, idx=idx)
+    X = res.evecs
+    gram = X.conj() @ X.transpose(1, 2)
+    assert float((gram - torch.eye(10, device=X.device)).abs().max()) < 1e-9
+    ef = res.efreqs.cpu().numpy()
+    assert np.all(np.diff(ef, axis=1) >= -1e-9)            # sorted spectra
+    assert np.max(np.abs(np.diff(ef, axis=0))) < 0.01       # smooth along the sweep (no skipped level)
+
+
 def test_config3_transmon_resonator_transmon():
     cr, oc = cs.trt()
     cr.set_trunc_nums([6, 6, 6])
