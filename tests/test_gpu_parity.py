@@ -173,6 +173,23 @@ def test_config2_bench_path_continuation_at_full_size():
     assert np.max(np.abs(np.diff(ef, axis=0))) < 0.01       # smooth along the sweep (no skipped level)
 
 
+def test_zero_pi_gate_charge_sweep_with_continuation():
+    """Gate-charge sweep of the 0-pi qubit at a size that goes through Davidson: the LC diagonal, the
+    low-energy index set and the banded preconditioner now differ from point to point, and the
+    continuation gathers warm starts along the charge axis.  Sampled points against the oracle."""
+    cr, lp, oc, ol = cs.zero_pi()
+    cr.set_trunc_nums([40, 21])
+    oc.set_trunc_nums([40, 21])
+    mode = next(iter(cr.charge_islands)) + 1
+    ngs = np.linspace(0.0, 0.5, 81)
+    cr.set_charge_offset(mode, 0.0)
+    lp.set_flux(0.23)
+    ol.set_flux(0.23)
+    res = cr.sweep_diag(8, charge_offsets={mode: ngs})
+    idx = [0, 33, 80]
+    _check(res, oc, lambda g: oc.set_charge_offset(mode, float(g)), ngs[idx], 8, ['capacitive', 'charge', 'cc'], idx=idx)
+
+
 def test_config3_transmon_resonator_transmon():
     cr, oc = cs.trt()
     cr.set_trunc_nums([6, 6, 6])
