@@ -225,9 +225,14 @@ def our_arm(args):
         args.gpus = world
     torch.cuda.set_device(local)
     dev = f'cuda:{local}'
-    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-        os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the single JSON line
+    # stdout must carry the single JSON line only: NCCL prints its version banner to fd 1 when the
+    # communicator is created (NCCL_DEBUG=VERSION / WARN / INFO), so fd 1 points at stderr until the
+    # first collective has run
+    saved_stdout = None
     if world > 1:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=torch.device(dev))
 
     import __graft_entry__ as ge
@@ -235,6 +240,10 @@ def our_arm(args):
         ge.build()
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     import sqcircuit_b200 as sq
     from sqcircuit_b200.kernels import Kernels
     from sqcircuit_b200.sharding import gather_to_root
