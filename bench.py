@@ -268,7 +268,7 @@ def our_arm(args):
             fl = fluxes_host.to(dev, non_blocking=True).cpu().numpy()   # H2D of the step's inputs
         else:
             fl = fluxes_host.numpy()
-        res = cr.sweep_diag(N_EIG, loop_fluxes={loop: fl}, tol=args.tol, max_basis=args.mmax, lowblock=args.lowblock, **({'coarse_stride': tuple(int(x) for x in args.strides.split(','))} if args.strides else {}))
+        res = cr.sweep_diag(N_EIG, loop_fluxes={loop: fl}, tol=args.tol, max_basis=args.mmax, lowblock=args.lowblock, block_size=args.block, **({'coarse_stride': tuple(int(x) for x in args.strides.split(','))} if args.strides else {}))
         rates = [res.dec_rate(d, states=(1, 0)) for d in DEC_TYPES]
         if world > 1:
             # the only collective of the path: final gather of the per-point results to rank 0
@@ -451,6 +451,7 @@ def main():
     ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--mmax', type=int, default=None, help='maximum Davidson basis size (default 4 x block)')
     ap.add_argument('--lowblock', type=int, default=512)
+    ap.add_argument('--block', type=int, default=None, help='Davidson block size p (default k + 2)')
     ap.add_argument('--strides', default='', help='continuation level strides, e.g. 64,16,4,1 (default 64,8,1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
