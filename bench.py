@@ -380,6 +380,9 @@ def our_arm(args):
         # measured DMMA issue rate (tools/cu/dmma_peak.cu, profiles/r01_dmma_peak.txt): 37.1 TFLOP/s
         roof['fp64_tensor_peak_tflops'] = 37.1
         roof['fp64_tensor_frac'] = roof['fp64_tflops'] / 37.1
+        # ceiling of the HBM fraction for this operator: 2*2*m useful flop per 32 algorithmic bytes at
+        # the FP64 tensor peak (m = 100: 12.5 flop/B against a ridge of 5.7 flop/B)
+        roof['hbm_frac_ceiling_fp64_bound'] = (37.1e12 / (2.0 * 2 * cr.m[0] / 32.0)) / 1e9 / hbm_peak
     roof['calls'] = hx_calls
 
     # ---- cpu baseline: bounded sample of the same workload on the host cores ----
