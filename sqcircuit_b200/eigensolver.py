@@ -340,6 +340,7 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
     converged = False
     lowblock = None
     best_left, best_it = B + 1, 0
+    res_hist = []
     async_count = dev.type == 'cuda'
     if async_count:
         host_count = torch.zeros((1,), dtype=i32).pin_memory()
@@ -408,8 +409,12 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
         # points every iteration once the first ones converge, and a cold start needs ~35)
         if left < best_left:
             best_left, best_it = left, it
-        elif it - best_it >= 30 and it >= 60:
-            break
+        elif it % 10 == 0:
+            # ... and the worst residual has not halved over those 30 iterations either (a single
+            # hard point may legitimately need more than 60 iterations while converging steadily)
+            res_hist.append(float((resmax * (1 - done)).max()))
+            if it - best_it >= 30 and it >= 60 and len(res_hist) > 3 and res_hist[-1] > 0.5 * res_hist[-4]:
+                break
     # the Ritz block of every point sits at the row its last judged iteration wrote it to
     rows = xlast.long().unsqueeze(1) + torch.arange(p, device=dev).unsqueeze(0)
     ritz = V[torch.arange(B, device=dev).unsqueeze(1), rows]
