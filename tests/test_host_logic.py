@@ -261,3 +261,24 @@ def test_warm_start_gather_and_cold_start_block():
         assert torch.equal(V0[0, j], e) and torch.equal(V0[1, j], e)
     for j in (4, 5):
         assert int((V0[0, j] != 0).sum()) > 6 and abs(V0[0, j][low[j]] - 1) < 0.05
+
+
+def test_low_block_sharing_only_between_neighbouring_points():
+    """Factorisations are shared by groups of consecutive sweep points only when consecutive points
+    are close in parameter space (sorted dense sweeps), never for points in arbitrary order."""
+    from sqcircuit_b200.operators import HamiltonianOperator
+    K = EmulKernels()
+    cr, lp, _, _ = cs.zero_pi(K)
+    cr.set_trunc_nums([25, 13])
+    ops = cr._operators()
+    lv0, ng0 = cr._current_point()
+
+    def group_of(fluxes):
+        lv = np.repeat(lv0, len(fluxes), axis=0)
+        lv[:, 0] = 2 * np.pi * np.asarray(fluxes)
+        return HamiltonianOperator(ops, lv, ng0)._auto_lowblock_group()
+    assert group_of(np.linspace(0.1, 0.1 + 63 / 4096, 64)) == 8          # dense sorted sweep
+    assert group_of(np.linspace(0.0, 0.5, 9)) == 1                        # coarse sweep
+    rng = np.random.default_rng(0)
+    assert group_of(rng.permutation(np.linspace(0.0, 1.0, 64))) == 1      # arbitrary order
+    assert group_of([0.3]) == 1
