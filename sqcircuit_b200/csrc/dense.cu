@@ -495,7 +495,9 @@ block_update_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, int ldc
 #define UPD2_THREADS 256
 #define UPD2_MT 4
 #define UPD2_DEPTH 10            // ring slots per warp (k-steps in flight = DEPTH - 1)
-#define UPD2_SLOT (2 * 32 * 2)   // doubles per slot: 2 vectors x 32 positions x (re, im)
+#define UPD2_VS 72                // doubles per staged vector piece: 32 positions x (re, im) + 8 of padding, so the two
+                                  // vectors of a k-step sit 16 banks apart (64 would put them on the same banks)
+#define UPD2_SLOT (2 * UPD2_VS)   // doubles per slot: 2 vectors
 
 template <int NCT>
 __global__ void __launch_bounds__(UPD2_THREADS, 2)
@@ -534,10 +536,10 @@ block_update_dmma_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, in
             for (int v = 0; v < 2; ++v) {
                 const int i = 2 * s + v;
                 if (i < na && n < N) {
-                    cp_async16(dst + v * 64, a + (int64_t)i * N + n);
+                    cp_async16(dst + v * UPD2_VS, a + (int64_t)i * N + n);
                 } else {
-                    dst[v * 64] = 0.0;
-                    dst[v * 64 + 1] = 0.0;
+                    dst[v * UPD2_VS] = 0.0;
+                    dst[v * UPD2_VS + 1] = 0.0;
                 }
             }
         }
@@ -557,7 +559,7 @@ block_update_dmma_kernel(sqc_block_t A, const cplx* __restrict__ Cf, int ldr, in
         // A fragment: row n = 8 mt + g, k = (vector t>>1, part t&1)
         double af[UPD2_MT];
 #pragma unroll
-        for (int mt = 0; mt < UPD2_MT; ++mt) af[mt] = slot[(t >> 1) * 64 + 2 * (8 * mt + g) + (t & 1)];
+        for (int mt = 0; mt < UPD2_MT; ++mt) af[mt] = slot[(t >> 1) * UPD2_VS + 2 * (8 * mt + g) + (t & 1)];
 #pragma unroll
         for (int j = 0; j < NCT; ++j) {
             const double bf = smem[(4 * s + t) * ldm + 8 * j + g];
@@ -646,8 +648,8 @@ extern "C" int sqc_block_update(sqc_block_t A, const void* Cf, int32_t ldr, int3
 // ---------------------------------------------------------------------------------------
 #define UPD3_THREADS 256
 #define UPD3_MT 4
-#define UPD3_DEPTH 10
-#define UPD3_SLOT (2 * 32 * 2)   // doubles per slot: 2 vectors x 32 positions x (re, im)
+#define UPD3_DEPTH 9             // 9 x 8 warps x 1.15 KB + coefficients stays under 113 KB: two CTAs per SM
+#define UPD3_SLOT (2 * UPD2_VS)   // doubles per slot: 2 vectors x (32 positions x (re, im) + padding)
 
 template <int NCT>
 __global__ void __launch_bounds__(UPD3_THREADS, 2)
@@ -694,10 +696,10 @@ ritz_update_dmma_kernel(sqc_block_t A, sqc_block_t A2, const cplx* __restrict__ 
                 for (int v = 0; v < 2; ++v) {
                     const int i = 2 * sl + v;
                     if (i < na && n < N) {
-                        cp_async16(dst + v * 64, a + (int64_t)i * N + n);
+                        cp_async16(dst + v * UPD2_VS, a + (int64_t)i * N + n);
                     } else {
-                        dst[v * 64] = 0.0;
-                        dst[v * 64 + 1] = 0.0;
+                        dst[v * UPD2_VS] = 0.0;
+                        dst[v * UPD2_VS + 1] = 0.0;
                     }
                 }
             }
@@ -722,7 +724,7 @@ ritz_update_dmma_kernel(sqc_block_t A, sqc_block_t A2, const cplx* __restrict__ 
                 // A fragment: row n = 8 mt + g, k = (vector t>>1, part t&1)
                 double af[UPD3_MT];
 #pragma unroll
-                for (int mt = 0; mt < UPD3_MT; ++mt) af[mt] = slot[(t >> 1) * 64 + 2 * (8 * mt + g) + (t & 1)];
+                for (int mt = 0; mt < UPD3_MT; ++mt) af[mt] = slot[(t >> 1) * UPD2_VS + 2 * (8 * mt + g) + (t & 1)];
 #pragma unroll
                 for (int j = 0; j < NCT; ++j) {
                     const double bf = smem[(4 * sl + t) * ldm + 8 * j + g];
