@@ -130,6 +130,29 @@ int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const double* Vo,
                  const sqc_potential_t* pot, const double* fdiag, int64_t fdiag_stride_b,
                  sqc_block_t X, sqc_block_t Y, int32_t B, void* stream);
 
+/* ---- real (time-reversal adapted) representation ------------------------------------------
+ * For one harmonic mode (mode 0, dim m) x one charge mode (mode 1, dim inner = 2 nc + 1) at zero gate
+ * charge the Hamiltonian commutes with T = (complex conjugation) x (n -> -n), so its eigenvectors can be
+ * chosen with z(i, -n) = conj z(i, n).  Such a vector is stored as N = m * inner REAL numbers
+ *     y[i][0] = z(i, 0),  y[i][n] = sqrt2 Re z(i, n),  y[i][nc + n] = sqrt2 Im z(i, n),  1 <= n <= nc,
+ * an orthonormal basis in which H is real symmetric.  Blocks keep the sqc_block_t convention with
+ * Nc = ceil(N / 2) complex elements per vector (two real amplitudes per element; the padding double of
+ * an odd N is zero), so the Gram / update kernels of section (3) serve both representations: the real
+ * part of a complex Gram entry of two such blocks is the real inner product.
+ *
+ * sqc_hx_fused_real: Y = fdiag .* X + V [ P ( V^T X ) ] on real vectors -- same operator, arguments and
+ * limits as sqc_hx_fused, except: fdiag is the LC diagonal in the real layout, [(B or 1)][2 Nc]
+ * (fdiag_stride_b in doubles), and inner must be odd and <= 127.  Panels are staged with TMA bulk copies
+ * (cp.async.bulk + mbarrier) and written back the same way. */
+int sqc_hx_fused_real(const sqc_space_t* sp, const double* Ve, const double* Vo,
+                      const sqc_potential_t* pot, const double* fdiag, int64_t fdiag_stride_b,
+                      sqc_block_t X, sqc_block_t Y, int32_t B, void* stream);
+
+/* Zc (complex, N elements per vector, Fock x charge basis of the reference) <- Xr (real representation),
+ * and the projection back, Xr <- T-symmetric part of Zc. */
+int sqc_real_to_complex(const sqc_space_t* sp, sqc_block_t Xr, sqc_block_t Zc, int32_t B, void* stream);
+int sqc_complex_to_real(const sqc_space_t* sp, sqc_block_t Zc, sqc_block_t Xr, int32_t B, void* stream);
+
 /* Z = P X with P as documented at sqc_potential_t (X, Z in the x/charge basis). */
 int sqc_potential_apply(const sqc_space_t* sp, const sqc_potential_t* pot, sqc_block_t X,
                         sqc_block_t Z, int32_t B, void* stream);
@@ -228,6 +251,10 @@ typedef struct {
     int32_t* xoff;
     int32_t* xlast;
     int32_t  xrow;
+    /* 1: the basis vectors are REAL arrays viewed as complex blocks (real representation, see
+     * sqc_hx_fused_real): only the real parts of the Gram / projection entries are meaningful and
+     * sqc_davidson_insert2 stores them with a zero imaginary part. */
+    int32_t  real_basis;
 } sqc_davidson_state_t;
 
 int sqc_davidson_decide(const sqc_davidson_state_t* st, int32_t B, void* stream);
@@ -242,6 +269,13 @@ int sqc_precond_residual(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const dou
                          int32_t ld_theta, const int32_t* act, int32_t ld_act,
                          const double* d, int64_t d_stride_b, const double* den_floor,
                          int64_t N, int32_t B, void* stream);
+
+/* sqc_precond_residual on a real-representation block: d has one entry per REAL amplitude,
+ * device[(B or 1)][2 N] (N = complex elements per vector, d_stride_b in doubles, even). */
+int sqc_precond_residual_real(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                              int32_t ld_theta, const int32_t* act, int32_t ld_act,
+                              const double* d, int64_t d_stride_b, const double* den_floor,
+                              int64_t N, int32_t B, void* stream);
 
 /* Two-level preconditioner (harmonic x charge layouts): the ns basis states S[.] with the smallest
  * LC energy get the exact inverse of (H_SS - sigma) instead of the diagonal one.
@@ -262,6 +296,24 @@ int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const doubl
                        int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
                        int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int32_t group,
                        int64_t N, int32_t B, void* stream);
+
+/* Real representation: S holds indices of REAL basis states (i * inner + j), d the real-layout LC
+ * diagonal; the block is real symmetric and stored as complex64 with zero imaginary parts, so
+ * sqc_hpd_inverse_c64 / sqc_lowband_factor apply unchanged.  The *_apply_real variants gather and
+ * scatter real amplitudes (N = complex elements per vector, as everywhere). */
+int sqc_lowblock_assemble_real(const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
+                               const void* Dt, const sqc_potential_t* pot, const double* d,
+                               int64_t d_stride_b, const double* sigma, double unit, void* out,
+                               int32_t B, void* stream);
+int sqc_lowblock_apply_real(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                            int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
+                            int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int32_t group,
+                            int64_t N, int32_t B, void* stream);
+int sqc_lowband_apply_real(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                           int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
+                           int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
+                           int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit, int32_t group,
+                           const int32_t* perm, int64_t N, int32_t B, void* stream);
 
 /* Banded form of the two-level preconditioner for LARGE low-energy blocks (ns up to 1024).
  * With the index set ordered charge-major (all kept Fock states of charge q form block q, index

@@ -568,8 +568,15 @@ class OCircuit:
         return w / (2 * np.pi * UNIT_FREQ), v
 
     # -- circuit.py:2397-2433 ---------------------------------------------------
+    _scale = False
+
     def _ip(self, a, op, b):
+        if self._scale:          # dec_rate_scale: ||op b|| bounds |<a|op|b>|
+            return np.linalg.norm(op @ b)
         return np.vdot(a, op @ b)
+
+    def _diff(self, x, y):
+        return x + y if self._scale else x - y
 
     def matrix_elements(self, ctype, nodes, states):
         op = self.coupling_op(ctype, nodes)
@@ -598,7 +605,7 @@ class OCircuit:
         # circuit.py:2828-2873
         pH = self.partial_H(el, b_sel)
         a, b = self.evecs[:, states[0]], self.evecs[:, states[1]]
-        return np.real(self._ip(a, pH, a) - self._ip(b, pH, b))
+        return np.real(self._diff(self._ip(a, pH, a), self._ip(b, pH, b)))
 
     @staticmethod
     def _dephasing(A, p_omega):
@@ -641,7 +648,7 @@ class OCircuit:
                     op = 0
                     for j in range(self.n):
                         op = op + self.cInvTrans[i, j] * self.Q[j] / np.sqrt(HBAR)
-                    po = np.abs(self._ip(s1, op, s1) - self._ip(s2, op, s2))
+                    po = np.abs(self._diff(self._ip(s1, op, s1), self._ip(s2, op, s2)))
                     decay += self._dephasing(self.ng_A[i] * 2 * E_CH, po)
         elif dec_type == 'cc':
             for (el, b_id) in self.cos_ops:
@@ -652,6 +659,19 @@ class OCircuit:
         else:
             raise ValueError(dec_type)
         return decay
+
+
+    def dec_rate_scale(self, dec_type, states, total=True):
+        """TEST HELPER (not in the reference): the same closed forms as ``dec_rate`` with every inner
+        product <a|O|b> replaced by its bound ||O b|| (and differences of expectation values by sums).
+        This is the size a rate would have if no symmetry suppressed it; rounding noise in a rate is
+        machine epsilon times this number, so parity tests use 1e-9 x it as the floor below which a
+        symmetry-forbidden rate (the reference itself returns noise there) is not compared."""
+        self._scale = True
+        try:
+            return self.dec_rate(dec_type, states, total)
+        finally:
+            self._scale = False
 
 
 # ---------------------------------------------------------------------------

@@ -40,7 +40,7 @@ class DavidsonState(C.Structure):
                 ('msz', c_vp), ('nact', c_vp), ('act', c_vp), ('restart', c_vp), ('done', c_vp),
                 ('n_not_done', c_vp), ('theta', c_vp), ('rn2', c_vp), ('resmax', c_vp),
                 ('den_floor', c_vp), ('G', c_vp), ('GB', c_vp), ('mtot', c_vp), ('nexp', c_i32),
-                ('xoff', c_vp), ('xlast', c_vp), ('xrow', c_i32)]
+                ('xoff', c_vp), ('xlast', c_vp), ('xrow', c_i32), ('real_basis', c_i32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/sqcircuit_b200.h
@@ -81,6 +81,18 @@ SIGNATURES = {
                                   c_vp, c_i32, c_dbl, c_i32, c_vp, c_i64, c_i32, c_vp]),
     'sqc_lowblock_apply': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32, c_dbl,
                                    c_i32, c_i64, c_i32, c_vp]),
+    'sqc_hx_fused_real': (c_i32, [C.POINTER(Space), c_vp, c_vp, C.POINTER(Potential), c_vp, c_i64, Block, Block, c_i32,
+                                  c_vp]),
+    'sqc_real_to_complex': (c_i32, [C.POINTER(Space), Block, Block, c_i32, c_vp]),
+    'sqc_complex_to_real': (c_i32, [C.POINTER(Space), Block, Block, c_i32, c_vp]),
+    'sqc_precond_residual_real': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp,
+                                          c_i64, c_i32, c_vp]),
+    'sqc_lowblock_assemble_real': (c_i32, [C.POINTER(Space), c_i32, c_vp, c_i64, c_vp, C.POINTER(Potential), c_vp,
+                                           c_i64, c_vp, c_dbl, c_vp, c_i32, c_vp]),
+    'sqc_lowband_apply_real': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32, c_vp,
+                                       c_i32, c_vp, c_i32, c_dbl, c_i32, c_vp, c_i64, c_i32, c_vp]),
+    'sqc_lowblock_apply_real': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32,
+                                        c_dbl, c_i32, c_i64, c_i32, c_vp]),
     'sqc_svqb_coeffs': (c_i32, [c_vp, c_i32, c_vp, c_dbl, c_vp, c_vp, c_vp, c_i32, c_vp]),
     'sqc_davidson_insert': (c_i32, [C.POINTER(DavidsonState), c_vp, c_i32, c_i32, c_i32, c_vp]),
 }
@@ -109,7 +121,7 @@ def load():
             raise SqcLibraryError(f'{LIB_PATH} does not export {name}') from e
         fn.restype = res
         fn.argtypes = args
-    if lib.sqc_abi_version() != 2:
+    if lib.sqc_abi_version() != 3:
         raise SqcLibraryError('sqcircuit_b200 ABI version mismatch')
     _lib = lib
     return lib

@@ -23,12 +23,19 @@ from .eigensolver import DENSE_MAX, solve_davidson, solve_davidson_gen, solve_de
 SOLVER = {'kind': 'gen'}
 
 
+class _RealRepresentationFailed(RuntimeError):
+    """The solve in the real representation did not converge; the caller redoes it with complex vectors."""
+
+
 def _davidson(*a, **kw):
     if SOLVER['kind'] == 'gen':
         kw.pop('impl', None)
         res = solve_davidson_gen(*a, **kw)
         if res.converged:
             return res
+        if getattr(a[1], 'real', False):
+            # the orthogonalised iteration below works on complex vectors only
+            raise _RealRepresentationFailed()
         # Safety net: the non-orthogonalised iteration can stagnate a little above the tolerance
         # when expansion vectors keep arriving almost inside the span of the basis (seen on
         # charge-dominated Hamiltonians with ||H|| >> the wanted eigenvalues).  The orthogonalised
@@ -39,7 +46,7 @@ def _davidson(*a, **kw):
 from .elements import Capacitor, Charge, Inductor, Junction, Loop
 from .exceptions import CircuitStateError
 from .noise_ops import SweepNoise
-from .operators import CircuitOperators, HamiltonianOperator
+from .operators import CircuitOperators, HamiltonianOperator, RealHamiltonianOperator
 from .settings import get_device, get_optim_mode
 from .topology import assemble, transform
 
@@ -235,12 +242,14 @@ class Circuit:
     def sweep_diag(self, n_eig, loop_fluxes: Optional[Dict] = None,
                    charge_offsets: Optional[Dict[int, Sequence[float]]] = None, tol=1e-9,
                    block_size=None, max_basis=None, maxit=300, stats=None,
-                   warm_start=True, coarse_stride=8, lowblock=512) -> SweepResult:
+                   warm_start=True, coarse_stride=8, lowblock=512, real=None) -> SweepResult:
         """Diagonalise at every point of a sweep in one batched GPU solve.
 
         loop_fluxes: {Loop: array[B]} external fluxes in units of Phi0 (as Loop.set_flux);
         charge_offsets: {mode (1-based): array[B]} gate charges (as set_charge_offset).
         Parameters not listed keep their current value.  Arrays must share the length B.
+        real: None (default) uses the real representation whenever the circuit admits it, False forces
+        complex vectors.
         """
         if not isinstance(n_eig, int):
             raise ValueError('n_eig (number of eigenvalues) should be an integer.')
@@ -263,14 +272,28 @@ class Circuit:
             ng = ng0
         hop = HamiltonianOperator(ops, lv, ng)
         kern = ops.kern
+        if isinstance(coarse_stride, (tuple, list)):
+            if len(coarse_stride) < 1:
+                raise ValueError('coarse_stride: at least one stride is needed')
+            min_warm = 4 * int(coarse_stride[-2] if len(coarse_stride) >= 2 else coarse_stride[-1])
+        else:
+            min_warm = 4 * coarse_stride
         if ops.N <= DENSE_MAX:
             res = solve_dense(kern, hop, B, ops.N, n_eig)
-        elif warm_start and B >= 4 * (coarse_stride[-2] if isinstance(coarse_stride, (tuple, list)) else coarse_stride):
-            res = self._solve_continuation(ops, lv, ng, n_eig, tol, block_size, max_basis, maxit,
-                                           stats, coarse_stride, lowblock)
         else:
-            res = _davidson(kern, hop, B, ops.N, n_eig, hop.diag, p=block_size, mmax=max_basis,
-                            tol=tol, maxit=maxit, stats=stats)
+            # zero gate charge on a harmonic x charge circuit: H commutes with a time reversal and is
+            # solved as a real symmetric problem (half the bytes and flops, csrc/hx_real.cu)
+            use_real = real if real is not None else ops.supports_real(ng)
+            res = None
+            if use_real:
+                try:
+                    res = self._solve(ops, hop, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats,
+                                      coarse_stride, lowblock, warm_start and B >= min_warm, True)
+                except _RealRepresentationFailed:
+                    res = None
+            if res is None:
+                res = self._solve(ops, hop, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats,
+                                  coarse_stride, lowblock, warm_start and B >= min_warm, False)
         if not res.converged:
             raise RuntimeError(f'batched Davidson did not converge in {maxit} iterations '
                                f'(worst relative residual {float(res.resmax.max()):.2e})')
@@ -280,8 +303,29 @@ class Circuit:
         out.noise = SweepNoise(kern, ops, hop, res.evals, evecs, self)
         return out
 
+    def _solve(self, ops, hop, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats, stride, lowblock,
+               continuation, real):
+        """One batched solve of all points, with complex vectors or in the real representation (the
+        eigenvectors are converted back to the reference's Fock x charge basis at the end)."""
+        from .eigensolver import EigResult
+        kern = ops.kern
+        if continuation:
+            res = self._solve_continuation(ops, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats,
+                                           stride, lowblock, real)
+        else:
+            op = RealHamiltonianOperator(ops, lv, ng, base=hop) if real else hop
+            res = _davidson(kern, op, lv.shape[0], op.Nc if real else ops.N, n_eig, op.diag, p=block_size,
+                            mmax=max_basis, tol=tol, maxit=maxit, stats=stats)
+        if real and res.converged:
+            out = torch.empty(res.evecs.shape[:2] + (ops.N,), dtype=torch.complex128, device=ops.device)
+            step = max(1, int(2 ** 31 // (16 * ops.N * res.evecs.shape[1])))
+            for c0 in range(0, out.shape[0], step):
+                ops.real_to_complex(res.evecs[c0:c0 + step], out=out[c0:c0 + step])
+            res = EigResult(res.evals, out, res.iterations, res.resmax, res.converged)
+        return res
+
     def _solve_continuation(self, ops, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats, stride,
-                            lowblock=512):
+                            lowblock=512, real=False):
         """Sweep continuation: eigenvectors vary smoothly along a sweep, so a coarse subset of the
         points is solved from a cold start and every other point starts from the union of the Ritz
         blocks of its two nearest already-solved neighbours (Rayleigh-Ritz in that subspace is
@@ -296,12 +340,15 @@ class Circuit:
         span = prm.max(axis=0) - prm.min(axis=0)
         vary = span > 0
 
+        Nv = (ops.N + 1) // 2 if real else ops.N       # complex elements per stored vector
+
         def sub(idx):
-            return HamiltonianOperator(ops, lv[idx], ng if ng.shape[0] == 1 else ng[idx])
+            cls = RealHamiltonianOperator if real else HamiltonianOperator
+            return cls(ops, lv[idx], ng if ng.shape[0] == 1 else ng[idx])
 
         def solve(idx, x0, st):
             hop = sub(idx)
-            return _davidson(kern, hop, len(idx), ops.N, n_eig, hop.diag, p=block_size,
+            return _davidson(kern, hop, len(idx), Nv, n_eig, hop.diag, p=block_size,
                              mmax=max_basis, tol=tol, maxit=maxit, x0=x0, stats=st,
                              lowblock_ns=lowblock)
         if not vary.any():
@@ -340,7 +387,7 @@ class Circuit:
                 p = r.ritz_block.shape[1]
                 k = r.evals.shape[1]
                 evals = torch.empty((B, k), dtype=torch.float64, device=dev)
-                evecs = torch.empty((B, k, ops.N), dtype=torch.complex128, device=dev)
+                evecs = torch.empty((B, k, Nv), dtype=torch.complex128, device=dev)
                 resmax = torch.empty((B,), dtype=torch.float64, device=dev)
                 # Ritz blocks (all p vectors) of solved points, kept until the last level starts
                 ritz = {int(i): j for j, i in enumerate(idx)}
@@ -358,7 +405,7 @@ class Circuit:
                 store = torch.cat(ritz_store, dim=0) if len(ritz_store) > 1 else ritz_store[0]
                 ritz_store = [store]
                 pos = np.array([ritz[int(i)] for i in solved])
-                chunk = max(1, min(len(idx), int(2.4e10 // (2 * p * ops.N * 16))))
+                chunk = max(1, min(len(idx), int(2.4e10 // (2 * p * Nv * 16))))
                 last = li == len(levels) - 1
                 new_blocks = []
                 for c0 in range(0, len(idx), chunk):

@@ -1,0 +1,411 @@
+// Fused matrix-free H.X in the REAL (time-reversal adapted) representation, for circuits with one
+// harmonic mode (mode 0) and one charge mode (mode 1) at zero gate charge -- the 0-pi flux sweep.
+//
+// With n_g = 0 the Hamiltonian of Circuit.hamiltonian() (circuit.py:2147-2164) commutes with
+// T = (complex conjugation in the Fock x charge basis) x (n -> -n):  every junction term
+// e^{i phi_ext} D(alpha) (x) d^{s} is mapped onto its own Hermitian conjugate.  T-invariant vectors have
+// z(i, -n) = conj z(i, n), so only the charges n >= 0 are stored, as N = m * inner REAL numbers
+//     y[i][0] = z(i, 0),   y[i][n] = sqrt2 Re z(i, n),   y[i][nc + n] = sqrt2 Im z(i, n)   (1 <= n <= nc)
+// ("planar" layout, inner = 2 nc + 1), an orthonormal real basis in which H is real symmetric.  Half the
+// bytes and half the transform flops of the complex kernel (hx_fused.cu), and no halo columns: the charge
+// -1 neighbour of column 0 is the conjugate of column 1.
+//
+// One CTA per SM, two independent 8-warp teams; a team owns one whole vector at a time:
+//   1. TMA bulk copies (cp.async.bulk + mbarrier, one per pair of Fock rows -- the row pitch of 8*inner
+//      bytes is an odd multiple of 8, so a 2-D tensor map cannot describe it) land the vector in shared
+//      memory in its natural row order; a pair of rows is padded so that DMMA fragment loads are
+//      conflict free.
+//   2. forward transform on the FP64 tensor cores with the parity split of the x basis
+//      (E = Ve^T X_even -> rows 2i, O = Vo^T X_odd -> rows 2i+1), in place, one parity half at a time;
+//   3. Z_i = E_i + O_i, Z_{m-1-i} = E_i - O_i, potential and mirror sums in place (warp = row pair,
+//      lanes = charges);
+//   4. backward transform (Y_even = Ve S, Y_odd = Vo D) + LC diagonal, written in place in natural row
+//      order, then TMA bulk stores.
+// While one team waits for its store / load, the other one keeps the tensor pipe busy.
+#include "common.cuh"
+
+#define HXR_MAXT 4
+#define HXR_TEAM_WARPS 8
+#define HXR_TEAM_THREADS (32 * HXR_TEAM_WARPS)
+#define HXR_MAXTILES 2      // column tiles per warp (inner <= 8 * 8 * 2 = 128)
+
+struct HxrGeom {
+    int m, he, ho;       // Fock dim, #even rows, #odd rows
+    int inner, nc;       // real columns per Fock row (2 nc + 1), charge cut-off
+    int pp;              // doubles per padded pair of rows in shared memory
+    int nct;             // 8-wide column tiles
+    int teams;           // teams per CTA (2, or 1 when two vectors do not fit)
+    int buf_doubles;     // shared-memory doubles of one team's vector buffer
+    int n_terms;
+    int shpack;          // junction charge shifts (-1, 0, +1), 2 bits each, biased by one
+    long long N;         // reals per vector (m * inner)
+    long long vstride;   // reals between consecutive vectors of a block (2 * Nc)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_store(void* dst, const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One half (PAR = 0: even Fock rows / Ve, PAR = 1: odd rows / Vo) of the parity-split transform of NT
+// column tiles (8 real columns each) of the team's buffer, all row tiles, in place:
+//   FWD : row(2i + PAR) <- sum_a V[a][i] row(2a + PAR)      (A[i][a] = V[a][i];  E_i resp. O_i)
+//   !FWD: row(2a + PAR) <- sum_i V[a][i] row(2i + PAR) (+ d .* X)   (A[a][i] = V[a][i];  Y_even resp. Y_odd)
+// The warp owns these columns of these rows, so a __syncwarp separates its reads from its writes.
+template <int KS, int NT, bool FWD>
+__device__ __forceinline__ void hxr_pass(const double* __restrict__ sV, double* buf, const HxrGeom& gm, int par,
+                                         const int (&col0)[NT], int gq, int tq, const double* __restrict__ xv,
+                                         const double* __restrict__ fd) {
+    constexpr int KP = 4 * KS, NRT = (KS + 1) / 2;
+    constexpr int VLD = (KP % 8 == 4) ? KP : KP + 4;
+    const int pp = gm.pp, inner = gm.inner;
+    const int hcnt = par ? gm.ho : gm.he;
+    double acc[NT][NRT][2];
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int r = 0; r < NRT; ++r) acc[n][r][0] = acc[n][r][1] = 0.0;
+    const double* va = FWD ? sV + tq * VLD + gq : sV + gq * VLD + tq;
+    double* rows = buf + par * inner;
+    const double* bp[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) bp[n] = rows + tq * pp + col0[n] + gq;
+#pragma unroll 2
+    for (int k = 0; k < KS; ++k) {
+        double bf[NT];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) bf[n] = bp[n][(4 * k) * pp];
+#pragma unroll
+        for (int r = 0; r < NRT; ++r) {
+            const double af = FWD ? va[4 * k * VLD + 8 * r] : va[8 * r * VLD + 4 * k];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) dmma884(acc[n][r][0], acc[n][r][1], af, bf[n]);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const int c = col0[n] + 2 * tq;
+        const bool ok0 = c < inner, ok1 = c + 1 < inner;
+#pragma unroll
+        for (int r = 0; r < NRT; ++r) {
+            const int i = 8 * r + gq;
+            if (i < hcnt) {
+                double* z = rows + i * pp + c;
+                double v0 = acc[n][r][0], v1 = acc[n][r][1];
+                if (!FWD && fd) {
+                    // epilogue: + d .* X (X and d from global memory: both sit in L2, the vector was loaded
+                    // a few microseconds ago and d is shared by every vector)
+                    const long long idx = (long long)(2 * i + par) * inner + c;
+                    if (ok0) v0 = fma(fd[idx], xv[idx], v0);
+                    if (ok1) v1 = fma(fd[idx + 1], xv[idx + 1], v1);
+                }
+                if (ok0) z[0] = v0;
+                if (ok1) z[1] = v1;
+            }
+        }
+    }
+}
+
+template <int KS, bool FWD>
+__device__ __forceinline__ void hxr_transform(const double* sVe, const double* sVo, double* buf, const HxrGeom& gm,
+                                              const int* mytile, int ntile, int gq, int tq,
+                                              const double* __restrict__ xv, const double* __restrict__ fd) {
+    if (ntile == 2) {
+        const int col0[2] = {8 * mytile[0], 8 * mytile[1]};
+        hxr_pass<KS, 2, FWD>(sVe, buf, gm, 0, col0, gq, tq, xv, fd);
+        hxr_pass<KS, 2, FWD>(sVo, buf, gm, 1, col0, gq, tq, xv, fd);
+    } else if (ntile == 1) {
+        const int col0[1] = {8 * mytile[0]};
+        hxr_pass<KS, 1, FWD>(sVe, buf, gm, 0, col0, gq, tq, xv, fd);
+        hxr_pass<KS, 1, FWD>(sVo, buf, gm, 1, col0, gq, tq, xv, fd);
+    }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(2 * HXR_TEAM_THREADS, 1)
+hx_real_kernel(HxrGeom gm, const double* __restrict__ Ve, const double* __restrict__ Vo,
+               const double* __restrict__ lam, const cplx* __restrict__ etab, long long etab_stride_b,
+               const double* __restrict__ g, const cplx* __restrict__ a,
+               const double* __restrict__ fdiag, long long fdiag_stride_b,
+               sqc_block_t X, sqc_block_t Y, int vmax, long long total_items) {
+    constexpr int KP = 4 * KS;
+    constexpr int VLD = (KP % 8 == 4) ? KP : KP + 4;
+    extern __shared__ double smem[];
+    double* sVe = smem;                                   // [KP][VLD]   Ve[a][i] = V[2a][i]
+    double* sVo = sVe + KP * VLD;                         // [KP][VLD]   Vo[a][i] = V[2a+1][i]
+    const int tid_cta = threadIdx.x;
+    const int team = tid_cta / HXR_TEAM_THREADS;
+    const int tid = tid_cta - team * HXR_TEAM_THREADS;
+    const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const int m = gm.m, he = gm.he, ho = gm.ho, inner = gm.inner, nc = gm.nc, pp = gm.pp;
+    const int team_doubles = gm.buf_doubles + ((m + 1) & ~1) + 2 * HXR_MAXT * m;
+    double* buf = sVo + KP * VLD + team * team_doubles;   // [KP pairs][pp]: rows 2a (offset 0), 2a+1 (offset inner)
+    double* sLin = buf + gm.buf_doubles;                  // [m]
+    cplx* sPh = reinterpret_cast<cplx*>(sLin + ((m + 1) & ~1));   // [n_terms][m]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sVo + KP * VLD + gm.teams * team_doubles);
+    unsigned long long* bar = bars + team;
+    auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(HXR_TEAM_THREADS) : "memory"); };
+
+    for (int e = tid_cta; e < KP * VLD; e += blockDim.x) {
+        const int r = e / VLD, c = e % VLD;
+        sVe[e] = (r < he && c < he) ? Ve[r * he + c] : 0.0;
+        sVo[e] = (r < ho && c < ho) ? Vo[r * ho + c] : 0.0;
+    }
+    if (team < gm.teams) {
+        for (int e = tid; e < gm.buf_doubles; e += HXR_TEAM_THREADS) buf[e] = 0.0;
+        if (tid == 0) mbar_init(bar, 1);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (team >= gm.teams) return;
+
+    // column tiles of this warp; the second team starts one warp later so that the two teams' double
+    // tiles fall on different SM sub-partitions
+    int mytile[HXR_MAXTILES];
+    int ntile = 0;
+    {
+        const int w = (warp + HXR_TEAM_WARPS - team) % HXR_TEAM_WARPS;
+        for (int t = w; t < gm.nct && ntile < HXR_MAXTILES; t += HXR_TEAM_WARPS) mytile[ntile++] = t;
+    }
+    const double rs2 = 0.70710678118654752440, s2 = 1.41421356237309504880;
+    const unsigned pair_bytes = 16u * (unsigned)inner;
+    // the last pair of an odd m carries one row plus the zero padding element of the vector
+    const unsigned last_bytes = (m & 1) ? 8u * (unsigned)(inner + 1) : pair_bytes;
+    const unsigned vec_bytes = (unsigned)(he - 1) * pair_bytes + last_bytes;
+    int loaded_b = -1;
+    unsigned phase = 0;
+    const long long stride = (long long)gridDim.x * gm.teams;
+    long long item = (long long)blockIdx.x * gm.teams + team;
+    // skip ahead to the first live item and issue its load
+    auto live = [&](long long it, int& b, int& v) {
+        b = (int)(it / vmax);
+        v = (int)(it % vmax);
+        return v < blk_count(X, b);
+    };
+    auto issue_load = [&](long long it) {          // warp 0 of the team
+        int b, v;
+        live(it, b, v);
+        const double* src = reinterpret_cast<const double*>(blk_vec(X, b, v, gm.vstride / 2));
+        if (lane == 0) mbar_expect_tx(bar, vec_bytes);
+        __syncwarp();
+        for (int p = lane; p < he; p += 32)
+            bulk_load(buf + p * pp, src + (long long)p * 2 * inner, p == he - 1 ? last_bytes : pair_bytes, bar);
+    };
+    {
+        int b, v;
+        while (item < total_items && !live(item, b, v)) item += stride;
+    }
+    if (item < total_items && warp == 0) issue_load(item);
+
+    while (item < total_items) {
+        int b, v;
+        live(item, b, v);
+        long long next = item + stride;
+        {
+            int b2, v2;
+            while (next < total_items && !live(next, b2, v2)) next += stride;
+        }
+        if (b != loaded_b) {
+            // per-sweep-point tables: lin(i) = g0 + g1 lam_i ;  ph_t(i) = a_t etab_t[i]
+            const double g0 = g[(long long)b * 3], g1 = g[(long long)b * 3 + 1];
+            for (int i = tid; i < m; i += HXR_TEAM_THREADS) sLin[i] = fma(g1, lam[i], g0);
+            for (int e = tid; e < gm.n_terms * m; e += HXR_TEAM_THREADS) {
+                const int t = e / m, i = e % m;
+                sPh[e] = cmul(a[(long long)b * gm.n_terms + t], etab[b * etab_stride_b + (long long)t * (m + inner) + i]);
+            }
+            loaded_b = b;
+        }
+        const double* xv = reinterpret_cast<const double*>(blk_vec(X, b, v, gm.vstride / 2));
+        double* yv = reinterpret_cast<double*>(blk_vec(Y, b, v, gm.vstride / 2));
+        mbar_wait(bar, phase);
+        phase ^= 1;
+
+        // ---- forward transform, in place: row 2i <- E_i, row 2i+1 <- O_i ----
+        hxr_transform<KS, true>(sVe, sVo, buf, gm, mytile, ntile, gq, tq, nullptr, nullptr);
+        team_sync();
+
+        // ---- potential + mirror combination, in place: a warp owns whole row pairs ----
+        // Z_i = E_i + O_i (x point i), Z_{m-1-i} = E_i - O_i (its mirror);  S = P Z_i + P Z_mirror -> row 2i,
+        // D = P Z_i - P Z_mirror -> row 2i+1
+        for (int i = warp; i < he; i += HXR_TEAM_WARPS) {
+            const bool pair = i < ho;
+            const int im = m - 1 - i;
+            double* re = buf + i * pp;
+            double* ro = re + inner;
+            const double lin_i = sLin[i], lin_m = pair ? sLin[im] : 0.0;
+            cplx S[2], D[2];
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int n = lane + 32 * pass;
+                S[pass] = D[pass] = cmake(0.0, 0.0);
+                if (n <= nc) {
+                    // y(n) and the (scaled) neighbours "y(n-1)", "y(n+1)" of a stored row: the charge -1
+                    // neighbour of column 0 is conj y(1) / sqrt2, columns 0 and 1 are linked by sqrt2
+                    auto ld = [&](const double* row, int q) -> cplx {
+                        return q == 0 ? cmake(row[0], 0.0) : cmake(row[q], row[nc + q]);
+                    };
+                    auto left = [&](const double* row) -> cplx {
+                        if (n >= 2) return ld(row, n - 1);
+                        if (n == 1) return cmake(s2 * row[0], 0.0);
+                        return nc >= 1 ? cmake(rs2 * row[1], -rs2 * row[nc + 1]) : cmake(0.0, 0.0);
+                    };
+                    auto right = [&](const double* row) -> cplx {
+                        if (n >= nc) return cmake(0.0, 0.0);
+                        if (n == 0) return cmake(rs2 * row[1], rs2 * row[nc + 1]);
+                        return ld(row, n + 1);
+                    };
+                    const cplx ec = ld(re, n), oc = ld(ro, n);
+                    const cplx el = left(re), ol = left(ro), er = right(re), orr = right(ro);
+                    const cplx ci = cadd(ec, oc), cm = csub(ec, oc);
+                    const cplx li = cadd(el, ol), lm_ = csub(el, ol), rgi = cadd(er, orr), rgm = csub(er, orr);
+                    cplx oi = cmake(lin_i * ci.x, lin_i * ci.y);
+                    cplx om = cmake(lin_m * cm.x, lin_m * cm.y);
+                    for (int t = 0; t < gm.n_terms; ++t) {
+                        const int sh = ((gm.shpack >> (2 * t)) & 3) - 1;
+                        const cplx pi_ = sPh[t * m + i];
+                        const cplx pm_ = pair ? sPh[t * m + im] : cmake(0.0, 0.0);
+                        // ph * y(n - sh) + conj(ph) * y(n + sh)
+                        const cplx ai = sh > 0 ? li : (sh < 0 ? rgi : ci), bi = sh > 0 ? rgi : (sh < 0 ? li : ci);
+                        const cplx am = sh > 0 ? lm_ : (sh < 0 ? rgm : cm), bm = sh > 0 ? rgm : (sh < 0 ? lm_ : cm);
+                        cfma(oi, pi_, ai);
+                        cfma(oi, cconj(pi_), bi);
+                        cfma(om, pm_, am);
+                        cfma(om, cconj(pm_), bm);
+                    }
+                    S[pass] = cadd(oi, om);
+                    D[pass] = pair ? csub(oi, om) : cmake(0.0, 0.0);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int n = lane + 32 * pass;
+                if (n <= nc) {
+                    re[n] = S[pass].x;
+                    ro[n] = D[pass].x;
+                    if (n >= 1) {
+                        re[nc + n] = S[pass].y;
+                        ro[nc + n] = D[pass].y;
+                    }
+                }
+            }
+        }
+        team_sync();
+
+        // ---- backward transform + LC diagonal, in place ----
+        const double* fd = fdiag ? fdiag + b * fdiag_stride_b : nullptr;
+        hxr_transform<KS, false>(sVe, sVo, buf, gm, mytile, ntile, gq, tq, xv, fd);
+        fence_async_smem();          // generic-proxy writes -> visible to the bulk store
+        team_sync();
+
+        // ---- TMA bulk stores, then the next vector's loads into the same buffer ----
+        if (warp == 0) {
+            for (int p = lane; p < he; p += 32)
+                bulk_store(yv + (long long)p * 2 * inner, buf + p * pp, p == he - 1 ? last_bytes : pair_bytes);
+            bulk_commit();
+            bulk_wait_read0();       // the stores have read the buffer
+            __syncwarp();
+            if (next < total_items) {
+                // the padding slot of an odd m received the vector's pad element; rows >= m stay zero because
+                // nothing ever writes them
+                issue_load(next);
+            }
+        }
+        item = next;
+    }
+    // the last bulk stores must be complete before the CTA's shared memory goes away
+    if (warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// The inner (charge) dimension the real kernel accepts: tiles per warp and shared memory for at least one team.
+extern "C" int sqc_hx_fused_real(const sqc_space_t* sp, const double* Ve, const double* Vo,
+                                 const sqc_potential_t* pot, const double* fdiag, int64_t fdiag_stride_b,
+                                 sqc_block_t X, sqc_block_t Y, int32_t B, void* stream) {
+    if (!sp || !pot || B <= 0 || X.cnt_fixed <= 0 || X.ptr == Y.ptr) return SQC_EINVAL;
+    if (sp->n_modes != 2 || !sp->harmonic[0] || sp->harmonic[1]) return SQC_ELIMIT;
+    if (pot->n_terms < 0 || pot->n_terms > HXR_MAXT || pot->diag) return SQC_ELIMIT;
+    HxrGeom gm;
+    gm.m = sp->dims[0];
+    gm.inner = sp->dims[1];
+    if (gm.m < 2 || gm.m > 128 || !(gm.inner & 1)) return SQC_ELIMIT;
+    gm.nc = (gm.inner - 1) / 2;
+    gm.he = (gm.m + 1) / 2;
+    gm.ho = gm.m / 2;
+    const int kp = (gm.he + 3) & ~3;
+    gm.N = (long long)gm.m * gm.inner;
+    gm.vstride = 2 * ((gm.N + 1) / 2);
+    gm.n_terms = pot->n_terms;
+    gm.shpack = 0;
+    for (int t = 0; t < gm.n_terms; ++t) {
+        const int sh = pot->shift[t][1];
+        if (sh < -1 || sh > 1) return SQC_ELIMIT;
+        gm.shpack |= (sh + 1) << (2 * t);
+    }
+    gm.nct = (gm.inner + 7) / 8;
+    if (gm.nct > HXR_TEAM_WARPS * HXR_MAXTILES || gm.nc + 1 > 64) return SQC_ELIMIT;
+    // pair pitch: even (16-byte aligned bulk copies) and == 4 or 12 (mod 16) doubles, so that the four
+    // k-rows of a DMMA B fragment (consecutive pairs) fall on disjoint banks
+    gm.pp = 2 * gm.inner;
+    while ((gm.pp & 15) != 4 && (gm.pp & 15) != 12) gm.pp += 2;
+    // + one pitch of slack: the last column tile reads a few doubles past the end of a row
+    gm.buf_doubles = kp * gm.pp + 16;
+    const int vld = (kp % 8 == 4) ? kp : kp + 4;
+    const int team_doubles = gm.buf_doubles + ((gm.m + 1) & ~1) + 2 * HXR_MAXT * gm.m;
+    size_t smem = 0;
+    for (gm.teams = 2; gm.teams >= 1; --gm.teams) {
+        smem = ((size_t)2 * kp * vld + (size_t)gm.teams * team_doubles + 2) * sizeof(double);
+        if (smem <= 227 * 1024) break;
+    }
+    if (gm.teams < 1) return SQC_ELIMIT;
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+    const long long total = (long long)B * X.cnt_fixed;
+    long long grid = nsm;
+    if (grid * gm.teams > total) grid = (total + gm.teams - 1) / gm.teams;
+#define HXR_CASE(R)                                                                                    \
+    case R: {                                                                                          \
+        cudaError_t e = cudaFuncSetAttribute(hx_real_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem);                                               \
+        if (e != cudaSuccess) return (int)e;                                                           \
+        hx_real_kernel<R><<<(unsigned)grid, 2 * HXR_TEAM_THREADS, smem, (cudaStream_t)stream>>>(       \
+            gm, Ve, Vo, pot->lam, (const cplx*)pot->etab, pot->etab_stride_b, pot->g, (const cplx*)pot->a, \
+            fdiag, fdiag_stride_b, X, Y, X.cnt_fixed, total);                                          \
+        break;                                                                                         \
+    }
+    switch (kp / 4) {
+        HXR_CASE(1) HXR_CASE(2) HXR_CASE(3) HXR_CASE(4) HXR_CASE(5) HXR_CASE(6) HXR_CASE(7) HXR_CASE(8)
+        HXR_CASE(9) HXR_CASE(10) HXR_CASE(11) HXR_CASE(12) HXR_CASE(13) HXR_CASE(14) HXR_CASE(15) HXR_CASE(16)
+        default: return SQC_ELIMIT;
+    }
+#undef HXR_CASE
+    SQC_LAUNCHED();
+    return 0;
+}

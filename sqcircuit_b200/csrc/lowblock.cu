@@ -73,6 +73,98 @@ extern "C" int sqc_lowblock_assemble(const sqc_space_t* sp, int32_t ns, const in
     return 0;
 }
 
+// Real (time-reversal adapted) representation, see hx_real.cu: the index set holds REAL basis states
+// R = i * inner + j (Fock i; j = 0: charge 0, 1 <= j <= nc: cos-type (|n> + |-n>)/sqrt2, j > nc: sin-type
+// i(|n> - |-n>)/sqrt2 with n = j resp. j - nc).  H_r[R][R'] = sum_{s,s'} conj(u_s) u'_s' h(i, s n; i', s' n')
+// is real; it is stored as complex64 with a zero imaginary part so that the factorisation and
+// substitution kernels below serve both representations.
+__device__ __forceinline__ cplx lb_h_elem(const LbGeom& gm, const cplx* __restrict__ Dt, const cplx* __restrict__ a,
+                                          double g0, double g1, int b, int n, int q, int n2, int q2) {
+    // element between (Fock n, charge q) and (Fock n2, charge q2), without the LC diagonal
+    double vr = 0.0, vi = 0.0;
+    if (q == q2) {
+        if (n == n2) vr += g0;
+        if (n == n2 + 1 || n2 == n + 1) vr += g1 * sqrt((double)max(n, n2));
+    }
+    for (int t = 0; t < gm.n_terms; ++t) {
+        const int sh = gm.shift[t];
+        const cplx at = a[(long long)b * gm.n_terms + t];
+        if (q2 == q - sh) {
+            const cplx w = cmul(at, Dt[((long long)t * gm.m + n) * gm.m + n2]);
+            vr += w.x;
+            vi += w.y;
+        }
+        if (q2 == q + sh) {
+            const cplx w = cmul(at, Dt[((long long)t * gm.m + n2) * gm.m + n]);
+            vr += w.x;
+            vi -= w.y;
+        }
+    }
+    return cmake(vr, vi);
+}
+
+__global__ void __launch_bounds__(256)
+lowblock_assemble_real_kernel(LbGeom gm, const int32_t* __restrict__ S, long long s_stride_b,
+                              const cplx* __restrict__ Dt, const cplx* __restrict__ a,
+                              const double* __restrict__ g, const double* __restrict__ d,
+                              long long d_stride_b, const double* __restrict__ sigma, double inv_unit,
+                              float2* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    const int ns = gm.ns;
+    if (e >= ns * ns) return;
+    const int r = e / ns, q = e % ns;
+    const int32_t* s = S + b * s_stride_b;
+    const int ir = s[r], iq = s[q];
+    const int nc = (gm.inner - 1) / 2;
+    const int n = ir / gm.inner, j = ir % gm.inner;
+    const int n2 = iq / gm.inner, j2 = iq % gm.inner;
+    const int c = j > nc ? j - nc : j, c2 = j2 > nc ? j2 - nc : j2;      // |charge|
+    const double rs2 = 0.70710678118654752440;
+    // u_+ , u_- of both states (only u_+ for charge 0)
+    const cplx up = j == 0 ? cmake(1.0, 0.0) : (j <= nc ? cmake(rs2, 0.0) : cmake(0.0, rs2));
+    const cplx um = j == 0 ? cmake(0.0, 0.0) : (j <= nc ? cmake(rs2, 0.0) : cmake(0.0, -rs2));
+    const cplx vp = j2 == 0 ? cmake(1.0, 0.0) : (j2 <= nc ? cmake(rs2, 0.0) : cmake(0.0, rs2));
+    const cplx vm = j2 == 0 ? cmake(0.0, 0.0) : (j2 <= nc ? cmake(rs2, 0.0) : cmake(0.0, -rs2));
+    const double g0 = g[(long long)b * 3], g1 = g[(long long)b * 3 + 1];
+    double acc = 0.0;
+    for (int sa = 0; sa < (j == 0 ? 1 : 2); ++sa) {
+        const cplx ua = sa ? um : up;
+        const int qa = sa ? -c : c;
+        for (int sb = 0; sb < (j2 == 0 ? 1 : 2); ++sb) {
+            const cplx ub = sb ? vm : vp;
+            const int qb = sb ? -c2 : c2;
+            if (abs(qa - qb) > 1) continue;
+            const cplx h = lb_h_elem(gm, Dt, a, g0, g1, b, n, qa, n2, qb);
+            const cplx w = cmul(cmulc(ua, ub), h);        // conj(u_a) u_b h
+            acc += w.x;
+        }
+    }
+    if (r == q) acc += d[b * d_stride_b + ir] - sigma[b];
+    out[(long long)b * ns * ns + e] = make_float2((float)(acc * inv_unit), 0.0f);
+}
+
+extern "C" int sqc_lowblock_assemble_real(const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
+                                          const void* Dt, const sqc_potential_t* pot, const double* d,
+                                          int64_t d_stride_b, const double* sigma, double unit, void* out,
+                                          int32_t B, void* stream) {
+    if (!sp || !pot || B <= 0 || ns <= 0) return SQC_EINVAL;
+    if (sp->n_modes != 2 || !sp->harmonic[0] || sp->harmonic[1] || pot->n_terms > LB_MAXT) return SQC_ELIMIT;
+    if (!(sp->dims[1] & 1)) return SQC_ELIMIT;
+    LbGeom gm;
+    gm.m = sp->dims[0];
+    gm.inner = sp->dims[1];
+    gm.ns = ns;
+    gm.n_terms = pot->n_terms;
+    for (int t = 0; t < gm.n_terms; ++t) gm.shift[t] = pot->shift[t][1];
+    dim3 grid((ns * ns + 255) / 256, B);
+    lowblock_assemble_real_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        gm, S, s_stride_b, (const cplx*)Dt, (const cplx*)pot->a, pot->g, d, d_stride_b, sigma, 1.0 / unit,
+        (float2*)out);
+    SQC_LAUNCHED();
+    return 0;
+}
+
 // In-place Gauss-Jordan inverse (no pivoting: the matrices are Hermitian positive definite),
 // whole matrix in shared memory, complex64.
 __device__ __forceinline__ float2 cmulf(float2 x, float2 y) {
@@ -129,6 +221,8 @@ extern "C" int sqc_hpd_inverse_c64(void* A, int32_t ns, int32_t B, void* stream)
 }
 
 // T[b][jj][S[r]] = (1/unit) * sum_q Ainv[b][r][q] * (HX_a - theta_a X_a)[S[q]],  a = act[b][jj]
+// REAL: the vectors are real arrays of 2 N doubles (real representation) and S holds real indices
+template <bool REAL>
 __global__ void __launch_bounds__(256)
 lowblock_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* __restrict__ theta,
                       int ld_theta, const int32_t* __restrict__ act, int ld_act,
@@ -146,8 +240,14 @@ lowblock_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double
         const int jj = e / ns, q = e % ns;
         const int av = act[(long long)b * ld_act + jj];
         const double th = theta[(long long)b * ld_theta + av];
-        const cplx x = blk_vec(X, b, av, N)[s[q]], h = blk_vec(HX, b, av, N)[s[q]];
-        rS[e] = cmake(h.x - th * x.x, h.y - th * x.y);
+        if (REAL) {
+            const double x = reinterpret_cast<const double*>(blk_vec(X, b, av, N))[s[q]];
+            const double h = reinterpret_cast<const double*>(blk_vec(HX, b, av, N))[s[q]];
+            rS[e] = cmake(h - th * x, 0.0);
+        } else {
+            const cplx x = blk_vec(X, b, av, N)[s[q]], h = blk_vec(HX, b, av, N)[s[q]];
+            rS[e] = cmake(h.x - th * x.x, h.y - th * x.y);
+        }
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -164,23 +264,43 @@ lowblock_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double
             }
             sr = warp_sum(sr);
             si = warp_sum(si);
-            if (lane == 0) blk_vec(T, b, jj, N)[s[r]] = cmake(sr * inv_unit, si * inv_unit);
+            if (lane == 0) {
+                if (REAL) reinterpret_cast<double*>(blk_vec(T, b, jj, N))[s[r]] = sr * inv_unit;
+                else blk_vec(T, b, jj, N)[s[r]] = cmake(sr * inv_unit, si * inv_unit);
+            }
         }
     }
+}
+
+template <bool REAL>
+static int lowblock_apply_launch(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                                 int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
+                                 int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int32_t group,
+                                 int64_t N, int32_t B, void* stream) {
+    if (B <= 0 || ns <= 0 || T.cnt_fixed <= 0 || group < 1) return SQC_EINVAL;
+    size_t smem = (size_t)T.cnt_fixed * ns * sizeof(cplx);
+    cudaError_t e = cudaFuncSetAttribute(lowblock_apply_kernel<REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    lowblock_apply_kernel<REAL><<<B, 256, smem, (cudaStream_t)stream>>>(X, HX, T, theta, ld_theta, act, ld_act, S,
+                                                                       s_stride_b, (const float2*)Ainv, ns, 1.0 / unit, group, N);
+    SQC_LAUNCHED();
+    return 0;
 }
 
 extern "C" int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
                                   int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
                                   int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int32_t group,
                                   int64_t N, int32_t B, void* stream) {
-    if (B <= 0 || ns <= 0 || T.cnt_fixed <= 0 || group < 1) return SQC_EINVAL;
-    size_t smem = (size_t)T.cnt_fixed * ns * sizeof(cplx);
-    cudaError_t e = cudaFuncSetAttribute(lowblock_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    lowblock_apply_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(X, HX, T, theta, ld_theta, act, ld_act, S,
-                                                                 s_stride_b, (const float2*)Ainv, ns, 1.0 / unit, group, N);
-    SQC_LAUNCHED();
-    return 0;
+    return lowblock_apply_launch<false>(X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, Ainv, ns, unit, group, N,
+                                        B, stream);
+}
+
+extern "C" int sqc_lowblock_apply_real(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                                       int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
+                                       int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int32_t group,
+                                       int64_t N, int32_t B, void* stream) {
+    return lowblock_apply_launch<true>(X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, Ainv, ns, unit, group, N,
+                                       B, stream);
 }
 
 // =====================================================================================
@@ -373,6 +493,7 @@ __device__ __forceinline__ f2x4 ld4(const float2* src) {
     return v;
 }
 
+template <bool REAL>
 __global__ void __launch_bounds__(32 * (16 / LBC))
 lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* __restrict__ theta,
                      int ld_theta, const int32_t* __restrict__ act, int ld_act,
@@ -436,9 +557,15 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
                 for (int j = lane; j < ns; j += 32) {
                     const int i = pm ? pm[j] : j;
                     const int idx = s[i];
-                    const cplx xv = x[idx], hv = h[idx];
-                    v[i * LBC + c] = make_float2((float)((hv.x - th * xv.x) * inv_unit),
-                                                 (float)((hv.y - th * xv.y) * inv_unit));
+                    if (REAL) {
+                        const double xr = reinterpret_cast<const double*>(x)[idx];
+                        const double hr = reinterpret_cast<const double*>(h)[idx];
+                        v[i * LBC + c] = make_float2((float)((hr - th * xr) * inv_unit), 0.0f);
+                    } else {
+                        const cplx xv = x[idx], hv = h[idx];
+                        v[i * LBC + c] = make_float2((float)((hv.x - th * xv.x) * inv_unit),
+                                                     (float)((hv.y - th * xv.y) * inv_unit));
+                    }
                 }
             } else {
                 for (int j = lane; j < ns; j += 32) v[j * LBC + c] = make_float2(0.0f, 0.0f);
@@ -501,11 +628,32 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
                 for (int j = lane; j < ns; j += 32) {
                     const int i = pm ? pm[j] : j;
                     const float2 w = v[i * LBC + c];
-                    t[s[i]] = cmake((double)w.x, (double)w.y);
+                    if (REAL) reinterpret_cast<double*>(t)[s[i]] = (double)w.x;
+                    else t[s[i]] = cmake((double)w.x, (double)w.y);
                 }
             }
         }
     }
+}
+
+template <bool REAL>
+static int lowband_apply_launch(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                                int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
+                                int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
+                                int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit, int32_t group,
+                                const int32_t* perm, int64_t N, int32_t B, void* stream) {
+    if (B <= 0 || ns <= 0 || T.cnt_fixed <= 0 || T.cnt_fixed > 16 || group < 1 || nbmax <= 0) return SQC_EINVAL;
+    const int nwarp = (T.cnt_fixed + LBC - 1) / LBC;
+    const size_t smem = ((size_t)4 * nbmax * (nbmax | 1) + 1 + (size_t)nwarp * ns * LBC + (size_t)nwarp * nbmax * LBC) *
+                        sizeof(float2);
+    if (smem > 227 * 1024) return SQC_ELIMIT;
+    cudaError_t e = cudaFuncSetAttribute(lowband_apply_kernel<REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    lowband_apply_kernel<REAL><<<B, 32 * nwarp, smem, (cudaStream_t)stream>>>(
+        X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, (const float2*)Afac, ns, blk_off, ld_off, nblk, nbmax,
+        1.0 / unit, group, N, perm);
+    SQC_LAUNCHED();
+    return 0;
 }
 
 extern "C" int sqc_lowband_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
@@ -513,16 +661,15 @@ extern "C" int sqc_lowband_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, c
                                  int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
                                  int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit, int32_t group,
                                  const int32_t* perm, int64_t N, int32_t B, void* stream) {
-    if (B <= 0 || ns <= 0 || T.cnt_fixed <= 0 || T.cnt_fixed > 16 || group < 1 || nbmax <= 0) return SQC_EINVAL;
-    const int nwarp = (T.cnt_fixed + LBC - 1) / LBC;
-    const size_t smem = ((size_t)4 * nbmax * (nbmax | 1) + 1 + (size_t)nwarp * ns * LBC + (size_t)nwarp * nbmax * LBC) *
-                        sizeof(float2);
-    if (smem > 227 * 1024) return SQC_ELIMIT;
-    cudaError_t e = cudaFuncSetAttribute(lowband_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    lowband_apply_kernel<<<B, 32 * nwarp, smem, (cudaStream_t)stream>>>(
-        X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, (const float2*)Afac, ns, blk_off, ld_off, nblk, nbmax,
-        1.0 / unit, group, N, perm);
-    SQC_LAUNCHED();
-    return 0;
+    return lowband_apply_launch<false>(X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, Afac, ns, blk_off, ld_off,
+                                       nblk, nbmax, unit, group, perm, N, B, stream);
+}
+
+extern "C" int sqc_lowband_apply_real(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
+                                      int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
+                                      int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
+                                      int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit, int32_t group,
+                                      const int32_t* perm, int64_t N, int32_t B, void* stream) {
+    return lowband_apply_launch<true>(X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, Afac, ns, blk_off, ld_off,
+                                      nblk, nbmax, unit, group, perm, N, B, stream);
 }

@@ -774,6 +774,7 @@ davidson_insert2_kernel(sqc_davidson_state_t st, const cplx* __restrict__ SA, co
             va = cmake(0.5 * (va.x + ua.x), 0.5 * (va.y - ua.y));
             vb = cmake(0.5 * (vb.x + ub.x), 0.5 * (vb.y - ub.y));
         }
+        if (st.real_basis) va.y = vb.y = 0.0;      // real vectors viewed as complex: Im is not an inner product
         G[i * ldg + msz + j] = va;
         G[(msz + j) * ldg + i] = cconj(va);
         GB[i * ldg + msz + j] = vb;

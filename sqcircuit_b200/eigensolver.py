@@ -18,7 +18,6 @@ All numerics run in the CUDA library; torch is used for allocation and trivial g
 """
 from dataclasses import dataclass
 
-import os
 import torch
 
 from .kernels import BlockView
@@ -51,31 +50,37 @@ def solve_dense(kern, op, B, N, k):
                      torch.zeros(B, dtype=torch.float64, device=dev), True)
 
 
-def cold_start_block(diag, B, p, N, dev, k=None):
+def cold_start_block(diag, B, p, N, dev, k=None, start_noise=0.03, real=False):
     """Start block of a cold solve: unit vectors on the p smallest entries of the LC diagonal plus a
     small deterministic perturbation on the 8p smallest.  The perturbation matters at symmetric
     operating points (e.g. the 0-pi qubit at zero flux): H then commutes with a parity, every
     Davidson vector stays inside the symmetry sectors of the start block, and a wanted eigenstate
-    whose sector is not represented is never found (the iteration "converges" to the wrong set)."""
-    c128 = torch.complex128
-    nl = min(8 * p, N)
+    whose sector is not represented is never found (the iteration "converges" to the wrong set).
+
+    real: ``diag`` has one entry per REAL amplitude (2 N of them, real representation); the block is
+    built as real amplitudes and returned as the [B][p][N] complex view of them."""
+    f64 = torch.float64
+    na = diag.shape[1]                                                    # amplitudes: N, or 2 N (real)
+    nl = min(8 * p, na)
     dlow, low = torch.topk(diag, nl, dim=1, largest=False)               # [1 or B][nl], ascending energy
     # damped with the LC energy above the start block, so that the Rayleigh quotients of the start
     # vectors are not swamped by high-energy basis states (charge-dominated circuits)
     spread = (dlow[:, p - 1:p] - dlow[:, :1]).clamp_min(1e-300)
     damp = spread / (spread + (dlow - dlow[:, :1]))                      # [1 or B][nl]
-    V0 = torch.zeros((B, p, N), dtype=c128, device=dev)
-    V0.scatter_(2, low[:, :p].expand(B, p).unsqueeze(2), torch.ones((B, p, 1), dtype=c128, device=dev))
-    i = torch.arange(nl, device=dev, dtype=torch.float64).unsqueeze(0)
-    j = torch.arange(p, device=dev, dtype=torch.float64).unsqueeze(1)
-    xi = float(os.environ.get("SQC_START_NOISE", "0.03")) * torch.cos(2.399963229728653 * (i + 1.0) * (j + 1.0) + 0.5 * j)      # [p][nl]
+    V0 = torch.zeros((B, p, na), dtype=f64, device=dev)
+    V0.scatter_(2, low[:, :p].expand(B, p).unsqueeze(2), torch.ones((B, p, 1), dtype=f64, device=dev))
+    i = torch.arange(nl, device=dev, dtype=f64).unsqueeze(0)
+    j = torch.arange(p, device=dev, dtype=f64).unsqueeze(1)
+    xi = start_noise * torch.cos(2.399963229728653 * (i + 1.0) * (j + 1.0) + 0.5 * j)      # [p][nl]
     if k is not None and k < p:
         # only the guard vectors carry the perturbation: the k wanted start vectors stay clean (they
         # are already eigenvectors of charge-dominated circuits), the guards seed the other sectors
         xi = xi * (torch.arange(p, device=dev) >= k).to(xi.dtype).unsqueeze(1)
-    pert = (xi.unsqueeze(0) * damp.unsqueeze(1)).to(c128).expand(B, p, nl).contiguous()
+    pert = (xi.unsqueeze(0) * damp.unsqueeze(1)).expand(B, p, nl).contiguous()
     V0.scatter_add_(2, low.unsqueeze(1).expand(B, p, nl), pert)
-    return V0
+    if real:
+        return torch.view_as_complex(V0.reshape(B, p, na // 2, 2))
+    return V0.to(torch.complex128)
 
 
 def solve_davidson(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
@@ -244,16 +249,8 @@ class RitzPairStart:
 DETAIL_STATS = None
 
 
-def EXPAND_DEFAULT(k, p):
-    """Ritz pairs that get a correction vector each iteration (the rest of the block are guards).
-    Measured on the 0-pi bench: expanding only the k wanted pairs needs 81 instead of 66 iterations
-    for the same wall time, so the guards are expanded too."""
-    return int(os.environ.get('SQC_EXPAND', '0')) or p
-
-
 def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
-                       stats=None, lowblock_ns=0, drop=float(os.environ.get("SQC_DROP", "1e-8")),
-                       cold_gate=float(os.environ.get("SQC_COLD_GATE", "0.25")), expand=None):
+                       stats=None, lowblock_ns=0, drop=1e-8, cold_gate=0.25, expand=None, start_noise=0.03):
     """Block Davidson WITHOUT orthogonalising the expansion block.
 
     The basis V is allowed to be non-orthogonal inside a restart cycle; Rayleigh-Ritz is the
@@ -262,8 +259,18 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
     paired Gram pass that produces the new columns of GA and GB together (``sqc_gram_pair``); the
     CGS2 / SVQB passes of ``solve_davidson`` disappear.  Thick restarts (V <- Ritz vectors, which
     are GB-orthonormal) put the basis back to an orthonormal one.  Same convergence and accuracy
-    as the orthogonalised iteration on every tested circuit (tools/proto_nonortho.py)."""
+    as the orthogonalised iteration on every tested circuit (tools/proto_nonortho.py).
+
+    Tuning knobs (all measured on the 0-pi bench, tools/): ``drop`` relative Cholesky pivot below which a
+    basis vector counts as dependent; ``cold_gate`` residual of the lowest pair (relative to the spectral
+    scale) below which a cold solve switches the two-level preconditioner on; ``expand`` Ritz pairs that get
+    a correction vector per iteration (None: all p -- expanding only the k wanted pairs needs 81 instead of
+    66 iterations for the same wall time); ``start_noise`` amplitude of the cold-start perturbation.
+
+    Real representation (``op.real``): the vectors are real amplitudes viewed as complex blocks of N =
+    ceil(N_real / 2) elements; the Gram entries keep only their real parts, everything else is unchanged."""
     dev = op.device
+    real = bool(getattr(op, 'real', False))
     if p is None:
         p = min(16, max(k + 2, (k * 6 + 4) // 5))
     p = min(p, 16, N)
@@ -303,7 +310,8 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
     Wp = BlockView(W, cnt_fixed=p)
     warm = x0 is not None
     if x0 is None:
-        x0 = cold_start_block(diag, B, p, N, dev, k)    # not orthonormal: goes through the general start
+        # not orthonormal: goes through the general start
+        x0 = cold_start_block(diag, B, p, N, dev, k, start_noise=start_noise, real=real)
     if True:
         m0 = min(x0.shape[1], mmax)
         if hasattr(x0, 'write_into'):
@@ -319,14 +327,14 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
             coff = torch.full((B,), c0, dtype=i32, device=dev)
             kern.gram_pair(Vi, BlockView(V, cnt_fixed=p, off=coff, cnt=ccnt),
                            BlockView(W, cnt_fixed=p, off=coff, cnt=ccnt), SB, SA)
-            GB[:, :, c0:c0 + p] = SB[:, :, :p]
-            GA[:, :, c0:c0 + p] = SA[:, :, :p]
+            GB[:, :, c0:c0 + p] = SB[:, :, :p].real if real else SB[:, :, :p]
+            GA[:, :, c0:c0 + p] = SA[:, :, :p].real if real else SA[:, :, :p]
     st = kern.davidson_state(p=p, k=k, mmax=mmax, ldg=ld, tol_rel=tol, tol_abs_floor=1e-300,
                              msz=msz, nact=nact, act=act, restart=restart, done=done,
                              n_not_done=n_not_done, theta=theta, rn2=rn2, resmax=resmax,
                              den_floor=den_floor, G=GA, GB=GB, mtot=mtot,
-                             nexp=EXPAND_DEFAULT(k, p) if expand is None else expand,
-                             xoff=xoff, xlast=xlast, xrow=mmax)
+                             nexp=p if expand is None else expand,
+                             xoff=xoff, xlast=xlast, xrow=mmax, real_basis=real)
     Xv = BlockView(V, cnt_fixed=p, off=xoff)         # where this iteration's Ritz block goes
     HXv = BlockView(W, cnt_fixed=p, off=xoff)
     Xl = BlockView(V, cnt_fixed=p, off=xlast)        # where the judged Ritz block is (after decide)
@@ -386,14 +394,14 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
                 DETAIL_STATS.append((it, B, left, int((nact * lv).sum()), int((msz * lv).sum()),
                                      int((((nact + 3) // 4) * lv).sum()), int(restart.sum())))
         if left != 0:
-            kern.precond_residual(Xl, HXl, Tv, theta, act, diag, den_floor)
+            kern.precond_residual(Xl, HXl, Tv, theta, act, diag, den_floor, real=real)
             if lowblock is not None and lowblock.get('band') is not None:
                 off, nblk, nbmax, perm = lowblock['band']
                 kern.lowband_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], off, nblk, nbmax,
-                                   lowblock['unit'], lowblock.get('group', 1), perm)
+                                   lowblock['unit'], lowblock.get('group', 1), perm, real=real)
             elif lowblock is not None:
                 kern.lowblock_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], lowblock['unit'],
-                                    lowblock.get('group', 1))
+                                    lowblock.get('group', 1), real=real)
             op.apply(Tv, HTv)
             kern.gram_pair(Vt, Tv, HTv, SB, SA)
             kern.davidson_insert2(st, SA, SB, B)

@@ -181,6 +181,24 @@ class Kernels:
         _lib.check(rc, 'sqc_hx_fused')
         return True
 
+    def hx_fused_real(self, sp, Ve, Vo, pot, fdiag, X, Y):
+        """Real-representation H.X (sqc_hx_fused_real); False when the layout / size is not supported."""
+        fsb = 0 if fdiag is None or fdiag.shape[0] == 1 else fdiag.stride(0)
+        rc = self.lib.sqc_hx_fused_real(C.byref(sp), _p(Ve), _p(Vo), C.byref(pot), _p(fdiag), fsb, X.c(), Y.c(),
+                                        X.B, _stream(self.dev))
+        if rc == _lib.ELIMIT:
+            return False
+        _lib.check(rc, 'sqc_hx_fused_real')
+        return True
+
+    def real_to_complex(self, sp, Xr, Zc):
+        _lib.check(self.lib.sqc_real_to_complex(C.byref(sp), Xr.c(), Zc.c(), Xr.B, _stream(self.dev)),
+                   'sqc_real_to_complex')
+
+    def complex_to_real(self, sp, Zc, Xr):
+        _lib.check(self.lib.sqc_complex_to_real(C.byref(sp), Zc.c(), Xr.c(), Zc.B, _stream(self.dev)),
+                   'sqc_complex_to_real')
+
     def block_rightmul(self, T, Cq, nout):
         B, ldr, ldc = Cq.shape
         _lib.check(self.lib.sqc_block_rightmul(T.c(), _p(Cq), ldr, ldc, _p(nout), T.N, B,
@@ -213,6 +231,7 @@ class Kernels:
         st.xoff = kw['xoff'].data_ptr() if kw.get('xoff') is not None else None
         st.xlast = kw['xlast'].data_ptr() if kw.get('xlast') is not None else None
         st.xrow = int(kw.get('xrow') or 0)
+        st.real_basis = int(bool(kw.get('real_basis')))
         st._keep = kw
         return st
 
@@ -223,29 +242,31 @@ class Kernels:
         _lib.check(self.lib.sqc_restart_copy(X.c(), HX.c(), V.c(), W.c(), _p(restart), X.N, V.B,
                                              _stream(self.dev)), 'sqc_restart_copy')
 
-    def precond_residual(self, X, HX, T, theta, act, d, den_floor):
+    def precond_residual(self, X, HX, T, theta, act, d, den_floor, real=False):
+        """real: the block holds real amplitudes (two per element) and d is [1 or B][2 N]."""
         dsb = 0 if d.shape[0] == 1 else d.stride(0)
-        _lib.check(self.lib.sqc_precond_residual(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act),
-                                                 act.shape[1], _p(d), dsb, _p(den_floor), X.N, X.B,
-                                                 _stream(self.dev)), 'sqc_precond_residual')
+        fn = self.lib.sqc_precond_residual_real if real else self.lib.sqc_precond_residual
+        _lib.check(fn(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act), act.shape[1], _p(d), dsb,
+                      _p(den_floor), X.N, X.B, _stream(self.dev)), 'sqc_precond_residual')
 
-    def lowblock_assemble(self, sp, S, Dt, pot, d, sigma, unit, out):
+    def lowblock_assemble(self, sp, S, Dt, pot, d, sigma, unit, out, real=False):
         B, ns, _ = out.shape
         ssb = 0 if S.shape[0] == 1 else S.stride(0)
         dsb = 0 if d.shape[0] == 1 else d.stride(0)
-        _lib.check(self.lib.sqc_lowblock_assemble(C.byref(sp), ns, _p(S), ssb, _p(Dt), C.byref(pot), _p(d), dsb,
-                                                  _p(sigma), unit, _p(out), B, _stream(self.dev)),
-                   'sqc_lowblock_assemble')
+        fn = self.lib.sqc_lowblock_assemble_real if real else self.lib.sqc_lowblock_assemble
+        _lib.check(fn(C.byref(sp), ns, _p(S), ssb, _p(Dt), C.byref(pot), _p(d), dsb, _p(sigma), unit, _p(out), B,
+                      _stream(self.dev)), 'sqc_lowblock_assemble')
 
     def hpd_inverse_c64(self, A):
         B, ns, _ = A.shape
         _lib.check(self.lib.sqc_hpd_inverse_c64(_p(A), ns, B, _stream(self.dev)), 'sqc_hpd_inverse_c64')
 
-    def lowblock_apply(self, X, HX, T, theta, act, S, Ainv, unit, group=1):
+    def lowblock_apply(self, X, HX, T, theta, act, S, Ainv, unit, group=1, real=False):
         ssb = 0 if S.shape[0] == 1 else S.stride(0)
         if Ainv.shape[0] * group < X.B:
             raise ValueError('lowblock_apply: not enough inverse slots for this group size')
-        _lib.check(self.lib.sqc_lowblock_apply(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act),
+        fn = self.lib.sqc_lowblock_apply_real if real else self.lib.sqc_lowblock_apply
+        _lib.check(fn(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act),
                                                act.shape[1], _p(S), ssb, _p(Ainv), Ainv.shape[1], unit, group,
                                                X.N, X.B, _stream(self.dev)), 'sqc_lowblock_apply')
 
@@ -254,11 +275,13 @@ class Kernels:
         _lib.check(self.lib.sqc_lowband_factor(_p(A), ns, _p(blk_off), blk_off.shape[1], _p(nblk), int(nbmax), B,
                                                _stream(self.dev)), 'sqc_lowband_factor')
 
-    def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1, perm=None):
+    def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1, perm=None,
+                      real=False):
         ssb = 0 if S.shape[0] == 1 else S.stride(0)
         if Afac.shape[0] * group < X.B:
             raise ValueError('lowband_apply: not enough factor slots for this group size')
-        _lib.check(self.lib.sqc_lowband_apply(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act),
+        fn = self.lib.sqc_lowband_apply_real if real else self.lib.sqc_lowband_apply
+        _lib.check(fn(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act),
                                               act.shape[1], _p(S), ssb, _p(Afac), Afac.shape[1], _p(blk_off),
                                               blk_off.shape[1], _p(nblk), int(nbmax), unit, group, _p(perm), X.N, X.B,
                                               _stream(self.dev)), 'sqc_lowband_apply')

@@ -34,6 +34,7 @@ def xbasis(kern, m):
 
 class CircuitOperators:
     use_fused = True      # class-level switch (tests compare the fused and unfused paths)
+    use_real = True       # class-level switch: real representation for zero-gate-charge sweeps
 
     def __init__(self, kern, topo, dims, transform_impl=0):
         self.kern = kern
@@ -237,6 +238,42 @@ class CircuitOperators:
         else:
             k.mode_transform(self.sp, last, self.V[last], 0, s2, Y, impl=self.impl)
 
+    # ---- real (time-reversal adapted) representation, see csrc/hx_real.cu ------------------------
+    def supports_real(self, ng):
+        """True when H(b) can be solved in the real representation: one harmonic x one charge mode
+        (the fused layout), zero gate charge on the charge mode, sizes the kernel accepts."""
+        if not (self.fused and self.use_fused and self.use_real):
+            return False
+        ng = np.asarray(ng, dtype=float).reshape(-1, self.M)
+        if np.any(ng[:, 1] != 0.0):
+            return False
+        m, inner = self.dims
+        if inner % 2 == 0 or inner > 127 or m > 128:
+            return False
+        # shared memory of one team of sqc_hx_fused_real (must mirror the launch code)
+        kp = ((m + 1) // 2 + 3) & ~3
+        vld = kp if kp % 8 == 4 else kp + 4
+        pp = 2 * inner
+        while pp % 16 not in (4, 12):
+            pp += 2
+        team = kp * pp + 16 + ((m + 1) & ~1) + 2 * 4 * m
+        return (2 * kp * vld + team + 2) * 8 <= 227 * 1024
+
+    def real_index_map(self):
+        """Complex charge index c = nc + n of every real column j (j = 0: n = 0, 1..nc: Re plane,
+        nc+1..2nc: Im plane): the LC diagonal of real amplitude (i, j) is d_LC[i][c(j)]."""
+        inner = self.dims[1]
+        nc = (inner - 1) // 2
+        return np.concatenate(([nc], nc + np.arange(1, nc + 1), nc + np.arange(1, nc + 1)))
+
+    def real_to_complex(self, Xr, out=None):
+        """[B][k][Nc] real-representation vectors -> [B][k][N] complex vectors in the reference's basis."""
+        Xr = Xr if Xr.is_contiguous() else Xr.contiguous()
+        if out is None:
+            out = torch.empty((Xr.shape[0], Xr.shape[1], self.N), dtype=torch.complex128, device=self.device)
+        self.kern.real_to_complex(self.sp, BlockView(Xr), BlockView(out))
+        return out
+
     def displacement_tables(self):
         """Dt[t] = V diag(etab_t) V^T: Fock-basis matrix of junction term t (the matrix the reference
         gets from qt.displace), only needed to assemble the low-energy preconditioner block."""
@@ -363,3 +400,120 @@ class HamiltonianOperator:
         else:
             kern.lowband_factor(Ainv, band[0], band[1], band[2])
         return {'S': S, 'Ainv': Ainv, 'unit': unit, 'ns': ns, 'group': group, 'band': band}
+
+
+class RealHamiltonianOperator(HamiltonianOperator):
+    """H(b) in the real (time-reversal adapted) representation (csrc/hx_real.cu): at zero gate charge H
+    commutes with T = (complex conjugation) x (n -> -n), its eigenvectors satisfy z(i, -n) = conj z(i, n)
+    and are stored as N real amplitudes -- half the bytes and half the H.X flops, and real Gram /
+    Rayleigh-Ritz arithmetic.  Blocks are complex128 tensors [B][nvec][Nc], Nc = ceil(N / 2): two real
+    amplitudes per element.  ``diag`` is the LC diagonal in the real layout, [1][2 Nc]."""
+    real = True
+
+    def __init__(self, ops: CircuitOperators, loop_vals, ng, base: HamiltonianOperator = None):
+        if base is None:
+            super().__init__(ops, loop_vals, ng)
+        else:           # share the coefficient tables of an existing complex operator of the same points
+            self.ops, self.device, self.B = ops, ops.device, base.B
+            self.a, self.g, self.diag, self.loop_vals, self.ng = base.a, base.g, base.diag, base.loop_vals, base.ng
+        m, inner = ops.dims
+        self.N = ops.N
+        self.Nc = (ops.N + 1) // 2
+        self.diag_c = self.diag
+        cmap = torch.as_tensor(ops.real_index_map(), device=self.device)
+        dr = self.diag_c.reshape(-1, m, inner)[:, :, cmap].reshape(-1, ops.N)
+        if 2 * self.Nc != ops.N:       # padding amplitude: never selected as a low-energy state, stays zero
+            dr = torch.cat([dr, torch.full((dr.shape[0], 1), 1e300, dtype=dr.dtype, device=self.device)], dim=1)
+        self.diag = dr.contiguous()
+
+    def apply(self, X: BlockView, Y: BlockView):
+        ops = self.ops
+        pot = ops.potential_struct(self.a, self.g, ops.etab)
+        if not ops.kern.hx_fused_real(ops.sp, ops.Ve, ops.Vo, pot, self.diag, X, Y):
+            raise RuntimeError('sqc_hx_fused_real rejected a layout that supports_real() accepted')
+
+    def to_complex(self, Xr, out=None):
+        return self.ops.real_to_complex(Xr, out)
+
+    def supports_lowblock(self):
+        return bool(self.ops.T >= 1)
+
+    def build_lowblock(self, sigma, ns, group=None):
+        """Two-level preconditioner block in the real representation.  The index set is the ns real basis
+        states of smallest LC energy, taken in whole (Fock i, |charge| n) units so that the cos- and sin-type
+        partners of a charge stay together, ordered charge-major: H_SS is block tridiagonal in n."""
+        ops, kern = self.ops, self.ops.kern
+        m, inner = ops.dims
+        nc = (inner - 1) // 2
+        ns = int(min(ns, 1024, ops.N // 2))
+        if group is None:
+            group = LOWBLOCK_GROUP or self._auto_lowblock_group()
+        group = int(max(1, min(group, self.B)))
+        unit = 2 * np.pi * 1e9
+        nslot = (self.B + group - 1) // group
+        if group == 1:
+            a, g, sig = self.a, self.g, sigma.contiguous()
+        else:
+            rep = torch.clamp(torch.arange(nslot, device=self.device) * group + group // 2, max=self.B - 1)
+            a, g, sig = self.a[rep].contiguous(), self.g[rep].contiguous(), sigma[rep].contiguous()
+        key = ('lowset', ns)
+        if key not in ops._scratch:
+            ops._scratch[key] = self._real_low_set(ns, m, inner, nc)
+        S, off, nblk, nbmax, perm = ops._scratch[key]
+        ns = S.shape[1]
+        pot = ops.potential_struct(a, g, ops.etab)
+        Ainv = torch.empty((nslot, ns, ns), dtype=torch.complex64, device=self.device)
+        kern.lowblock_assemble(ops.sp, S, ops.displacement_tables(), pot, self.diag, sig, unit, Ainv, real=True)
+        if off is None:
+            kern.hpd_inverse_c64(Ainv)
+            band = None
+        else:
+            offs = off.expand(nslot, -1).contiguous()
+            nb = nblk.expand(nslot).contiguous()
+            kern.lowband_factor(Ainv, offs, nb, nbmax)
+            band = (offs, nb, nbmax, perm)
+        return {'S': S, 'Ainv': Ainv, 'unit': unit, 'ns': ns, 'group': group, 'band': band, 'real': True}
+
+    def _real_low_set(self, ns, m, inner, nc):
+        """Index set (device int32 [1][ns']), block offsets, block count, largest block, address-sorting
+        permutation.  Host work, done once per circuit and size (the LC diagonal does not depend on the
+        sweep point at zero gate charge)."""
+        d = self.diag_c[0].reshape(m, inner).cpu().numpy()
+        units = sorted(((d[i, nc + n], n, i) for i in range(m) for n in range(nc + 1)))
+        chosen, cnt = [], 0
+        for e, n, i in units:
+            w = 1 if n == 0 else 2
+            if cnt + w > ns:
+                break
+            chosen.append((n, i))
+            cnt += w
+        chosen.sort()                                   # charge-major, Fock index inside
+        idx, blocks = [], []
+        for n, i in chosen:
+            if not blocks or blocks[-1][0] != n:
+                blocks.append([n, len(idx)])
+            idx.append(i * inner + n)
+            if n:
+                idx.append(i * inner + nc + n)
+        starts = np.array([b[1] for b in blocks] + [len(idx)])
+        S = torch.as_tensor(np.array(idx, dtype=np.int32), device=self.device).reshape(1, -1).contiguous()
+        if len(idx) <= 160:
+            return S, None, None, 0, None
+        # neighbouring small blocks (the thin ends of the low-energy ellipse) are merged up to one warp's
+        # width: still block tridiagonal, fewer sequential substitution steps
+        cap = max(32, int(np.diff(starts).max()))
+        out = [0]
+        for e in starts[1:]:
+            if len(out) >= 2 and e - out[-2] <= cap:
+                out[-1] = e
+            else:
+                out.append(e)
+        starts = np.array(out)
+        nbmax = int(np.diff(starts).max())
+        if nbmax > 64:
+            # blocks too large for the banded kernels: dense block on the 160 lowest states instead
+            return self._real_low_set(160, m, inner, nc)
+        off = torch.as_tensor(starts.astype(np.int32), device=self.device).reshape(1, -1)
+        nblk = torch.as_tensor(np.array([len(starts) - 1], dtype=np.int32), device=self.device)
+        perm = torch.argsort(S, dim=1).to(torch.int32).contiguous()
+        return S, off, nblk, nbmax, perm

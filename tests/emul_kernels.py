@@ -257,6 +257,8 @@ class EmulKernels:
             for S, G in ((SA, st.G), (SB, st.GB)):
                 s = S[b].numpy()
                 blk = s[:msz + na, :na].copy()
+                if getattr(st, 'real_basis', 0):
+                    blk = blk.real.astype(complex)
                 d = blk[msz:, :]
                 blk[msz:, :] = (d + d.conj().T) / 2
                 Gn = G[b].numpy()
@@ -266,6 +268,92 @@ class EmulKernels:
 
     def hx_fused(self, sp, Ve, Vo, pot, fdiag, X, Y):
         return False      # not emulated: callers fall back to transform + potential + transform
+
+    # ---- real (time-reversal adapted) representation ------------------------------------------
+    @staticmethod
+    def _r2c(y, m, inner):
+        """[nv][>= m*inner] real amplitudes (planar layout) -> [nv][m*inner] complex"""
+        nc = (inner - 1) // 2
+        y = y[:, :m * inner].reshape(-1, m, inner)
+        z = np.zeros((y.shape[0], m, inner), complex)
+        z[:, :, nc] = y[:, :, 0]
+        p = (y[:, :, 1:nc + 1] + 1j * y[:, :, nc + 1:]) / np.sqrt(2)
+        z[:, :, nc + 1:] = p
+        z[:, :, :nc] = p.conj()[:, :, ::-1]
+        return z.reshape(y.shape[0], -1)
+
+    @staticmethod
+    def _c2r(z, m, inner):
+        nc = (inner - 1) // 2
+        z = z.reshape(-1, m, inner)
+        N = m * inner
+        y = np.zeros((z.shape[0], m, inner))
+        y[:, :, 0] = z[:, :, nc].real
+        pos, neg = z[:, :, nc + 1:], z[:, :, :nc][:, :, ::-1]
+        y[:, :, 1:nc + 1] = (pos.real + neg.real) / np.sqrt(2)
+        y[:, :, nc + 1:] = (pos.imag - neg.imag) / np.sqrt(2)
+        out = np.zeros((z.shape[0], 2 * ((N + 1) // 2)))
+        out[:, :N] = y.reshape(z.shape[0], -1)
+        return out
+
+    def real_to_complex(self, sp, Xr, Zc):
+        m, inner = sp.dims[0], sp.dims[1]
+        for b in range(Xr.B):
+            y = _get(Xr, b)
+            if y.shape[0]:
+                _set(Zc, b, self._r2c(np.ascontiguousarray(y).view(np.float64), m, inner))
+
+    def complex_to_real(self, sp, Zc, Xr):
+        m, inner = sp.dims[0], sp.dims[1]
+        for b in range(Zc.B):
+            z = _get(Zc, b)
+            if z.shape[0]:
+                _set(Xr, b, self._c2r(z, m, inner).view(np.complex128))
+
+    def hx_fused_real(self, sp, Ve, Vo, pot, fdiag, X, Y):
+        """Y = H X on real-representation blocks: rotate to the complex basis, apply the complex operator
+        (transform, potential, transform back, LC diagonal), project back."""
+        from sqcircuit_b200.kernels import BlockView
+        m, inner = sp.dims[0], sp.dims[1]
+        nc = (inner - 1) // 2
+        N = m * inner
+        if inner % 2 == 0 or pot.n_terms > 4:
+            return False
+        V = np.zeros((m, m))
+        V[0::2, :Ve.shape[1]] = Ve.numpy()
+        V[1::2, :Vo.shape[1]] = Vo.numpy()
+        # mirror columns of the parity-structured x basis: V[n][m-1-i] = (-1)^n V[n][i]
+        sign = (-1.0) ** np.arange(m)
+        for i in range(m // 2):
+            V[:, m - 1 - i] = sign * V[:, i]
+        Vt = torch.from_numpy(V)
+        cmap = np.concatenate((nc - np.arange(nc, 0, -1), [nc], nc + np.arange(1, nc + 1)))   # complex col -> |n|
+        cmap = np.abs(np.arange(inner) - nc)
+        for b in range(X.B):
+            y = _get(X, b)
+            nv = y.shape[0]
+            if nv == 0:
+                continue
+            z = torch.from_numpy(self._r2c(np.ascontiguousarray(y).view(np.float64), m, inner)).reshape(1, nv, N)
+            s1, s2, out = torch.zeros_like(z), torch.zeros_like(z), torch.zeros_like(z)
+            a, g, etab = pot._keep[0], pot._keep[1], pot._keep[2]
+
+            class _P:
+                pass
+            pb = _P()
+            pb.n_terms, pb.shift, pb.lam = pot.n_terms, pot.shift, pot.lam
+            pb._keep = (a[b:b + 1], g[b:b + 1], etab[min(b, etab.shape[0] - 1)][None], None)
+            self.mode_transform(sp, 0, Vt, 1, BlockView(z), BlockView(s1))
+            self.potential_apply(sp, pb, BlockView(s1), BlockView(s2))
+            self.mode_transform(sp, 0, Vt, 0, BlockView(s2), BlockView(out))
+            r = self._c2r(out[0].numpy(), m, inner)
+            if fdiag is not None:
+                fd = fdiag[min(b, fdiag.shape[0] - 1)].numpy()
+                r = r + fd[None, :] * np.ascontiguousarray(y).view(np.float64)
+                if N % 2:
+                    r[:, N:] = 0.0
+            _set(Y, b, r.view(np.complex128))
+        return True
 
     def block_update(self, A, Cf, Out, op=0, trans=0, impl=0):
         for b in range(A.B):
@@ -403,12 +491,14 @@ class EmulKernels:
                 _set(V, b, _get(X, b))
                 _set(W, b, _get(HX, b))
 
-    def precond_residual(self, X, HX, T, theta, act, d, den_floor):
+    def precond_residual(self, X, HX, T, theta, act, d, den_floor, real=False):
         for b in range(X.B):
             n = _cnt(T, b)
             if n == 0:
                 continue
             x, hx = _rows(X, b), _rows(HX, b)
+            if real:
+                x, hx = np.ascontiguousarray(x).view(np.float64), np.ascontiguousarray(hx).view(np.float64)
             dd = d[min(b, d.shape[0] - 1)].numpy()
             fl = float(den_floor[b])
             out = []
@@ -418,9 +508,12 @@ class EmulKernels:
                 den = dd - th
                 den = np.where(np.abs(den) < fl, np.where(den < 0, -fl, fl), den)
                 out.append((hx[a] - th * x[a]) / den)
-            _set(T, b, np.array(out))
+            out = np.array(out)
+            _set(T, b, out.view(np.complex128) if real else out)
 
-    def lowblock_assemble(self, sp, S, Dt, pot, d, sigma, unit, out):
+    def lowblock_assemble(self, sp, S, Dt, pot, d, sigma, unit, out, real=False):
+        if real:
+            return self._lowblock_assemble_real(sp, S, Dt, pot, d, sigma, unit, out)
         a, g, etab, diag = pot._keep
         m, inner = sp.dims[0], sp.dims[1]
         Dtn = Dt.numpy()
@@ -442,11 +535,54 @@ class EmulKernels:
                 A += (c[None, :] == c[:, None] + sh) * np.conj(at * Dtn[t][n[None, :], n[:, None]])
             out[b] = torch.from_numpy((A / unit).astype(np.complex64))
 
+    def _lowblock_assemble_real(self, sp, S, Dt, pot, d, sigma, unit, out):
+        """H_r = U^H H_c U on the real index set (each real state is a combination of charges +-n)."""
+        a, g = pot._keep[0], pot._keep[1]
+        m, inner = sp.dims[0], sp.dims[1]
+        nc = (inner - 1) // 2
+        Dtn = Dt.numpy()
+        B, ns, _ = out.shape
+        for b in range(B):
+            s = S[min(b, S.shape[0] - 1)].numpy()
+            dd = d[min(b, d.shape[0] - 1)].numpy()
+            # complex closure: every (Fock, +-|n|) that a member of the set touches
+            comp, U = {}, []
+            for r, idx in enumerate(s):
+                i, j = idx // inner, idx % inner
+                n = j if j <= nc else j - nc
+                for q, coef in (((n, 1.0),) if j == 0 else
+                                ((n, 2 ** -0.5), (-n, 2 ** -0.5)) if j <= nc else
+                                ((n, 1j * 2 ** -0.5), (-n, -1j * 2 ** -0.5))):
+                    key = (i, q)
+                    if key not in comp:
+                        comp[key] = len(comp)
+                    U.append((comp[key], r, coef))
+            keys = sorted(comp, key=comp.get)
+            n_ = np.array([k[0] for k in keys])
+            c = np.array([k[1] for k in keys])
+            nk = len(keys)
+            A = np.zeros((nk, nk), complex)
+            same_c = c[:, None] == c[None, :]
+            g0, g1 = float(g[b, 0]), float(g[b, 1])
+            A += same_c * (g0 * (n_[:, None] == n_[None, :]) +
+                           g1 * (np.abs(n_[:, None] - n_[None, :]) == 1) * np.sqrt(np.maximum(n_[:, None], n_[None, :])))
+            for t in range(pot.n_terms):
+                sh = int(pot.shift[t][1])
+                at = complex(a[b, t])
+                A += (c[None, :] == c[:, None] - sh) * at * Dtn[t][n_[:, None], n_[None, :]]
+                A += (c[None, :] == c[:, None] + sh) * np.conj(at * Dtn[t][n_[None, :], n_[:, None]])
+            Um = np.zeros((nk, ns), complex)
+            for ci, r, coef in U:
+                Um[ci, r] = coef
+            Hr = (Um.conj().T @ A @ Um).real
+            Hr[np.arange(ns), np.arange(ns)] += dd[s] - float(sigma[b])
+            out[b] = torch.from_numpy((Hr / unit).astype(np.complex64))
+
     def hpd_inverse_c64(self, A):
         for b in range(A.shape[0]):
             A[b] = torch.from_numpy(np.linalg.inv(A[b].numpy().astype(complex)).astype(np.complex64))
 
-    def lowblock_apply(self, X, HX, T, theta, act, S, Ainv, unit, group=1):
+    def lowblock_apply(self, X, HX, T, theta, act, S, Ainv, unit, group=1, real=False):
         for b in range(X.B):
             n = _cnt(T, b)
             if n == 0:
@@ -454,12 +590,14 @@ class EmulKernels:
             s = S[min(b // group, S.shape[0] - 1)].numpy()
             x, hx = _rows(X, b), _rows(HX, b)
             t = _get(T, b).copy()
+            if real:
+                x, hx, t = (np.ascontiguousarray(v).view(np.float64) for v in (x, hx, t))
             ai = Ainv[b // group].numpy().astype(complex)
             for jj in range(n):
                 av = int(act[b, jj])
                 r = hx[av][s] - float(theta[b, av]) * x[av][s]
-                t[jj][s] = ai @ r / unit
-            _set(T, b, t)
+                t[jj][s] = (ai @ r / unit).real if real else ai @ r / unit
+            _set(T, b, t.view(np.complex128) if real else t)
 
     def lowband_factor(self, A, blk_off, nblk, nbmax):
         """block LDL^H of the block-tridiagonal matrix: diagonal blocks <- inverse Schur complements"""
@@ -478,7 +616,8 @@ class EmulKernels:
                 a[o:o1, o:o1] = pprev
             A[b] = torch.from_numpy(a.astype(np.complex64))
 
-    def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1, perm=None):
+    def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1, perm=None,
+                      real=False):
         for b in range(X.B):
             n = _cnt(T, b)
             if n == 0:
@@ -490,9 +629,11 @@ class EmulKernels:
             nb = int(nblk[sl])
             x, hx = _rows(X, b), _rows(HX, b)
             t = _get(T, b).copy()
+            if real:
+                x, hx, t = (np.ascontiguousarray(v).view(np.float64) for v in (x, hx, t))
             for jj in range(n):
                 av = int(act[b, jj])
-                v = (hx[av][s] - float(theta[b, av]) * x[av][s]) / unit
+                v = ((hx[av][s] - float(theta[b, av]) * x[av][s]) / unit).astype(complex)
                 for q in range(nb):
                     o, o1 = int(off[q]), int(off[q + 1])
                     y = v[o:o1].copy()
@@ -503,8 +644,8 @@ class EmulKernels:
                 for q in range(nb - 2, -1, -1):
                     o, o1, o2 = int(off[q]), int(off[q + 1]), int(off[q + 2])
                     v[o:o1] = v[o:o1] - a[o:o1, o:o1] @ (a[o:o1, o1:o2] @ v[o1:o2])
-                t[jj][s] = v
-            _set(T, b, t)
+                t[jj][s] = v.real if real else v
+            _set(T, b, t.view(np.complex128) if real else t)
 
     def svqb_coeffs(self, S, nact, drop, Cq, msz=None, mtot=None):
         B, ld, _ = S.shape

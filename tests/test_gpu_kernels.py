@@ -545,3 +545,153 @@ def test_lowband_factor_and_apply(kern):
     sol = np.linalg.solve(A[0], r)
     got = Vd.cpu()[b, int(msz[b]) + jj].numpy()[s]
     assert np.abs(got - sol).max() / np.abs(sol).max() < 1e-4
+
+
+def _real_case(kern, m, inner, B, T=2, seed=40):
+    """Random harmonic x charge operator tables with a charge-symmetric LC diagonal (zero gate charge)."""
+    from sqcircuit_b200._lib import Potential
+    N = m * inner
+    nc = (inner - 1) // 2
+    sp = make_space([m, inner], [1, 0])
+    V, lam = kern.xbasis(m)
+    lamcat = torch.zeros(m + inner, dtype=torch.float64, device='cuda')
+    lamcat[:m] = lam
+    s = torch.tensor([[[0.61, 0.0], [-0.37, 0.0]]], dtype=torch.float64, device='cuda')
+    etab = torch.empty((1, T, m + inner), dtype=torch.complex128, device='cuda')
+    kern.phase_tables(sp, T, lamcat, s, etab)
+    g = torch.Generator().manual_seed(seed)
+    a = rnd((B, T), seed + 1).cuda()
+    gl = torch.randn((B, 3), dtype=torch.float64, generator=g).cuda()
+    half = torch.randn((1, m, nc + 1), dtype=torch.float64, generator=g)
+    fdc = torch.cat([half.flip(2)[:, :, :nc], half], dim=2).reshape(1, N).contiguous().cuda()   # d(i, -n) = d(i, n)
+    cmap = torch.as_tensor(np.concatenate(([nc], nc + np.arange(1, nc + 1), nc + np.arange(1, nc + 1))))
+    fdr = fdc.reshape(1, m, inner)[:, :, cmap.cuda()].reshape(1, N)
+    if N % 2:
+        fdr = torch.cat([fdr, torch.full((1, 1), 1e300, dtype=torch.float64, device='cuda')], dim=1)
+    fdr = fdr.contiguous()
+
+    def pot_struct(shifts=(1, -1)):
+        pot = Potential()
+        pot.n_terms = T
+        for t in range(T):
+            pot.shift[t][1] = shifts[t]
+        pot.lam, pot.etab, pot.etab_stride_b = lamcat.data_ptr(), etab.data_ptr(), 0
+        pot.g, pot.a, pot.diag, pot.diag_stride_b = gl.data_ptr(), a.data_ptr(), None, 0
+        pot._keep = (a, gl, etab)
+        return pot
+    return sp, V, etab, a, gl, fdc, fdr, pot_struct
+
+
+@pytest.mark.parametrize('dims', [[100, 51], [25, 13], [30, 19], [7, 3], [101, 41], [2, 61], [128, 127], [33, 1],
+                                  [100, 101]])
+@pytest.mark.parametrize('shifts', [(1, -1), (1, 0)])
+def test_hx_real_matches_complex(kern, dims, shifts):
+    """Real-representation H.X (TMA staged) against the complex fused kernel on time-reversal
+    symmetric vectors, through the conversion kernels."""
+    m, inner = dims
+    N, Nc = m * inner, (m * inner + 1) // 2
+    B, nv = 3, 5
+    sp, V, etab, a, gl, fdc, fdr, pot_struct = _real_case(kern, m, inner, B)
+    cnt = torch.tensor([5, 2, 0], dtype=torch.int32, device='cuda')
+    Z = rnd((B, nv, N), 41).cuda()
+    Xr = torch.zeros((B, nv, Nc), dtype=torch.complex128, device='cuda')
+    kern.complex_to_real(sp, BlockView(Z, cnt=cnt), BlockView(Xr, cnt=cnt))
+    Zs = torch.zeros_like(Z)
+    kern.real_to_complex(sp, BlockView(Xr, cnt=cnt), BlockView(Zs, cnt=cnt))
+    # the round trip is the projection on T-symmetric vectors: z(i, -n) = conj z(i, n)
+    Zv = Zs.reshape(B, nv, m, inner)
+    assert relerr(Zv.flip(3).conj().cpu(), Zv.cpu()) < 1e-15
+    ref = 0.5 * (Z.reshape(B, nv, m, inner) + Z.reshape(B, nv, m, inner).flip(3).conj())
+    live = (torch.arange(nv, device='cuda')[None, :] < cnt[:, None])[:, :, None, None]
+    assert relerr((Zv * live).cpu(), (ref * live).cpu()) < 1e-15
+    # norms agree (orthonormal real basis)
+    xr = torch.view_as_real(Xr)
+    assert relerr((xr ** 2).sum(dim=(2, 3)).cpu(), (Zs.abs() ** 2).sum(dim=2).cpu()) < 1e-13
+    he, ho = (m + 1) // 2, m // 2
+    Ve, Vo = V[0::2, :he].contiguous(), V[1::2, :ho].contiguous()
+    for use_fd in (True, False):
+        Yc = torch.zeros_like(Zs)
+        assert kern.hx_fused(sp, Ve, Vo, pot_struct(shifts), fdc if use_fd else None, BlockView(Zs, cnt=cnt),
+                             BlockView(Yc, cnt=cnt))
+        Yr = torch.zeros_like(Xr)
+        assert kern.hx_fused_real(sp, Ve, Vo, pot_struct(shifts), fdr if use_fd else None, BlockView(Xr, cnt=cnt),
+                                  BlockView(Yr, cnt=cnt))
+        Yrc = torch.zeros_like(Zs)
+        kern.real_to_complex(sp, BlockView(Yr, cnt=cnt), BlockView(Yrc, cnt=cnt))
+        assert relerr(Yrc.cpu(), Yc.cpu()) < 2e-13, (dims, use_fd)
+        if N % 2:     # the padding double of an odd N stays zero
+            assert float(torch.view_as_real(Yr)[:, :, -1, 1].abs().max()) == 0.0
+
+
+def test_hx_real_many_vectors(kern):
+    """More vectors than resident teams: the persistent loop reuses the shared buffers (TMA store ->
+    next TMA load), per-point offsets / counts."""
+    m, inner = 100, 51
+    N, Nc = m * inner, (m * inner + 1) // 2
+    B, nv = 40, 12
+    sp, V, etab, a, gl, fdc, fdr, pot_struct = _real_case(kern, m, inner, B, seed=50)
+    g = torch.Generator().manual_seed(7)
+    cnt = torch.randint(0, nv + 1, (B,), dtype=torch.int32, generator=g).cuda()
+    off = torch.randint(0, 5, (B,), dtype=torch.int32, generator=g).cuda()
+    Zs = torch.zeros((B, nv + 4, N), dtype=torch.complex128, device='cuda')
+    Xr = torch.view_as_complex(torch.randn((B, nv + 4, Nc, 2), dtype=torch.float64, generator=g).cuda())
+    kern.real_to_complex(sp, BlockView(Xr), BlockView(Zs))
+    he, ho = (m + 1) // 2, m // 2
+    Ve, Vo = V[0::2, :he].contiguous(), V[1::2, :ho].contiguous()
+    Yc = torch.zeros_like(Zs)
+    kern.hx_fused(sp, Ve, Vo, pot_struct(), fdc, BlockView(Zs, cnt_fixed=nv, off=off, cnt=cnt),
+                  BlockView(Yc, cnt_fixed=nv, off=off, cnt=cnt))
+    Yr = torch.zeros_like(Xr)
+    assert kern.hx_fused_real(sp, Ve, Vo, pot_struct(), fdr, BlockView(Xr, cnt_fixed=nv, off=off, cnt=cnt),
+                              BlockView(Yr, cnt_fixed=nv, off=off, cnt=cnt))
+    Yrc = torch.zeros_like(Zs)
+    kern.real_to_complex(sp, BlockView(Yr), BlockView(Yrc))
+    assert relerr(Yrc.cpu(), Yc.cpu()) < 2e-13
+    # H is real symmetric in this representation: <x, H y> = <H x, y>
+    xr, yr = torch.view_as_real(Xr).reshape(B, nv + 4, -1), torch.view_as_real(Yr).reshape(B, nv + 4, -1)
+    b = int(torch.argmax(cnt))
+    o0, c = int(off[b]), int(cnt[b])
+    G = xr[b, o0:o0 + c] @ yr[b, o0:o0 + c].T
+    assert relerr(G.cpu(), G.T.cpu()) < 1e-12
+
+
+def test_lowblock_assemble_real_is_the_rotated_complex_block(kern):
+    """Low-energy block in the real basis = U^H (complex block on the +-n closure of the set) U."""
+    m, inner, B = 25, 13, 2
+    nc = (inner - 1) // 2
+    N = m * inner
+    sp, V, etab, a, gl, fdc, fdr, pot_struct = _real_case(kern, m, inner, B, seed=60)
+    Dt = torch.einsum('ni,ti,ki->tnk', V.to(torch.complex128), etab[0, :, :m], V.to(torch.complex128)).contiguous()
+    units = [(i, n) for i in range(6) for n in range(4)]          # whole (Fock, |charge|) units
+    Sr, Sc = [], []
+    for i, n in units:
+        Sr.append(i * inner + n)
+        Sc.append(i * inner + nc + n)
+        if n:
+            Sr.append(i * inner + nc + n)
+            Sc.append(i * inner + nc - n)
+    ns = len(Sr)
+    U = np.zeros((ns, ns), dtype=complex)       # columns: real basis states in terms of the complex ones
+    r = 0
+    for i, n in units:
+        if n == 0:
+            U[r, r] = 1.0
+            r += 1
+        else:           # complex order (+n, -n); real order (cos, sin): c = (|n>+|-n>)/sqrt2, s = i(|n>-|-n>)/sqrt2
+            U[r, r], U[r + 1, r] = 2 ** -0.5, 2 ** -0.5
+            U[r, r + 1], U[r + 1, r + 1] = 1j * 2 ** -0.5, -1j * 2 ** -0.5
+            r += 2
+    sigma = torch.tensor([-3.0, -4.0], dtype=torch.float64, device='cuda')
+    Srd = torch.tensor([Sr], dtype=torch.int32, device='cuda')
+    Scd = torch.tensor([Sc], dtype=torch.int32, device='cuda')
+    outc = torch.empty((B, ns, ns), dtype=torch.complex64, device='cuda')
+    kern.lowblock_assemble(sp, Scd, Dt, pot_struct(), fdc, sigma, 1.0, outc)
+    outr = torch.empty((B, ns, ns), dtype=torch.complex64, device='cuda')
+    kern.lowblock_assemble(sp, Srd, Dt, pot_struct(), fdr, sigma, 1.0, outr, real=True)
+    Ut = torch.as_tensor(U, device='cuda')
+    # the real-representation amplitudes are y = U^H z (y = sqrt2 Re z, sqrt2 Im z): H_r = U^H H_c U ... with the
+    # kernel's convention z = U y
+    ref = Ut.conj().T @ outc.to(torch.complex128) @ Ut
+    assert float(ref.imag.abs().max()) < 1e-5 * float(ref.abs().max())
+    assert relerr(outr.to(torch.complex128).cpu(), ref.cpu()) < 1e-6
+    assert float(outr.imag.abs().max()) == 0.0
