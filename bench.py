@@ -172,7 +172,7 @@ class ClockSampler:
 class TimedKernels:
     """Wraps the CUDA backend: CUDA events on the launching stream around every C-ABI call,
     so per-kernel device time is measured live inside the timed region (no profiler)."""
-    TIMED = ['hx_fused', 'mode_transform', 'potential_apply', 'gram', 'gram_pair', 'gen_rr', 'davidson_insert2',
+    TIMED = ['hx_fused', 'hx_fused_real', 'real_to_complex', 'complex_to_real', 'mode_transform', 'potential_apply', 'gram', 'gram_pair', 'gen_rr', 'davidson_insert2',
              'lowblock_assemble', 'hpd_inverse_c64', 'lowblock_apply', 'lowband_factor', 'lowband_apply', 'block_update', 'ritz_update', 'block_rightmul', 'heev',
              'residual_norms', 'precond_residual', 'restart_copy', 'svqb_coeffs', 'davidson_decide',
              'davidson_insert', 'diag_mul', 'ladder_apply']
@@ -268,7 +268,7 @@ def our_arm(args):
             fl = fluxes_host.to(dev, non_blocking=True).cpu().numpy()   # H2D of the step's inputs
         else:
             fl = fluxes_host.numpy()
-        res = cr.sweep_diag(N_EIG, loop_fluxes={loop: fl}, tol=args.tol, max_basis=args.mmax, lowblock=args.lowblock, block_size=args.block, **({'coarse_stride': tuple(int(x) for x in args.strides.split(','))} if args.strides else {}))
+        res = cr.sweep_diag(N_EIG, loop_fluxes={loop: fl}, tol=args.tol, max_basis=args.mmax, lowblock=args.lowblock, block_size=args.block, real=(False if args.complex else None), **({'coarse_stride': tuple(int(x) for x in args.strides.split(','))} if args.strides else {}))
         rates = [res.dec_rate(d, states=(1, 0)) for d in DEC_TYPES]
         if world > 1:
             # the only collective of the path: final gather of the per-point results to rank 0
@@ -315,14 +315,16 @@ def our_arm(args):
     # timed region: only the dominant kernel (the fused H.X) carries CUDA events -- bracketing all
     # ~900 C-ABI calls of a step costs ~60 ms of host time per step (measured), which would be
     # charged to `value`.  The full per-kernel breakdown comes from one extra, untimed step below.
-    kern.only = {'hx_fused', 'mode_transform', 'potential_apply'}
+    kern.only = {'hx_fused', 'hx_fused_real', 'mode_transform', 'potential_apply'}
     kern.enabled = True
     l0 = kern.launch_count()
     ms_dev, last = timed(args.steps, False)
     launches = kern.launch_count() - l0
     kern.enabled = False
     hx_kernel = kern.summary()
-    nvec = HX_COUNTER['vectors'] + (int(HX_COUNTER['dev'].item()) if 'dev' in HX_COUNTER else 0)
+    nvec = HX_COUNTER.get('vectors', 0) + (int(HX_COUNTER['vectors_dev'].item()) if 'vectors_dev' in HX_COUNTER else 0)
+    nvec_real = HX_COUNTER.get('real_vectors', 0) + (int(HX_COUNTER['real_vectors_dev'].item())
+                                                      if 'real_vectors_dev' in HX_COUNTER else 0)
     ms_e2e, last_e2e = timed(args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
     iters = last[2].iterations
@@ -350,39 +352,47 @@ def our_arm(args):
         peaks = json.load(open(pk))
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'MEASURED_PEAKS.json (sustained copy)' if peaks else 'fallback 6.65 TB/s'
-    hx_ms = sum(hx_kernel.get(k, [0, 0])[0] for k in ('hx_fused', 'mode_transform', 'potential_apply'))
-    hx_calls = hx_kernel.get('hx_fused', hx_kernel.get('potential_apply', [0, 1]))[1]
-    # algorithmic bytes of one H.X: read X once + write Y once, 16 B per complex amplitude
+    # the dominant H.X kernel of this run: the real-representation kernel (zero gate charge) or the complex one
+    real_ms = hx_kernel.get('hx_fused_real', [0.0, 0])[0]
+    cplx_ms = sum(hx_kernel.get(k, [0, 0])[0] for k in ('hx_fused', 'mode_transform', 'potential_apply'))
+    use_real = real_ms > cplx_ms
     total_ms = sum(v[0] for v in per_kernel.values())
     shares = {k: {'ms': round(v[0], 3), 'calls': v[1], 'share': round(v[0] / total_ms, 4)}
               for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}
-    roof = {'bound': 'hbm', 'kernel': 'H.X apply (sqc_hx_fused: transform + potential + transform in one kernel)',
-            'unit': 'GB/s', 'peak': hbm_peak, 'peak_source': peak_src, 'traffic': None,
-            'achieved': None, 'frac': None}
-    if hx_ms > 0 and nvec > 0:
-        alg_bytes = 32.0 * N * nvec
+    if use_real:
+        hx_ms, hx_calls, nv = real_ms, hx_kernel['hx_fused_real'][1], nvec_real
+        bytes_per_vec = 16 * N        # read N doubles, write N doubles
+        kname = 'H.X apply, real representation (sqc_hx_fused_real: TMA load, transform + potential + transform, TMA store)'
+    else:
+        hx_ms, nv = cplx_ms, nvec
+        hx_calls = hx_kernel.get('hx_fused', hx_kernel.get('potential_apply', [0, 1]))[1]
+        bytes_per_vec = 32 * N        # read N complex, write N complex
+        kname = 'H.X apply (sqc_hx_fused: transform + potential + transform in one kernel)'
+    roof = {'bound': 'hbm', 'kernel': kname, 'unit': 'GB/s', 'peak': hbm_peak, 'peak_source': peak_src,
+            'traffic': None, 'achieved': None, 'frac': None}
+    if hx_ms > 0 and nv > 0:
+        alg_bytes = float(bytes_per_vec) * nv
         roof['achieved'] = alg_bytes / (hx_ms / 1e3) / 1e9
         roof['frac'] = roof['achieved'] / hbm_peak
-        roof['algorithmic_bytes_per_vector'] = 32 * N
-        # DRAM bytes of the kernel from the ncu --set full capture (profiles/r01_ncu_full_v28_hx_fused.txt):
-        # 331.4 MB read + 283.0 MB written for a launch of 1751 vectors = 1.0855 x its algorithmic bytes
-        # (halo columns + LC diagonal).  Reported per launch, scaled to this run's average launch.
-        roof['traffic'] = NCU_HX_TRAFFIC_RATIO * alg_bytes / max(hx_calls, 1)
+        roof['algorithmic_bytes_per_vector'] = bytes_per_vec
         roof['algorithmic_bytes_per_launch'] = alg_bytes / max(hx_calls, 1)
-        roof['traffic_source'] = 'ncu dram__bytes_read+write / algorithmic = 1.0855 (profiles/r01_ncu_full_v28_hx_fused.txt)'
-        roof['vectors'] = nvec
+        ratio, src = NCU_HX_TRAFFIC.get('real' if use_real else 'complex', (None, None))
+        if ratio is not None:
+            # DRAM bytes of the kernel from its ncu --set full capture, as a ratio to the algorithmic bytes of
+            # the captured launch; reported per launch, scaled to this run's average launch
+            roof['traffic'] = ratio * alg_bytes / max(hx_calls, 1)
+            roof['traffic_source'] = src
+        roof['vectors'] = nv
         roof['ms'] = hx_ms
-        # FP64 work of the same apply with the parity-split transforms: two real (m/2 x m/2)
-        # contractions per parity half and direction on complex data = 2*2*m flops per amplitude
-        flops = 2.0 * (2 * cr.m[0]) * N * nvec
+        # FP64 work with the parity-split transforms: 2 m flop per real amplitude (forward + backward), twice
+        # that per complex amplitude
+        flops = (2.0 if use_real else 4.0) * cr.m[0] * N * nv
         roof['fp64_tflops'] = flops / (hx_ms / 1e3) / 1e12
-        # the kernel is FP64-tensor-bound (12.5 flop/B): context for the HBM fraction above.  Peak =
-        # measured DMMA issue rate (tools/cu/dmma_peak.cu, profiles/r01_dmma_peak.txt): 37.1 TFLOP/s
+        # the kernel is FP64-tensor-bound (12.5 flop/B in both representations): context for the HBM fraction.
+        # Peak = measured DMMA issue rate (tools/cu/dmma_peak.cu, profiles/r01_dmma_peak.txt): 37.1 TFLOP/s
         roof['fp64_tensor_peak_tflops'] = 37.1
         roof['fp64_tensor_frac'] = roof['fp64_tflops'] / 37.1
-        # ceiling of the HBM fraction for this operator: 2*2*m useful flop per 32 algorithmic bytes at
-        # the FP64 tensor peak (m = 100: 12.5 flop/B against a ridge of 5.7 flop/B)
-        roof['hbm_frac_ceiling_fp64_bound'] = (37.1e12 / (2.0 * 2 * cr.m[0] / 32.0)) / 1e9 / hbm_peak
+        roof['hbm_frac_ceiling_fp64_bound'] = (37.1e12 / (flops / alg_bytes)) / 1e9 / hbm_peak
     roof['calls'] = hx_calls
 
     # ---- cpu baseline: bounded sample of the same workload on the host cores ----
@@ -402,12 +412,12 @@ def our_arm(args):
     line = {
         'metric': 'diagonalisations/sec (k=10), 0-pi flux sweep', 'value': value, 'unit': 'diag/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 (complex128)',
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': {'workload': '0-pi qubit, trunc_nums [100,51] (N=10100), 4096-point flux sweep per GPU, k=10, '
                                '6 T1/Tphi channels on (1,0)',
                    'points_per_gpu': points, 'n_eig': N_EIG, 'hilbert_dim': N, 'tol_rel_residual': args.tol,
-                   'davidson_iterations': iters, 'l2': 'working set (>60 GB) larger than L2',
+                   'davidson_iterations': iters, 'representation': 'real (time-reversal adapted)' if use_real else 'complex', 'l2': 'working set (>60 GB) larger than L2',
                    'parallelism': f'sweep points sharded over {world} GPU(s), final NCCL gather'},
         'e2e': {'value': e2e_value, 'unit': 'diag/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
@@ -423,7 +433,9 @@ def our_arm(args):
         dist.destroy_process_group()
 
 
-NCU_HX_TRAFFIC_RATIO = 1.0855
+NCU_HX_TRAFFIC = {
+    'complex': (1.0855, 'ncu dram__bytes_read+write / algorithmic = 1.0855 (profiles/r01_ncu_full_v28_hx_fused.txt)'),
+}
 HX_COUNTER = {'vectors': 0}
 DEBUG = bool(os.environ.get('SQC_BENCH_DEBUG'))
 
@@ -432,16 +444,19 @@ def _install_hx_counter():
     """Count the state vectors that go through H.X inside the timed region (for the roofline)."""
     from sqcircuit_b200 import operators
 
-    orig = operators.HamiltonianOperator.apply
+    def hook(cls, key):
+        orig = cls.apply
 
-    def apply(self, X, Y):
-        if getattr(self.ops.kern, 'enabled', False):
-            if X.cnt is not None:      # device-side accumulation: no host sync in the timed region
-                HX_COUNTER['dev'] = HX_COUNTER.get('dev', 0) + X.cnt.sum()
-            else:
-                HX_COUNTER['vectors'] += X.B * X.cnt_fixed
-        return orig(self, X, Y)
-    operators.HamiltonianOperator.apply = apply
+        def apply(self, X, Y):
+            if getattr(self.ops.kern, 'enabled', False):
+                if X.cnt is not None:      # device-side accumulation: no host sync in the timed region
+                    HX_COUNTER[key + '_dev'] = HX_COUNTER.get(key + '_dev', 0) + X.cnt.sum()
+                else:
+                    HX_COUNTER[key] = HX_COUNTER.get(key, 0) + X.B * X.cnt_fixed
+            return orig(self, X, Y)
+        cls.apply = apply
+    hook(operators.HamiltonianOperator, 'vectors')
+    hook(operators.RealHamiltonianOperator, 'real_vectors')
 
 
 def main():
@@ -457,6 +472,7 @@ def main():
     ap.add_argument('--block', type=int, default=None, help='Davidson block size p (default k + 2)')
     ap.add_argument('--strides', default='', help='continuation level strides, e.g. 64,16,4,1 (default 64,8,1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--complex', action='store_true', help='force complex vectors (no real representation)')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)

@@ -202,6 +202,13 @@ int sqc_heev(const void* A, const int32_t* n, int32_t n_fixed, int32_t ld, doubl
 int sqc_gen_rr(const void* GA, const void* GB, const int32_t* n, int32_t ld, double drop, double* w,
                void* Zt, int32_t B, void* stream);
 
+/* sqc_gen_rr for a REAL symmetric pencil (Davidson basis of the real representation): only the real parts
+ * of GA / GB are read, the arithmetic is real, and only the n_out lowest Ritz vectors are written to Zt
+ * (rows [0, min(n_out, n)), zero imaginary parts; the other rows are left untouched).  w as sqc_gen_rr.
+ * One 128-thread CTA per sweep point, five resident per SM. */
+int sqc_gen_rr_real(const void* GA, const void* GB, const int32_t* n, int32_t ld, double drop, double* w,
+                    void* Zt, int32_t n_out, int32_t B, void* stream);
+
 /* Ritz block in one pass over the basis A and its image A2 (same counts):
  *   Out[b][j] = sum_i Cf[b][j][i] A[b][i],  Out2[b][j] = sum_i Cf[b][j][i] A2[b][i],
  *   rn2[b][j] = || Out2_j - theta[b][j] Out_j ||^2,   j < count(Out, b)   (row stride Out.cnt_fixed).

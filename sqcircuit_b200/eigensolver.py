@@ -357,7 +357,7 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
         live = 1 - done
         nrr = msz * live
         xcnt = (p * live).to(i32)
-        kern.gen_rr(GA, GB, nrr, drop, theta, Zt)
+        kern.gen_rr(GA, GB, nrr, drop, theta, Zt, real=real, n_out=p)
         if lowblock is None and lowblock_ns > 0 and getattr(op, 'supports_lowblock', lambda: False)():
             # two-level preconditioner.  sigma must stay below the spectrum of H_SS (>= lambda_0): warm
             # starts know lambda_0 to ~1e-6 at once; cold starts wait until every point's lowest Ritz

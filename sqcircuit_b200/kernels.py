@@ -146,8 +146,13 @@ class Kernels:
                                           _p(self._gram_work) if need else C.c_void_p(0), _stream(self.dev)),
                    'sqc_gram_pair')
 
-    def gen_rr(self, GA, GB, n, drop, w, Zt):
+    def gen_rr(self, GA, GB, n, drop, w, Zt, real=False, n_out=None):
+        """real: real symmetric pencil (sqc_gen_rr_real), only the n_out lowest Ritz vectors are written."""
         B, ld, _ = GA.shape
+        if real:
+            _lib.check(self.lib.sqc_gen_rr_real(_p(GA), _p(GB), _p(n), ld, drop, _p(w), _p(Zt),
+                                                int(n_out or ld), B, _stream(self.dev)), 'sqc_gen_rr_real')
+            return
         _lib.check(self.lib.sqc_gen_rr(_p(GA), _p(GB), _p(n), ld, drop, _p(w), _p(Zt), B, _stream(self.dev)),
                    'sqc_gen_rr')
 

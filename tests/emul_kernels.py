@@ -213,7 +213,7 @@ class EmulKernels:
         self.gram(A, Bm, C1)
         self.gram(A, Bm2, C2)
 
-    def gen_rr(self, GA, GB, n, drop, w, Zt):
+    def gen_rr(self, GA, GB, n, drop, w, Zt, real=False, n_out=None):
         B, ld, _ = GA.shape
         for b in range(B):
             nb = int(n[b])
@@ -221,6 +221,8 @@ class EmulKernels:
                 continue
             a = GA[b, :nb, :nb].numpy().copy()
             g = GB[b, :nb, :nb].numpy().copy()
+            if real:
+                a, g = a.real.astype(complex), g.real.astype(complex)
             a = (a + a.conj().T) / 2
             g = (g + g.conj().T) / 2
             gd = np.real(np.diag(g)).copy()
@@ -246,8 +248,10 @@ class EmulKernels:
             c[alive, :] = Li.conj().T @ y
             w[b] = float('inf')
             w[b, :len(alive)] = torch.from_numpy(ww)
-            Zt[b, :nb, :nb] = 0
-            Zt[b, :len(alive), :nb] = torch.from_numpy(np.ascontiguousarray(c.T))
+            rows = min(nb, n_out) if (real and n_out) else nb
+            Zt[b, :rows, :nb] = 0
+            keep = min(len(alive), rows)
+            Zt[b, :keep, :nb] = torch.from_numpy(np.ascontiguousarray(c.T[:keep].real if real else c.T[:keep]))
 
     def davidson_insert2(self, st, SA, SB, B):
         for b in range(B):

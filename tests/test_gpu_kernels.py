@@ -582,7 +582,7 @@ def _real_case(kern, m, inner, B, T=2, seed=40):
     return sp, V, etab, a, gl, fdc, fdr, pot_struct
 
 
-@pytest.mark.parametrize('dims', [[100, 51], [25, 13], [30, 19], [7, 3], [101, 41], [2, 61], [128, 127], [33, 1],
+@pytest.mark.parametrize('dims', [[100, 51], [25, 13], [30, 19], [7, 3], [101, 41], [2, 61], [112, 127], [33, 1],
                                   [100, 101]])
 @pytest.mark.parametrize('shifts', [(1, -1), (1, 0)])
 def test_hx_real_matches_complex(kern, dims, shifts):

@@ -66,6 +66,27 @@ if not only or 'hx' in only:
     Ve, Vo = Vx[0::2, :50].contiguous(), Vx[1::2, :50].contiguous()
     ms = timeit(lambda: k.hx_fused(sp, Ve, Vo, pot, fd, BlockView(X), BlockView(Y)))
     report('hx_fused 12 vec/pt', ms, 32.0 * N * p * B, 2.0 * 2 * m * N * p * B)
+if not only or 'hxr' in only:
+    # real-representation H.X at the bench size: m = 100, inner = 101 (trunc_nums [100, 51])
+    m, inner = 100, 101
+    Nc = (m * inner + 1) // 2
+    sp = make_space([m, inner], [1, 0])
+    Vx, lam = k.xbasis(m)
+    lamcat = torch.zeros(m + inner, dtype=torch.float64, device=dev); lamcat[:m] = lam
+    s = torch.tensor([[[0.61, 0.0], [-0.61, 0.0]]], dtype=torch.float64, device=dev)
+    etab = torch.empty((1, 2, m + inner), dtype=torch.complex128, device=dev)
+    k.phase_tables(sp, 2, lamcat, s, etab)
+    a = torch.randn((B, 2), dtype=torch.complex128, device=dev)
+    g = torch.randn((B, 3), dtype=torch.float64, device=dev)
+    fd = torch.randn((1, 2 * Nc), dtype=torch.float64, device=dev)
+    pot = Potential(); pot.n_terms = 2; pot.shift[0][1] = 1; pot.shift[1][1] = -1
+    pot.lam, pot.etab, pot.etab_stride_b = lamcat.data_ptr(), etab.data_ptr(), 0
+    pot.g, pot.a, pot.diag, pot.diag_stride_b = g.data_ptr(), a.data_ptr(), None, 0
+    Ve, Vo = Vx[0::2, :50].contiguous(), Vx[1::2, :50].contiguous()
+    Xr = torch.randn((B, p, Nc), dtype=torch.complex128, device=dev)
+    Yr = torch.zeros_like(Xr)
+    ms = timeit(lambda: k.hx_fused_real(sp, Ve, Vo, pot, fd, BlockView(Xr), BlockView(Yr)))
+    report('hx_fused_real 12 vec/pt', ms, 16.0 * N * p * B, 2.0 * m * N * p * B)
 if not only or 'pair' in only:
     W = torch.randn((B, mm, N), dtype=torch.complex128, device=dev)
     for msz in (12, 24, 28):
