@@ -142,11 +142,15 @@ int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const double* Vo,
  *
  * sqc_hx_fused_real: Y = fdiag .* X + V [ P ( V^T X ) ] on real vectors -- same operator, arguments and
  * limits as sqc_hx_fused, except: fdiag is the LC diagonal in the real layout, [(B or 1)][2 Nc]
- * (fdiag_stride_b in doubles), and inner must be odd and <= 127.  Panels are staged with TMA bulk copies
- * (cp.async.bulk + mbarrier) and written back the same way. */
+ * (fdiag_stride_b in doubles), and inner must be odd and <= 127.  Vectors are staged with TMA bulk copies
+ * (cp.async.bulk + mbarrier) and written back the same way.
+ * fdiag_sep (optional, device [m + inner], shared by all sweep points): the same diagonal in separable form,
+ * d(i, j) = fdiag_sep[i] + fdiag_sep[m + j] (LC energies of one harmonic and one charge mode add up); when
+ * given it is used INSTEAD of fdiag: the charge part is applied in the x basis (exact, V is orthogonal) and
+ * the epilogue only needs one Fock-energy scalar per row. */
 int sqc_hx_fused_real(const sqc_space_t* sp, const double* Ve, const double* Vo,
                       const sqc_potential_t* pot, const double* fdiag, int64_t fdiag_stride_b,
-                      sqc_block_t X, sqc_block_t Y, int32_t B, void* stream);
+                      const double* fdiag_sep, sqc_block_t X, sqc_block_t Y, int32_t B, void* stream);
 
 /* Zc (complex, N elements per vector, Fock x charge basis of the reference) <- Xr (real representation),
  * and the projection back, Xr <- T-symmetric part of Zc. */
@@ -205,7 +209,7 @@ int sqc_gen_rr(const void* GA, const void* GB, const int32_t* n, int32_t ld, dou
 /* sqc_gen_rr for a REAL symmetric pencil (Davidson basis of the real representation): only the real parts
  * of GA / GB are read, the arithmetic is real, and only the n_out lowest Ritz vectors are written to Zt
  * (rows [0, min(n_out, n)), zero imaginary parts; the other rows are left untouched).  w as sqc_gen_rr.
- * One 128-thread CTA per sweep point, five resident per SM. */
+ * One 384-thread CTA per sweep point, five resident per SM (mmax = 40). */
 int sqc_gen_rr_real(const void* GA, const void* GB, const int32_t* n, int32_t ld, double drop, double* w,
                     void* Zt, int32_t n_out, int32_t B, void* stream);
 
@@ -305,17 +309,22 @@ int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const doubl
                        int64_t N, int32_t B, void* stream);
 
 /* Real representation: S holds indices of REAL basis states (i * inner + j), d the real-layout LC
- * diagonal; the block is real symmetric and stored as complex64 with zero imaginary parts, so
- * sqc_hpd_inverse_c64 / sqc_lowband_factor apply unchanged.  The *_apply_real variants gather and
- * scatter real amplitudes (N = complex elements per vector, as everywhere). */
+ * diagonal; the block is real symmetric.  real_storage = 0: stored as complex64 with zero imaginary parts
+ * (for sqc_hpd_inverse_c64 + sqc_lowblock_apply_real, the dense variant); real_storage = 1: stored as
+ * float [ns][ns] (for sqc_lowband_factor_real + sqc_lowband_apply_real).  The *_apply_real variants gather
+ * and scatter real amplitudes (N = complex elements per vector, as everywhere). */
 int sqc_lowblock_assemble_real(const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
                                const void* Dt, const sqc_potential_t* pot, const double* d,
                                int64_t d_stride_b, const double* sigma, double unit, void* out,
-                               int32_t B, void* stream);
+                               int32_t real_storage, int32_t B, void* stream);
 int sqc_lowblock_apply_real(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
                             int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
                             int64_t s_stride_b, const void* Ainv, int32_t ns, double unit, int32_t group,
                             int64_t N, int32_t B, void* stream);
+/* Banded variant in float storage: same contract as sqc_lowband_factor / sqc_lowband_apply below with a
+ * real symmetric block; a warp carries four right-hand sides as one float4 per row. */
+int sqc_lowband_factor_real(void* A, int32_t ns, const int32_t* blk_off, int32_t ld_off, const int32_t* nblk,
+                            int32_t nbmax, int32_t B, void* stream);
 int sqc_lowband_apply_real(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
                            int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
                            int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,

@@ -82,14 +82,15 @@ SIGNATURES = {
                                   c_vp, c_i32, c_dbl, c_i32, c_vp, c_i64, c_i32, c_vp]),
     'sqc_lowblock_apply': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32, c_dbl,
                                    c_i32, c_i64, c_i32, c_vp]),
-    'sqc_hx_fused_real': (c_i32, [C.POINTER(Space), c_vp, c_vp, C.POINTER(Potential), c_vp, c_i64, Block, Block, c_i32,
-                                  c_vp]),
+    'sqc_hx_fused_real': (c_i32, [C.POINTER(Space), c_vp, c_vp, C.POINTER(Potential), c_vp, c_i64, c_vp, Block, Block,
+                                  c_i32, c_vp]),
     'sqc_real_to_complex': (c_i32, [C.POINTER(Space), Block, Block, c_i32, c_vp]),
     'sqc_complex_to_real': (c_i32, [C.POINTER(Space), Block, Block, c_i32, c_vp]),
     'sqc_precond_residual_real': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp,
                                           c_i64, c_i32, c_vp]),
     'sqc_lowblock_assemble_real': (c_i32, [C.POINTER(Space), c_i32, c_vp, c_i64, c_vp, C.POINTER(Potential), c_vp,
-                                           c_i64, c_vp, c_dbl, c_vp, c_i32, c_vp]),
+                                           c_i64, c_vp, c_dbl, c_vp, c_i32, c_i32, c_vp]),
+    'sqc_lowband_factor_real': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp]),
     'sqc_lowband_apply_real': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32, c_vp,
                                        c_i32, c_vp, c_i32, c_dbl, c_i32, c_vp, c_i64, c_i32, c_vp]),
     'sqc_lowblock_apply_real': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32,

@@ -108,7 +108,7 @@ lowblock_assemble_real_kernel(LbGeom gm, const int32_t* __restrict__ S, long lon
                               const cplx* __restrict__ Dt, const cplx* __restrict__ a,
                               const double* __restrict__ g, const double* __restrict__ d,
                               long long d_stride_b, const double* __restrict__ sigma, double inv_unit,
-                              float2* __restrict__ out) {
+                              float2* __restrict__ out, int real_storage) {
     const int b = blockIdx.y;
     const int e = blockIdx.x * 256 + threadIdx.x;
     const int ns = gm.ns;
@@ -141,13 +141,14 @@ lowblock_assemble_real_kernel(LbGeom gm, const int32_t* __restrict__ S, long lon
         }
     }
     if (r == q) acc += d[b * d_stride_b + ir] - sigma[b];
-    out[(long long)b * ns * ns + e] = make_float2((float)(acc * inv_unit), 0.0f);
+    if (real_storage) reinterpret_cast<float*>(out)[(long long)b * ns * ns + e] = (float)(acc * inv_unit);
+    else out[(long long)b * ns * ns + e] = make_float2((float)(acc * inv_unit), 0.0f);
 }
 
 extern "C" int sqc_lowblock_assemble_real(const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
                                           const void* Dt, const sqc_potential_t* pot, const double* d,
                                           int64_t d_stride_b, const double* sigma, double unit, void* out,
-                                          int32_t B, void* stream) {
+                                          int32_t real_storage, int32_t B, void* stream) {
     if (!sp || !pot || B <= 0 || ns <= 0) return SQC_EINVAL;
     if (sp->n_modes != 2 || !sp->harmonic[0] || sp->harmonic[1] || pot->n_terms > LB_MAXT) return SQC_ELIMIT;
     if (!(sp->dims[1] & 1)) return SQC_ELIMIT;
@@ -160,7 +161,7 @@ extern "C" int sqc_lowblock_assemble_real(const sqc_space_t* sp, int32_t ns, con
     dim3 grid((ns * ns + 255) / 256, B);
     lowblock_assemble_real_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         gm, S, s_stride_b, (const cplx*)Dt, (const cplx*)pot->a, pot->g, d, d_stride_b, sigma, 1.0 / unit,
-        (float2*)out);
+        (float2*)out, real_storage);
     SQC_LAUNCHED();
     return 0;
 }
@@ -493,7 +494,6 @@ __device__ __forceinline__ f2x4 ld4(const float2* src) {
     return v;
 }
 
-template <bool REAL>
 __global__ void __launch_bounds__(32 * (16 / LBC))
 lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* __restrict__ theta,
                      int ld_theta, const int32_t* __restrict__ act, int ld_act,
@@ -557,15 +557,9 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
                 for (int j = lane; j < ns; j += 32) {
                     const int i = pm ? pm[j] : j;
                     const int idx = s[i];
-                    if (REAL) {
-                        const double xr = reinterpret_cast<const double*>(x)[idx];
-                        const double hr = reinterpret_cast<const double*>(h)[idx];
-                        v[i * LBC + c] = make_float2((float)((hr - th * xr) * inv_unit), 0.0f);
-                    } else {
-                        const cplx xv = x[idx], hv = h[idx];
-                        v[i * LBC + c] = make_float2((float)((hv.x - th * xv.x) * inv_unit),
-                                                     (float)((hv.y - th * xv.y) * inv_unit));
-                    }
+                    const cplx xv = x[idx], hv = h[idx];
+                    v[i * LBC + c] = make_float2((float)((hv.x - th * xv.x) * inv_unit),
+                                                 (float)((hv.y - th * xv.y) * inv_unit));
                 }
             } else {
                 for (int j = lane; j < ns; j += 32) v[j * LBC + c] = make_float2(0.0f, 0.0f);
@@ -628,15 +622,13 @@ lowband_apply_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double*
                 for (int j = lane; j < ns; j += 32) {
                     const int i = pm ? pm[j] : j;
                     const float2 w = v[i * LBC + c];
-                    if (REAL) reinterpret_cast<double*>(t)[s[i]] = (double)w.x;
-                    else t[s[i]] = cmake((double)w.x, (double)w.y);
+                    t[s[i]] = cmake((double)w.x, (double)w.y);
                 }
             }
         }
     }
 }
 
-template <bool REAL>
 static int lowband_apply_launch(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
                                 int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
                                 int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
@@ -647,9 +639,9 @@ static int lowband_apply_launch(sqc_block_t X, sqc_block_t HX, sqc_block_t T, co
     const size_t smem = ((size_t)4 * nbmax * (nbmax | 1) + 1 + (size_t)nwarp * ns * LBC + (size_t)nwarp * nbmax * LBC) *
                         sizeof(float2);
     if (smem > 227 * 1024) return SQC_ELIMIT;
-    cudaError_t e = cudaFuncSetAttribute(lowband_apply_kernel<REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lowband_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    lowband_apply_kernel<REAL><<<B, 32 * nwarp, smem, (cudaStream_t)stream>>>(
+    lowband_apply_kernel<<<B, 32 * nwarp, smem, (cudaStream_t)stream>>>(
         X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, (const float2*)Afac, ns, blk_off, ld_off, nblk, nbmax,
         1.0 / unit, group, N, perm);
     SQC_LAUNCHED();
@@ -661,15 +653,261 @@ extern "C" int sqc_lowband_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, c
                                  int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
                                  int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit, int32_t group,
                                  const int32_t* perm, int64_t N, int32_t B, void* stream) {
-    return lowband_apply_launch<false>(X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, Afac, ns, blk_off, ld_off,
+    return lowband_apply_launch(X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, Afac, ns, blk_off, ld_off,
                                        nblk, nbmax, unit, group, perm, N, B, stream);
 }
 
+
+
+// =====================================================================================
+// Real-storage variants of the banded preconditioner (real representation, see hx_real.cu): the low block
+// is real symmetric, so the factor is kept as float [ns][ns] (half the shared-memory traffic of the
+// complex64 kernels, a quarter of the multiply-adds) and a warp carries FOUR right-hand sides as one float4
+// per row.  Same block LDL^T algebra as above.
+// =====================================================================================
+__device__ void gj_inverse_smem_real(float* M, int n, int ld, float* rk, float* ck) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int k = 0; k < n; ++k) {
+        if (tid < n) {
+            const float dinv = 1.0f / M[k * ld + k];
+            rk[tid] = ((tid == k) ? 1.0f : M[k * ld + tid]) * dinv;
+            ck[tid] = M[tid * ld + k];
+        }
+        __syncthreads();
+        for (int e = tid; e < n * n; e += nt) {
+            const int i = e / n, j = e % n;
+            float v;
+            if (i == k) v = rk[j];
+            else v = ((j == k) ? 0.0f : M[i * ld + j]) - ck[i] * rk[j];
+            M[i * ld + j] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(LBN_THREADS)
+lowband_factor_real_kernel(float* __restrict__ Aio, int ns, const int32_t* __restrict__ blk_off, int ld_off,
+                           const int32_t* __restrict__ nblk, int nbmax) {
+    extern __shared__ float smr[];
+    const int ld = nbmax | 1;
+    float* M = smr;                    // current Schur complement -> P_q
+    float* Pp = M + nbmax * ld;        // P_{q-1}
+    float* E = Pp + nbmax * ld;        // E_{q-1}  [n_{q-1}][n_q]
+    float* Tm = E + nbmax * ld;        // P_{q-1} E_{q-1}
+    float* rk = Tm + nbmax * ld;
+    float* ck = rk + nbmax;
+    const int slot = blockIdx.x, tid = threadIdx.x;
+    float* A = Aio + (long long)slot * ns * ns;
+    const int32_t* off = blk_off + (long long)slot * ld_off;
+    const int nb = nblk[slot];
+    int nprev = 0, oprev = 0;
+    for (int q = 0; q < nb; ++q) {
+        const int o = off[q], n = off[q + 1] - o;
+        for (int e = tid; e < n * n; e += LBN_THREADS) M[(e / n) * ld + (e % n)] = A[(long long)(o + e / n) * ns + o + e % n];
+        if (q > 0)
+            for (int e = tid; e < nprev * n; e += LBN_THREADS)
+                E[(e / n) * ld + (e % n)] = A[(long long)(oprev + e / n) * ns + o + e % n];
+        __syncthreads();
+        if (q > 0) {
+            for (int e = tid; e < nprev * n; e += LBN_THREADS) {          // Tm = Pp E
+                const int i = e / n, j = e % n;
+                float acc = 0.0f;
+                for (int k = 0; k < nprev; ++k) acc = fmaf(Pp[i * ld + k], E[k * ld + j], acc);
+                Tm[i * ld + j] = acc;
+            }
+            __syncthreads();
+            for (int e = tid; e < n * n; e += LBN_THREADS) {              // M -= E^T Tm
+                const int i = e / n, j = e % n;
+                float acc = 0.0f;
+                for (int k = 0; k < nprev; ++k) acc = fmaf(E[k * ld + i], Tm[k * ld + j], acc);
+                M[i * ld + j] -= acc;
+            }
+            __syncthreads();
+        }
+        gj_inverse_smem_real(M, n, ld, rk, ck);
+        for (int e = tid; e < n * n; e += LBN_THREADS) {
+            const float v = M[(e / n) * ld + (e % n)];
+            A[(long long)(o + e / n) * ns + o + e % n] = v;
+            Pp[(e / n) * ld + (e % n)] = v;
+        }
+        __syncthreads();
+        nprev = n;
+        oprev = o;
+    }
+}
+
+extern "C" int sqc_lowband_factor_real(void* A, int32_t ns, const int32_t* blk_off, int32_t ld_off,
+                                       const int32_t* nblk, int32_t nbmax, int32_t B, void* stream) {
+    if (B <= 0 || ns <= 0 || !A || !blk_off || !nblk || nbmax <= 0) return SQC_EINVAL;
+    if (nbmax > 128) return SQC_ELIMIT;
+    const size_t smem = ((size_t)4 * nbmax * (nbmax | 1) + 2 * (size_t)nbmax) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(lowband_factor_real_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    lowband_factor_real_kernel<<<B, LBN_THREADS, smem, (cudaStream_t)stream>>>((float*)A, ns, blk_off, ld_off, nblk, nbmax);
+    SQC_LAUNCHED();
+    return 0;
+}
+
+#define LBR 4          // right-hand sides per warp (one float4 per row)
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void fma4(float4& acc, float m, const float4& x) {
+    acc.x = fmaf(m, x.x, acc.x);
+    acc.y = fmaf(m, x.y, acc.y);
+    acc.z = fmaf(m, x.z, acc.z);
+    acc.w = fmaf(m, x.w, acc.w);
+}
+
+__global__ void __launch_bounds__(32 * (16 / LBR))
+lowband_apply_real_kernel(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* __restrict__ theta,
+                          int ld_theta, const int32_t* __restrict__ act, int ld_act,
+                          const int32_t* __restrict__ S, long long s_stride_b, const float* __restrict__ Afac,
+                          int ns, const int32_t* __restrict__ blk_off, int ld_off, const int32_t* __restrict__ nblk,
+                          int nbmax, double inv_unit, int group, long long N, const int32_t* __restrict__ perm) {
+    extern __shared__ float4 smr4[];
+    const int b = blockIdx.x;
+    const int na = blk_count(T, b);
+    if (na <= 0) return;
+    const int ld = nbmax | 1;
+    const int nwarp = blockDim.x >> 5;
+    const int bufsz = 2 * nbmax * ld;          // P block + E block (floats)
+    float4* vec = smr4;                        // [nwarp][ns]  r -> z -> x, one float4 (LBR right-hand sides) per row
+    float4* tmp = vec + (size_t)nwarp * ns;    // [nwarp][nbmax]
+    float* buf = reinterpret_cast<float*>(tmp + (size_t)nwarp * nbmax);      // two buffers of (P, E)
+    const int slot = b / group;
+    const int32_t* s = S + slot * s_stride_b;
+    const int32_t* pm = perm ? perm + slot * s_stride_b : nullptr;
+    const float* A = Afac + (long long)slot * ns * ns;
+    const int32_t* off = blk_off + (long long)slot * ld_off;
+    const int nb = nblk[slot];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c0 = warp * LBR;
+    const bool mine = c0 < na;
+    float4* v = vec + (size_t)warp * ns;
+    float4* u = tmp + (size_t)warp * nbmax;
+    auto stage = [&](int st) {
+        if (st <= 2 * nb - 2) {
+            float* P = buf + (st & 1) * bufsz;
+            float* E = P + nbmax * ld;
+            const bool fwd = st < nb;
+            const int q = fwd ? st : 2 * nb - 2 - st;
+            const int o = off[q], n = off[q + 1] - o;
+            for (int e = tid; e < n * n; e += blockDim.x)
+                cp_async4(P + (e / n) * ld + (e % n), A + (long long)(o + e / n) * ns + o + e % n);
+            if (fwd && q > 0) {
+                const int op = off[q - 1], np_ = o - op;
+                for (int e = tid; e < np_ * n; e += blockDim.x)
+                    cp_async4(E + (e / n) * ld + (e % n), A + (long long)(op + e / n) * ns + o + e % n);
+            } else if (!fwd) {
+                const int on = off[q + 1], nn = off[q + 2] - on;
+                for (int e = tid; e < n * nn; e += blockDim.x)
+                    cp_async4(E + (e / nn) * ld + (e % nn), A + (long long)(o + e / nn) * ns + on + e % nn);
+            }
+        }
+        cp_async_commit();
+    };
+    stage(0);
+    if (mine) {
+        // gather the residual entries of the index set (ascending-address order through perm)
+        const double* xp[LBR];
+        const double* hp[LBR];
+        double th[LBR];
+#pragma unroll
+        for (int c = 0; c < LBR; ++c) {
+            const bool on = c0 + c < na;
+            const int av = on ? act[(long long)b * ld_act + c0 + c] : 0;
+            th[c] = on ? theta[(long long)b * ld_theta + av] : 0.0;
+            xp[c] = on ? reinterpret_cast<const double*>(blk_vec(X, b, av, N)) : nullptr;
+            hp[c] = on ? reinterpret_cast<const double*>(blk_vec(HX, b, av, N)) : nullptr;
+        }
+        for (int j = lane; j < ns; j += 32) {
+            const int i = pm ? pm[j] : j;
+            const int idx = s[i];
+            float r[LBR];
+#pragma unroll
+            for (int c = 0; c < LBR; ++c)
+                r[c] = xp[c] ? (float)((hp[c][idx] - th[c] * xp[c][idx]) * inv_unit) : 0.0f;
+            v[i] = make_float4(r[0], r[1], r[2], r[3]);
+        }
+    }
+    for (int st = 0; st <= 2 * nb - 2; ++st) {
+        __syncthreads();                       // everyone is done with buffer (st + 1) & 1 (step st - 1)
+        stage(st + 1);
+        cp_async_wait<1>();
+        __syncthreads();
+        const float* P = buf + (st & 1) * bufsz;
+        const float* E = P + nbmax * ld;
+        if (!mine) continue;
+        if (st < nb) {
+            // ---- forward:  y = r_q - E_{q-1}^T z_{q-1},  z_q = P_q y ----
+            const int q = st, o = off[q], n = off[q + 1] - o;
+            const int op = q > 0 ? off[q - 1] : 0, np_ = q > 0 ? o - op : 0;
+            for (int i = lane; i < n; i += 32) {
+                float4 acc = v[o + i];
+                for (int k = 0; k < np_; ++k) fma4(acc, -E[k * ld + i], v[op + k]);
+                u[i] = acc;
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {              // P symmetric: column walk = consecutive lanes
+                float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                for (int k = 0; k < n; ++k) fma4(acc, P[k * ld + i], u[k]);
+                v[o + i] = acc;
+            }
+            __syncwarp();
+        } else {
+            // ---- backward:  x_q = z_q - P_q (E_q x_{q+1}) ----
+            const int q = 2 * nb - 2 - st, o = off[q], n = off[q + 1] - o;
+            const int on = off[q + 1], nn = off[q + 2] - on;
+            for (int i = lane; i < n; i += 32) {
+                float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                for (int k = 0; k < nn; ++k) fma4(acc, E[i * ld + k], v[on + k]);
+                u[i] = acc;
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                float4 acc = v[o + i];
+                for (int k = 0; k < n; ++k) fma4(acc, -P[k * ld + i], u[k]);
+                v[o + i] = acc;
+            }
+            __syncwarp();
+        }
+    }
+    cp_async_wait<0>();
+    if (mine) {
+        double* tp[LBR];
+#pragma unroll
+        for (int c = 0; c < LBR; ++c)
+            tp[c] = c0 + c < na ? reinterpret_cast<double*>(blk_vec(T, b, c0 + c, N)) : nullptr;
+        for (int j = lane; j < ns; j += 32) {
+            const int i = pm ? pm[j] : j;
+            const int idx = s[i];
+            const float4 w = v[i];
+            if (tp[0]) tp[0][idx] = (double)w.x;
+            if (tp[1]) tp[1][idx] = (double)w.y;
+            if (tp[2]) tp[2][idx] = (double)w.z;
+            if (tp[3]) tp[3][idx] = (double)w.w;
+        }
+    }
+}
+
 extern "C" int sqc_lowband_apply_real(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
-                                      int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
-                                      int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
-                                      int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit, int32_t group,
-                                      const int32_t* perm, int64_t N, int32_t B, void* stream) {
-    return lowband_apply_launch<true>(X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, Afac, ns, blk_off, ld_off,
-                                      nblk, nbmax, unit, group, perm, N, B, stream);
+                                        int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,
+                                        int64_t s_stride_b, const void* Afac, int32_t ns, const int32_t* blk_off,
+                                        int32_t ld_off, const int32_t* nblk, int32_t nbmax, double unit,
+                                        int32_t group, const int32_t* perm, int64_t N, int32_t B, void* stream) {
+    if (B <= 0 || ns <= 0 || T.cnt_fixed <= 0 || T.cnt_fixed > 16 || group < 1 || nbmax <= 0) return SQC_EINVAL;
+    const int nwarp = (T.cnt_fixed + LBR - 1) / LBR;
+    const size_t smem = ((size_t)nwarp * ns + (size_t)nwarp * nbmax) * sizeof(float4) +
+                        (size_t)4 * nbmax * (nbmax | 1) * sizeof(float);
+    if (smem > 227 * 1024) return SQC_ELIMIT;
+    cudaError_t e = cudaFuncSetAttribute(lowband_apply_real_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    lowband_apply_real_kernel<<<B, 32 * nwarp, smem, (cudaStream_t)stream>>>(
+        X, HX, T, theta, ld_theta, act, ld_act, S, s_stride_b, (const float*)Afac, ns, blk_off, ld_off, nblk, nbmax,
+        1.0 / unit, group, N, perm);
+    SQC_LAUNCHED();
+    return 0;
 }

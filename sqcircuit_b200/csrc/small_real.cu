@@ -3,15 +3,17 @@
 // of numerically dependent basis vectors, M = L^-1 GA L^-T, cyclic Jacobi on M, c = L^-T y, eigenpairs in
 // ascending order -- in real arithmetic.
 //
-// The complex kernel is latency bound (one 512-thread CTA per sweep point, two CTA barriers per Jacobi step,
-// 79 KB of shared memory: two CTAs per SM).  Here a problem gets ONE 128-thread CTA and 39 KB (mmax = 40), so
-// five problems are resident per SM, a barrier costs a fraction, and the rotations are real (a quarter of the
-// flops): what limits the kernel is the FP64 issue rate, not the barrier latency.
+// The complex kernel is latency bound (one 512-thread CTA per sweep point, 79 KB of shared memory: two CTAs
+// per SM).  Here a problem takes 39 KB (mmax = 40) and a 384-thread CTA, so five problems are resident per SM
+// and the rotations are real (a quarter of the flops).  The time of a call is (waves of resident problems) x
+// (latency of one problem), and a level of the continuation only fills ~3 waves: the thread count is chosen
+// for the latency of ONE problem (one round of 2x2 blocks per thread, three of eigenvector elements).
 #include <math.h>
 #include "common.cuh"
 
-#define RRR_THREADS 128
-#define RRR_BLK_THREADS 64        // threads that rotate the 2x2 blocks of A; the others rotate the rows of Z
+#define RRR_THREADS 384
+#define RRR_WARPS (RRR_THREADS / 32)
+#define RRR_BLK_THREADS 128       // threads that rotate the 2x2 blocks of A; the others rotate the rows of Z
 #define RRR_MAX_SWEEPS 30
 #define RRR_BIG 1.0e300
 #define RRR_REG_BLOCKS 4          // blocks per thread whose (P, Q) indices are kept in registers
@@ -27,7 +29,7 @@ __device__ __forceinline__ void rrr_tri_index(int u, int half, int& P, int& Q) {
 // Parallel cyclic (round-robin) two-sided Jacobi for an n x n real symmetric matrix in shared memory.
 //   A : np x np, leading dim lda, np even, rows / columns >= n are padding
 //   Zt: np rows of length ldz; on exit row j = eigenvector of A[j][j]
-//   rot: np doubles, prs: np ints, red: 8 doubles of shared scratch.  All RRR_THREADS threads must call.
+//   rot: np doubles, prs: np ints, red: 2 RRR_WARPS doubles of shared scratch.  All RRR_THREADS threads must call.
 __device__ void jacobi_syev_real(double* A, int n, int np, int lda, double* Zt, int ldz, double* rot, int* prs,
                                  double* red) {
     const int tid = threadIdx.x;
@@ -60,10 +62,15 @@ __device__ void jacobi_syev_real(double* A, int n, int np, int lda, double* Zt, 
         dg = warp_sum(dg);
         if ((tid & 31) == 0) {
             red[tid >> 5] = off;
-            red[4 + (tid >> 5)] = dg;
+            red[RRR_WARPS + (tid >> 5)] = dg;
         }
         __syncthreads();
-        const double o = red[0] + red[1] + red[2] + red[3], d = red[4] + red[5] + red[6] + red[7];
+        double o = 0.0, d = 0.0;
+#pragma unroll
+        for (int w_ = 0; w_ < RRR_WARPS; ++w_) {
+            o += red[w_];
+            d += red[RRR_WARPS + w_];
+        }
         __syncthreads();
         // quadratic convergence: once the off-diagonal mass is below 1e-11 relative, one more sweep leaves
         // it at rounding level
@@ -174,8 +181,8 @@ gen_rr_real_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
     double* Lm = A + (size_t)np_max * lda;                // GB -> L -> tmp -> compacted M -> eigenvalues
     double* Zs = Lm + (size_t)np_max * lda;               // L^-1
     double* rot = Zs + (size_t)np_max * lda;              // [np_max]
-    double* red = rot + np_max;                           // [8]
-    double* gbd = red + 8;                                // original diagonal of GB
+    double* red = rot + np_max;                           // [2 RRR_WARPS]
+    double* gbd = red + 2 * RRR_WARPS;                                // original diagonal of GB
     double* wv = gbd + np_max;
     int* prs = reinterpret_cast<int*>(wv + np_max);
     int* rank = prs + np_max;
@@ -303,7 +310,7 @@ extern "C" int sqc_gen_rr_real(const void* GA, const void* GB, const int32_t* n,
                                double* w, void* Zt, int32_t n_out, int32_t B, void* stream) {
     if (B <= 0 || ld <= 0 || ld > 68 || !n || n_out <= 0) return SQC_EINVAL;
     const int np_max = (ld + 1) & ~1;
-    const size_t bytes = 3 * (size_t)np_max * (np_max | 1) * sizeof(double) + (3 * np_max + 8) * sizeof(double) +
+    const size_t bytes = 3 * (size_t)np_max * (np_max | 1) * sizeof(double) + (3 * np_max + 2 * RRR_WARPS) * sizeof(double) +
                          (3 * np_max + 4) * sizeof(int) + 16;
     cudaError_t e = cudaFuncSetAttribute(gen_rr_real_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;

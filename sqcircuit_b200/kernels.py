@@ -186,11 +186,12 @@ class Kernels:
         _lib.check(rc, 'sqc_hx_fused')
         return True
 
-    def hx_fused_real(self, sp, Ve, Vo, pot, fdiag, X, Y):
-        """Real-representation H.X (sqc_hx_fused_real); False when the layout / size is not supported."""
+    def hx_fused_real(self, sp, Ve, Vo, pot, fdiag, X, Y, fdiag_sep=None):
+        """Real-representation H.X (sqc_hx_fused_real); False when the layout / size is not supported.
+        fdiag_sep: [m + inner] separable form of the same diagonal (used instead of fdiag when given)."""
         fsb = 0 if fdiag is None or fdiag.shape[0] == 1 else fdiag.stride(0)
-        rc = self.lib.sqc_hx_fused_real(C.byref(sp), _p(Ve), _p(Vo), C.byref(pot), _p(fdiag), fsb, X.c(), Y.c(),
-                                        X.B, _stream(self.dev))
+        rc = self.lib.sqc_hx_fused_real(C.byref(sp), _p(Ve), _p(Vo), C.byref(pot), _p(fdiag), fsb, _p(fdiag_sep),
+                                        X.c(), Y.c(), X.B, _stream(self.dev))
         if rc == _lib.ELIMIT:
             return False
         _lib.check(rc, 'sqc_hx_fused_real')
@@ -258,9 +259,16 @@ class Kernels:
         B, ns, _ = out.shape
         ssb = 0 if S.shape[0] == 1 else S.stride(0)
         dsb = 0 if d.shape[0] == 1 else d.stride(0)
-        fn = self.lib.sqc_lowblock_assemble_real if real else self.lib.sqc_lowblock_assemble
-        _lib.check(fn(C.byref(sp), ns, _p(S), ssb, _p(Dt), C.byref(pot), _p(d), dsb, _p(sigma), unit, _p(out), B,
-                      _stream(self.dev)), 'sqc_lowblock_assemble')
+        if real:
+            # float storage for the banded kernels, complex64 (zero imaginary parts) for the dense ones
+            _lib.check(self.lib.sqc_lowblock_assemble_real(C.byref(sp), ns, _p(S), ssb, _p(Dt), C.byref(pot), _p(d),
+                                                           dsb, _p(sigma), unit, _p(out),
+                                                           int(out.dtype == torch.float32), B, _stream(self.dev)),
+                       'sqc_lowblock_assemble_real')
+            return
+        _lib.check(self.lib.sqc_lowblock_assemble(C.byref(sp), ns, _p(S), ssb, _p(Dt), C.byref(pot), _p(d), dsb,
+                                                  _p(sigma), unit, _p(out), B, _stream(self.dev)),
+                   'sqc_lowblock_assemble')
 
     def hpd_inverse_c64(self, A):
         B, ns, _ = A.shape
@@ -276,15 +284,19 @@ class Kernels:
                                                X.N, X.B, _stream(self.dev)), 'sqc_lowblock_apply')
 
     def lowband_factor(self, A, blk_off, nblk, nbmax):
+        """A: complex64 [B][ns][ns], or float32 (real representation, sqc_lowband_factor_real)."""
         B, ns, _ = A.shape
-        _lib.check(self.lib.sqc_lowband_factor(_p(A), ns, _p(blk_off), blk_off.shape[1], _p(nblk), int(nbmax), B,
-                                               _stream(self.dev)), 'sqc_lowband_factor')
+        fn = self.lib.sqc_lowband_factor_real if A.dtype == torch.float32 else self.lib.sqc_lowband_factor
+        _lib.check(fn(_p(A), ns, _p(blk_off), blk_off.shape[1], _p(nblk), int(nbmax), B, _stream(self.dev)),
+                   'sqc_lowband_factor')
 
     def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1, perm=None,
                       real=False):
         ssb = 0 if S.shape[0] == 1 else S.stride(0)
         if Afac.shape[0] * group < X.B:
             raise ValueError('lowband_apply: not enough factor slots for this group size')
+        if real != (Afac.dtype == torch.float32):
+            raise ValueError('lowband_apply: the real representation takes a float32 factor (and only it)')
         fn = self.lib.sqc_lowband_apply_real if real else self.lib.sqc_lowband_apply
         _lib.check(fn(X.c(), HX.c(), T.c(), _p(theta), theta.shape[1], _p(act),
                                               act.shape[1], _p(S), ssb, _p(Afac), Afac.shape[1], _p(blk_off),

@@ -248,7 +248,7 @@ class CircuitOperators:
         if np.any(ng[:, 1] != 0.0):
             return False
         m, inner = self.dims
-        if inner % 2 == 0 or inner > 127 or m > 128:
+        if inner % 2 == 0 or inner > 127 or m > 112:
             return False
         # shared memory of one team of sqc_hx_fused_real (must mirror the launch code)
         kp = ((m + 1) // 2 + 3) & ~3
@@ -256,8 +256,9 @@ class CircuitOperators:
         pp = 2 * inner
         while pp % 16 not in (4, 12):
             pp += 2
-        team = kp * pp + 16 + ((m + 1) & ~1) + 2 * 4 * m
-        return (2 * kp * vld + team + 2) * 8 <= 227 * 1024
+        team = kp * pp + 16 + ((m + 1) & ~1) + 2 * 4 * m + 8
+        nc = (inner - 1) // 2
+        return (2 * kp * vld + team + ((m + 1) & ~1) + ((nc + 2) & ~1) + 4) * 8 <= 227 * 1024
 
     def real_index_map(self):
         """Complex charge index c = nc + n of every real column j (j = 0: n = 0, 1..nc: Re plane,
@@ -425,11 +426,19 @@ class RealHamiltonianOperator(HamiltonianOperator):
         if 2 * self.Nc != ops.N:       # padding amplitude: never selected as a low-energy state, stays zero
             dr = torch.cat([dr, torch.full((dr.shape[0], 1), 1e300, dtype=dr.dtype, device=self.device)], dim=1)
         self.diag = dr.contiguous()
+        # separable form d(i, j) = dh[i] + dc[j] (the LC energies of a harmonic and a charge mode add up): the
+        # kernel then applies the charge part in the x basis and needs one scalar per row in its epilogue
+        self.diag_sep = None
+        if self.diag.shape[0] == 1:
+            d2 = dr[0, :ops.N].reshape(m, inner)
+            dh, dc = d2[:, 0] - d2[0, 0], d2[0, :]
+            if float((d2 - dh[:, None] - dc[None, :]).abs().max()) <= 4e-16 * float(d2.abs().max()):
+                self.diag_sep = torch.cat([dh, dc]).contiguous()
 
     def apply(self, X: BlockView, Y: BlockView):
         ops = self.ops
         pot = ops.potential_struct(self.a, self.g, ops.etab)
-        if not ops.kern.hx_fused_real(ops.sp, ops.Ve, ops.Vo, pot, self.diag, X, Y):
+        if not ops.kern.hx_fused_real(ops.sp, ops.Ve, ops.Vo, pot, self.diag, X, Y, fdiag_sep=self.diag_sep):
             raise RuntimeError('sqc_hx_fused_real rejected a layout that supports_real() accepted')
 
     def to_complex(self, Xr, out=None):
@@ -462,7 +471,9 @@ class RealHamiltonianOperator(HamiltonianOperator):
         S, off, nblk, nbmax, perm = ops._scratch[key]
         ns = S.shape[1]
         pot = ops.potential_struct(a, g, ops.etab)
-        Ainv = torch.empty((nslot, ns, ns), dtype=torch.complex64, device=self.device)
+        # banded: float storage (sqc_lowband_*_real); dense: complex64 with zero imaginary parts
+        Ainv = torch.empty((nslot, ns, ns), dtype=torch.complex64 if off is None else torch.float32,
+                           device=self.device)
         kern.lowblock_assemble(ops.sp, S, ops.displacement_tables(), pot, self.diag, sig, unit, Ainv, real=True)
         if off is None:
             kern.hpd_inverse_c64(Ainv)

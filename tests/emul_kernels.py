@@ -314,7 +314,7 @@ class EmulKernels:
             if z.shape[0]:
                 _set(Xr, b, self._c2r(z, m, inner).view(np.complex128))
 
-    def hx_fused_real(self, sp, Ve, Vo, pot, fdiag, X, Y):
+    def hx_fused_real(self, sp, Ve, Vo, pot, fdiag, X, Y, fdiag_sep=None):
         """Y = H X on real-representation blocks: rotate to the complex basis, apply the complex operator
         (transform, potential, transform back, LC diagonal), project back."""
         from sqcircuit_b200.kernels import BlockView
@@ -351,7 +351,12 @@ class EmulKernels:
             self.potential_apply(sp, pb, BlockView(s1), BlockView(s2))
             self.mode_transform(sp, 0, Vt, 0, BlockView(s2), BlockView(out))
             r = self._c2r(out[0].numpy(), m, inner)
-            if fdiag is not None:
+            if fdiag_sep is not None:
+                sep = fdiag_sep.numpy()
+                fd = np.zeros(2 * ((N + 1) // 2))
+                fd[:N] = (sep[:m, None] + sep[None, m:]).reshape(-1)
+                r = r + fd[None, :] * np.ascontiguousarray(y).view(np.float64)
+            elif fdiag is not None:
                 fd = fdiag[min(b, fdiag.shape[0] - 1)].numpy()
                 r = r + fd[None, :] * np.ascontiguousarray(y).view(np.float64)
                 if N % 2:
@@ -580,7 +585,7 @@ class EmulKernels:
                 Um[ci, r] = coef
             Hr = (Um.conj().T @ A @ Um).real
             Hr[np.arange(ns), np.arange(ns)] += dd[s] - float(sigma[b])
-            out[b] = torch.from_numpy((Hr / unit).astype(np.complex64))
+            out[b] = torch.from_numpy((Hr / unit).astype(np.float32 if out.dtype == torch.float32 else np.complex64))
 
     def hpd_inverse_c64(self, A):
         for b in range(A.shape[0]):
@@ -618,7 +623,7 @@ class EmulKernels:
                     m = m - e.conj().T @ pprev @ e
                 pprev = np.linalg.inv(m)
                 a[o:o1, o:o1] = pprev
-            A[b] = torch.from_numpy(a.astype(np.complex64))
+            A[b] = torch.from_numpy(a.real.astype(np.float32) if A.dtype == torch.float32 else a.astype(np.complex64))
 
     def lowband_apply(self, X, HX, T, theta, act, S, Afac, blk_off, nblk, nbmax, unit, group=1, perm=None,
                       real=False):

@@ -590,6 +590,7 @@ def test_hx_real_matches_complex(kern, dims, shifts):
     symmetric vectors, through the conversion kernels."""
     m, inner = dims
     N, Nc = m * inner, (m * inner + 1) // 2
+    nc_ = (inner - 1) // 2
     B, nv = 3, 5
     sp, V, etab, a, gl, fdc, fdr, pot_struct = _real_case(kern, m, inner, B)
     cnt = torch.tensor([5, 2, 0], dtype=torch.int32, device='cuda')
@@ -609,13 +610,21 @@ def test_hx_real_matches_complex(kern, dims, shifts):
     assert relerr((xr ** 2).sum(dim=(2, 3)).cpu(), (Zs.abs() ** 2).sum(dim=2).cpu()) < 1e-13
     he, ho = (m + 1) // 2, m // 2
     Ve, Vo = V[0::2, :he].contiguous(), V[1::2, :ho].contiguous()
-    for use_fd in (True, False):
+    # separable diagonal d(i, j) = dh[i] + dc[j] (the form the LC energies really have)
+    g = torch.Generator().manual_seed(77)
+    dh = torch.randn(m, dtype=torch.float64, generator=g)
+    dc_half = torch.randn(nc_ + 1, dtype=torch.float64, generator=g)
+    dc_r = torch.cat([dc_half, dc_half[1:]])                          # real layout: cos and sin planes
+    sep = torch.cat([dh, dc_r]).cuda()
+    fdc_sep = (dh[:, None] + torch.cat([dc_half.flip(0)[:nc_], dc_half])[None, :]).reshape(1, N).contiguous().cuda()
+    for use_fd in (True, False, 'sep'):
         Yc = torch.zeros_like(Zs)
-        assert kern.hx_fused(sp, Ve, Vo, pot_struct(shifts), fdc if use_fd else None, BlockView(Zs, cnt=cnt),
-                             BlockView(Yc, cnt=cnt))
+        fd_c = fdc_sep if use_fd == 'sep' else (fdc if use_fd else None)
+        assert kern.hx_fused(sp, Ve, Vo, pot_struct(shifts), fd_c, BlockView(Zs, cnt=cnt), BlockView(Yc, cnt=cnt))
         Yr = torch.zeros_like(Xr)
-        assert kern.hx_fused_real(sp, Ve, Vo, pot_struct(shifts), fdr if use_fd else None, BlockView(Xr, cnt=cnt),
-                                  BlockView(Yr, cnt=cnt))
+        assert kern.hx_fused_real(sp, Ve, Vo, pot_struct(shifts), fdr if use_fd is True else None,
+                                  BlockView(Xr, cnt=cnt), BlockView(Yr, cnt=cnt),
+                                  fdiag_sep=sep if use_fd == 'sep' else None)
         Yrc = torch.zeros_like(Zs)
         kern.real_to_complex(sp, BlockView(Yr, cnt=cnt), BlockView(Yrc, cnt=cnt))
         assert relerr(Yrc.cpu(), Yc.cpu()) < 2e-13, (dims, use_fd)
@@ -695,3 +704,112 @@ def test_lowblock_assemble_real_is_the_rotated_complex_block(kern):
     assert float(ref.imag.abs().max()) < 1e-5 * float(ref.abs().max())
     assert relerr(outr.to(torch.complex128).cpu(), ref.cpu()) < 1e-6
     assert float(outr.imag.abs().max()) == 0.0
+    outf = torch.empty((B, ns, ns), dtype=torch.float32, device='cuda')         # float storage (banded kernels)
+    kern.lowblock_assemble(sp, Srd, Dt, pot_struct(), fdr, sigma, 1.0, outf, real=True)
+    assert torch.equal(outf, outr.real)
+
+
+@pytest.mark.parametrize('mm,sizes', [(40, [40, 36, 24, 12, 1, 0, 33]), (64, [64, 61, 12]), (16, [16, 7])])
+def test_gen_rr_real(kern, mm, sizes):
+    """Real symmetric generalised Rayleigh-Ritz (128-thread CTA per pencil) against scipy: eigenvalues,
+    GB-orthonormal coefficient vectors, dependent basis vector removed, only the n_out lowest vectors
+    written."""
+    import scipy.linalg
+    B, n_out = len(sizes), 12
+    g = torch.Generator().manual_seed(51)
+    Q = torch.randn((B, mm, 150), dtype=torch.float64, generator=g)
+    if sizes[1] > 8:
+        Q[1, 7] = 0.5 * Q[1, 3] - 0.25 * Q[1, 5]          # dependent -> must be removed
+    Hs = torch.randn((B, 150, 150), dtype=torch.float64, generator=g)
+    Hs = Hs + Hs.transpose(1, 2)
+    GB = (Q @ Q.transpose(1, 2)).to(torch.complex128)
+    GA = (Q @ Hs @ Q.transpose(1, 2)).to(torch.complex128)
+    # the imaginary parts of a real-representation Gram matrix are meaningless: must be ignored
+    GBd = GB + 1j * torch.randn((B, mm, mm), dtype=torch.float64, generator=g)
+    GAd = GA + 1j * torch.randn((B, mm, mm), dtype=torch.float64, generator=g)
+    nn = torch.tensor(sizes, dtype=torch.int32)
+    w = torch.full((B, mm), -7.0, dtype=torch.float64, device='cuda')
+    Zt = torch.full((B, mm, mm), 3.0 + 2.0j, dtype=torch.complex128, device='cuda')
+    kern.gen_rr(GAd.cuda(), GBd.cuda(), nn.cuda(), 1e-8, w, Zt, real=True, n_out=n_out)
+    w, Zt = w.cpu(), Zt.cpu()
+    for b in range(B):
+        nb = sizes[b]
+        if nb == 0:
+            assert float(w[b, 0]) == -7.0
+            continue
+        a, gm = GA[b, :nb, :nb].real.numpy(), GB[b, :nb, :nb].real.numpy()
+        keep = [i for i in range(nb) if not (b == 1 and sizes[1] > 8 and i == 7)]
+        wr = scipy.linalg.eigh(a[np.ix_(keep, keep)], gm[np.ix_(keep, keep)], eigvals_only=True)
+        k = len(wr)
+        assert np.abs(w[b, :k].numpy() - wr).max() < 1e-10 * np.abs(wr).max(), (b, nb)
+        assert np.all(np.isinf(w[b, k:].numpy()))
+        ko = min(k, n_out)
+        c = Zt[b, :ko, :nb].numpy().T
+        assert np.abs(c.imag).max() == 0.0
+        c = c.real
+        assert np.abs(c.T @ gm @ c - np.eye(ko)).max() < 1e-9
+        assert np.abs(a @ c - gm @ c * w[b, :ko].numpy()[None, :]).max() < 1e-9 * np.abs(wr).max() * np.abs(c).max()
+        if nb > n_out:      # rows beyond n_out are not written
+            assert complex(Zt[b, n_out, 0]) == 3.0 + 2.0j
+
+
+def test_lowband_real_factor_and_apply(kern):
+    """Float-storage banded preconditioner of the real representation: block LDL^T factor and substitution
+    (four right-hand sides per warp) against the emulation and a dense solve; real amplitudes are gathered
+    from / scattered to blocks of complex elements."""
+    rng = np.random.default_rng(9)
+    sizes = [[3, 7, 12, 33, 40, 12, 6, 3], [5, 5, 50, 36, 20], [64, 52]]
+    B, ns, Nc, p = 5, 116, 400, 7
+    nslot, group = 3, 2
+    off = np.zeros((nslot, 9), dtype=np.int32)
+    nblk = np.zeros(nslot, dtype=np.int32)
+    A = np.zeros((nslot, ns, ns))
+    for sl, sz in enumerate(sizes):
+        assert sum(sz) == ns
+        o = np.concatenate(([0], np.cumsum(sz)))
+        off[sl, :len(o)] = o
+        nblk[sl] = len(sz)
+        for q in range(len(sz)):
+            a, b_ = o[q], o[q + 1]
+            d = rng.standard_normal((sz[q], sz[q]))
+            A[sl, a:b_, a:b_] = d @ d.T / sz[q] + 4 * np.eye(sz[q])
+            if q + 1 < len(sz):
+                c = o[q + 2]
+                e = 0.3 * rng.standard_normal((sz[q], sz[q + 1]))
+                A[sl, a:b_, b_:c] = e
+                A[sl, b_:c, a:b_] = e.T
+    A32 = torch.from_numpy(A.astype(np.float32))
+    offt, nbt = torch.from_numpy(off), torch.from_numpy(nblk)
+    E = EmulKernels()
+    fref = A32.clone()
+    E.lowband_factor(fref, offt, nbt, 64)
+    fac = A32.clone().cuda()
+    kern.lowband_factor(fac, offt.cuda(), nbt.cuda(), 64)
+    assert relerr(fac.cpu().double(), fref.double()) < 2e-5
+    S = torch.stack([torch.randperm(2 * Nc, generator=torch.Generator().manual_seed(s))[:ns] for s in range(nslot)]).to(torch.int32)
+    X, HX = rnd((B, p, Nc), 61), rnd((B, p, Nc), 62)
+    Vb = rnd((B, 20, Nc), 63)
+    theta = torch.randn((B, 48), dtype=torch.float64, generator=torch.Generator().manual_seed(64))
+    msz = torch.tensor([6, 10, 13, 3, 8], dtype=torch.int32)
+    nact = torch.tensor([7, 2, 0, 5, 1], dtype=torch.int32)
+    act = torch.tensor([[0, 1, 2, 3, 4, 5, 6], [4, 1, 0, 0, 0, 0, 0], [0] * 7, [5, 3, 2, 0, 6, 0, 0], [2, 0, 0, 0, 0, 0, 0]],
+                       dtype=torch.int32)
+    refV = Vb.clone()
+    E.lowband_apply(BlockView(X), BlockView(HX), BlockView(refV, cnt_fixed=p, off=msz, cnt=nact), theta, act, S,
+                    fref, offt, nbt, 64, 2.0, group=group, real=True)
+    for perm in (None, torch.argsort(S, dim=1).to(torch.int32).cuda()):
+        Vd = Vb.cuda()
+        kern.lowband_apply(BlockView(X.cuda()), BlockView(HX.cuda()),
+                           BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()), theta.cuda(), act.cuda(),
+                           S.cuda(), fac, offt.cuda(), nbt.cuda(), 64, 2.0, group=group, perm=perm, real=True)
+        assert relerr(torch.view_as_real(Vd.cpu()), torch.view_as_real(refV)) < 2e-5
+    b, jj = 0, 1
+    s = S[0].long().numpy()
+    xr, hr = torch.view_as_real(X)[b, jj].reshape(-1).numpy(), torch.view_as_real(HX)[b, jj].reshape(-1).numpy()
+    sol = np.linalg.solve(A[0], (hr[s] - float(theta[b, jj]) * xr[s]) / 2.0)
+    got = torch.view_as_real(Vd.cpu())[b, int(msz[b]) + jj].reshape(-1).numpy()[s]
+    assert np.abs(got - sol).max() / np.abs(sol).max() < 1e-4
+    with pytest.raises(ValueError):
+        kern.lowband_apply(BlockView(X.cuda()), BlockView(HX.cuda()),
+                           BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()), theta.cuda(), act.cuda(),
+                           S.cuda(), fac, offt.cuda(), nbt.cuda(), 64, 2.0, group=group, real=False)

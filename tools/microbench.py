@@ -86,7 +86,12 @@ if not only or 'hxr' in only:
     Xr = torch.randn((B, p, Nc), dtype=torch.complex128, device=dev)
     Yr = torch.zeros_like(Xr)
     ms = timeit(lambda: k.hx_fused_real(sp, Ve, Vo, pot, fd, BlockView(Xr), BlockView(Yr)))
-    report('hx_fused_real 12 vec/pt', ms, 16.0 * N * p * B, 2.0 * m * N * p * B)
+    report('hx_fused_real 12 vec/pt (full diagonal)', ms, 16.0 * N * p * B, 2.0 * m * N * p * B)
+    sep = torch.randn(m + inner, dtype=torch.float64, device=dev)
+    ms = timeit(lambda: k.hx_fused_real(sp, Ve, Vo, pot, None, BlockView(Xr), BlockView(Yr), fdiag_sep=sep))
+    report('hx_fused_real 12 vec/pt (separable diagonal)', ms, 16.0 * N * p * B, 2.0 * m * N * p * B)
+    ms = timeit(lambda: k.hx_fused_real(sp, Ve, Vo, pot, None, BlockView(Xr), BlockView(Yr)))
+    report('hx_fused_real 12 vec/pt (no diagonal)', ms, 16.0 * N * p * B, 2.0 * m * N * p * B)
 if not only or 'pair' in only:
     W = torch.randn((B, mm, N), dtype=torch.complex128, device=dev)
     for msz in (12, 24, 28):
