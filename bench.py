@@ -190,6 +190,12 @@ class TimedKernels:
     def __getattr__(self, name):
         return getattr(self._k, name)
 
+    def eager_ops(self):
+        """Instrumented entry points carry CUDA events and must stay outside the solver's CUDA graphs."""
+        if not self.enabled:
+            return frozenset()
+        return frozenset(self.TIMED if self.only is None else self.only)
+
     def _wrap(self, name):
         fn = getattr(self._k, name)
         torch = self._torch
@@ -249,6 +255,8 @@ def our_arm(args):
     from sqcircuit_b200.sharding import gather_to_root
     sq.set_device(dev)
     kern = TimedKernels(Kernels(dev))
+    if args.no_graphs:
+        kern._k.use_graphs = False
 
     loop = sq.Loop()
     C, CJ = sq.Capacitor(0.15, 'GHz'), sq.Capacitor(10, 'GHz')
@@ -473,6 +481,7 @@ def main():
     ap.add_argument('--strides', default='', help='continuation level strides, e.g. 64,16,4,1 (default 64,8,1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--complex', action='store_true', help='force complex vectors (no real representation)')
+    ap.add_argument('--no-graphs', action='store_true', help='enqueue every solver iteration kernel by kernel')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)

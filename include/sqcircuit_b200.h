@@ -181,6 +181,11 @@ int sqc_gram(sqc_block_t A, sqc_block_t Bm, int64_t N, int32_t B, void* C, int32
  * the projected Hamiltonian in the non-orthogonalised Davidson iteration. */
 int sqc_gram_pair(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int32_t B, void* C,
                   void* C2, int32_t ldr, int32_t ldc, void* work, void* stream);
+/* sqc_gram_pair on blocks of the real representation (real arrays viewed as complex blocks, see
+ * sqc_hx_fused_real): C = Re(A^H Bm), C2 = Re(A^H Bm2), imaginary parts zero.  A column tile of the tensor-core
+ * product holds eight right-hand vectors instead of four (re, im) pairs: half the DMMAs. */
+int sqc_gram_pair_real(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int32_t B, void* C,
+                       void* C2, int32_t ldr, int32_t ldc, void* work, void* stream);
 
 /* Out[b][j][n] (op)= sum_i Cf[b][j][i] A[b][i][n],  i < count(A), j < count(Out);
  * op: 0 assign, 1 subtract from Out.  Cf: device complex [B][ldr][ldc]; the coefficient of

@@ -59,6 +59,7 @@ SIGNATURES = {
     'sqc_gram_work_bytes': (c_i64, [c_i32, c_i32, c_i32, c_i64]),
     'sqc_gram': (c_i32, [Block, Block, c_i64, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_vp]),
     'sqc_gram_pair': (c_i32, [Block, Block, Block, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    'sqc_gram_pair_real': (c_i32, [Block, Block, Block, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     'sqc_gen_rr': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_dbl, c_vp, c_vp, c_i32, c_vp]),
     'sqc_gen_rr_real': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_dbl, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'sqc_davidson_insert2': (c_i32, [C.POINTER(DavidsonState), c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),

@@ -28,16 +28,17 @@ long long g_sqc_launches = 0;
 // Tensor-core work of one staged chunk for exactly NATR populated row tiles.  The row-tile count
 // is a template parameter (dispatched by a warp-uniform switch) because a run-time guard is
 // compiled to PREDICATED DMMAs, and predicated-off DMMAs still occupy the FP64 tensor pipe.
+// B fragment of column tile j: row (brow + bstep * j) of the staged right-hand block, element k0 + bcol.
 template <int NATR, int NCTR, int NAT, int NCT, int KW>
 __device__ __forceinline__ void gram_chunk(double (&acc)[NAT][NCT][2], const double* __restrict__ sAb,
                                            const double* __restrict__ sBb, int warp, int g, int t,
-                                           int bcol, double bsign) {
+                                           int bcol, double bsign, int brow, int bstep) {
 #pragma unroll
     for (int ks = 0; ks < (2 * GRAM_CH / 4) / KW; ++ks) {
         const int k0 = 4 * (warp + KW * ks);
         double bf[NCTR];
 #pragma unroll
-        for (int j = 0; j < NCTR; ++j) bf[j] = bsign * sBb[(4 * j + (g >> 1)) * GRAM_LD + k0 + bcol];
+        for (int j = 0; j < NCTR; ++j) bf[j] = bsign * sBb[(bstep * j + brow) * GRAM_LD + k0 + bcol];
 #pragma unroll
         for (int i = 0; i < NATR; ++i) {
             const double af = sAb[(8 * i + g) * GRAM_LD + k0 + t];
@@ -51,12 +52,12 @@ __device__ __forceinline__ void gram_chunk(double (&acc)[NAT][NCT][2], const dou
 template <int NATR, int NAT, int NCT, int KW>
 __device__ __forceinline__ void gram_chunk_cols(double (&acc)[NAT][NCT][2], const double* __restrict__ sAb,
                                                 const double* __restrict__ sBb, int warp, int g, int t,
-                                                int bcol, double bsign, int nctr) {
+                                                int bcol, double bsign, int brow, int bstep, int nctr) {
     switch (nctr) {
-        case 1: gram_chunk<NATR, 1, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign); break;
-        case 2: if constexpr (NCT >= 2) gram_chunk<NATR, 2, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign); break;
-        case 3: if constexpr (NCT >= 3) gram_chunk<NATR, 3, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign); break;
-        default: if constexpr (NCT >= 4) gram_chunk<NATR, 4, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign); break;
+        case 1: gram_chunk<NATR, 1, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign, brow, bstep); break;
+        case 2: if constexpr (NCT >= 2) gram_chunk<NATR, 2, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign, brow, bstep); break;
+        case 3: if constexpr (NCT >= 3) gram_chunk<NATR, 3, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign, brow, bstep); break;
+        default: if constexpr (NCT >= 4) gram_chunk<NATR, 4, NAT, NCT, KW>(acc, sAb, sBb, warp, g, t, bcol, bsign, brow, bstep); break;
     }
 }
 
@@ -64,12 +65,15 @@ __device__ __forceinline__ void gram_chunk_cols(double (&acc)[NAT][NCT][2], cons
 // columns (column 2j = Re C[.][j], column 2j+1 = Im C[.][j]).
 // PAIR: two B blocks (Bm -> C, Bm2 -> C2) against the same A in ONE pass over A: warps 0,1 take
 // Bm, warps 2,3 take Bm2, each pair splitting K two ways.
-template <int NAT, int NCT, bool PAIR>
+// REAL: the vectors are real arrays viewed as complex blocks (real representation, hx_real.cu): only the real
+// inner products exist, a column tile holds EIGHT right-hand vectors (12 vectors = 2 tiles instead of 3, half
+// the DMMAs of the paired kernel) and the results are stored with zero imaginary parts.
+template <int NAT, int NCT, bool PAIR, bool REAL>
 __global__ void __launch_bounds__(GRAM_THREADS)
 gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int nsplit,
                  cplx* __restrict__ C, cplx* __restrict__ C2, int ldr, int ldc, cplx* __restrict__ work,
                  int smem_doubles) {
-    constexpr int NA = NAT * 8, NB = NCT * 4;
+    constexpr int NA = NAT * 8, NB = NCT * (REAL ? 8 : 4);
     constexpr int NBLK = PAIR ? 2 : 1;          // B blocks
     constexpr int KW = GRAM_WARPS / NBLK;       // warps that split K for one B block
     extern __shared__ double smem[];
@@ -98,7 +102,8 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int 
     }
     const int nat = (na + 7) >> 3;          // row tiles actually populated for this sweep point
     // column tiles (4 vectors each) populated in this warp's right-hand block
-    const int nctr = max(1, ((PAIR && grp == 1 ? nb2 : nb) + 3) >> 2);
+    const int nctr = REAL ? max(1, ((PAIR && grp == 1 ? nb2 : nb) + 7) >> 3)
+                          : max(1, ((PAIR && grp == 1 ? nb2 : nb) + 3) >> 2);
     // stages are sized by the rows this point really has, so small bases get a deeper pipeline
     const int stage_doubles = (nat * 8 + NBLK * NB) * GRAM_LD;
     int nstage = smem_doubles / stage_doubles;     // >= 2 by construction of the launch
@@ -167,9 +172,11 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int 
 
     // B fragment of packed column n = 8ct + g:  vector j = 4ct + (g>>1), part = g&1
     //   part 0: B[j][k]        part 1: (k even) ? B[j][k+1] : -B[j][k-1]      (k = k0 + t)
-    const int bpart = g & 1;
+    // REAL: packed column n = 8ct + g is vector j = 8ct + g itself
+    const int bpart = REAL ? 0 : (g & 1);
     const int bcol = t ^ bpart;
     const double bsign = (bpart && (t & 1)) ? -1.0 : 1.0;
+    const int brow = REAL ? g : (g >> 1), bstep = REAL ? 8 : 4;
 
     for (int e = tid; e < nstage * stage_doubles; e += GRAM_THREADS) smem[e] = 0.0;
     __syncthreads();
@@ -181,14 +188,14 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int 
         const double* sAb = smem + (int)((ch - c_lo) % nstage) * stage_doubles;
         const double* sBb = sAb + (nat * 8 + grp * NB) * GRAM_LD;
         switch (nat) {
-            case 1: gram_chunk_cols<1, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
-            case 2: if constexpr (NAT >= 2) gram_chunk_cols<2, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
-            case 3: if constexpr (NAT >= 3) gram_chunk_cols<3, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
-            case 4: if constexpr (NAT >= 4) gram_chunk_cols<4, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
-            case 5: if constexpr (NAT >= 5) gram_chunk_cols<5, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
-            case 6: if constexpr (NAT >= 6) gram_chunk_cols<6, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
-            case 7: if constexpr (NAT >= 7) gram_chunk_cols<7, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
-            default: if constexpr (NAT >= 8) gram_chunk_cols<8, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, nctr); break;
+            case 1: gram_chunk_cols<1, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, brow, bstep, nctr); break;
+            case 2: if constexpr (NAT >= 2) gram_chunk_cols<2, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, brow, bstep, nctr); break;
+            case 3: if constexpr (NAT >= 3) gram_chunk_cols<3, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, brow, bstep, nctr); break;
+            case 4: if constexpr (NAT >= 4) gram_chunk_cols<4, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, brow, bstep, nctr); break;
+            case 5: if constexpr (NAT >= 5) gram_chunk_cols<5, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, brow, bstep, nctr); break;
+            case 6: if constexpr (NAT >= 6) gram_chunk_cols<6, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, brow, bstep, nctr); break;
+            case 7: if constexpr (NAT >= 7) gram_chunk_cols<7, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, brow, bstep, nctr); break;
+            default: if constexpr (NAT >= 8) gram_chunk_cols<8, NAT, NCT, KW>(acc, sAb, sBb, kw, g, t, bcol, bsign, brow, bstep, nctr); break;
         }
     }
     cp_async_wait<0>();
@@ -199,8 +206,14 @@ gram_dmma_kernel(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int 
 #pragma unroll
     for (int i = 0; i < NAT; ++i)
 #pragma unroll
-        for (int j = 0; j < NCT; ++j)
-            red[(warp * NA + 8 * i + g) * NB + 4 * j + t] = cmake(acc[i][j][0], acc[i][j][1]);
+        for (int j = 0; j < NCT; ++j) {
+            if (REAL) {
+                red[(warp * NA + 8 * i + g) * NB + 8 * j + 2 * t] = cmake(acc[i][j][0], 0.0);
+                red[(warp * NA + 8 * i + g) * NB + 8 * j + 2 * t + 1] = cmake(acc[i][j][1], 0.0);
+            } else {
+                red[(warp * NA + 8 * i + g) * NB + 4 * j + t] = cmake(acc[i][j][0], acc[i][j][1]);
+            }
+        }
     __syncthreads();
     for (int o = 0; o < NBLK; ++o) {
         for (int e = tid; e < out_rows * out_cols; e += GRAM_THREADS) {
@@ -352,24 +365,27 @@ extern "C" int64_t sqc_gram_work_bytes(int32_t B, int32_t na_max, int32_t nb_max
     gram_tiles(na_max, nb_max, &nat, &nct);
     int ns = gram_nsplit(B, N, true);   // upper bound over both kernel flavours
     if (ns == 1) return 0;
-    return 2 * (int64_t)B * ns * (nat * 8) * (nct * 4) * (int64_t)sizeof(cplx);
+    int nbv = nct * 4;                                  // complex kernels: 4 vectors per column tile ...
+    if (nbv < ((nb_max + 7) / 8) * 8) nbv = ((nb_max + 7) / 8) * 8;      // ... the real one: 8
+    return 2 * (int64_t)B * ns * (nat * 8) * nbv * (int64_t)sizeof(cplx);
 }
 
-template <int NAT, int NCT, bool PAIR>
+template <int NAT, int NCT, bool PAIR, bool REAL = false>
 static int launch_gram(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int B, cplx* C, cplx* C2,
                        int ldr, int ldc, cplx* work, cudaStream_t st) {
+    constexpr int NBV = NCT * (REAL ? 8 : 4);        // right-hand vectors the column tiles can hold
     const int ns = gram_nsplit(B, N, PAIR);
     if (ns > 1 && !work) return SQC_EINVAL;
     // always 112 KB so that TWO CTAs (8 warps) are resident per SM: one CTA alone cannot keep the
     // FP64 tensor pipe busy.  The kernel cuts it into stages sized by the rows the sweep point
     // really has (>= 2 stages even for a full 64-row basis, >= 3 up to 40 rows + a pair of blocks).
-    size_t stage_bytes = (size_t)(NAT * 8 + (PAIR ? 2 : 1) * NCT * 4) * GRAM_LD * sizeof(double);
+    size_t stage_bytes = (size_t)(NAT * 8 + (PAIR ? 2 : 1) * NBV) * GRAM_LD * sizeof(double);
     size_t smem = 112 * 1024;
     if (smem < 2 * stage_bytes) smem = 2 * stage_bytes;
-    size_t red_bytes = GRAM_WARPS * (size_t)(NAT * 8) * (NCT * 4) * sizeof(cplx);
+    size_t red_bytes = GRAM_WARPS * (size_t)(NAT * 8) * NBV * sizeof(cplx);
     if (smem < red_bytes) smem = red_bytes;
     if (smem > 227 * 1024) return SQC_ELIMIT;
-    auto kern = gram_dmma_kernel<NAT, NCT, PAIR>;
+    auto kern = gram_dmma_kernel<NAT, NCT, PAIR, REAL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<B * ns, GRAM_THREADS, smem, st>>>(A, Bm, Bm2, N, ns, C, C2, ldr, ldc, work, (int)(smem / sizeof(double)));
@@ -377,10 +393,10 @@ static int launch_gram(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N
     if (ns > 1) {
         int rows = A.cnt_fixed < ldr ? A.cnt_fixed : ldr, cols = Bm.cnt_fixed < ldc ? Bm.cnt_fixed : ldc;
         const int nblk = PAIR ? 2 : 1;
-        gram_reduce_kernel<<<B, 128, 0, st>>>(work, ns, NAT * 8, NCT * 4, nblk, 0, C, ldr, ldc, rows, cols);
+        gram_reduce_kernel<<<B, 128, 0, st>>>(work, ns, NAT * 8, NBV, nblk, 0, C, ldr, ldc, rows, cols);
         SQC_LAUNCHED();
         if (PAIR) {
-            gram_reduce_kernel<<<B, 128, 0, st>>>(work, ns, NAT * 8, NCT * 4, nblk, 1, C2, ldr, ldc, rows, cols);
+            gram_reduce_kernel<<<B, 128, 0, st>>>(work, ns, NAT * 8, NBV, nblk, 1, C2, ldr, ldc, rows, cols);
             SQC_LAUNCHED();
         }
     }
@@ -436,6 +452,24 @@ extern "C" int sqc_gram_pair(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int
     GRAMP_CASE(1, 3); GRAMP_CASE(2, 3); GRAMP_CASE(4, 3); GRAMP_CASE(6, 3); GRAMP_CASE(8, 3);
     GRAMP_CASE(1, 4); GRAMP_CASE(2, 4); GRAMP_CASE(4, 4); GRAMP_CASE(6, 4); GRAMP_CASE(8, 4);
 #undef GRAMP_CASE
+    return SQC_ELIMIT;
+}
+
+// sqc_gram_pair for blocks of the real representation (real arrays viewed as complex blocks, N = complex
+// elements per vector): C = Re(A^H Bm), C2 = Re(A^H Bm2) with zero imaginary parts.
+extern "C" int sqc_gram_pair_real(sqc_block_t A, sqc_block_t Bm, sqc_block_t Bm2, int64_t N, int32_t B, void* C,
+                                  void* C2, int32_t ldr, int32_t ldc, void* work, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || N <= 0 || A.cnt_fixed <= 0 || Bm.cnt_fixed <= 0 || Bm.cnt_fixed != Bm2.cnt_fixed) return SQC_EINVAL;
+    if (A.cnt_fixed > 64 || Bm.cnt_fixed > 16) return SQC_ELIMIT;
+    int nat, nct;
+    gram_tiles(A.cnt_fixed, Bm.cnt_fixed, &nat, &nct);
+    nct = (Bm.cnt_fixed + 7) / 8;        // 8 real right-hand vectors per column tile
+#define GRAMR_CASE(a, b_) \
+    if (nat == a && nct == b_) return launch_gram<a, b_, true, true>(A, Bm, Bm2, N, B, (cplx*)C, (cplx*)C2, ldr, ldc, (cplx*)work, st)
+    GRAMR_CASE(1, 1); GRAMR_CASE(2, 1); GRAMR_CASE(4, 1); GRAMR_CASE(6, 1); GRAMR_CASE(8, 1);
+    GRAMR_CASE(1, 2); GRAMR_CASE(2, 2); GRAMR_CASE(4, 2); GRAMR_CASE(6, 2); GRAMR_CASE(8, 2);
+#undef GRAMR_CASE
     return SQC_ELIMIT;
 }
 

@@ -247,6 +247,8 @@ class RitzPairStart:
 
 
 DETAIL_STATS = None
+# entry points of op.apply: the only ones an instrumented backend may keep out of the CUDA graphs
+_APPLY_OPS = frozenset({'hx_fused', 'hx_fused_real', 'mode_transform', 'potential_apply'})
 
 
 def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
@@ -326,7 +328,7 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
             ccnt = torch.clamp(msz - c0, min=0, max=p).to(i32)
             coff = torch.full((B,), c0, dtype=i32, device=dev)
             kern.gram_pair(Vi, BlockView(V, cnt_fixed=p, off=coff, cnt=ccnt),
-                           BlockView(W, cnt_fixed=p, off=coff, cnt=ccnt), SB, SA)
+                           BlockView(W, cnt_fixed=p, off=coff, cnt=ccnt), SB, SA, real=real)
             GB[:, :, c0:c0 + p] = SB[:, :, :p].real if real else SB[:, :, :p]
             GA[:, :, c0:c0 + p] = SA[:, :, :p].real if real else SA[:, :, :p]
     st = kern.davidson_state(p=p, k=k, mmax=mmax, ldg=ld, tol_rel=tol, tol_abs_floor=1e-300,
@@ -349,51 +351,86 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
     lowblock = None
     best_left, best_it = B + 1, 0
     res_hist = []
-    async_count = dev.type == 'cuda'
-    if async_count:
+    on_gpu = dev.type == 'cuda'
+    live = torch.empty((B,), dtype=i32, device=dev)
+    nrr = torch.empty((B,), dtype=i32, device=dev)
+    xcnt = torch.empty((B,), dtype=i32, device=dev)
+    Xv.cnt = xcnt
+    HXv.cnt = xcnt
+    if on_gpu:
         host_count = torch.zeros((1,), dtype=i32).pin_memory()
-        count_ready = torch.cuda.Event()
-    for it in range(1, maxit + 1):
-        live = 1 - done
-        nrr = msz * live
-        xcnt = (p * live).to(i32)
+        count_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    want_lowblock = lowblock_ns > 0 and getattr(op, 'supports_lowblock', lambda: False)()
+    detail = stats is not None and DETAIL_STATS is not None
+
+    # One iteration = three pieces, all enqueued without host synchronisation and all no-ops for finished
+    # points: rayleigh_ritz (generalised RR, Ritz block + residual norms, convergence / restart decisions,
+    # count of unfinished points -> pinned host memory, preconditioned residuals), op.apply on the
+    # correction block, and project (new Gram columns).  Once the two-level preconditioner exists the
+    # pieces are captured into CUDA graphs and replayed: a lock-step iteration is ~15 launches plus a few
+    # torch element-wise kernels, and on the small levels of a continuation the Python / launch overhead of
+    # enqueueing them one by one exceeds their GPU time.
+    def rayleigh_ritz():
+        torch.bitwise_xor(done, 1, out=live)
+        torch.mul(msz, live, out=nrr)
+        torch.mul(live, p, out=xcnt)
         kern.gen_rr(GA, GB, nrr, drop, theta, Zt, real=real, n_out=p)
-        if lowblock is None and lowblock_ns > 0 and getattr(op, 'supports_lowblock', lambda: False)():
-            # two-level preconditioner.  sigma must stay below the spectrum of H_SS (>= lambda_0): warm
-            # starts know lambda_0 to ~1e-6 at once; cold starts wait until every point's lowest Ritz
-            # value has settled, then sigma = theta_0 - 5 %.
-            if warm:
-                sigma = theta[:, 0] - 0.05 * theta[:, 0].abs()
-                lowblock = op.build_lowblock(sigma, lowblock_ns)
-            elif it > 1:
-                # cold: the lowest Ritz pair converges first; once its own residual is below
-                # cold_gate x |theta_0| there is an eigenvalue within ||r_0|| of theta_0, and the shift
-                # keeps that distance plus the 5 % margin
-                r0 = rn2[:, 0].sqrt()
-                scale = torch.maximum(theta[:, 0].abs(), theta[:, p - 1] - theta[:, 0])
-                if bool((r0 < cold_gate * scale).all()):
-                    sigma = theta[:, 0] - 0.05 * theta[:, 0].abs() - r0
-                    lowblock = op.build_lowblock(sigma, lowblock_ns)
-        Xv.cnt = xcnt
-        HXv.cnt = xcnt
         kern.ritz_update(Vm, Wm, Zt, Xv, HXv, theta, rn2)       # X = V c, HX = W c, ||HX - theta X||^2
         kern.davidson_decide(st, B)
-        # The host needs the number of unfinished points to stop the loop.  Reading it right here would
-        # drain the GPU once per iteration; instead the counter is copied to pinned memory
-        # asynchronously, the rest of the iteration is enqueued (all of it is a no-op for finished
-        # points), and only then does the host wait for the copy.
-        detail = stats is not None and DETAIL_STATS is not None
-        if async_count and not detail:
+        if on_gpu:
             host_count.copy_(n_not_done, non_blocking=True)
-            count_ready.record()
-            left = None
-        else:
-            left = int(n_not_done.item())
-            if detail:      # dev instrumentation (tools/nact_stats.py): costs syncs
-                lv = (1 - done)
-                DETAIL_STATS.append((it, B, left, int((nact * lv).sum()), int((msz * lv).sum()),
-                                     int((((nact + 3) // 4) * lv).sum()), int(restart.sum())))
-        if left != 0:
+        kern.precond_residual(Xl, HXl, Tv, theta, act, diag, den_floor, real=real)
+        if lowblock is not None and lowblock.get('band') is not None:
+            off, nblk, nbmax, perm = lowblock['band']
+            kern.lowband_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], off, nblk, nbmax,
+                               lowblock['unit'], lowblock.get('group', 1), perm, real=real)
+        elif lowblock is not None:
+            kern.lowblock_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], lowblock['unit'],
+                                lowblock.get('group', 1), real=real)
+
+    def project():
+        kern.gram_pair(Vt, Tv, HTv, SB, SA, real=real)
+        kern.davidson_insert2(st, SA, SB, B)
+
+    def whole():
+        rayleigh_ritz()
+        op.apply(Tv, HTv)
+        project()
+
+    graphs = None          # None: not captured yet; False: run eagerly; else the captured pieces
+    eager = frozenset(getattr(kern, 'eager_ops', frozenset)())
+    if not (on_gpu and getattr(kern, 'use_graphs', False)) or detail or not eager <= _APPLY_OPS:
+        graphs = False
+    lag_left = None        # count of the iteration before the last one (graph mode reads one iteration late)
+    for it in range(1, maxit + 1):
+        if want_lowblock and lowblock is None:
+            # The two-level preconditioner needs a shift below the spectrum of H_SS (>= lambda_0): warm
+            # starts know lambda_0 to ~1e-6 at once; cold starts wait until every point's lowest Ritz value
+            # has settled (its own residual below cold_gate x the spectral scale: then an eigenvalue lies
+            # within ||r_0|| of theta_0).  Until then the iteration is run piece by piece: the decision
+            # needs this iteration's Ritz values on the host.
+            torch.bitwise_xor(done, 1, out=live)
+            torch.mul(msz, live, out=nrr)
+            kern.gen_rr(GA, GB, nrr, drop, theta, Zt, real=real, n_out=p)
+            ready = warm
+            if not warm and it > 1:
+                r0 = rn2[:, 0].sqrt()
+                scale = torch.maximum(theta[:, 0].abs(), theta[:, p - 1] - theta[:, 0])
+                ready = bool((r0 < cold_gate * scale).all())
+            if ready:
+                # margin from the spectral scale, not from |theta_0| alone (a ground energy near zero
+                # would leave no margin for the unpivoted complex64 / float32 factorisation)
+                spread = torch.maximum(theta[:, 0].abs(), theta[:, min(p, N) - 1] - theta[:, 0])
+                sigma = theta[:, 0] - 0.05 * spread
+                if not warm:
+                    sigma = sigma - rn2[:, 0].sqrt()
+                lowblock = op.build_lowblock(sigma, lowblock_ns)
+            torch.mul(live, p, out=xcnt)
+            kern.ritz_update(Vm, Wm, Zt, Xv, HXv, theta, rn2)
+            kern.davidson_decide(st, B)
+            if on_gpu:
+                host_count.copy_(n_not_done, non_blocking=True)
+                count_ready[it & 1].record()
             kern.precond_residual(Xl, HXl, Tv, theta, act, diag, den_floor, real=real)
             if lowblock is not None and lowblock.get('band') is not None:
                 off, nblk, nbmax, perm = lowblock['band']
@@ -403,11 +440,52 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
                 kern.lowblock_apply(Xl, HXl, Tv, theta, act, lowblock['S'], lowblock['Ainv'], lowblock['unit'],
                                     lowblock.get('group', 1), real=real)
             op.apply(Tv, HTv)
-            kern.gram_pair(Vt, Tv, HTv, SB, SA)
-            kern.davidson_insert2(st, SA, SB, B)
-        if left is None:
-            count_ready.synchronize()
-            left = int(host_count[0])
+            project()
+            if on_gpu:
+                count_ready[it & 1].synchronize()
+                left = int(host_count[0])
+            else:
+                left = int(n_not_done.item())
+        elif graphs is False or it == 1:
+            # (the first iteration always runs eagerly: lazily grown work buffers must not be born inside a capture)
+            rayleigh_ritz()
+            if on_gpu:
+                count_ready[it & 1].record()      # right after the count copy: the rest overlaps the wait
+                op.apply(Tv, HTv)
+                project()
+                count_ready[it & 1].synchronize()
+                left = int(host_count[0])
+            else:
+                op.apply(Tv, HTv)
+                project()
+                left = int(n_not_done.item())
+            if detail:      # dev instrumentation (tools/nact_stats.py): costs syncs
+                lv = (1 - done)
+                DETAIL_STATS.append((it, B, left, int((nact * lv).sum()), int((msz * lv).sum()),
+                                     int((((nact + 3) // 4) * lv).sum()), int(restart.sum())))
+        else:
+            if graphs is None:
+                # every buffer and table of the iteration exists now (the previous iterations ran eagerly)
+                if eager:                         # instrumented H.X: stays outside the graphs
+                    graphs = (kern.capture(rayleigh_ritz), kern.capture(project))
+                else:
+                    graphs = (kern.capture(whole),)
+            if len(graphs) == 1:
+                kern.replay(graphs[0])
+            else:
+                kern.replay(graphs[0])
+                op.apply(Tv, HTv)
+                kern.replay(graphs[1])
+            count_ready[it & 1].record()
+            # The host reads the count of the PREVIOUS iteration while this one runs (the count never
+            # increases, so a value that is one iteration newer than expected is just as good): the GPU
+            # never waits for the host, at the price of one no-op iteration at the end.
+            if lag_left is None:
+                lag_left = True
+                left = B                           # unknown yet
+            else:
+                count_ready[(it - 1) & 1].synchronize()
+                left = int(host_count[0])
         if stats is not None:
             stats.append((it, left))
         if left == 0:
@@ -423,6 +501,10 @@ def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, max
             res_hist.append(float((resmax * (1 - done)).max()))
             if it - best_it >= 30 and it >= 60 and len(res_hist) > 3 and res_hist[-1] > 0.5 * res_hist[-4]:
                 break
+    if not converged and graphs not in (None, False):
+        # the last replay has not been judged on the host yet
+        torch.cuda.current_stream(dev).synchronize()
+        converged = int(host_count[0]) == 0
     # the Ritz block of every point sits at the row its last judged iteration wrote it to
     rows = xlast.long().unsqueeze(1) + torch.arange(p, device=dev).unsqueeze(0)
     ritz = V[torch.arange(B, device=dev).unsqueeze(1), rows]

@@ -60,6 +60,9 @@ class Kernels:
             raise _lib.SqcLibraryError('sqcircuit_b200 kernels need a CUDA device')
         self._gram_work = None
         self._ws = {}
+        self.graph_launches = 0        # kernel launches replayed through CUDA graphs (not seen by the C counter)
+        self.use_graphs = True         # solver iterations are captured into CUDA graphs (see eigensolver.py)
+        self._capture_stream = None
 
     def workspace(self, key, shape, dtype):
         """Persistent device scratch (grown on demand, reused by later calls): the Davidson basis
@@ -136,15 +139,16 @@ class Kernels:
                                      _p(self._gram_work) if need else C.c_void_p(0), impl,
                                      _stream(self.dev)), 'sqc_gram')
 
-    def gram_pair(self, A, Bm, Bm2, C1, C2):
-        """C1 = A^H Bm, C2 = A^H Bm2 in one pass over A."""
+    def gram_pair(self, A, Bm, Bm2, C1, C2, real=False):
+        """C1 = A^H Bm, C2 = A^H Bm2 in one pass over A.  real: blocks of the real representation (only the
+        real inner products exist; sqc_gram_pair_real)."""
         B, ldr, ldc = C1.shape
         need = self.lib.sqc_gram_work_bytes(B, A.cnt_fixed, Bm.cnt_fixed, A.N)
         if need and (self._gram_work is None or self._gram_work.numel() < need):
             self._gram_work = torch.empty(need, dtype=torch.uint8, device=self.dev)
-        _lib.check(self.lib.sqc_gram_pair(A.c(), Bm.c(), Bm2.c(), A.N, B, _p(C1), _p(C2), ldr, ldc,
-                                          _p(self._gram_work) if need else C.c_void_p(0), _stream(self.dev)),
-                   'sqc_gram_pair')
+        fn = self.lib.sqc_gram_pair_real if real else self.lib.sqc_gram_pair
+        _lib.check(fn(A.c(), Bm.c(), Bm2.c(), A.N, B, _p(C1), _p(C2), ldr, ldc,
+                      _p(self._gram_work) if need else C.c_void_p(0), _stream(self.dev)), 'sqc_gram_pair')
 
     def gen_rr(self, GA, GB, n, drop, w, Zt, real=False, n_out=None):
         """real: real symmetric pencil (sqc_gen_rr_real), only the n_out lowest Ritz vectors are written."""
@@ -314,4 +318,32 @@ class Kernels:
                    'sqc_davidson_insert')
 
     def launch_count(self):
-        return int(self.lib.sqc_launch_count())
+        """Kernels launched by this process: direct launches (C counter) + launches replayed by CUDA graphs."""
+        return int(self.lib.sqc_launch_count()) + self.graph_launches
+
+    def eager_ops(self):
+        """Entry points that must not be captured into a CUDA graph (none; instrumented wrappers override)."""
+        return frozenset()
+
+    def capture(self, body):
+        """Capture ``body()`` (kernel launches on the current stream, no allocation, no host sync) into a CUDA
+        graph.  Returns (graph, launches per replay)."""
+        if self._capture_stream is None:
+            self._capture_stream = torch.cuda.Stream(device=self.dev)
+        g = torch.cuda.CUDAGraph()
+        cur = torch.cuda.current_stream(self.dev)
+        s = self._capture_stream
+        s.wait_stream(cur)
+        n0 = int(self.lib.sqc_launch_count())
+        with torch.cuda.stream(s):
+            g.capture_begin(capture_error_mode='thread_local')
+            try:
+                body()
+            finally:
+                g.capture_end()
+        cur.wait_stream(s)
+        return g, int(self.lib.sqc_launch_count()) - n0
+
+    def replay(self, graph_and_count):
+        graph_and_count[0].replay()
+        self.graph_launches += graph_and_count[1]

@@ -209,9 +209,12 @@ class EmulKernels:
             if a.shape[0] and c.shape[0]:
                 Cout[b, :a.shape[0], :c.shape[0]] = torch.from_numpy(a.conj() @ c.T)
 
-    def gram_pair(self, A, Bm, Bm2, C1, C2):
+    def gram_pair(self, A, Bm, Bm2, C1, C2, real=False):
         self.gram(A, Bm, C1)
         self.gram(A, Bm2, C2)
+        if real:          # real representation: only the real inner products exist
+            C1.imag.zero_()
+            C2.imag.zero_()
 
     def gen_rr(self, GA, GB, n, drop, w, Zt, real=False, n_out=None):
         B, ld, _ = GA.shape

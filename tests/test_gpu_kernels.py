@@ -813,3 +813,31 @@ def test_lowband_real_factor_and_apply(kern):
         kern.lowband_apply(BlockView(X.cuda()), BlockView(HX.cuda()),
                            BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()), theta.cuda(), act.cuda(),
                            S.cuda(), fac, offt.cuda(), nbt.cuda(), 64, 2.0, group=group, real=False)
+
+
+@pytest.mark.parametrize('B,mm,p,N', [(5, 48, 12, 3001), (3, 40, 12, 5050), (300, 24, 8, 777), (4, 16, 16, 130), (2, 64, 5, 64)])
+def test_gram_pair_real(kern, B, mm, p, N):
+    """Paired Gram pass of the real representation (eight right-hand vectors per DMMA column tile): real
+    inner products over the 2 N doubles of every vector, zero imaginary parts."""
+    g = torch.Generator().manual_seed(71)
+    V, W = rnd((B, mm, N), 72), rnd((B, mm, N), 73)
+    msz = torch.randint(0, mm - p + 1, (B,), dtype=torch.int32, generator=g)
+    nact = torch.randint(0, p + 1, (B,), dtype=torch.int32, generator=g)
+    msz[0], nact[0] = mm - p, p
+    mtot = msz + nact
+    Vd, Wd = V.cuda(), W.cuda()
+    o1 = torch.full((B, mm, 16), 3.0 + 1j, dtype=torch.complex128, device='cuda')
+    o2 = torch.full((B, mm, 16), 3.0 + 1j, dtype=torch.complex128, device='cuda')
+    kern.gram_pair(BlockView(Vd, cnt_fixed=mm, cnt=mtot.cuda()), BlockView(Vd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()),
+                   BlockView(Wd, cnt_fixed=p, off=msz.cuda(), cnt=nact.cuda()), o1, o2, real=True)
+    Vr, Wr = torch.view_as_real(V).reshape(B, mm, 2 * N), torch.view_as_real(W).reshape(B, mm, 2 * N)
+    for b in range(B):
+        a = Vr[b, :int(mtot[b])]
+        t, ht = Vr[b, int(msz[b]):int(mtot[b])], Wr[b, int(msz[b]):int(mtot[b])]
+        na = int(nact[b])
+        if na == 0 or int(mtot[b]) == 0:
+            continue
+        r1, r2 = a @ t.T, a @ ht.T
+        got1, got2 = o1[b, :int(mtot[b]), :na].cpu(), o2[b, :int(mtot[b]), :na].cpu()
+        assert float(got1.imag.abs().max()) == 0.0 and float(got2.imag.abs().max()) == 0.0
+        assert relerr(got1.real, r1) < 1e-13 and relerr(got2.real, r2) < 1e-13, b

@@ -108,6 +108,18 @@ if not only or 'pair' in only:
         nn = torch.full((B,), n, dtype=torch.int32, device=dev)
         ms = timeit(lambda: k.gen_rr(GA, GB, nn, 1e-8, w, Zt))
         report(f'gen_rr n={n}', ms, 0, 0)
+if only and 'rrr' in only:
+    # real generalised Rayleigh-Ritz: latency of one wave (<= 740 resident problems) and of several
+    for Bq in (64, 740, 2048):
+        for n in (12, 24, 36, 40):
+            GAr = torch.randn((Bq, 40, 40), dtype=torch.float64, device=dev); GAr = GAr + GAr.transpose(1, 2)
+            Q = torch.randn((Bq, 40, 80), dtype=torch.float64, device=dev); GBr = Q @ Q.transpose(1, 2) / 80
+            GAc, GBc = GAr.to(torch.complex128), GBr.to(torch.complex128)
+            w = torch.zeros((Bq, 40), dtype=torch.float64, device=dev); Zt = torch.zeros_like(GAc)
+            nn = torch.full((Bq,), n, dtype=torch.int32, device=dev)
+            ms = timeit(lambda: k.gen_rr(GAc, GBc, nn, 1e-8, w, Zt, real=True, n_out=12))
+            ms2 = timeit(lambda: k.gen_rr(GAc, GBc, nn, 1e-8, w, Zt))
+            print(json.dumps({'kernel': f'gen_rr B={Bq} n={n}', 'real_ms': round(ms, 3), 'complex_ms': round(ms2, 3)}))
 if not only or 'heev' in only:
     for n in (24, 36, 48):
         G = torch.randn((B, mm, mm), dtype=torch.complex128, device=dev); G = G + G.conj().transpose(1, 2)
