@@ -10,6 +10,11 @@ every point plus the six T1/Tphi decoherence channels for the (1, 0) transition.
         algorithm (oracle port: scipy CSR Hamiltonian + ARPACK eigs 'SR', circuit.py:1938-1986)
         on the host cores, a bounded sample of the same sweep per step.
 
+  --config {zeropi4096 (default, the headline), fluxonium1024, trt1e5}   the other named circuits of
+        BASELINE.json (configs[1], configs[3]); same JSON line, same arms.
+Multi-GPU (torchrun): weak scaling with IDENTICAL work per GPU (`value`, `per_rank`), and in the same
+invocation the strong scaling of the one named sweep split over the GPUs (`strong`).
+
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
@@ -25,16 +30,151 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TRUNC = [100, 51]
 N_EIG = 10
-POINTS = 4096
-DEC_TYPES = ['capacitive', 'inductive', 'quasiparticle', 'charge', 'cc', 'flux']
+STATES = (1, 0)
 
 
-def flux_grid(points, rank, world):
-    """The global grid has world*points fluxes in [0, 1); rank r owns a contiguous shard."""
-    total = points * world
-    return (np.arange(total, dtype=np.float64)[rank * points:(rank + 1) * points] + 0.5) / total
+# --------------------------------------------------------------------------------------------
+# workloads: BASELINE.json configs[2] (the headline, default), configs[1] and configs[3]
+# --------------------------------------------------------------------------------------------
+class Workload:
+    """One named sweep: circuit builders for the product package and for the oracle, the per-rank grid."""
+    name = ''
+    text = ''
+    points = 0
+    dec_types = []
+
+    def build(self, sq, kern):
+        raise NotImplementedError
+
+    def oracle(self, o):
+        """(oracle circuit, setter(param)) -- used by the reference arm / cpu baseline"""
+        raise NotImplementedError
+
+    def grid(self, points, rank, world, strong=False):
+        """Per-rank parameter array [n][d].  Weak scaling: EVERY rank sweeps the same range with the same
+        number of points and the same spacing (offset by a fraction of the spacing, so no two ranks solve
+        the same point): identical work per GPU.  strong=True: `points` is the size of the ONE global
+        grid and the rank owns a contiguous shard of it."""
+        raise NotImplementedError
+
+    def sweep_args(self, prm):
+        raise NotImplementedError
+
+    @staticmethod
+    def _line(points, rank, world, strong):
+        from sqcircuit_b200.sharding import shard_bounds
+        if strong:
+            lo, hi = shard_bounds(points, rank, world)
+            return (np.arange(lo, hi, dtype=np.float64) + 0.5) / points
+        return (np.arange(points, dtype=np.float64) + (rank + 0.5) / world) / points
+
+
+class ZeroPi(Workload):
+    name = 'zeropi4096'
+    text = '0-pi qubit, trunc_nums [100,51] (N=10100), 4096-point flux sweep per GPU, k=10, 6 T1/Tphi channels on (1,0)'
+    metric = 'diagonalisations/sec (k=10), 0-pi flux sweep'
+    points = 4096
+    trunc = [100, 51]
+    dec_types = ['capacitive', 'inductive', 'quasiparticle', 'charge', 'cc', 'flux']
+
+    def build(self, sq, kern):
+        self.loop = sq.Loop()
+        C, CJ = sq.Capacitor(0.15, 'GHz'), sq.Capacitor(10, 'GHz')
+        JJ, L = sq.Junction(5, 'GHz', loops=[self.loop]), sq.Inductor(0.13, 'GHz', loops=[self.loop])
+        cr = sq.Circuit({(0, 1): [CJ, JJ], (0, 2): [L], (0, 3): [C], (1, 2): [C], (1, 3): [L], (2, 3): [CJ, JJ]},
+                        kernels=kern)
+        cr.set_trunc_nums(self.trunc)
+        return cr
+
+    def oracle(self, o):
+        lp = o.OLoop()
+        c = o.zero_pi(lp)
+        c.set_trunc_nums(self.trunc)
+        return c, lambda prm: lp.set_flux(float(prm[0]))
+
+    def grid(self, points, rank, world, strong=False):
+        return self._line(points, rank, world, strong)[:, None]
+
+    def sweep_args(self, prm):
+        return {'loop_fluxes': {self.loop: prm[:, 0]}}
+
+
+class Fluxonium(Workload):
+    name = 'fluxonium1024'
+    text = 'fluxonium, harmonic basis trunc=100 (N=100), 1024-point flux sweep per GPU, k=10, 5 T1/Tphi channels on (1,0)'
+    metric = 'diagonalisations/sec (k=10), fluxonium flux sweep'
+    points = 1024
+    dec_types = ['capacitive', 'inductive', 'quasiparticle', 'cc', 'flux']
+
+    def build(self, sq, kern):
+        self.loop = sq.Loop()
+        cap = sq.Capacitor(3.6, 'GHz', Q=1e6)
+        ind = sq.Inductor(0.46, 'GHz', Q=500e6, loops=[self.loop])
+        junc = sq.Junction(10.2, 'GHz', cap=cap, A=1e-7, x=3e-06, loops=[self.loop])
+        cr = sq.Circuit({(0, 1): [ind, junc]}, flux_dist='all', kernels=kern)
+        cr.set_trunc_nums([100])
+        return cr
+
+    def oracle(self, o):
+        lp = o.OLoop()
+        c = o.fluxonium(lp)
+        c.set_trunc_nums([100])
+        return c, lambda prm: lp.set_flux(float(prm[0]))
+
+    def grid(self, points, rank, world, strong=False):
+        return self._line(points, rank, world, strong)[:, None]
+
+    def sweep_args(self, prm):
+        return {'loop_fluxes': {self.loop: prm[:, 0]}}
+
+
+class TransmonResonatorTransmon(Workload):
+    name = 'trt1e5'
+    text = ('transmon-resonator-transmon, trunc_nums [10,50,50] (N=98010), 16x16 gate-charge grid per GPU, k=10, '
+            '3 T1/Tphi channels on (1,0)')
+    metric = 'diagonalisations/sec (k=10), transmon-resonator-transmon gate-charge grid'
+    points = 256
+    trunc = [10, 50, 50]
+    dec_types = ['capacitive', 'charge', 'cc']
+
+    def build(self, sq, kern):
+        cr = sq.Circuit({(0, 1): [sq.Capacitor(0.5, 'GHz'), sq.Inductor(8.0, 'GHz')],
+                         (0, 2): [sq.Capacitor(0.30, 'GHz'), sq.Junction(14.0, 'GHz')],
+                         (0, 3): [sq.Capacitor(0.27, 'GHz'), sq.Junction(17.0, 'GHz')],
+                         (1, 2): [sq.Capacitor(12.0, 'GHz')], (1, 3): [sq.Capacitor(15.0, 'GHz')]}, kernels=kern)
+        cr.set_trunc_nums(self.trunc)
+        self.modes = [i + 1 for i in sorted(cr.charge_islands)]
+        return cr
+
+    def oracle(self, o):
+        c = o.OCircuit({(0, 1): [o.OCap(0.5, 'GHz'), o.OInd(8.0, 'GHz')],
+                        (0, 2): [o.OCap(0.30, 'GHz'), o.OJJ(14.0, 'GHz')],
+                        (0, 3): [o.OCap(0.27, 'GHz'), o.OJJ(17.0, 'GHz')],
+                        (1, 2): [o.OCap(12.0, 'GHz')], (1, 3): [o.OCap(15.0, 'GHz')]})
+        c.set_trunc_nums(self.trunc)
+        modes = [i + 1 for i in range(c.n) if c.is_charge(i)]
+
+        def setter(prm):
+            for md, v in zip(modes, prm):
+                c.set_charge_offset(md, float(v))
+        return c, setter
+
+    def grid(self, points, rank, world, strong=False):
+        # square grid over [0, 0.5)^2, row-major; the line index of _line walks the grid
+        side = int(round(np.sqrt(points)))
+        t = self._line(side * side, rank, world, strong) * side * side      # fractional cell index
+        cell = np.floor(t).astype(int)
+        frac = t - cell
+        return np.stack([((cell // side) + frac) / side * 0.5, ((cell % side) + 0.5) / side * 0.5], axis=1)
+
+    def sweep_args(self, prm):
+        return {'charge_offsets': {self.modes[0]: prm[:, 0], self.modes[1]: prm[:, 1]}}
+
+
+WORKLOADS = {w.name: w for w in (ZeroPi, Fluxonium, TransmonResonatorTransmon)}
+# bounded CPU sample: sweep points per host core and step (~10-30 s of CPU work per step)
+REF_POINTS_PER_CORE = {'zeropi4096': 1, 'fluxonium1024': 512, 'trt1e5': 1}
 
 
 # --------------------------------------------------------------------------------------------
@@ -54,34 +194,48 @@ def _ref_init():
         pass
 
 
-def _ref_one(flux):
+_REF_CACHE = {}
+
+
+def _ref_one(job):
+    """One sweep point the way the reference does it: CSR Hamiltonian from Kronecker products, ARPACK
+    eigs(which='SR') (circuit.py:1962-1969), then the decoherence rates with those eigenvectors."""
     import warnings
     warnings.filterwarnings('ignore')
     import scipy.sparse.linalg as spla
     from oracle import sqc_oracle as o
-    lp = o.OLoop(float(flux))
-    c = o.zero_pi(lp)
-    c.set_trunc_nums(TRUNC)
+    name, prm = job
+    if name not in _REF_CACHE:          # one circuit per worker process, like a Sweep over one Circuit object
+        wl = WORKLOADS[name]()
+        _REF_CACHE[name] = (wl,) + tuple(wl.oracle(o))
+    wl, c, setter = _REF_CACHE[name]
+    setter(prm)
     H = c.hamiltonian()
     w, v = spla.eigs(H, k=N_EIG, which='SR')      # the reference's call (circuit.py:1963)
     order = np.argsort(w.real)
     c.efreqs_rad, c.evecs = w.real[order], v[:, order]
-    rates = [float(np.real(c.dec_rate(d, (1, 0)))) for d in DEC_TYPES]
+    rates = [float(np.real(c.dec_rate(d, STATES))) for d in wl.dec_types]
     return c.efreqs_rad[:2].tolist(), rates
 
 
-def run_reference_sample(n_points, procs):
+def run_reference_sample(wl, n_points, procs):
     """Diagonalise n_points sweep points with `procs` worker processes; returns seconds."""
     import multiprocessing as mp
-    fl = (np.arange(n_points) + 0.5) / n_points
+    prm = wl.grid(n_points, 0, 1)
+    jobs = [(wl.name, prm[i]) for i in range(n_points)]
     t0 = time.perf_counter()
     if procs <= 1:
-        for f in fl:
-            _ref_one(f)
+        for jb in jobs:
+            _ref_one(jb)
     else:
         with mp.get_context('fork').Pool(procs, initializer=_ref_init) as pool:
-            pool.map(_ref_one, list(fl), chunksize=1)
+            pool.map(_ref_one, jobs, chunksize=1)
     return time.perf_counter() - t0
+
+
+def _host_procs():
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    return max(1, min(cores, 64))
 
 
 def reference_arm(args):
@@ -90,24 +244,27 @@ def reference_arm(args):
         return
     for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
         os.environ[var] = '1'
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-    procs = max(1, min(cores, 64))
-    n_points = procs          # one point per worker per step: ~10 s of wall clock per step
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        run_reference_sample(n_points, procs)
-    times = [run_reference_sample(n_points, procs) for _ in range(max(1, args.steps))]
+    wl = WORKLOADS[args.config]()
+    procs = _host_procs()
+    # bounded sample: the small circuit is cheap per point, so it gets more points per worker
+    n_points = procs * (REF_POINTS_PER_CORE.get(wl.name, 1))
+    # a CPU loop has no clocks or caches to warm beyond the first pass: one warm-up pass whatever W asks for
+    for _ in range(1 if args.warmup >= 1 else 0):
+        run_reference_sample(wl, n_points, procs)
+    times = [run_reference_sample(wl, n_points, procs) for _ in range(max(1, args.steps))]
     t = float(np.mean(times))
     value = n_points / t
     line = {
-        'impl': 'reference', 'metric': 'diagonalisations/sec (k=10), 0-pi flux sweep', 'value': value,
+        'impl': 'reference', 'metric': wl.metric, 'value': value,
         'unit': 'diag/s', 'n_gpus': args.gpus, 'steps': max(1, args.steps), 'warmup': min(args.warmup, 1),
+        'warmup_note': 'CPU loop: one warm-up pass is run whatever --warmup asks for',
         'ms_per_step': 1e3 * t, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64 (complex128)', 'data': 'synthetic',
-        'config': {'workload': '0-pi qubit, trunc_nums [100,51] (N=10100), flux sweep, k=10, 6 T1/Tphi channels',
-                   'points_per_step': n_points, 'note': 'bounded sample of the 4096-point sweep'},
+        'config': {'workload': wl.text, 'points_per_step': n_points,
+                   'note': f'bounded sample of the {wl.points}-point sweep'},
         'cpu_baseline': {'value': value, 'unit': 'diag/s', 'cores': procs, 'kind': 'port',
                          'sample': f'{n_points} sweep points per step, one process per core, scipy CSR build + '
-                                   'ARPACK eigs(k=10, which=SR) + dec_rate x6 (oracle/sqc_oracle.py)'},
+                                   'ARPACK eigs(k=10, which=SR) + dec_rate per channel (oracle/sqc_oracle.py)'},
         'e2e': {'value': value, 'unit': 'diag/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -258,39 +415,41 @@ def our_arm(args):
     if args.no_graphs:
         kern._k.use_graphs = False
 
-    loop = sq.Loop()
-    C, CJ = sq.Capacitor(0.15, 'GHz'), sq.Capacitor(10, 'GHz')
-    JJ, L = sq.Junction(5, 'GHz', loops=[loop]), sq.Inductor(0.13, 'GHz', loops=[loop])
-    cr = sq.Circuit({(0, 1): [CJ, JJ], (0, 2): [L], (0, 3): [C], (1, 2): [C], (1, 3): [L], (2, 3): [CJ, JJ]},
-                    kernels=kern)
-    cr.set_trunc_nums(TRUNC)
-    points = args.points
-    fluxes_host = torch.from_numpy(flux_grid(points, rank, world)).pin_memory()
+    wl = WORKLOADS[args.config]()
+    cr = wl.build(sq, kern)
+    points = args.points or wl.points
     N = int(np.prod(cr.m))
-    lib_launch0 = kern.launch_count()
+    solver_kw = dict(tol=args.tol, max_basis=args.mmax, lowblock=args.lowblock, block_size=args.block,
+                     real=(False if args.complex else None))
+    if args.strides:
+        solver_kw['coarse_stride'] = tuple(int(x) for x in args.strides.split(','))
 
-    def step(e2e):
-        """One pass of the hot path over this rank's shard.  e2e=True: host flux array in,
-        host eigenfrequencies + rates out (the user-facing call); otherwise device-resident."""
-        if e2e:
-            fl = fluxes_host.to(dev, non_blocking=True).cpu().numpy()   # H2D of the step's inputs
-        else:
-            fl = fluxes_host.numpy()
-        res = cr.sweep_diag(N_EIG, loop_fluxes={loop: fl}, tol=args.tol, max_basis=args.mmax, lowblock=args.lowblock, block_size=args.block, real=(False if args.complex else None), **({'coarse_stride': tuple(int(x) for x in args.strides.split(','))} if args.strides else {}))
-        rates = [res.dec_rate(d, states=(1, 0)) for d in DEC_TYPES]
-        if world > 1:
-            # the only collective of the path: final gather of the per-point results to rank 0
-            gather_to_root(res.efreqs.contiguous(), points * world)
-        if e2e:
-            return res.efreqs.cpu(), rates, res
-        return res.efreqs, rates, res
+    def make_step(prm_host, n_total):
+        """One pass of the hot path over this rank's points.  e2e=True: host parameter array in, host
+        eigenfrequencies + rates out (the user-facing call); otherwise device-resident."""
+        def step(e2e):
+            if e2e:
+                prm = prm_host.to(dev, non_blocking=True).cpu().numpy()   # H2D of the step's inputs
+            else:
+                prm = prm_host.numpy()
+            res = cr.sweep_diag(N_EIG, **wl.sweep_args(prm), **solver_kw)
+            rates = [res.dec_rate(d, states=STATES) for d in wl.dec_types]
+            if world > 1:
+                # the only collective of the path: final gather of the per-point results to rank 0
+                gather_to_root(res.efreqs.contiguous(), n_total)
+            if e2e:
+                return res.efreqs.cpu(), rates, res
+            return res.efreqs, rates, res
+        return step
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, e2e):
+    def timed(step, nsteps, e2e):
+        """K steps bracketed by barrier + synchronize; returns (max over ranks of the device time, this
+        rank's own device time, last result)."""
         sync()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
@@ -309,33 +468,66 @@ def our_arm(args):
                       f'{st_["reserved_bytes.all.current"] / 2**30:.1f} GiB peak-alloc '
                       f'{st_["allocated_bytes.all.peak"] / 2**30:.1f} GiB', file=sys.stderr)
         t1.record()
+        torch.cuda.synchronize()
+        own = t0.elapsed_time(t1)          # this rank alone, before the closing barrier
         sync()
-        ms = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+        ms = torch.tensor([own], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), last
+        return float(ms.item()), own, last
 
+    def per_rank(values):
+        """[world] list of a per-rank scalar, on every rank"""
+        t = torch.tensor([float(values)], device=dev, dtype=torch.float64)
+        if world == 1:
+            return [float(values)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(x.item()) for x in out]
+
+    prm_weak = torch.from_numpy(np.ascontiguousarray(wl.grid(points, rank, world))).pin_memory()
+    step = make_step(prm_weak, points * world)
     for _ in range(args.warmup):
         step(False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # timed region: only the dominant kernel (the fused H.X) carries CUDA events -- bracketing all
+    # timed region: only the dominant kernel (the H.X apply) carries CUDA events -- bracketing all
     # ~900 C-ABI calls of a step costs ~60 ms of host time per step (measured), which would be
     # charged to `value`.  The full per-kernel breakdown comes from one extra, untimed step below.
-    kern.only = {'hx_fused', 'hx_fused_real', 'mode_transform', 'potential_apply'}
+    kern.only = {'hx_fused', 'hx_fused_real', 'mode_transform', 'potential_apply', 'heev'}
     kern.enabled = True
     l0 = kern.launch_count()
-    ms_dev, last = timed(args.steps, False)
+    ms_dev, own_dev, last = timed(step, args.steps, False)
     launches = kern.launch_count() - l0
     kern.enabled = False
     hx_kernel = kern.summary()
     nvec = HX_COUNTER.get('vectors', 0) + (int(HX_COUNTER['vectors_dev'].item()) if 'vectors_dev' in HX_COUNTER else 0)
     nvec_real = HX_COUNTER.get('real_vectors', 0) + (int(HX_COUNTER['real_vectors_dev'].item())
                                                       if 'real_vectors_dev' in HX_COUNTER else 0)
-    ms_e2e, last_e2e = timed(args.steps, True)
+    ms_e2e, own_e2e, last_e2e = timed(step, args.steps, True)
     clocks = sampler.stop() if rank == 0 else None
     iters = last[2].iterations
+    rank_ms = per_rank(own_dev / args.steps)
+    rank_iters = per_rank(iters)
+
+    # ---- strong scaling of the same sweep: ONE grid of `points` fluxes split over the ranks ----
+    strong = None
+    if world > 1 and not args.no_strong:
+        prm_strong = torch.from_numpy(np.ascontiguousarray(wl.grid(points, rank, world, strong=True))).pin_memory()
+        sstep = make_step(prm_strong, points)
+        for _ in range(max(2, min(args.warmup, 3))):
+            sstep(False)
+        ms_s, own_s, last_s = timed(sstep, args.steps, False)
+        s_rank_ms = per_rank(own_s / args.steps)
+        s_rank_iters = per_rank(last_s[2].iterations)
+        strong = {'points_total': points, 'points_per_gpu': int(prm_strong.shape[0]),
+                  'value': points * args.steps / (ms_s / 1e3), 'unit': 'diag/s', 'ms_per_step': ms_s / args.steps,
+                  'per_rank_ms_per_step': [round(x, 2) for x in s_rank_ms],
+                  'per_rank_iterations': [int(x) for x in s_rank_iters],
+                  'note': 'the named 4096-point sweep split into contiguous shards, same timing rules; '
+                          'efficiency = value / (n_gpus x the 1-GPU value of this bench)'}
+
     kern.records = []
     kern.only = None
     kern.enabled = True
@@ -353,83 +545,112 @@ def our_arm(args):
     value = total_points * args.steps / (ms_dev / 1e3)
     e2e_value = total_points * args.steps / (ms_e2e / 1e3)
 
-    # ---- roofline of the H.X apply (transform -> potential -> transform), measured live ----
+    # ---- roofline of the dominant kernel, measured live ----
     peaks = {}
     pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'MEASURED_PEAKS.json (sustained copy)' if peaks else 'fallback 6.65 TB/s'
-    # the dominant H.X kernel of this run: the real-representation kernel (zero gate charge) or the complex one
-    real_ms = hx_kernel.get('hx_fused_real', [0.0, 0])[0]
-    cplx_ms = sum(hx_kernel.get(k, [0, 0])[0] for k in ('hx_fused', 'mode_transform', 'potential_apply'))
-    use_real = real_ms > cplx_ms
     total_ms = sum(v[0] for v in per_kernel.values())
     shares = {k: {'ms': round(v[0], 3), 'calls': v[1], 'share': round(v[0] / total_ms, 4)}
               for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}
-    if use_real:
-        hx_ms, hx_calls, nv = real_ms, hx_kernel['hx_fused_real'][1], nvec_real
-        bytes_per_vec = 16 * N        # read N doubles, write N doubles
-        kname = 'H.X apply, real representation (sqc_hx_fused_real: TMA load, transform + potential + transform, TMA store)'
+    real_ms = hx_kernel.get('hx_fused_real', [0.0, 0])[0]
+    cplx_ms = sum(hx_kernel.get(k, [0, 0])[0] for k in ('hx_fused', 'mode_transform', 'potential_apply'))
+    heev_ms = hx_kernel.get('heev', [0.0, 0])[0]
+    use_real = real_ms > cplx_ms
+    m0 = cr.m[0]
+    if heev_ms > max(real_ms, cplx_ms):
+        # dense path (N <= 112): the batched Jacobi eigensolver dominates; judged against the FP64 pipe.
+        # Algorithmic work of a Hermitian eigendecomposition with vectors: ~9 n^3 complex multiply-adds
+        # (tridiagonalisation 4/3 + QR with vectors ~6 + back-transformation 2) = 72 n^3 real flop
+        calls = hx_kernel['heev'][1]
+        nmat = points * args.steps
+        flops = 72.0 * N ** 3 * nmat
+        roof = {'bound': 'tensor', 'kernel': 'sqc_heev (batched Hermitian Jacobi eigensolver, one CTA per sweep '
+                'point; SIMT FP64 -- there is no FP64 tcgen05, the FP64 pipe is the bound)', 'unit': 'TFLOP/s',
+                'peak': 37.1, 'peak_source': 'measured FP64 DMMA/DFMA issue rate (tools/cu/dmma_peak.cu, '
+                'profiles/r01_dmma_peak.txt); MEASURED_PEAKS.json has no FP64 figure',
+                'achieved': flops / (heev_ms / 1e3) / 1e12, 'traffic': None, 'calls': calls, 'ms': heev_ms,
+                'algorithmic_flops_per_matrix': 72.0 * N ** 3, 'matrices': nmat}
+        roof['frac'] = roof['achieved'] / roof['peak']
     else:
-        hx_ms, nv = cplx_ms, nvec
-        hx_calls = hx_kernel.get('hx_fused', hx_kernel.get('potential_apply', [0, 1]))[1]
-        bytes_per_vec = 32 * N        # read N complex, write N complex
-        kname = 'H.X apply (sqc_hx_fused: transform + potential + transform in one kernel)'
-    roof = {'bound': 'hbm', 'kernel': kname, 'unit': 'GB/s', 'peak': hbm_peak, 'peak_source': peak_src,
-            'traffic': None, 'achieved': None, 'frac': None}
-    if hx_ms > 0 and nv > 0:
-        alg_bytes = float(bytes_per_vec) * nv
-        roof['achieved'] = alg_bytes / (hx_ms / 1e3) / 1e9
-        roof['frac'] = roof['achieved'] / hbm_peak
-        roof['algorithmic_bytes_per_vector'] = bytes_per_vec
-        roof['algorithmic_bytes_per_launch'] = alg_bytes / max(hx_calls, 1)
-        ratio, src = NCU_HX_TRAFFIC.get('real' if use_real else 'complex', (None, None))
-        if ratio is not None:
-            # DRAM bytes of the kernel from its ncu --set full capture, as a ratio to the algorithmic bytes of
-            # the captured launch; reported per launch, scaled to this run's average launch
-            roof['traffic'] = ratio * alg_bytes / max(hx_calls, 1)
-            roof['traffic_source'] = src
-        roof['vectors'] = nv
-        roof['ms'] = hx_ms
-        # FP64 work with the parity-split transforms: 2 m flop per real amplitude (forward + backward), twice
-        # that per complex amplitude
-        flops = (2.0 if use_real else 4.0) * cr.m[0] * N * nv
-        roof['fp64_tflops'] = flops / (hx_ms / 1e3) / 1e12
-        # the kernel is FP64-tensor-bound (12.5 flop/B in both representations): context for the HBM fraction.
-        # Peak = measured DMMA issue rate (tools/cu/dmma_peak.cu, profiles/r01_dmma_peak.txt): 37.1 TFLOP/s
-        roof['fp64_tensor_peak_tflops'] = 37.1
-        roof['fp64_tensor_frac'] = roof['fp64_tflops'] / 37.1
-        roof['hbm_frac_ceiling_fp64_bound'] = (37.1e12 / (flops / alg_bytes)) / 1e9 / hbm_peak
-    roof['calls'] = hx_calls
+        if use_real:
+            hx_ms, hx_calls, nv = real_ms, hx_kernel['hx_fused_real'][1], nvec_real
+            bytes_per_vec = 16 * N        # read N doubles, write N doubles
+            kname = ('H.X apply, real representation (sqc_hx_fused_real: TMA load, transform + potential + '
+                     'transform, TMA store)')
+            flops_per_vec = 2.0 * m0 * N
+        elif hx_kernel.get('hx_fused', [0.0, 0])[0] > 0:
+            hx_ms, nv = cplx_ms, nvec
+            hx_calls = hx_kernel['hx_fused'][1]
+            bytes_per_vec = 32 * N        # read N complex, write N complex
+            kname = 'H.X apply (sqc_hx_fused: transform + potential + transform in one kernel)'
+            flops_per_vec = 4.0 * m0 * N
+        else:
+            hx_ms, nv = cplx_ms, nvec
+            hx_calls = hx_kernel.get('potential_apply', [0, 1])[1]
+            bytes_per_vec = 32 * N
+            kname = ('H.X apply, generic layout (sqc_mode_transform per harmonic mode + sqc_potential_apply: '
+                     'several passes over the vector; algorithmic bytes = one read + one write)')
+            flops_per_vec = 4.0 * sum(d for d, h in zip(cr.m, cr._operators().harm) if h and d > 1) * N
+        roof = {'bound': 'hbm', 'kernel': kname, 'unit': 'GB/s', 'peak': hbm_peak, 'peak_source': peak_src,
+                'traffic': None, 'achieved': None, 'frac': None}
+        if hx_ms > 0 and nv > 0:
+            alg_bytes = float(bytes_per_vec) * nv
+            roof['achieved'] = alg_bytes / (hx_ms / 1e3) / 1e9
+            roof['frac'] = roof['achieved'] / hbm_peak
+            roof['algorithmic_bytes_per_vector'] = bytes_per_vec
+            roof['algorithmic_bytes_per_launch'] = alg_bytes / max(hx_calls, 1)
+            ratio, src = NCU_HX_TRAFFIC.get((wl.name, 'real' if use_real else 'complex'), (None, None))
+            if ratio is not None:
+                # DRAM bytes of the kernel from its ncu --set full capture, as a ratio to the algorithmic bytes
+                # of the captured launch; reported per launch, scaled to this run's average launch
+                roof['traffic'] = ratio * alg_bytes / max(hx_calls, 1)
+                roof['traffic_source'] = src
+            roof['vectors'] = nv
+            roof['ms'] = hx_ms
+            flops = flops_per_vec * nv
+            roof['fp64_tflops'] = flops / (hx_ms / 1e3) / 1e12
+            # context for the HBM fraction: FP64 issue is the real bound of the harmonic-mode transforms.
+            # Peak = measured DMMA issue rate (tools/cu/dmma_peak.cu, profiles/r01_dmma_peak.txt)
+            roof['fp64_tensor_peak_tflops'] = 37.1
+            roof['fp64_tensor_frac'] = roof['fp64_tflops'] / 37.1
+            roof['hbm_frac_ceiling_fp64_bound'] = min(1.0, (37.1e12 / (flops / alg_bytes)) / 1e9 / hbm_peak)
+        roof['calls'] = hx_calls
 
     # ---- cpu baseline: bounded sample of the same workload on the host cores ----
     cpu = None
     if not args.no_cpu_baseline:
         for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
             os.environ[var] = '1'
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-        procs = max(1, min(cores, 64))
-        t = run_reference_sample(procs, procs)
-        cpu = {'value': procs / t, 'unit': 'diag/s', 'cores': procs, 'kind': 'port',
-               'sample': f'{procs} sweep points of the same sweep, one process per core (oracle port of the '
-                         f'reference: scipy CSR build + ARPACK eigs SR + 6 rates), {t:.1f} s'}
+        procs = _host_procs()
+        npts = procs * (REF_POINTS_PER_CORE.get(wl.name, 1))
+        t = run_reference_sample(wl, npts, procs)
+        cpu = {'value': npts / t, 'unit': 'diag/s', 'cores': procs, 'kind': 'port',
+               'sample': f'{npts} sweep points of the same sweep, one process per core (oracle port of the '
+                         f'reference: scipy CSR build + ARPACK eigs SR + the rates), {t:.1f} s'}
 
-    h2d = points * 8
-    d2h = points * N_EIG * 8 + len(DEC_TYPES) * points * 8
+    h2d = int(prm_weak.numel()) * 8
+    d2h = points * N_EIG * 8 + len(wl.dec_types) * points * 8
     line = {
-        'metric': 'diagonalisations/sec (k=10), 0-pi flux sweep', 'value': value, 'unit': 'diag/s',
+        'metric': wl.metric, 'value': value, 'unit': 'diag/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': '0-pi qubit, trunc_nums [100,51] (N=10100), 4096-point flux sweep per GPU, k=10, '
-                               '6 T1/Tphi channels on (1,0)',
+        'config': {'workload': wl.text, 'name': wl.name,
                    'points_per_gpu': points, 'n_eig': N_EIG, 'hilbert_dim': N, 'tol_rel_residual': args.tol,
-                   'davidson_iterations': iters, 'representation': 'real (time-reversal adapted)' if use_real else 'complex', 'l2': 'working set (>60 GB) larger than L2',
-                   'parallelism': f'sweep points sharded over {world} GPU(s), final NCCL gather'},
+                   'davidson_iterations': iters,
+                   'representation': 'real (time-reversal adapted)' if use_real else 'complex',
+                   'l2': 'working set (tens of GB of basis vectors) larger than L2' if N > 112 else
+                         'per-point matrices live in shared memory; inputs are a few KB',
+                   'parallelism': f'every one of the {world} GPU(s) sweeps the same range with {points} points '
+                                  '(offset by a fraction of the spacing): identical work per GPU, final NCCL gather'},
         'e2e': {'value': e2e_value, 'unit': 'diag/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
+        'per_rank': {'ms_per_step': [round(x, 2) for x in rank_ms], 'iterations': [int(x) for x in rank_iters]},
+        'strong': strong,
         'roofline': roof,
         'kernel_time_breakdown': shares,
         'kernel_time_breakdown_note': 'ms of ONE extra fully instrumented step run after the timed region',
@@ -442,7 +663,10 @@ def our_arm(args):
 
 
 NCU_HX_TRAFFIC = {
-    'complex': (1.0855, 'ncu dram__bytes_read+write / algorithmic = 1.0855 (profiles/r01_ncu_full_v28_hx_fused.txt)'),
+    ('zeropi4096', 'complex'): (1.0855, 'ncu dram__bytes_read+write / algorithmic = 1.0855 '
+                                        '(profiles/r01_ncu_full_v28_hx_fused.txt)'),
+    ('zeropi4096', 'real'): (0.98, 'ncu dram__bytes_read+write / algorithmic = 0.98: 996 MB + 950 MB for 12288 '
+                                   'vectors of 161.6 kB (profiles/r02_ncu_full_hx_real_v1.txt)'),
 }
 HX_COUNTER = {'vectors': 0}
 DEBUG = bool(os.environ.get('SQC_BENCH_DEBUG'))
@@ -473,7 +697,9 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--points', type=int, default=POINTS, help='sweep points per GPU')
+    ap.add_argument('--points', type=int, default=0, help='sweep points per GPU (default: the workload\'s)')
+    ap.add_argument('--config', default='zeropi4096', choices=sorted(WORKLOADS), help='named workload (default: the headline)')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling section of a multi-GPU run')
     ap.add_argument('--tol', type=float, default=1e-9)
     ap.add_argument('--mmax', type=int, default=None, help='maximum Davidson basis size (default 4 x block)')
     ap.add_argument('--lowblock', type=int, default=512)
