@@ -80,6 +80,9 @@ int         sqc_abi_version(void);
 const char* sqc_error_string(int code);
 /* number of kernels launched by this library since load (bench.py gpu_launches) */
 int64_t     sqc_launch_count(void);
+/* SHA-256 (hex) of the kernel sources + this header the library was built from; the Python loader
+ * refuses a library whose hash differs from the sources next to it (no stale binaries). */
+const char* sqc_source_hash(void);
 
 /* ---- (1) operator construction ---------------------------------------- */
 /* x-basis of one harmonic mode: eigen-decomposition of the truncated a + a^dag

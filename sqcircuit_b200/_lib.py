@@ -48,6 +48,7 @@ SIGNATURES = {
     'sqc_abi_version': (c_i32, []),
     'sqc_error_string': (C.c_char_p, [c_i32]),
     'sqc_launch_count': (c_i64, []),
+    'sqc_source_hash': (C.c_char_p, []),
     'sqc_xbasis': (c_i32, [c_i32, c_vp, c_vp, c_vp]),
     'sqc_phase_tables': (c_i32, [C.POINTER(Space), c_i32, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp]),
     'sqc_lc_diagonal': (c_i32, [C.POINTER(Space), c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp]),
@@ -103,6 +104,21 @@ SIGNATURES = {
 _lib = None
 
 
+def source_hash():
+    """SHA-256 over csrc/*.cu, csrc/*.cuh and include/sqcircuit_b200.h (names and contents, sorted): the
+    identity the build embeds in the library (csrc/buildinfo.cu) and ``load`` checks."""
+    import hashlib
+    csrc = os.path.join(_HERE, 'csrc')
+    files = sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(('.cu', '.cuh')))
+    files.append(os.path.join(os.path.dirname(_HERE), 'include', 'sqcircuit_b200.h'))
+    h = hashlib.sha256()
+    for f in files:
+        h.update(os.path.basename(f).encode() + b'\0')
+        with open(f, 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 class SqcLibraryError(RuntimeError):
     pass
 
@@ -126,6 +142,11 @@ def load():
         fn.argtypes = args
     if lib.sqc_abi_version() != 3:
         raise SqcLibraryError('sqcircuit_b200 ABI version mismatch')
+    built, here = lib.sqc_source_hash().decode(), source_hash()
+    if built != here:
+        raise SqcLibraryError(
+            f'{LIB_PATH} is stale: built from sources {built[:12]}, the tree holds {here[:12]} '
+            '(rebuild with `python __graft_entry__.py`)')
     _lib = lib
     return lib
 

@@ -21,6 +21,8 @@ from .eigensolver import DENSE_MAX, solve_davidson, solve_davidson_gen, solve_de
 # iteration used by sweep_diag: 'gen' (non-orthogonalised basis, generalised Rayleigh-Ritz; 3 passes
 # over the basis per iteration) or 'orth' (CGS2 + SVQB; 7 passes)
 SOLVER = {'kind': 'gen'}
+# the Davidson kernels work on blocks of <= 16 vectors, two of which are guard vectors
+MAX_EIG_DAVIDSON = 14
 
 
 class _RealRepresentationFailed(RuntimeError):
@@ -42,7 +44,36 @@ def _davidson(*a, **kw):
         # iteration (CGS2 + SVQB: seven basis passes instead of three) does not have that floor.
         kw = {k: v for k, v in kw.items() if k not in ('drop', 'cold_gate', 'expand')}
         kw['lowblock_ns'] = 0          # plain diagonal preconditioner: slower, nothing to go wrong
+        a[0].release_workspace()       # the fallback allocates its own (larger) basis buffers
     return solve_davidson(*a, **kw)
+
+
+def _solver_sizes(k, N, block_size=None, max_basis=None):
+    """(p, mmax) exactly as the solvers choose them (eigensolver.solve_davidson_gen)."""
+    p = block_size if block_size is not None else min(16, max(k + 2, (k * 6 + 4) // 5))
+    p = min(p, 16, N)
+    mmax = max_basis if max_basis is not None else 3 * p + 4
+    return p, min(mmax, 64, N)
+
+
+def _points_per_chunk(kern, Nv, k, block_size=None, max_basis=None, fraction=0.8):
+    """Sweep points one batched Davidson call may take: the basis buffers V and W = H V (2 (mmax + p) vectors
+    per point) plus the gathered Ritz block, the returned vectors and the Gram / coefficient matrices have to
+    fit into ``fraction`` of what the device has free right now (kern.free_bytes)."""
+    p, mmax = _solver_sizes(k, Nv, block_size, max_basis)
+    per_point = 16 * Nv * (2 * (mmax + p) + 2 * p + k) + 16 * (3 * mmax * mmax + 2 * 16 * mmax) + 4096
+    return max(1, int(fraction * kern.free_bytes() // per_point))
+
+
+def _cat_results(parts):
+    """Concatenate the EigResults of consecutive chunks of one level."""
+    from .eigensolver import EigResult
+    if len(parts) == 1:
+        return parts[0]
+    cat = lambda name: torch.cat([getattr(r, name) for r in parts], dim=0)
+    return EigResult(cat('evals'), cat('evecs'), max(r.iterations for r in parts), cat('resmax'),
+                     all(r.converged for r in parts),
+                     ritz_block=cat('ritz_block') if parts[0].ritz_block is not None else None)
 from .elements import Capacitor, Charge, Inductor, Junction, Loop
 from .exceptions import CircuitStateError
 from .noise_ops import SweepNoise
@@ -281,6 +312,9 @@ class Circuit:
         if ops.N <= DENSE_MAX:
             res = solve_dense(kern, hop, B, ops.N, n_eig)
         else:
+            if n_eig > MAX_EIG_DAVIDSON:
+                raise ValueError(f'n_eig = {n_eig}: the batched block Davidson iteration (Hilbert dimension > '
+                                 f'{DENSE_MAX}) finds at most {MAX_EIG_DAVIDSON} eigenpairs per call')
             # zero gate charge on a harmonic x charge circuit: H commutes with a time reversal and is
             # solved as a real symmetric problem (half the bytes and flops, csrc/hx_real.cu)
             use_real = real if real is not None else ops.supports_real(ng)
@@ -295,8 +329,10 @@ class Circuit:
                 res = self._solve(ops, hop, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats,
                                   coarse_stride, lowblock, warm_start and B >= min_warm, False)
         if not res.converged:
-            raise RuntimeError(f'batched Davidson did not converge in {maxit} iterations '
-                               f'(worst relative residual {float(res.resmax.max()):.2e})')
+            why = 'iteration limit' if res.iterations >= maxit else 'stagnation guard'
+            raise RuntimeError(f'batched Davidson did not converge: stopped after {res.iterations} lock-step '
+                               f'iterations ({why}, limit {maxit}), worst relative residual '
+                               f'{float(res.resmax.max()):.2e}')
         evecs = res.evecs if res.evecs.is_contiguous() else res.evecs.contiguous()
         out = SweepResult(res.evals / (2 * np.pi * unt.get_unit_freq()), res.evals, evecs,
                           res.iterations, res.converged, res.resmax)
@@ -313,9 +349,21 @@ class Circuit:
             res = self._solve_continuation(ops, lv, ng, n_eig, tol, block_size, max_basis, maxit, stats,
                                            stride, lowblock, real)
         else:
-            op = RealHamiltonianOperator(ops, lv, ng, base=hop) if real else hop
-            res = _davidson(kern, op, lv.shape[0], op.Nc if real else ops.N, n_eig, op.diag, p=block_size,
-                            mmax=max_basis, tol=tol, maxit=maxit, stats=stats)
+            B = lv.shape[0]
+            Nv = (ops.N + 1) // 2 if real else ops.N
+            chunk = _points_per_chunk(kern, Nv, n_eig, block_size, max_basis)
+            parts = []
+            for c0 in range(0, B, chunk):
+                if chunk >= B:
+                    op = RealHamiltonianOperator(ops, lv, ng, base=hop) if real else hop
+                else:
+                    cls = RealHamiltonianOperator if real else HamiltonianOperator
+                    op = cls(ops, lv[c0:c0 + chunk], ng if ng.shape[0] == 1 else ng[c0:c0 + chunk])
+                parts.append(_davidson(kern, op, op.B, Nv, n_eig, op.diag, p=block_size, mmax=max_basis,
+                                       tol=tol, maxit=maxit, stats=stats))
+                if not parts[-1].converged:
+                    break
+            res = _cat_results(parts)
         if real and res.converged:
             out = torch.empty(res.evecs.shape[:2] + (ops.N,), dtype=torch.complex128, device=ops.device)
             step = max(1, int(2 ** 31 // (16 * ops.N * res.evecs.shape[1])))
@@ -351,8 +399,12 @@ class Circuit:
             return _davidson(kern, hop, len(idx), Nv, n_eig, hop.diag, p=block_size,
                              mmax=max_basis, tol=tol, maxit=maxit, x0=x0, stats=st,
                              lowblock_ns=lowblock)
+
+        def solve_cold(idx, st):
+            chunk = _points_per_chunk(kern, Nv, n_eig, block_size, max_basis)
+            return _cat_results([solve(idx[c0:c0 + chunk], None, st) for c0 in range(0, len(idx), chunk)])
         if not vary.any():
-            return solve(np.arange(B), None, stats)
+            return solve_cold(np.arange(B), stats)
         q = prm[:, vary] / span[vary]
         order = np.lexsort(q.T[::-1])
         # level sets: strides stride^2, stride, 1 over the sorted sweep (coarsest kept >= 32 points)
@@ -383,7 +435,7 @@ class Circuit:
         for li, idx in enumerate(levels):
             st = [] if stats is not None else None
             if li == 0:
-                r = solve(idx, None, st)
+                r = solve_cold(idx, st)
                 p = r.ritz_block.shape[1]
                 k = r.evals.shape[1]
                 evals = torch.empty((B, k), dtype=torch.float64, device=dev)
@@ -405,7 +457,7 @@ class Circuit:
                 store = torch.cat(ritz_store, dim=0) if len(ritz_store) > 1 else ritz_store[0]
                 ritz_store = [store]
                 pos = np.array([ritz[int(i)] for i in solved])
-                chunk = max(1, min(len(idx), int(2.4e10 // (2 * p * Nv * 16))))
+                chunk = min(len(idx), _points_per_chunk(kern, Nv, n_eig, block_size, max_basis))
                 last = li == len(levels) - 1
                 new_blocks = []
                 for c0 in range(0, len(idx), chunk):

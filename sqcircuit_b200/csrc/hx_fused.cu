@@ -15,19 +15,6 @@
 #include "common.cuh"
 
 #define HX_MAXT 4        // junction terms
-// timing ablations for tools/hx_variants.sh (wrong results when set)
-#ifndef HX_ABL_NOPOT
-#define HX_ABL_NOPOT 0
-#endif
-#ifndef HX_ABL_NOSTAGE
-#define HX_ABL_NOSTAGE 0
-#endif
-#ifndef HX_ABL_NOEPI
-#define HX_ABL_NOEPI 0
-#endif
-#ifndef HX_ABL_NODMMA
-#define HX_ABL_NODMMA 0
-#endif
 #ifndef HX_TEAMS
 #define HX_TEAMS 1      // 1: a single 8-warp team (30 + 2 column panels); 2: two independent 4-warp teams per
                         // CTA (14 + 2 column panels) -- measured slower (7.5 vs 6.7 ms at 2048 x 12 vectors): the extra
@@ -135,7 +122,7 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
             // Fock row n -> (n even ? n/2 : KP + n/2); padding rows stay zero from the start
             {
                 double* dcol = sP + 2 * pcc;
-                if (!HX_ABL_NOSTAGE && c >= 0 && c < gm.inner) {
+                if (c >= 0 && c < gm.inner) {
                     const cplx* src = xv + c;
                     for (int a2 = gq; a2 < he; a2 += 8)
                         cp_async16(dcol + a2 * pld, src + (long long)(2 * a2) * gm.inner);
@@ -159,7 +146,7 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
             const double* ve = sVe + tq * VLD + gq;               // A[i][a] = Ve[a][i]
             const double* vo = sVo + tq * VLD + gq;
 #pragma unroll KU
-            for (int k = 0; k < (HX_ABL_NODMMA ? 1 : KS); ++k) {
+            for (int k = 0; k < KS; ++k) {
                 const double bE = bp[(4 * k) * pld];
                 const double bO = bp[(KP + 4 * k) * pld];
 #pragma unroll
@@ -187,7 +174,7 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
         // ---- 3. potential + mirror combination, in place ----
         // a warp owns pg whole row pairs; the (at most 32) columns of a row are done by its lanes:
         // read, warp sync, write back -- nothing waits on the CTA inside the pass.
-        for (int i_base = warp * gm.pg; i_base < (HX_ABL_NOPOT ? 0 : he); i_base += nwarp * gm.pg) {
+        for (int i_base = warp * gm.pg; i_base < he; i_base += nwarp * gm.pg) {
             const int i_end = min(i_base + gm.pg, he);
             auto eval = [&](int i, int pc, cplx& S, cplx& D) {
                 const bool pair = i < ho;                 // centre row of an odd m has no mirror
@@ -248,7 +235,7 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
             const double* ve = sVe + gq * VLD + tq;               // A[a][i] = Ve[a][i]
             const double* vo = sVo + gq * VLD + tq;
 #pragma unroll KU
-            for (int k = 0; k < (HX_ABL_NODMMA ? 1 : KS); ++k) {
+            for (int k = 0; k < KS; ++k) {
                 const double bS = bp[(4 * k) * pld];
                 const double bD = bp[(KP + 4 * k) * pld];
 #pragma unroll
@@ -262,7 +249,7 @@ hx_fused_kernel(HxGeom gm, const double* __restrict__ Ve, const double* __restri
             // as far as the compiler knows)
             if (pcc >= 1 && pcc <= gm.TC && c < gm.inner) {
                 cplx* yv = blk_vec(Y, b, v, gm.N);
-                const double* fd = (fdiag && !HX_ABL_NOEPI) ? fdiag + b * fdiag_stride_b : nullptr;
+                const double* fd = fdiag ? fdiag + b * fdiag_stride_b : nullptr;
                 constexpr int EB = HX_EB;                       // rows per batch
 #pragma unroll
                 for (int r0 = 0; r0 < NRT; r0 += EB) {

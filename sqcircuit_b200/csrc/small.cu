@@ -664,12 +664,21 @@ davidson_decide_kernel(sqc_davidson_state_t st) {
     if (tid == 0) {
         const int msz = st.msz[b];
         const int pe = min(p, msz);
+        // A wanted Ritz value that is not finite (the generalised Rayleigh-Ritz dropped dependent basis vectors
+        // and fewer than k pairs are alive) is NOT converged: without the test its relative residual would
+        // be rn / inf = 0 (or NaN, which fmax and > both discard) and the point would be marked done.
         double scale = st.tol_abs_floor;
-        for (int j = 0; j < min(k, pe); ++j) scale = fmax(scale, fabs(theta[j]));
-        double rmax = 0.0;
+        bool finite = pe >= min(k, p);
+        for (int j = 0; j < min(k, pe); ++j) {
+            if (isfinite(theta[j])) scale = fmax(scale, fabs(theta[j]));
+            else finite = false;
+        }
+        double rmax = finite ? 0.0 : 1e300;
         int n = 0;
         for (int j = 0; j < pe; ++j) {
-            const double rel = sqrt(st.rn2[(int64_t)b * p + j]) / scale;
+            const double rn2 = st.rn2[(int64_t)b * p + j];
+            if (!isfinite(theta[j]) || !isfinite(rn2)) continue;       // no correction vector for a dead pair
+            const double rel = sqrt(rn2) / scale;
             if (j < k) rmax = fmax(rmax, rel);
             if (rel > 0.5 * st.tol_rel && j < nexp) st.act[(int64_t)b * p + n++] = j;
         }
@@ -701,8 +710,10 @@ davidson_decide_kernel(sqc_davidson_state_t st) {
             st.restart[b] = rnext;
             st.xoff[b] = rnext ? 0 : st.xrow;
         }
-        double fl = fmax(fabs(theta[0]), fabs(theta[pe - 1]));
-        fl = fmax(fl, theta[pe - 1] - theta[0]);
+        int hi = pe - 1;                                   // largest finite Ritz value of the block
+        while (hi > 0 && !isfinite(theta[hi])) --hi;
+        double fl = isfinite(theta[0]) ? fmax(fabs(theta[0]), fabs(theta[hi])) : 0.0;
+        if (isfinite(theta[0])) fl = fmax(fl, theta[hi] - theta[0]);
         st.den_floor[b] = fmax(1e-3 * fl, 1e-300);
         s_restart = restart;
         if (restart) st.msz[b] = pe;

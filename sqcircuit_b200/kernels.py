@@ -82,6 +82,14 @@ class Kernels:
     def release_workspace(self):
         self._ws = {}
 
+    def free_bytes(self):
+        """Device bytes a new batched solve may claim: free device memory, the caching allocator's unused
+        reserve, and the persistent workspace (the next solve reuses it)."""
+        free, _ = torch.cuda.mem_get_info(self.dev)
+        cached = torch.cuda.memory_reserved(self.dev) - torch.cuda.memory_allocated(self.dev)
+        ws = sum(int(b.numel()) for b in self._ws.values() if b is not None)
+        return int(free) + int(cached) + ws
+
     # ---- (1) operators ---------------------------------------------------
     def xbasis(self, m):
         V = torch.empty((m, m), dtype=torch.float64, device=self.dev)

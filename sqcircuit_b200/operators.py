@@ -14,7 +14,6 @@ coupling operators needed for matrix elements and decoherence rates.
 """
 import ctypes as C
 
-import os
 import numpy as np
 import torch
 
@@ -290,7 +289,7 @@ class CircuitOperators:
 
 
 # sweep points per shared low-block inverse of the two-level preconditioner (see build_lowblock)
-LOWBLOCK_GROUP = int(os.environ.get('SQC_LOWBLOCK_GROUP', '0'))     # 0 = choose from the sweep spacing
+LOWBLOCK_GROUP = 0     # 0 = choose from the sweep spacing (tests / tools may set a fixed group size)
 
 
 class HamiltonianOperator:

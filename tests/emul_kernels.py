@@ -49,6 +49,14 @@ class EmulKernels:
     def workspace(self, key, shape, dtype):
         return torch.empty(tuple(int(d) for d in shape), dtype=dtype)
 
+    free_bytes_value = 1 << 60     # tests shrink it to exercise the memory guard of Circuit.sweep_diag
+
+    def free_bytes(self):
+        return self.free_bytes_value
+
+    def release_workspace(self):
+        pass
+
     def launch_count(self):
         return self.launches
 
@@ -449,9 +457,13 @@ class EmulKernels:
             msz = int(st.msz[b])
             pe = min(p, msz)
             th = st.theta[b].numpy()
-            scale = max(st.tol_abs_floor, np.max(np.abs(th[:min(k, pe)])))
-            rmax, n = 0.0, 0
+            want = th[:min(k, pe)]
+            finite = bool(np.all(np.isfinite(want))) and pe >= min(k, p)
+            scale = max(st.tol_abs_floor, np.max(np.abs(want[np.isfinite(want)]), initial=0.0))
+            rmax, n = (0.0 if finite else 1e300), 0
             for j in range(pe):
+                if not (np.isfinite(th[j]) and np.isfinite(float(st.rn2[b, j]))):
+                    continue
                 rel = np.sqrt(float(st.rn2[b, j])) / scale
                 if j < k:
                     rmax = max(rmax, rel)
@@ -483,7 +495,10 @@ class EmulKernels:
                 rnext = int(mnext + n > st.mmax)
                 st.restart[b] = rnext
                 st.xoff[b] = 0 if rnext else st.xrow
-            fl = max(abs(th[0]), abs(th[pe - 1]), th[pe - 1] - th[0])
+            hi = pe - 1
+            while hi > 0 and not np.isfinite(th[hi]):
+                hi -= 1
+            fl = max(abs(th[0]), abs(th[hi]), th[hi] - th[0]) if np.isfinite(th[0]) else 0.0
             st.den_floor[b] = max(1e-3 * fl, 1e-300)
             if restart:
                 st.msz[b] = pe

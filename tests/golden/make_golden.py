@@ -219,6 +219,10 @@ def part_trt():
 
 
 
+# (Fock index, charge number) of the golden Hamiltonian columns at the bench truncation
+H_COLS_100_51 = [(0, 0), (3, 1), (3, -1), (50, 25), (50, -25), (99, 50), (99, -50), (17, 7), (17, -7), (64, 0)]
+
+
 def part_zeropi_big():
     # --- zero-pi at the bench truncation (N = 10100): a few exact eigenvalue sets --------
     cr, lp = zero_pi([100, 51])
@@ -230,8 +234,14 @@ def part_zeropi_big():
         H = cr.hamiltonian().data_as('csr_matrix')
         w = spla.eigsh(H, k=10, which='SA', tol=0, ncv=60)[0]
         ws.append(np.sort(w) / (2 * np.pi * 1e9))
+    # columns of the reference Hamiltonian at flux 0.31 (Fock i, charge n pairs +-n), dense per column
+    lp.set_flux(0.31)
+    H = cr.hamiltonian().data_as('csr_matrix').tocsc()
+    inner, nc = 101, 50
+    cols = [i * inner + nc + n for i, n in H_COLS_100_51]
+    Hc = np.stack([np.asarray(H[:, c].todense()).ravel() for c in cols], axis=1)
     np.savez_compressed(os.path.join(HERE, 'zeropi_100_51.npz'), params=np.array(fl),
-                        efreqs_exact=np.array(ws))
+                        efreqs_exact=np.array(ws), H_cols=np.array(cols), H_cols_at_0p31=Hc)
 
 
 PARTS = dict(zeropi=part_zeropi, fluxonium=part_fluxonium, transmon=part_transmon,

@@ -432,6 +432,12 @@ def test_davidson_decide_matches_emulation(kern, planned):
             t['xlast'] = torch.full((B,), mmax, dtype=torch.int32)
         return {kk: v.to(dev) for kk, v in t.items()}
     tc, tg = fresh('cpu'), fresh('cuda')
+    # a few points carry non-finite wanted / guard Ritz values (dependent vectors dropped by the generalised
+    # Rayleigh-Ritz): they must stay unfinished and give finite preconditioner floors
+    for t in (tc, tg):
+        t['theta'][3, k - 1:] = float('inf')
+        t['theta'][7, p - 1:] = float('inf')
+        t['theta'][11, 0:] = float('inf')
     E = EmulKernels()
     extra = dict(xrow=mmax) if planned else {}
     sc = E.davidson_state(p=p, k=k, mmax=mmax, ldg=ld, tol_rel=1e-3, tol_abs_floor=1e-300, **tc, **extra)
@@ -442,9 +448,12 @@ def test_davidson_decide_matches_emulation(kern, planned):
         tg['rn2'].copy_(rn.cuda())
         E.davidson_decide(sc, B)
         kern.davidson_decide(sg, B)
+        assert not bool(tg['done'][3]) and not bool(tg['done'][11]) and bool(torch.isfinite(tg['den_floor']).all())
         for name in tc:
             a, b_ = tc[name], tg[name].cpu()
-            if name == 'act':       # entries past nact are unspecified
+            if name == 'theta':
+                assert torch.equal(a, b_)
+            elif name == 'act':       # entries past nact are unspecified
                 for b in range(B):
                     n = int(tc['nact'][b])
                     assert torch.equal(a[b, :n], b_[b, :n])

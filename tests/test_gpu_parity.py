@@ -175,6 +175,83 @@ def test_config2_zero_pi_bench_size_points():
     assert np.max(np.abs(res2.efreqs.cpu().numpy() - ef[1][None, :]) / np.abs(ef[1])) < 1e-9
 
 
+def test_hamiltonian_columns_at_bench_truncation_match_reference_golden():
+    """N = 10100: columns of the reference's own Hamiltonian matrix (tests/golden/make_golden.py, flux 0.31)
+    against the fused complex H.X kernel applied to unit vectors, and against the real-representation kernel
+    applied to the time-reversal symmetric combinations e(i, n) + e(i, -n) and i (e(i, n) - e(i, -n))."""
+    from sqcircuit_b200.kernels import BlockView
+    from sqcircuit_b200.operators import HamiltonianOperator, RealHamiltonianOperator
+    g = np.load(os.path.join(G, 'zeropi_100_51.npz'))
+    cols, Hc = g['H_cols'], g['H_cols_at_0p31']
+    cr, lp, _, _ = cs.zero_pi()
+    cr.set_trunc_nums([100, 51])
+    lp.set_flux(0.31)
+    ops = cr._operators()
+    lv, ng = cr._current_point()
+    hop = HamiltonianOperator(ops, lv, ng)
+    N, dev = ops.N, ops.device
+    X = torch.zeros((1, len(cols), N), dtype=torch.complex128, device=dev)
+    X[0, torch.arange(len(cols)), torch.as_tensor(cols, device=dev)] = 1.0
+    Y = torch.empty_like(X)
+    hop.apply(BlockView(X), BlockView(Y))
+    scale = np.abs(Hc).max()
+    assert np.abs(Y[0].cpu().numpy().T - Hc).max() <= 1e-12 * scale
+    # real representation: T-symmetric combinations of the +-n column pairs
+    assert ops.supports_real(ng)
+    rop = RealHamiltonianOperator(ops, lv, ng, base=hop)
+    inner, nc = ops.dims[1], (ops.dims[1] - 1) // 2
+    pos = {int(c): j for j, c in enumerate(cols)}
+    comb, ref = [], []
+    for c in cols:
+        i, n = int(c) // inner, int(c) % inner - nc
+        if n > 0 and (i * inner + nc - n) in pos:
+            a, b = pos[int(c)], pos[i * inner + nc - n]
+            comb.append((a, b, 1.0, 1.0))
+            ref.append(Hc[:, a] + Hc[:, b])
+            comb.append((a, b, 1j, -1j))
+            ref.append(1j * Hc[:, a] - 1j * Hc[:, b])
+        elif n == 0:
+            comb.append((pos[int(c)], pos[int(c)], 0.5, 0.5))
+            ref.append(Hc[:, pos[int(c)]])
+    Zc = torch.zeros((1, len(comb), N), dtype=torch.complex128, device=dev)
+    for j, (a, b, ca, cb) in enumerate(comb):
+        Zc[0, j, int(cols[a])] += ca
+        Zc[0, j, int(cols[b])] += cb
+    Xr = torch.zeros((1, len(comb), rop.Nc), dtype=torch.complex128, device=dev)
+    ops.kern.complex_to_real(ops.sp, BlockView(Zc), BlockView(Xr))
+    Yr = torch.empty_like(Xr)
+    rop.apply(BlockView(Xr), BlockView(Yr))
+    got = ops.real_to_complex(Yr)[0].cpu().numpy().T
+    assert np.abs(got - np.stack(ref, axis=1)).max() <= 1e-12 * scale
+
+
+def test_config1_fluxonium_1024_point_sweep():
+    """BASELINE configs[1] at its named size: fluxonium, harmonic basis trunc = 100, 1024-point flux sweep,
+    k = 10.  Every 64th point against the oracle (eigenvalues, subspaces, five channels); all points:
+    agreement with the 17-point reference golden where the grids coincide, orthonormal vectors, the
+    flux -> 1 - flux mirror symmetry of the spectrum and smoothness along the sweep."""
+    cr, lp, oc, ol = cs.fluxonium()
+    cr.set_trunc_nums([100])
+    oc.set_trunc_nums([100])
+    fl = np.arange(1025) / 1024.0
+    res = cr.sweep_diag(10, loop_fluxes={lp: fl[:1024]})
+    ef = res.efreqs.cpu().numpy()
+    assert ef.shape == (1024, 10)
+    decs = ['capacitive', 'inductive', 'quasiparticle', 'cc', 'flux']
+    idx = list(range(0, 1024, 64)) + [1023]
+    _check(res, oc, ol.set_flux, fl[idx], 10, decs, idx=idx)
+    g = np.load(os.path.join(G, 'fluxonium_100.npz'))
+    for j, f in enumerate(g['params'][:-1]):                 # 0, 1/16, ... 15/16 are grid points
+        i = int(round(f * 1024))
+        assert np.max(np.abs(ef[i] - g['efreqs_exact'][j]) / np.abs(g['efreqs_exact'][j])) < 1e-9
+    X = res.evecs
+    gram = X.conj() @ X.transpose(1, 2)
+    assert float((gram - torch.eye(10, device=X.device)).abs().max()) < 1e-10
+    assert np.max(np.abs(ef[1:] - ef[1:][::-1]) / np.abs(ef[1:])) < 1e-9     # E(f) = E(1 - f)
+    assert np.all(np.diff(ef, axis=1) >= -1e-9)
+    assert np.max(np.abs(np.diff(ef, axis=0))) < 0.2
+
+
 def test_config2_bench_path_continuation_at_full_size():
     """The bench path itself: N = 10100, a flux sweep long enough for the four-level continuation
     (cold level, warm starts gathered from solved neighbours, banded two-level preconditioner with

@@ -30,6 +30,17 @@ def test_abi_library_exports_every_declared_symbol():
     assert _lib.load().sqc_error_string(-1).decode().startswith('sqcircuit_b200')
 
 
+def test_loader_refuses_a_library_built_from_other_sources(monkeypatch):
+    """The library carries the hash of the sources it was built from (csrc/buildinfo.cu); the loader
+    compares it with the tree and refuses a stale binary."""
+    from sqcircuit_b200 import _lib
+    assert _lib.load().sqc_source_hash().decode() == _lib.source_hash()
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'source_hash', lambda: '0' * 64)
+    with pytest.raises(_lib.SqcLibraryError, match='stale'):
+        _lib.load()
+
+
 def test_struct_layouts_match_header():
     from sqcircuit_b200 import _lib
     assert ctypes.sizeof(_lib.Block) == 40
@@ -119,6 +130,49 @@ def test_davidson_orchestration_zero_pi():
     res = cr.sweep_diag(10, loop_fluxes={lp: fl})
     assert res.converged and res.iterations < 80
     _check(res, oc, ol.set_flux, fl, 10, ['capacitive', 'inductive', 'quasiparticle', 'charge', 'cc', 'flux'])
+
+
+def test_memory_guard_chunks_the_batch_and_n_eig_limit():
+    """sweep_diag sizes every batched Davidson call from the free device memory (Kernels.free_bytes): with
+    room for two points per call a five-point sweep is solved in three calls, same results; more eigenpairs
+    than the block iteration supports is an error, not a silent truncation."""
+    from sqcircuit_b200 import circuit as cm
+    K = EmulKernels()
+    cr, lp, oc, ol = cs.zero_pi(K)
+    cr.set_trunc_nums([12, 7])
+    oc.set_trunc_nums([12, 7])
+    fl = np.linspace(0.05, 0.45, 5)
+    ref = cr.sweep_diag(4, loop_fluxes={lp: fl}, real=False).efreqs.numpy()
+    Nv, (p, mmax) = cr._operators().N, cm._solver_sizes(4, cr._operators().N)
+    per_point = 16 * Nv * (2 * (mmax + p) + 2 * p + 4) + 16 * (3 * mmax * mmax + 2 * 16 * mmax) + 4096
+    K.free_bytes_value = int(2.5 * per_point / 0.8)
+    assert cm._points_per_chunk(K, Nv, 4) == 2
+    st = []
+    got = cr.sweep_diag(4, loop_fluxes={lp: fl}, real=False, stats=st)
+    assert np.max(np.abs(got.efreqs.numpy() - ref)) < 1e-9 * np.abs(ref).max()
+    assert sum(1 for it, left in st if it == 1) == 3          # three separate solves
+    K.free_bytes_value = 1 << 60
+    with pytest.raises(ValueError, match='at most 14'):
+        cr.sweep_diag(15, loop_fluxes={lp: fl})
+
+
+def test_decide_does_not_converge_on_non_finite_ritz_values():
+    """A wanted Ritz value that came back +inf (dependent basis vectors dropped by the generalised
+    Rayleigh-Ritz) must keep the point unfinished (emulated contract of sqc_davidson_decide; the CUDA
+    kernel is checked against the same case in tests/test_gpu_kernels.py)."""
+    K = EmulKernels()
+    p, k, B = 4, 3, 2
+    i32, f64 = torch.int32, torch.float64
+    theta = torch.tensor([[1.0, 2.0, float('inf'), float('inf')], [1.0, 2.0, 3.0, 4.0]], dtype=f64)
+    st = K.davidson_state(p=p, k=k, mmax=12, ldg=12, tol_rel=1e-9, tol_abs_floor=1e-300,
+                          msz=torch.full((B,), 4, dtype=i32), nact=torch.zeros(B, dtype=i32),
+                          act=torch.zeros((B, p), dtype=i32), restart=torch.zeros(B, dtype=i32),
+                          done=torch.zeros(B, dtype=i32), n_not_done=torch.zeros(1, dtype=i32), theta=theta,
+                          rn2=torch.zeros((B, p), dtype=f64), resmax=torch.zeros(B, dtype=f64),
+                          den_floor=torch.zeros(B, dtype=f64), G=torch.zeros((B, 12, 12), dtype=torch.complex128))
+    K.davidson_decide(st, B)
+    assert st.done.tolist() == [0, 1] and int(st.n_not_done[0]) == 1
+    assert np.isfinite(float(st.den_floor[0]))
 
 
 def test_real_representation_host_logic():
