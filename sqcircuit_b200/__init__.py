@@ -10,6 +10,7 @@ from .elements import Capacitor, Charge, Inductor, Junction, Loop  # noqa: F401
 from .exceptions import CircuitStateError, ModeError  # noqa: F401
 from .settings import get_device, get_engine, get_optim_mode, set_device, set_engine, set_optim_mode  # noqa: F401
 from .sweep import Sweep  # noqa: F401
+from .batch import CircuitBatch  # noqa: F401
 from .autograd import set_max_eigenvector_grad  # noqa: F401
 from .units import (get_unit_cap, get_unit_freq, get_unit_ind, get_unit_JJ, set_unit_cap,  # noqa: F401
                     set_unit_freq, set_unit_ind, set_unit_JJ)

@@ -1,21 +1,22 @@
-"""Autograd through ``Circuit.diag`` (PyTorch engine).
+"""Autograd through ``Circuit.diag`` and the decoherence rates (PyTorch engine).
 
-Mirrors the reference's ``torch_extensions.EigenSolver`` (torch_extensions.py:135-279): the forward
-pass diagonalises on the GPU (detached); the once-differentiable backward uses
+Mirrors the reference's ``torch_extensions`` (torch_extensions.py:135-1016): ``EigenSolver`` (forward:
+diagonalise, detached; once-differentiable backward from
 
     d omega_m / dx = <m| dH/dx |m>                                  (circuit.py:2777-2826)
     d |m> / dx     = sum_{n != m} <n| dH/dx |m> / (omega_m - omega_n + eps) |n>   (circuit.py:2875-2921)
 
-over the computed eigenpairs, with dH/dx of ``Circuit._get_partial_H`` (circuit.py:2704-2775)
-applied matrix-free to the eigenvector block (ladder / diagonal / potential kernels) and the
-k x k matrices <n| dH/dx |m> from the tensor-core Gram kernel.
+over the computed eigenpairs) and ``DecRateCharge / DecRateCC / DecRateFlux`` (second derivatives of the
+transition frequency).  All operator work runs on the GPU and is shared by every element and state
+(``gradients.GradEngine``); ``BatchEigenSolverFn`` does the same for a batch of circuits of one graph in ONE
+batched solve (``batch.CircuitBatch``).  T1-type rates (capacitive, inductive, quasiparticle) are composed from
+torch operations on the eigenvectors like in the reference, with the operators applied matrix-free by
+``LinearOpFn``.
 """
 import numpy as np
 import torch
 
-from . import units as unt
-from .elements import Capacitor, Inductor, Junction, Loop
-from .kernels import BlockView
+from .gradients import GradEngine
 
 EIGENVECTOR_MAX_GRAD = {'n': None}
 
@@ -24,91 +25,12 @@ def set_max_eigenvector_grad(n):
     EIGENVECTOR_MAX_GRAD['n'] = n
 
 
-def gram_blocks(kern, A, Bm):
-    """<A_i | Bm_j> for [1][ka][N] x [1][kb][N] blocks of any size (the tensor-core Gram kernel takes
-    <= 64 left and <= 16 right vectors per call)."""
-    ka, kb = A.shape[1], Bm.shape[1]
-    out = torch.empty((1, ka, kb), dtype=torch.complex128, device=A.device)
-    for r0 in range(0, ka, 64):
-        ra = A[:, r0:r0 + 64].contiguous()
-        for c0 in range(0, kb, 16):
-            cb = Bm[:, c0:c0 + 16].contiguous()
-            tmp = torch.empty((1, ra.shape[1], cb.shape[1]), dtype=torch.complex128, device=A.device)
-            kern.gram(BlockView(ra), BlockView(cb), tmp)
-            out[:, r0:r0 + ra.shape[1], c0:c0 + cb.shape[1]] = tmp
-    return out
-
-
-class PartialH:
-    """dH/dx applied to a block of state vectors [B=1][k][N] for one circuit at one point."""
-
-    def __init__(self, circuit, noise):
-        self.cr = circuit
-        self.nz = noise                 # SweepNoise of the diagonalisation (operators, phases, kernels)
-        self.ops = noise.ops
-        self.kern = noise.kern
-        self.dev = noise.dev
-
-    # --- single-mode operators (circuit.py:1471-1524) -------------------------------------------
-    def _apply_mode_op(self, kind, i, X):
-        ops = self.ops
-        k = np.zeros(ops.M)
-        k[i] = 1.0
-        if kind == 'Q':
-            return self.nz._apply_charge_comb(X, k)
-        return self.nz._apply_pot(X, self.nz._zeros_a(), ops._phi_lin(k))
-
-    def _quadratic(self, kind, A, X):
-        """(1/2 sum_i A_ii O_i^2 + sum_{i<j} A_ij O_i O_j) X  (circuit.py:2649-2702)."""
-        M = self.ops.M
-        Z = [self._apply_mode_op(kind, j, X) for j in range(M)]
-        Y = torch.zeros_like(X)
-        for i in range(M):
-            comb = torch.zeros_like(X)
-            used = False
-            for j in range(i, M):
-                c = 0.5 * A[i, i] if i == j else A[i, j]
-                if c != 0:
-                    comb += c * Z[j]
-                    used = True
-            if used:
-                Y += self._apply_mode_op(kind, i, comb)
-        return Y
-
-    def apply(self, el, X):
-        cr, t, ops = self.cr, self.cr._top, self.ops
-        M = ops.M
-        if isinstance(el, Capacitor):
-            cinv = np.linalg.inv(t.C)
-            A = -t.R.T @ cinv @ t.partial_mats[el] @ cinv @ t.R
-            return self._quadratic('Q', A[:M, :M], X)
-        if isinstance(el, Inductor):
-            A = -t.S.T @ t.partial_mats[el] @ t.S
-            Y = self._quadratic('phi', A[:M, :M], X)
-            for edge, li, b_id in t.ind_keys:
-                if li is el:
-                    phi = self.ops.ext_flux(self.nz.hop.loop_vals, b_id)[0]
-                    coef = -phi / el.si() ** 2 / np.sqrt(unt.hbar) * (unt.Phi0 / 2 / np.pi)
-                    if coef != 0:
-                        Y += coef * self.nz.apply_coupling(X, 'inductive', edge)
-            return Y
-        if isinstance(el, Loop):
-            li_ = t.loops.index(el)
-            g = np.zeros(1 + M)
-            for edge, li, b_id in t.ind_keys:
-                g += (t.B[b_id, li_] / li.si() * unt.Phi0 / np.sqrt(unt.hbar) / 2 / np.pi
-                      * ops._phi_lin(ops._kcoef('inductive', edge)))
-            a = self.nz._zeros_a()
-            for _, jj, b_id, w_id in t.jj_keys:
-                a[:, w_id] += t.B[b_id, li_] * jj.si() * self.nz._phases(b_id) / 2j
-            return self.nz._apply_pot(X, a, g)
-        if isinstance(el, Junction):
-            a = self.nz._zeros_a()
-            for _, jj, b_id, w_id in t.jj_keys:
-                if jj is el:
-                    a[:, w_id] += -self.nz._phases(b_id) / 2
-            return self.nz._apply_pot(X, a, np.zeros(1 + M))
-        raise NotImplementedError(type(el))
+def _engine_of(circuit):
+    """GradEngine of the circuit's last diagonalisation (cached on its SweepResult)."""
+    res = circuit._last
+    if getattr(res, '_grad_engine', None) is None:
+        res._grad_engine = GradEngine(res.noise, [circuit])
+    return res._grad_engine
 
 
 class EigenSolverFn(torch.autograd.Function):
@@ -118,7 +40,7 @@ class EigenSolverFn(torch.autograd.Function):
         circuit._last = res
         ctx.circuit = circuit
         ctx.res = res
-        ctx.elems = list(circuit._parameters.keys())
+        ctx.n_params = len(circuit._parameters)
         ctx.out_shape = element_tensors.shape
         ev = res.evals_rad[0].cpu().to(torch.complex128).unsqueeze(-1)
         return torch.cat([ev, res.evecs[0].cpu()], dim=-1)
@@ -127,27 +49,139 @@ class EigenSolverFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_output):
         res, cr = ctx.res, ctx.circuit
-        nz = res.noise
-        dev = nz.dev
-        k = res.evecs.shape[1]
-        g_val = grad_output[:, 0]
-        g_vec = grad_output[:, 1:].to(dev).contiguous().unsqueeze(0)          # [1][k][N]
-        psi = res.evecs[:1].contiguous()                                       # [1][k][N]
-        w = res.evals_rad[0].cpu().numpy()
-        nmax = EIGENVECTOR_MAX_GRAD['n'] if EIGENVECTOR_MAX_GRAD['n'] is not None else k
-        # <g_m | psi_n>
-        ov = gram_blocks(nz.kern, g_vec, psi)[0].cpu().numpy()                 # ov[m][n]
-        ph = PartialH(cr, nz)
-        grads = []
-        for el in ctx.elems:
-            Y = ph.apply(el, psi)
-            Mx = gram_blocks(nz.kern, psi, Y)[0].cpu().numpy()                 # Mx[n][m] = <n|dH|m>
-            gval = np.sum(np.real(np.diag(Mx)) * np.conj(g_val.numpy()))
-            gvec = 0.0
-            for m in range(min(nmax, k)):
-                for n in range(k):
-                    if n != m:
-                        gvec += Mx[n, m] / (w[m] - w[n] + 1e-12) * ov[m, n]
-            grads.append(float(np.real(gval + gvec)))
-        out = torch.tensor(grads, dtype=torch.float64).view(ctx.out_shape)
-        return out, None, None
+        if getattr(res, '_grad_engine', None) is None:
+            res._grad_engine = GradEngine(res.noise, [cr])
+        eng = res._grad_engine
+        dev = eng.dev
+        g_val = grad_output[:, 0].unsqueeze(0)                                   # [1][k]
+        g_vec = grad_output[:, 1:].to(dev).contiguous().unsqueeze(0)            # [1][k][N]
+        if not bool((g_vec != 0).any()):
+            g_vec = None
+        out = eng.eigensolver_backward(ctx.n_params, g_val, g_vec, EIGENVECTOR_MAX_GRAD['n'])
+        return out[0].cpu().view(ctx.out_shape), None, None
+
+
+class BatchEigenSolverFn(torch.autograd.Function):
+    """Eigenpairs of B circuits of one graph in one batched GPU solve; ``element_tensors`` [B][P] stacks the
+    optimisation parameters of every circuit.  Outputs: eigenvalues [B][k] (rad/s) and eigenvectors [B][k][N],
+    both on the device."""
+
+    @staticmethod
+    def forward(ctx, element_tensors, batch, n_eig):
+        res = batch._solve(n_eig)
+        ctx.batch = batch
+        ctx.res = res
+        ctx.shape = element_tensors.shape
+        ctx.in_device = element_tensors.device
+        return res.evals_rad, res.evecs
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_val, g_vec):
+        res, batch = ctx.res, ctx.batch
+        if getattr(res, '_grad_engine', None) is None:
+            res._grad_engine = GradEngine(res.noise, batch.circuits)
+        eng = res._grad_engine
+        if g_vec is not None and not bool((g_vec != 0).any()):
+            g_vec = None
+        if g_val is None:
+            g_val = torch.zeros_like(res.evals_rad)
+        out = eng.eigensolver_backward(ctx.shape[1], g_val, g_vec, EIGENVECTOR_MAX_GRAD['n'])
+        return out.to(ctx.in_device).view(ctx.shape), None, None
+
+
+class LinearOpFn(torch.autograd.Function):
+    """Y = O X for a Hermitian operator O applied matrix-free on the GPU to a [k][N] block of (CPU or device)
+    state vectors; backward: grad_X = O grad_Y.  ``apply_fn`` maps a device block [1][k][N] to O times it."""
+
+    @staticmethod
+    def forward(ctx, X, apply_fn, dev):
+        ctx.apply_fn, ctx.dev, ctx.in_dev = apply_fn, dev, X.device
+        Y = apply_fn(X.detach().to(dev).contiguous().unsqueeze(0))[0]
+        return Y.to(X.device)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gY):
+        gX = ctx.apply_fn(gY.to(ctx.dev).contiguous().unsqueeze(0))[0]
+        return gX.to(ctx.in_dev), None, None
+
+
+def operator_inner_product(state_m, apply_fn, state_n, dev):
+    """<m| O |n> with autograd through both states (functions.py operator_inner_product)."""
+    Y = LinearOpFn.apply(state_n.unsqueeze(0), apply_fn, dev)[0]
+    return torch.sum(state_m.conj() * Y)
+
+
+class _DecRateFn(torch.autograd.Function):
+    """Common wrapper of the three dephasing channels (torch_extensions.py:620-657, 789-827, 979-1016):
+    forward = the rate of the NumPy path, backward = grad_output x d rate / d element."""
+    kind = ''
+
+    @staticmethod
+    def _run(ctx, cls, circuit_parameters, circuit, states):
+        rate = circuit._last.dec_rate(cls.kind, states)[0]
+        ctx.circuit, ctx.states, ctx.shape = circuit, tuple(states), circuit_parameters.shape
+        return torch.as_tensor(float(rate), dtype=torch.float64)
+
+    @staticmethod
+    def _back(ctx, cls, grad_output):
+        eng = _engine_of(ctx.circuit)
+        n = len(ctx.circuit._parameters)
+        g = getattr(eng, 'grad_dec_' + cls.kind)(ctx.states, n)[0].cpu()
+        return (grad_output * g).view(ctx.shape), None, None
+
+
+class DecRateCharge(_DecRateFn):
+    kind = 'charge'
+
+    @staticmethod
+    def forward(ctx, circuit_parameters, circuit, states):
+        return _DecRateFn._run(ctx, DecRateCharge, circuit_parameters, circuit, states)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        return _DecRateFn._back(ctx, DecRateCharge, grad_output)
+
+
+class DecRateCC(_DecRateFn):
+    kind = 'cc'
+
+    @staticmethod
+    def forward(ctx, circuit_parameters, circuit, states):
+        return _DecRateFn._run(ctx, DecRateCC, circuit_parameters, circuit, states)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        return _DecRateFn._back(ctx, DecRateCC, grad_output)
+
+
+class DecRateFlux(_DecRateFn):
+    kind = 'flux'
+
+    @staticmethod
+    def forward(ctx, circuit_parameters, circuit, states):
+        return _DecRateFn._run(ctx, DecRateFlux, circuit_parameters, circuit, states)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        return _DecRateFn._back(ctx, DecRateFlux, grad_output)
+
+
+def _params(circuit):
+    return torch.stack(circuit.parameters) if circuit._parameters else torch.tensor([])
+
+
+def dec_rate_charge_torch(circuit, states):
+    return DecRateCharge.apply(_params(circuit), circuit, states)
+
+
+def dec_rate_cc_torch(circuit, states):
+    return DecRateCC.apply(_params(circuit), circuit, states)
+
+
+def dec_rate_flux_torch(circuit, states):
+    return DecRateFlux.apply(_params(circuit), circuit, states)

@@ -535,12 +535,133 @@ class Circuit:
             raise CircuitStateError('Please diagonalize the circuit first.')
         if ctype not in ('capacitive', 'inductive'):
             raise ValueError("The coupling type must be either 'capacitive' or 'inductive'.")
+        if get_optim_mode():
+            return self._matrix_elements_torch(ctype, nodes, states)
         return complex(self._last.matrix_elements(ctype, nodes, states)[0])
 
     def dec_rate(self, dec_type, states, total=True):
         if self._last is None:
             raise CircuitStateError('Please diagonalize the circuit first.')
+        if get_optim_mode():
+            return self._dec_rate_torch(dec_type, states, total)
         return float(self._last.dec_rate(dec_type, states, total)[0])
+
+    # ---- PyTorch engine: rates as differentiable tensors (circuit.py:2529-2647 in optim mode) -------------
+    def _inner_torch(self, states, apply_fn):
+        from .autograd import operator_inner_product
+        return operator_inner_product(self._evecs[states[0]], apply_fn, self._evecs[states[1]], self._last.noise.dev)
+
+    def _matrix_elements_torch(self, ctype, nodes, states):
+        """<m| coupling_op |n>: the node-to-mode coefficients K are torch expressions of the element values
+        (K = C^-1 R depends on the capacitances, circuit.py:2356-2393), the mode operators are constants."""
+        nz = self._last.noise
+        ops = nz.ops
+        top = self._top
+        if ctype == 'capacitive':
+            K = torch.linalg.inv(self._C_torch()) @ torch.as_tensor(np.real(top.R), dtype=torch.float64)
+        else:
+            K = torch.as_tensor(np.real(top.S), dtype=torch.float64)
+        n1, n2 = nodes
+        if 0 in nodes:
+            row = K[n1 + n2 - 1, :]
+        elif ctype == 'capacitive':
+            row = K[n2 - 1, :] - K[n1 - 1, :]
+        else:
+            row = K[n1 - 1, :] - K[n2 - 1, :]
+        out = 0
+        for i in range(ops.M):
+            unit = np.zeros((1, ops.M))
+            unit[0, i] = 1.0
+            if ctype == 'capacitive':
+                fn = lambda X, unit=unit: nz._apply_charge_comb(X, unit)
+            else:
+                fn = lambda X, unit=unit: nz._apply_pot(X, nz._zeros_a(), ops.phi_lin_b(unit))
+            out = out + row[i] * self._inner_torch(states, fn)
+        return out
+
+    def _C_torch(self):
+        """Capacitance matrix as a torch expression of the element tensors (circuit.py:743-835)."""
+        from .topology import edge_matrix
+        n = self._top.n_nodes
+        Cm = torch.zeros((n, n), dtype=torch.float64)
+        for edge, els in self.elements.items():
+            em = torch.as_tensor(edge_matrix(edge, n), dtype=torch.float64)
+            for el in els:
+                cap = el if isinstance(el, Capacitor) else el.cap
+                Cm = Cm + cap.get_value() * em
+        return Cm
+
+    def _dec_rate_torch(self, dec_type, states, total=True):
+        from . import autograd as ag
+        from .noise import ENV
+        nz = self._last.noise
+        ops, t = nz.ops, self._top
+        omega1, omega2 = self._efreqs[states[0]], self._efreqs[states[1]]
+        omega = torch.abs(omega2 - omega1)
+        decay = torch.zeros((), dtype=torch.float64)
+        alpha = unt.hbar * omega / (unt.k_B * ENV['T'])
+        if float(alpha.detach()) > 709:
+            down, up = 2, 0
+        else:
+            down = 1 + 1 / torch.tanh(alpha / 2)
+            up = down * torch.exp(-alpha)
+        if not total:
+            tempS = down if states[0] > states[1] else up
+        else:
+            tempS = down + up
+        if dec_type == 'capacitive':
+            for edge, els in self.elements.items():
+                for el in els:
+                    cap = el if isinstance(el, Capacitor) else el.cap
+                    if cap.Q:
+                        me = self._matrix_elements_torch('capacitive', edge, states)
+                        decay = decay + tempS * cap.get_value() / cap.Q(omega) * torch.abs(me) ** 2
+        elif dec_type == 'inductive':
+            for edge, el, b_id in t.ind_keys:
+                Q = el.Q(omega, ENV['T'])
+                if np.isnan(float(Q.detach()) if isinstance(Q, torch.Tensor) else float(Q)):
+                    continue
+                # the stored 'ind_hamil' operator of the reference is a constant (numpy coefficients)
+                fn = lambda X, edge=edge: nz.apply_coupling(X, 'inductive', edge)
+                decay = decay + tempS / Q / el.get_value() * torch.abs(self._inner_torch(states, fn)) ** 2
+        elif dec_type == 'quasiparticle':
+            for _, el, b_id, w_id in t.jj_keys:
+                Y = el.Y(omega, ENV['T'])
+                if np.isnan(float(Y.detach()) if isinstance(Y, torch.Tensor) else float(Y)):
+                    continue
+                # circuit.py:1899-1936: sin_half = (e^{i phi/2} root_exp - h.c.) / 2i with phi a torch
+                # expression of the loop values; split into the cos(phi/2) and sin(phi/2) parts
+                phi = self._ext_flux_torch(b_id)
+                fc = lambda X, w_id=w_id: self._apply_half(nz, X, w_id, 0.5 / 1j)       # (root_exp - h.c.) / 2i
+                fs = lambda X, w_id=w_id: self._apply_half(nz, X, w_id, 0.5)            # (root_exp + h.c.) / 2
+                me = torch.cos(phi / 2) * self._inner_torch(states, fc) + torch.sin(phi / 2) * self._inner_torch(states, fs)
+                decay = decay + tempS * Y * omega * el.get_value() * unt.hbar * torch.abs(me) ** 2
+        elif dec_type == 'charge':
+            decay = decay + ag.dec_rate_charge_torch(self, states)
+        elif dec_type == 'cc':
+            decay = decay + ag.dec_rate_cc_torch(self, states)
+        elif dec_type == 'flux':
+            decay = decay + ag.dec_rate_flux_torch(self, states)
+        else:
+            raise ValueError(f'The decoherence type {dec_type} is not supported.')
+        return decay
+
+    @staticmethod
+    def _apply_half(nz, X, w_id, coef):
+        """(coef root_exp_w + conj(coef) root_exp_w^dag) X: half-angle junction operator without flux phase."""
+        a = nz._zeros_a()
+        a[:, w_id] = coef
+        return nz._apply_pot(X, a, np.zeros((1, 1 + nz.ops.M)), etab=nz.ops.etab_half(),
+                             shift=np.zeros_like(nz.ops.shift))
+
+    def _ext_flux_torch(self, b_id):
+        """phi_ext at inductive element b_id as a torch expression of the loop values (circuit.py:1759-1786)."""
+        phi = torch.zeros((), dtype=torch.float64)
+        for li, lp in enumerate(self.loops):
+            v = lp.internal_value
+            v = v if isinstance(v, torch.Tensor) else torch.as_tensor(float(v), dtype=torch.float64)
+            phi = phi + v * float(self._top.B[b_id, li])
+        return phi
 
     def charge_op(self, mode, basis='original'):
         """Charge operator of a mode as a dense matrix (circuit.py:1831-1875); host-side helper for

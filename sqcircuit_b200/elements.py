@@ -19,10 +19,48 @@ def _np(x):
     return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x
 
 
+class _K0e(torch.autograd.Function):
+    """exp(x) K0(x) on tensors, evaluated with scipy like the NumPy engine; d/dx = exp(x) (K0 - K1)
+    (torch's own scaled_modified_bessel_k0 has no usable derivative; functions.py:141-156)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.as_tensor(kve(0, _np(x)), dtype=torch.float64)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x = _np(ctx.saved_tensors[0])
+        return g * torch.as_tensor(kve(0, x) - kve(1, x), dtype=torch.float64)
+
+
+class _LogK0(torch.autograd.Function):
+    """log K0(x) = log(exp(x) K0(x)) - x on tensors; d/dx = -K1 / K0 (functions.py:159-186)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        xn = _np(x)
+        return torch.as_tensor(np.log(kve(0, xn)) - xn, dtype=torch.float64)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x = _np(ctx.saved_tensors[0])
+        return g * torch.as_tensor(-kve(1, x) / kve(0, x), dtype=torch.float64)
+
+
 def _k0e(x):
     if isinstance(x, torch.Tensor):
-        return torch.special.scaled_modified_bessel_k0(x)
+        return _K0e.apply(x)
     return kve(0, x)
+
+
+def _log_k0(x):
+    if isinstance(x, torch.Tensor):
+        return _LogK0.apply(x)
+    return np.log(kve(0, x)) - x
 
 
 def _exp(x):
@@ -192,8 +230,7 @@ class Inductor(_Valued):
 
     @staticmethod
     def _default_q_ind(omega, T):
-        def log_k0(x):
-            return _log(_k0e(x)) - x
+        log_k0 = _log_k0
 
         def log_sinh(x):
             return x + _log(1 - _exp(-2 * x)) - math.log(2)

@@ -46,27 +46,29 @@ class SweepNoise:
     def _apply_pot(self, X, a, g, etab=None, shift=None):
         ops = self.ops
         Y = torch.empty_like(X)
-        g = np.broadcast_to(g, (self.B, 1 + ops.M))
+        g = np.broadcast_to(np.asarray(g, dtype=float).reshape(-1, 1 + ops.M), (self.B, 1 + ops.M))
         ops.apply_potential_op(BlockView(X), BlockView(Y), ops.to_device(a, torch.complex128),
                                ops.to_device(g, torch.float64), etab=etab, shift=shift)
         return Y
 
     def _apply_charge_comb(self, X, k):
-        """Y = (sum_i k_i Q_i) X  with Q_i of circuit.py:1471-1497 (normalised by sqrt(hbar))."""
+        """Y = (sum_i k_i Q_i) X  with Q_i of circuit.py:1471-1497 (normalised by sqrt(hbar)); k: [M], or one
+        row per point [B][M] (batched circuits)."""
         ops = self.ops
         Y = torch.zeros_like(X)
         ng = self.hop.ng
-        Bn = ng.shape[0]
+        k = np.asarray(k, dtype=float).reshape(-1, ops.M)
+        Bn = max(ng.shape[0], k.shape[0])
         c = 2 * unt.e / np.sqrt(unt.hbar)
         dvec = torch.zeros((Bn,) + tuple(ops.dims), dtype=torch.float64, device=self.dev)
         any_charge = False
         for i in range(ops.M):
-            if ops.harm[i] or k[i] == 0:
+            if ops.harm[i] or not np.any(k[:, i] != 0):
                 continue
             any_charge = True
             nmax = (ops.dims[i] - 1) // 2
-            vals = (np.arange(-nmax, nmax + 1)[None, :] - ng[:, i:i + 1]) * (k[i] * c)
-            shape = [Bn] + [1] * ops.M
+            vals = (np.arange(-nmax, nmax + 1)[None, :] - ng[:, i:i + 1]) * (k[:, i:i + 1] * c)
+            shape = [vals.shape[0]] + [1] * ops.M
             shape[1 + i] = ops.dims[i]
             dvec += torch.as_tensor(vals, dtype=torch.float64, device=self.dev).reshape(shape)
         first = True
@@ -74,21 +76,22 @@ class SweepNoise:
             self.kern.diag_mul(BlockView(X), BlockView(Y), dvec.reshape(Bn, ops.N).contiguous(), False)
             first = False
         for i in range(ops.M):
-            if not ops.harm[i] or ops.dims[i] == 1 or k[i] == 0:
+            if not ops.harm[i] or ops.dims[i] == 1 or not np.any(k[:, i] != 0):
                 continue
-            qzp = -1j * np.sqrt(0.5 / ops.Z[i]) * k[i]          # Q = qzp (a - a^dag)
-            cdn = torch.full((self.B,), qzp, dtype=torch.complex128, device=self.dev)
-            cup = torch.full((self.B,), -qzp, dtype=torch.complex128, device=self.dev)
+            qzp = -1j * np.sqrt(0.5 / ops.Zb[:, i]) * k[:, i]          # Q = qzp (a - a^dag), per point
+            qzp = np.broadcast_to(qzp, (self.B,))
+            cdn = ops.to_device(qzp, torch.complex128)
+            cup = ops.to_device(-qzp, torch.complex128)
             self.kern.ladder_apply(ops.sp, i, cdn, cup, BlockView(X), BlockView(Y), not first)
             first = False
         return Y
 
     # ---- operators of the reference ----------------------------------------------------------
     def apply_coupling(self, X, ctype, nodes):
-        k = self.ops._kcoef(ctype, nodes)
+        k = self.ops.kcoef_b(ctype, nodes)
         if ctype == 'capacitive':
             return self._apply_charge_comb(X, k)
-        return self._apply_pot(X, self._zeros_a(), self.ops._phi_lin(k))
+        return self._apply_pot(X, self._zeros_a(), self.ops.phi_lin_b(k))
 
     def apply_junction_fn(self, X, kind, w_id, b_id, weight=1.0):
         """cos / sin / sin_half operator of one junction (circuit.py:1809-1825)."""

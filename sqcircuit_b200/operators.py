@@ -36,12 +36,21 @@ class CircuitOperators:
     use_real = True       # class-level switch: real representation for zero-gate-charge sweeps
 
     def __init__(self, kern, topo, dims, transform_impl=0):
+        """``topo``: the transformed Topology of one circuit, or a list of them -- circuits of ONE graph (same
+        edges, element kinds, loops, truncation) with different element values, which then play the role of
+        sweep points: point b uses the tables of circuit b (``nb`` = number of circuits)."""
+        topos = list(topo) if isinstance(topo, (list, tuple)) else [topo]
+        topo = topos[0]
         self.kern = kern
         self.device = kern.dev
+        self._scratch = {}
+        self._keep = []
+        self.topos = topos
+        self.nb = len(topos)
         self.topo = topo
         self.dims = [int(d) for d in dims]
         self.M = len(dims)
-        self.harm = [bool(topo.omega[i] != 0) for i in range(self.M)]
+        self.harm = [bool(np.real(topo.omega[i]) != 0) for i in range(self.M)]
         self.N = int(np.prod(self.dims))
         self.sp = make_space(self.dims, self.harm)
         self.impl = transform_impl
@@ -56,25 +65,43 @@ class CircuitOperators:
             self.V[i] = Vi
             lam[self.toff[i]:self.toff[i] + self.dims[i]] = li
         self.lam = lam
-        # impedance / zero-point flux of the harmonic modes (circuit.py:1455-1469, 1585-1601)
-        self.Z = np.zeros(self.M)
-        self.phi_zp = np.zeros(self.M)
-        for i in range(self.M):
-            if self.harm[i]:
-                self.Z[i] = np.sqrt(topo.cInvTrans[i, i] / topo.lTrans[i, i])
-                self.phi_zp[i] = (2 * np.pi / unt.Phi0) * np.sqrt(unt.hbar / 2 * self.Z[i])
         # junction terms: one per row of W (junctions on the same edge share the operator)
         self.T = topo.wTrans.shape[0] if len(topo.W) else 0
-        self.s = np.zeros((max(self.T, 1), self.M))
-        self.shift = np.zeros((max(self.T, 1), self.M), dtype=int)
-        for t in range(self.T):
+        nt = max(self.T, 1)
+        # per circuit: impedance / zero-point flux of the harmonic modes (circuit.py:1455-1469, 1585-1601),
+        # displacement amplitudes s[t][i] of the junction terms; shared: the charge shifts
+        self.Zb = np.zeros((self.nb, self.M))
+        self.phi_zp_b = np.zeros((self.nb, self.M))
+        self.s_b = np.zeros((self.nb, nt, self.M))
+        self.shift = np.zeros((nt, self.M), dtype=int)
+        for c, tp in enumerate(topos):
+            if [bool(np.real(tp.omega[i]) != 0) for i in range(self.M)] != self.harm or \
+                    (tp.wTrans.shape[0] if len(tp.W) else 0) != self.T:
+                raise ValueError('the circuits of a batch must share one graph (same harmonic / charge modes '
+                                 'and junction terms)')
+            shift = np.zeros((nt, self.M), dtype=int)
             for i in range(self.M):
-                w = topo.wTrans[t, i]
                 if self.harm[i]:
-                    self.s[t, i] = self.phi_zp[i] * w if self.dims[i] > 1 else 0.0
-                else:
-                    self.shift[t, i] = int(np.sign(w))
-        self.etab = self._tables(self.s)
+                    self.Zb[c, i] = np.sqrt(np.real(tp.cInvTrans[i, i]) / np.real(tp.lTrans[i, i]))
+                    self.phi_zp_b[c, i] = (2 * np.pi / unt.Phi0) * np.sqrt(unt.hbar / 2 * self.Zb[c, i])
+            for t in range(self.T):
+                for i in range(self.M):
+                    w = float(np.real(tp.wTrans[t, i]))
+                    if self.harm[i]:
+                        self.s_b[c, t, i] = self.phi_zp_b[c, i] * w if self.dims[i] > 1 else 0.0
+                    else:
+                        shift[t, i] = int(np.sign(w))
+            if c == 0:
+                self.shift = shift
+            elif not np.array_equal(shift, self.shift):
+                raise ValueError('the circuits of a batch must share the charge shifts of their junction terms')
+        self.Z, self.phi_zp, self.s = self.Zb[0], self.phi_zp_b[0], self.s_b[0]
+        # element values and flux distribution per circuit (same element order in every circuit)
+        self.EJ_b = np.array([[el.si() for _, el, _, _ in tp.jj_keys] for tp in topos]).reshape(self.nb, -1)
+        self.Lind_b = np.array([[el.si() for _, el, _ in tp.ind_keys] for tp in topos]).reshape(self.nb, -1)
+        self.Bmat_b = np.stack([np.asarray(tp.B, dtype=float).reshape(-1, max(len(tp.loops), 1))
+                                if len(tp.loops) else np.zeros((0, 1)) for tp in topos])
+        self.etab = self._tables(self.s_b)
         self._etab_half = None
         # parity halves of the x basis for the fused kernel (one harmonic x one charge mode)
         self.fused = (self.M == 2 and self.harm[0] and not self.harm[1] and self.dims[0] > 1
@@ -84,20 +111,20 @@ class CircuitOperators:
             he, ho = (self.dims[0] + 1) // 2, self.dims[0] // 2
             self.Ve = Vfull[0::2, :he].contiguous()
             self.Vo = Vfull[1::2, :ho].contiguous()
-        self._scratch = {}
-        self._keep = []
 
     # ---- tables --------------------------------------------------------------------------
     def _tables(self, s):
+        """Phase tables exp(i s lam) of every junction term: [nb][T][tlen] for s of shape [nb][T][M]."""
         nt = max(self.T, 1)
-        etab = torch.empty((1, nt, self.tlen), dtype=torch.complex128, device=self.device)
-        sd = torch.as_tensor(s, dtype=torch.float64, device=self.device).reshape(1, nt, self.M).contiguous()
+        s = np.asarray(s, dtype=float).reshape(-1, nt, self.M)
+        etab = torch.empty((s.shape[0], nt, self.tlen), dtype=torch.complex128, device=self.device)
+        sd = torch.as_tensor(s, dtype=torch.float64, device=self.device).contiguous()
         self.kern.phase_tables(self.sp, nt, self.lam, sd, etab)
         return etab
 
     def etab_half(self):
         if self._etab_half is None:
-            self._etab_half = self._tables(self.s / 2)
+            self._etab_half = self._tables(self.s_b / 2)
         return self._etab_half
 
     # ---- per-sweep-point coefficients (host, tiny) ------------------------------------------
@@ -105,78 +132,93 @@ class CircuitOperators:
         """phi_ext at inductive element b_id for every sweep point (circuit.py:1759-1786)."""
         if not self.topo.loops:
             return np.zeros(loop_vals.shape[0])
-        return loop_vals @ self.topo.B[b_id, :]
+        return np.sum(loop_vals * self.Bmat_b[:, b_id, :], axis=1)
+
+    def kcoef_b(self, ctype, nodes):
+        """Node-to-mode coefficients of a coupling operator, one row per circuit [nb][M] (circuit.py:2356-2393;
+        like the reference, the first n columns of the full transformation matrix are used)."""
+        key = ('kcoef', ctype, tuple(nodes))
+        if key in self._scratch:
+            return self._scratch[key]
+        out = np.zeros((self.nb, self.M))
+        n1, n2 = nodes
+        for c, t in enumerate(self.topos):
+            K = np.linalg.inv(t.C) @ t.R if ctype == 'capacitive' else t.S
+            if 0 in nodes:
+                row = K[n1 + n2 - 1, :]
+            elif ctype == 'capacitive':
+                row = K[n2 - 1, :] - K[n1 - 1, :]
+            else:
+                row = K[n1 - 1, :] - K[n2 - 1, :]
+            out[c] = np.real(row[:self.M])
+        self._scratch[key] = out
+        return out
 
     def _kcoef(self, ctype, nodes):
-        """Node-to-mode coefficients of a coupling operator (circuit.py:2356-2393; like the
-        reference, the first n columns of the full transformation matrix are used)."""
-        t = self.topo
-        K = np.linalg.inv(t.C) @ t.R if ctype == 'capacitive' else t.S
-        n1, n2 = nodes
-        if 0 in nodes:
-            row = K[n1 + n2 - 1, :]
-        elif ctype == 'capacitive':
-            row = K[n2 - 1, :] - K[n1 - 1, :]
-        else:
-            row = K[n1 - 1, :] - K[n2 - 1, :]
-        return row[:self.M]
+        return self.kcoef_b(ctype, nodes)[0]
 
     def hamiltonian_coeffs(self, loop_vals):
         """a[b][t], g[b][1+M] of the Hamiltonian's potential part for loop values [B][nloops]."""
         B = loop_vals.shape[0]
         a = np.zeros((B, max(self.T, 1)), dtype=complex)
-        for _, el, b_id, w_id in self.topo.jj_keys:
-            a[:, w_id] += -el.si() / 2 * np.exp(1j * self.ext_flux(loop_vals, b_id))
+        for j, (_, el, b_id, w_id) in enumerate(self.topo.jj_keys):
+            a[:, w_id] += -self.EJ_b[:, j] / 2 * np.exp(1j * self.ext_flux(loop_vals, b_id))
         g = np.zeros((B, 1 + self.M))
-        for edge, el, b_id in self.topo.ind_keys:
-            coef = (1 / el.si()) * self.ext_flux(loop_vals, b_id) * (unt.Phi0 / 2 / np.pi) / np.sqrt(unt.hbar)
-            g += coef[:, None] * self._phi_lin(self._kcoef('inductive', edge))[None, :]
+        for j, (edge, el, b_id) in enumerate(self.topo.ind_keys):
+            coef = (1 / self.Lind_b[:, j]) * self.ext_flux(loop_vals, b_id) * (unt.Phi0 / 2 / np.pi) / np.sqrt(unt.hbar)
+            g = g + coef[:, None] * self.phi_lin_b(self.kcoef_b('inductive', edge))
         return a, g
 
-    def _phi_lin(self, k):
-        """Linear x-basis coefficients [1+M] of sum_i k_i phi_i (circuit.py:1499-1524):
-        phi_i = sqrt(Z_i/2)(a+a^dag) for harmonic modes (0 when truncated to one level),
-        identity for charge modes."""
-        g = np.zeros(1 + self.M)
+    def phi_lin_b(self, k):
+        """Linear x-basis coefficients [nb][1+M] of sum_i k_i phi_i for k [nb or 1][M] (circuit.py:1499-1524):
+        phi_i = sqrt(Z_i/2)(a+a^dag) for harmonic modes (0 when truncated to one level), identity for charge
+        modes."""
+        k = np.asarray(k, dtype=float).reshape(-1, self.M)
+        g = np.zeros((max(k.shape[0], self.nb), 1 + self.M))
         for i in range(self.M):
             if self.harm[i]:
                 if self.dims[i] > 1:
-                    g[1 + i] = k[i] * np.sqrt(self.Z[i] / 2)
+                    g[:, 1 + i] = k[:, i] * np.sqrt(self.Zb[:, i] / 2)
             else:
-                g[0] += k[i]
+                g[:, 0] += k[:, i]
         return g
 
+    def _phi_lin(self, k):
+        return self.phi_lin_b(k)[0]
+
     def lc_params(self, ng):
-        """omega, q, ng arrays for sqc_lc_diagonal (circuit.py:1716-1757)."""
-        t = self.topo
+        """omega [nb][M], q [nb][M][M], ng arrays for sqc_lc_diagonal (circuit.py:1716-1757)."""
         c2 = (2 * unt.e) ** 2 / unt.hbar
-        q = np.zeros((self.M, self.M))
-        for i in range(self.M):
-            for j in range(i, self.M):
-                cij = t.cInvTrans[i, j]
-                if i == j:
-                    if not self.harm[i]:
-                        q[i, i] = c2 * cij / 2
-                elif cij != 0:
-                    small = abs(cij) <= 1e-10 * np.sqrt(abs(t.cInvTrans[i, i] * t.cInvTrans[j, j]))
-                    if self.harm[i] or self.harm[j]:
-                        if not small and self.dims[i] > 1 and self.dims[j] > 1:
-                            raise NotImplementedError(
-                                'capacitive cross coupling that involves a harmonic mode survived the '
-                                'mode transformation; not supported by the matrix-free operator')
-                    else:
-                        q[i, j] = c2 * cij
-        omega = np.array([t.omega[i] if self.harm[i] else 0.0 for i in range(self.M)])
+        q = np.zeros((self.nb, self.M, self.M))
+        omega = np.zeros((self.nb, self.M))
+        for c, t in enumerate(self.topos):
+            for i in range(self.M):
+                if self.harm[i]:
+                    omega[c, i] = np.real(t.omega[i])
+                for j in range(i, self.M):
+                    cij = float(np.real(t.cInvTrans[i, j]))
+                    if i == j:
+                        if not self.harm[i]:
+                            q[c, i, i] = c2 * cij / 2
+                    elif cij != 0:
+                        small = abs(cij) <= 1e-10 * np.sqrt(abs(t.cInvTrans[i, i] * t.cInvTrans[j, j]))
+                        if self.harm[i] or self.harm[j]:
+                            if not small and self.dims[i] > 1 and self.dims[j] > 1:
+                                raise NotImplementedError(
+                                    'capacitive cross coupling that involves a harmonic mode survived the '
+                                    'mode transformation; not supported by the matrix-free operator')
+                        else:
+                            q[c, i, j] = c2 * cij
         return omega, q, np.asarray(ng, dtype=float).reshape(-1, self.M)
 
     def lc_diagonal(self, ng):
         omega, q, ng = self.lc_params(ng)
-        B = ng.shape[0]
+        B = max(ng.shape[0], self.nb)
         dev = self.device
         out = torch.empty((B, self.N), dtype=torch.float64, device=dev)
         om = torch.as_tensor(np.broadcast_to(omega, (B, self.M)).copy(), dtype=torch.float64, device=dev)
         qq = torch.as_tensor(np.broadcast_to(q, (B, self.M, self.M)).copy(), dtype=torch.float64, device=dev)
-        ngd = torch.as_tensor(ng, dtype=torch.float64, device=dev).contiguous()
+        ngd = torch.as_tensor(np.broadcast_to(ng, (B, self.M)).copy(), dtype=torch.float64, device=dev)
         self.kern.lc_diagonal(self.sp, om, qq, ngd, out)
         return out
 
@@ -241,7 +283,7 @@ class CircuitOperators:
     def supports_real(self, ng):
         """True when H(b) can be solved in the real representation: one harmonic x one charge mode
         (the fused layout), zero gate charge on the charge mode, sizes the kernel accepts."""
-        if not (self.fused and self.use_fused and self.use_real):
+        if not (self.fused and self.use_fused and self.use_real and self.nb == 1):
             return False
         ng = np.asarray(ng, dtype=float).reshape(-1, self.M)
         if np.any(ng[:, 1] != 0.0):
@@ -310,7 +352,8 @@ class HamiltonianOperator:
         self.ops.apply_potential_op(X, Y, self.a, self.g, fock_diag=self.diag)
 
     def supports_lowblock(self):
-        return bool(self.ops.fused and self.ops.T >= 1)
+        # (the low block is assembled from one set of displacement tables: single-circuit sweeps only)
+        return bool(self.ops.fused and self.ops.T >= 1 and self.ops.nb == 1)
 
     def _auto_lowblock_group(self, max_group=8, budget=0.05):
         """Largest power-of-two group whose members differ by less than ``budget`` (relative) in the

@@ -244,7 +244,64 @@ def part_zeropi_big():
                         efreqs_exact=np.array(ws), H_cols=np.array(cols), H_cols_at_0p31=Hc)
 
 
-PARTS = dict(zeropi=part_zeropi, fluxonium=part_fluxonium, transmon=part_transmon,
+
+# ---- gradients from the reference's PyTorch engine (torch_extensions.py) -------------------------------------
+from grad_cases import grad_circuits, discovery_values  # noqa: E402,F401  (shared with the tests)
+
+
+def part_grad():
+    """Values and gradients from the reference's PyTorch engine: transition frequency, every decoherence
+    channel the circuit has (T1 channels through the eigenvector backward, dephasing channels through
+    DecRateCharge / DecRateCC / DecRateFlux), all eigenfrequencies of the 4-mode circuits."""
+    import torch
+    from SQcircuit.settings import set_optim_mode
+    set_optim_mode(True)
+    rec = {}
+    cases = {'fluxonium': ['capacitive', 'inductive', 'quasiparticle', 'cc', 'flux'],
+             'flux_transmon': ['capacitive', 'charge', 'cc', 'flux'],
+             'zeropi': ['inductive', 'charge', 'cc', 'flux']}   # (capacitive: the reference's sp_add fails on sparse tensors with this torch for n > 1)
+    for kind, decs in cases.items():
+        cr, els, trunc, k = grad_circuits(sq, kind)
+        cr.set_trunc_nums(trunc)
+        if kind == 'flux_transmon':
+            cr.set_charge_offset(1, 0.17)
+        names = list(els)
+
+        def grads():
+            g = np.array([0.0 if els[n].grad is None else float(els[n].grad) for n in names])
+            cr.zero_grad()
+            return g
+        ef, _ = cr.diag(k)
+        rec[kind + '/names'] = np.array(names)
+        rec[kind + '/efreqs'] = ef.detach().numpy()
+        (ef[1] - ef[0]).backward()
+        rec[kind + '/grad_f10'] = grads()
+        for d in decs:
+            cr.diag(k)
+            r = cr.dec_rate(d, (0, 1))
+            r.backward()
+            rec[kind + '/dec_' + d] = float(r)
+            rec[kind + '/grad_dec_' + d] = grads()
+    for idx in range(3):
+        kind = 'discovery%d' % idx
+        cr, els, trunc, k = grad_circuits(sq, kind)
+        cr.set_trunc_nums(trunc)
+        names = list(els)
+        rec[kind + '/names'] = np.array(names)
+        G = []
+        for m in range(k):
+            ef, _ = cr.diag(k)
+            if m == 0:
+                rec[kind + '/efreqs'] = ef.detach().numpy()
+            ef[m].backward()
+            G.append([0.0 if els[n].grad is None else float(els[n].grad) for n in names])
+            cr.zero_grad()
+        rec[kind + '/grad_efreqs'] = np.array(G)           # [k][P]
+    set_optim_mode(False)
+    np.savez_compressed(os.path.join(HERE, 'gradients.npz'), **rec)
+
+
+PARTS = dict(grad=part_grad, zeropi=part_zeropi, fluxonium=part_fluxonium, transmon=part_transmon,
              coupled=part_coupled, trt=part_trt, zeropi_big=part_zeropi_big)
 
 if __name__ == '__main__':
