@@ -10,8 +10,8 @@ every point plus the six T1/Tphi decoherence channels for the (1, 0) transition.
         algorithm (oracle port: scipy CSR Hamiltonian + ARPACK eigs 'SR', circuit.py:1938-1986)
         on the host cores, a bounded sample of the same sweep per step.
 
-  --config {zeropi4096 (default, the headline), fluxonium1024, trt1e5}   the other named circuits of
-        BASELINE.json (configs[1], configs[3]); same JSON line, same arms.
+  --config {zeropi4096 (default, the headline), fluxonium1024, trt1e5, discovery512}   the other named
+        circuits of BASELINE.json (configs[1], configs[3], configs[4]); same JSON line, same arms.
 Multi-GPU (torchrun): weak scaling with IDENTICAL work per GPU (`value`, `per_rank`), and in the same
 invocation the strong scaling of the one named sweep split over the GPUs (`strong`).
 
@@ -172,9 +172,86 @@ class TransmonResonatorTransmon(Workload):
         return {'charge_offsets': {self.modes[0]: prm[:, 0], self.modes[1]: prm[:, 1]}}
 
 
-WORKLOADS = {w.name: w for w in (ZeroPi, Fluxonium, TransmonResonatorTransmon)}
+class Discovery(Workload):
+    """BASELINE configs[4]: qubit-discovery batch -- 512 candidates of one 4-mode circuit graph (two harmonic and
+    two charge modes after the transformation, three junction terms, one flux loop; element values = a base
+    design times a deterministic +-20 % spread), every candidate diagonalised (k = 10) and the gradient of its
+    01 transition frequency taken with respect to its 12 element values and its loop flux.  One step = new
+    element values in (host), eigenfrequencies [B][10] and gradients [B][13] out (host)."""
+    name = 'discovery512'
+    text = ('4-mode qubit-discovery circuit, trunc_nums [10,10,5,5] (N=8100), batch of 512 element-value sets per GPU, '
+            'k=10, torch autograd gradients of the 01 transition frequency w.r.t. 13 parameters per circuit')
+    metric = 'diagonalisations/sec (k=10) with element-value gradients, 4-mode discovery batch'
+    points = 512
+    trunc = [10, 10, 5, 5]
+    dec_types = []
+    NAMES = ['C01', 'J01', 'C12', 'L12', 'C20', 'J20', 'C23', 'C30', 'J30', 'C34', 'C40', 'L40']
+    BASE = np.array([3.0, 8.0, 5.0, 0.6, 4.0, 6.0, 20.0, 1.2, 12.0, 25.0, 0.8, 1.5])
+
+    def values(self, idx):
+        rng = np.random.default_rng(1000 + int(idx))
+        return self.BASE * (1 + 0.2 * rng.uniform(-1, 1, len(self.BASE))) if idx else self.BASE.copy()
+
+    def grid(self, points, rank, world, strong=False):
+        from sqcircuit_b200.sharding import shard_bounds
+        lo, hi = shard_bounds(points, rank, world) if strong else (rank * points, (rank + 1) * points)
+        return np.stack([self.values(i) for i in range(lo, hi)])
+
+    def _circuit(self, sq, kern, v):
+        lp = sq.Loop(0.37, requires_grad=True)
+        mk = {'C': sq.Capacitor, 'J': sq.Junction, 'L': sq.Inductor}
+        els = {}
+        for nm, val in zip(self.NAMES, v):
+            extra = {'loops': [lp]} if nm in ('J01', 'L12', 'J20') else {}
+            els[nm] = mk[nm[0]](float(val), 'GHz', requires_grad=True, **extra)
+        cr = sq.Circuit({(0, 1): [els['C01'], els['J01']], (1, 2): [els['C12'], els['L12']],
+                         (2, 0): [els['C20'], els['J20']], (2, 3): [els['C23']],
+                         (3, 0): [els['C30'], els['J30']], (3, 4): [els['C34']],
+                         (4, 0): [els['C40'], els['L40']]}, kernels=kern)
+        cr.set_trunc_nums(self.trunc)
+        els['loop'] = lp
+        return cr, els
+
+    def build(self, sq, kern):
+        """The Circuit returned only carries the truncation for the bench's bookkeeping; batches are built per
+        grid by make_batch."""
+        sq.set_engine('PyTorch')
+        self.sq, self.kern = sq, kern
+        self._batches = {}
+        return self._circuit(sq, kern, self.BASE)[0]
+
+    def make_batch(self, n):
+        if n not in self._batches:
+            pairs = [self._circuit(self.sq, self.kern, self.BASE) for _ in range(n)]
+            self._batches[n] = (self.sq.CircuitBatch([c for c, _ in pairs], kernels=self.kern), [e for _, e in pairs])
+        return self._batches[n]
+
+    def step(self, prm, torch):
+        """prm: host array [n][12] of element values (GHz).  Returns (efreqs [n][k] device tensor, grads [n][13]
+        host array, SweepResult)."""
+        batch, elss = self.make_batch(prm.shape[0])
+        with torch.no_grad():
+            for els, v in zip(elss, prm):
+                for nm, val in zip(self.NAMES, v):
+                    el = els[nm]
+                    el.set_value(float(val), 'GHz')
+                    el.requires_grad = True
+                    el.grad = None
+                els['loop'].grad = None
+        batch.update()
+        ef, _ = batch.diag(N_EIG)
+        (ef[:, 1] - ef[:, 0]).sum().backward()
+        names = self.NAMES + ['loop']
+        grads = np.array([[float(els[nm].grad) for nm in names] for els in elss])
+        return ef.detach(), grads, batch._last
+
+    def oracle(self, o):
+        raise NotImplementedError('built per candidate in _ref_one')
+
+
+WORKLOADS = {w.name: w for w in (ZeroPi, Fluxonium, TransmonResonatorTransmon, Discovery)}
 # bounded CPU sample: sweep points per host core and step (~10-30 s of CPU work per step)
-REF_POINTS_PER_CORE = {'zeropi4096': 1, 'fluxonium1024': 512, 'trt1e5': 1}
+REF_POINTS_PER_CORE = {'zeropi4096': 1, 'fluxonium1024': 512, 'trt1e5': 1, 'discovery512': 1}
 
 
 # --------------------------------------------------------------------------------------------
@@ -205,6 +282,19 @@ def _ref_one(job):
     import scipy.sparse.linalg as spla
     from oracle import sqc_oracle as o
     name, prm = job
+    if name == 'discovery512':
+        # one candidate the way the reference's optimisation loop does it: a new Circuit (transformation,
+        # operator memory), diag, then torch_extensions.EigenSolver.backward = get_partial_omega per
+        # (element, state) -- circuit.py:2777-2826 -- for the two states of the loss
+        lp = o.OLoop(0.37)
+        c, els = o.discovery(prm, lp)
+        c.set_trunc_nums(Discovery.trunc)
+        H = c.hamiltonian()
+        w, v = spla.eigs(H, k=N_EIG, which='SR')
+        order = np.argsort(w.real)
+        c.efreqs_rad, c.evecs = w.real[order], v[:, order]
+        g = [c.partial_omega(els[nm], 1) - c.partial_omega(els[nm], 0) for nm in Discovery.NAMES + ['loop']]
+        return c.efreqs_rad[:2].tolist(), g
     if name not in _REF_CACHE:          # one circuit per worker process, like a Sweep over one Circuit object
         wl = WORKLOADS[name]()
         _REF_CACHE[name] = (wl,) + tuple(wl.oracle(o))
@@ -432,6 +522,13 @@ def our_arm(args):
                 prm = prm_host.to(dev, non_blocking=True).cpu().numpy()   # H2D of the step's inputs
             else:
                 prm = prm_host.numpy()
+            if hasattr(wl, 'step'):
+                # batched circuits with gradients: the element values ARE the step's input (operator tables are
+                # rebuilt from them every step, e2e or not), gradients come back to the host
+                ef, grads, res = wl.step(prm, torch)
+                if world > 1:
+                    gather_to_root(ef.contiguous(), n_total)
+                return (ef.cpu() if e2e else ef), grads, res
             res = cr.sweep_diag(N_EIG, **wl.sweep_args(prm), **solver_kw)
             rates = [res.dec_rate(d, states=STATES) for d in wl.dec_types]
             if world > 1:
@@ -632,7 +729,7 @@ def our_arm(args):
                          f'reference: scipy CSR build + ARPACK eigs SR + the rates), {t:.1f} s'}
 
     h2d = int(prm_weak.numel()) * 8
-    d2h = points * N_EIG * 8 + len(wl.dec_types) * points * 8
+    d2h = points * N_EIG * 8 + len(wl.dec_types) * points * 8 + (points * 13 * 8 if hasattr(wl, 'step') else 0)
     line = {
         'metric': wl.metric, 'value': value, 'unit': 'diag/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev / args.steps,

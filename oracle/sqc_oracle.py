@@ -599,7 +599,39 @@ class OCircuit:
                 if jj is el and (b_sel is None or b_sel == b_id):
                     out = out - self.cos_ops[(el, b_id)]
             return out
+        M = len(self.m)
+        if isinstance(el, OCap):
+            cinv = np.linalg.inv(self.C)
+            A = -self.R.T @ cinv @ self.partial_mats[el] @ cinv @ self.R
+            return self._quadratic(self.Q, A[:M, :M])
+        if isinstance(el, OInd):
+            A = -self.S.T @ self.partial_mats[el] @ self.S
+            out = self._quadratic(self.PHI, A[:M, :M])
+            for _, li, b_id in self.ind_keys:
+                if li is el:
+                    out = out - (self.ind_ops[(el, b_id)] / el.value ** 2 / np.sqrt(HBAR)
+                                 * (PHI0 / 2 / np.pi) * self.ext_flux(b_id))
+            return out
         raise NotImplementedError
+
+    def _quadratic(self, ops, A):
+        # circuit.py:2649-2702: 1/2 sum_i A_ii O_i^2 + sum_{i<j} A_ij O_i O_j
+        out = 0
+        for i in range(len(ops)):
+            for j in range(i, len(ops)):
+                if A[i, j] != 0:
+                    out = out + (0.5 if i == j else 1.0) * A[i, j] * (ops[i] @ ops[j])
+        return out
+
+    def partial_omega(self, el, m, subtract_ground=False):
+        # circuit.py:2777-2826 (Hellmann-Feynman on the computed eigenvectors; hamiltonian() must have run)
+        pH = self.partial_H(el)
+        v = self.evecs[:, m]
+        out = np.real(np.vdot(v, pH @ v))
+        if subtract_ground:
+            v0 = self.evecs[:, 0]
+            out -= np.real(np.vdot(v0, pH @ v0))
+        return out
 
     def _partial_omega_mn(self, el, states, b_sel=None):
         # circuit.py:2828-2873
@@ -683,6 +715,25 @@ def zero_pi(loop: OLoop, EC=0.15, ECJ=10.0, EJ=5.0, EL=0.13):
     JJ, L = OJJ(EJ, 'GHz', loops=[loop]), OInd(EL, 'GHz', loops=[loop])
     return OCircuit({(0, 1): [CJ, JJ], (0, 2): [L], (0, 3): [C], (1, 2): [C], (1, 3): [L],
                      (2, 3): [CJ, JJ]})
+
+
+DISCOVERY_NAMES = ['C01', 'J01', 'C12', 'L12', 'C20', 'J20', 'C23', 'C30', 'J30', 'C34', 'C40', 'L40']
+
+
+def discovery(values, loop: OLoop):
+    """BASELINE configs[4]: the 4-mode circuit (two harmonic, two charge modes) of tests/golden/grad_cases.py,
+    element values in GHz in the order of DISCOVERY_NAMES.  Returns (circuit, {name: element})."""
+    mk = {'C': OCap, 'J': OJJ, 'L': OInd}
+    els = {}
+    for nm, val in zip(DISCOVERY_NAMES, values):
+        extra = {'loops': [loop]} if nm in ('J01', 'L12', 'J20') else {}
+        els[nm] = mk[nm[0]](float(val), 'GHz', **extra)
+    cr = OCircuit({(0, 1): [els['C01'], els['J01']], (1, 2): [els['C12'], els['L12']],
+                   (2, 0): [els['C20'], els['J20']], (2, 3): [els['C23']],
+                   (3, 0): [els['C30'], els['J30']], (3, 4): [els['C34']],
+                   (4, 0): [els['C40'], els['L40']]})
+    els['loop'] = loop
+    return cr, els
 
 
 def fluxonium(loop: OLoop):

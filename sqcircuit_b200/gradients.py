@@ -45,8 +45,20 @@ class Primitives:
         self._m = {}
 
     def gram(self, X, Y):
-        out = torch.empty((self.B, X.shape[1], Y.shape[1]), dtype=torch.complex128, device=self.dev)
-        self.kern.gram(BlockView(X), BlockView(Y), out)
+        """<X_i | Y_j> per point, [B][ka][kb]; the tensor-core Gram kernel takes <= 64 left and <= 16 right
+        vectors per call, larger blocks go through it in tiles."""
+        ka, kb = X.shape[1], Y.shape[1]
+        out = torch.empty((self.B, ka, kb), dtype=torch.complex128, device=self.dev)
+        if ka <= 64 and kb <= 16:
+            self.kern.gram(BlockView(X), BlockView(Y), out)
+            return out
+        for r0 in range(0, ka, 64):
+            xa = X[:, r0:r0 + 64].contiguous()
+            for c0 in range(0, kb, 16):
+                yb = Y[:, c0:c0 + 16].contiguous()
+                tmp = torch.empty((self.B, xa.shape[1], yb.shape[1]), dtype=torch.complex128, device=self.dev)
+                self.kern.gram(BlockView(xa), BlockView(yb), tmp)
+                out[:, r0:r0 + xa.shape[1], c0:c0 + yb.shape[1]] = tmp
         return out
 
     def _unit(self, i):

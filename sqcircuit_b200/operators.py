@@ -327,7 +327,10 @@ class CircuitOperators:
         return self._Dt
 
     def to_device(self, arr, dtype):
-        return torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype, device=self.device).contiguous()
+        arr = np.ascontiguousarray(arr)
+        if not arr.flags.writeable:          # broadcast views: torch wants an array it may write to
+            arr = arr.copy()
+        return torch.as_tensor(arr, dtype=dtype, device=self.device).contiguous()
 
 
 # sweep points per shared low-block inverse of the two-level preconditioner (see build_lowblock)
