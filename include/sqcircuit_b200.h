@@ -133,6 +133,18 @@ int sqc_hx_fused(const sqc_space_t* sp, const double* Ve, const double* Vo,
                  const sqc_potential_t* pot, const double* fdiag, int64_t fdiag_stride_b,
                  sqc_block_t X, sqc_block_t Y, int32_t B, void* stream);
 
+/* Y = fdiag .* X + (x_i V_i) [ P ( (x_i V_i^T) X ) ] in ONE kernel for any layout whose harmonic modes (more than
+ * one level each, at most four of them, at most 32 levels each) lead the Kronecker order, followed by up to eight
+ * charge modes with junction shifts in {-1, 0, 1}: the operator sqc_mode_transform (forward, one call per
+ * harmonic mode) + sqc_potential_apply + sqc_mode_transform (backward) compute in 2 n_harmonic + 1 passes over
+ * the block.  Vcat: the x-basis matrices V_i (m_i x m_i, row-major, as returned by sqc_xbasis) of the harmonic
+ * modes with m_i > 1, concatenated in mode order.  pot->diag must be NULL; fdiag [(B or 1)][N] may be NULL.
+ * A CTA stages all harmonic indices x a window of charge columns (+ halo) in shared memory with TMA bulk copies.
+ * Returns SQC_ELIMIT when the layout is not supported (callers then use the unfused sequence).
+ * Replaces the CSR mat-vec on the matrix of Circuit.hamiltonian() (circuit.py:2147-2164). */
+int sqc_hx_generic(const sqc_space_t* sp, const double* Vcat, const sqc_potential_t* pot, const double* fdiag,
+                   int64_t fdiag_stride_b, sqc_block_t X, sqc_block_t Y, int32_t B, void* stream);
+
 /* ---- real (time-reversal adapted) representation ------------------------------------------
  * For one harmonic mode (mode 0, dim m) x one charge mode (mode 1, dim inner = 2 nc + 1) at zero gate
  * charge the Hamiltonian commutes with T = (complex conjugation) x (n -> -n), so its eigenvectors can be

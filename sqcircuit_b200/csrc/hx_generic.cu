@@ -1,0 +1,415 @@
+// sqc_hx_generic: H.X in ONE kernel for any layout whose harmonic modes lead the Kronecker order
+// (up to four harmonic modes of up to 32 levels each, up to eight charge modes):
+//
+//     Y = d .* X  +  (x_i V_i) [ P ( (x_i V_i^T) X ) ]
+//
+// A state vector is a matrix [H][C]: H = product of the harmonic dimensions (rows), C = product of the charge
+// dimensions (columns, contiguous in memory).  The mode transforms act on the rows, the junction terms shift
+// along the columns.  One CTA (512 threads) owns a tile of ALL rows x a window of columns:
+//   1. TMA bulk copies (cp.async.bulk + mbarrier), one per row: window + halo -> shared memory
+//   2. forward transforms, one harmonic mode after the other, in place: a thread owns whole fibres (the m
+//      amplitudes of one mode at fixed other indices), holds them in registers and writes the m outputs back
+//      -- plain FP64 FMAs: B200 issues DFMA at the DMMA rate, and m ~ 10 would waste half of an 8x8x4 tile
+//   3. potential: linear terms and junction cosines (phase table per row x unit shifts along the columns,
+//      masks per column from the charge indices); every thread first gathers its results in registers, the
+//      CTA synchronises, then they overwrite the tile -- no second buffer
+//   4. backward transforms (window columns only), epilogue + d .* X (X re-read through L2), TMA bulk stores.
+// When the whole vector fits in shared memory (e.g. a 4-mode circuit of dimension 8100) the window is the
+// vector and there is no halo; otherwise the halo is the largest column offset of a junction shift.
+// HBM traffic: X read once (+ halo), Y written once -- instead of one read + one write per harmonic mode and
+// direction plus one for the potential (sqc_mode_transform / sqc_potential_apply).
+// Replaces the CSR mat-vec on the Hamiltonian of Circuit.hamiltonian() (circuit.py:2147-2164).
+#include "common.cuh"
+
+#define HXG_THREADS 512
+#define HXG_MAXH 4          // harmonic modes
+#define HXG_MAXE 8         // tile elements per thread and pass of the potential phase
+
+struct HxgGeom {
+    int nh;                          // harmonic modes with more than one level
+    int hm[HXG_MAXH];                // their dimensions
+    int hs[HXG_MAXH];                // row stride of the mode inside [H]
+    int htoff[HXG_MAXH];             // offset of the mode inside lam / etab rows
+    int hvoff[HXG_MAXH];             // offset of V_i inside the concatenated matrices
+    int hg[HXG_MAXH];                // index of the mode's linear coefficient in g[b][:]
+    int H, C;
+    int nc;                          // charge modes with more than one state
+    int cd[SQC_MAX_MODES];           // their dimensions
+    int cs[SQC_MAX_MODES];           // their column strides
+    int n_terms;
+    int tsh[SQC_MAX_TERMS][SQC_MAX_MODES];   // shift of term t on charge mode j
+    int tdelta[SQC_MAX_TERMS];       // the same shift as a column offset
+    int halo, ncore, ntile, ld;      // tile geometry: window columns, tiles per vector, row pitch (complex)
+    int tlen, gcount, vlen;
+    long long N;
+};
+
+__device__ __forceinline__ unsigned hxg_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void hxg_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hxg_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void hxg_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hxg_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hxg_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "HXG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra HXG_DONE;\n"
+        "bra HXG_WAIT;\n"
+        "HXG_DONE:\n"
+        "}\n" ::"r"(hxg_smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void hxg_bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(hxg_smem_u32(dst)), "l"(src), "r"(bytes), "r"(hxg_smem_u32(bar)) : "memory");
+}
+// TMA bulk copy shared -> global
+__device__ __forceinline__ void hxg_bulk_store(void* dst, const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(hxg_smem_u32(src)), "r"(bytes) : "memory");
+}
+
+// One harmonic mode, all fibres of the tile columns [c_lo, c_hi), in place.  FWD: out[j] = sum_k V[k][j] in[k]
+// (to the x basis); else out[k] = sum_j V[k][j] in[j].
+template <int MAXM, bool FWD>
+__device__ __forceinline__ void hxg_transform(cplx* __restrict__ T, const double* __restrict__ sV, int m, int s,
+                                              int H, int ld, int c_lo, int c_hi, int tid) {
+    const int ncol = c_hi - c_lo;
+    const long long step = (long long)s * ld;
+    if (MAXM <= 12) {
+        // a thread owns complex fibres: one V element serves two FMAs
+        const int ntask = (H / m) * ncol;
+        for (int task = tid; task < ntask; task += HXG_THREADS) {
+            const int f = task / ncol, c = c_lo + task - f * ncol;
+            const int o = f / s, r = f - o * s;
+            cplx* base = T + (long long)(o * m * s + r) * ld + c;
+            cplx in[MAXM];
+#pragma unroll
+            for (int k = 0; k < MAXM; ++k)
+                if (k < m) in[k] = base[k * step];
+            for (int j = 0; j < m; ++j) {
+                const double* vp = FWD ? sV + j : sV + j * m;
+                const int vs = FWD ? m : 1;
+                double ax = 0.0, ay = 0.0;
+#pragma unroll
+                for (int k = 0; k < MAXM; ++k) {
+                    if (k < m) {
+                        const double v = vp[k * vs];
+                        ax = fma(v, in[k].x, ax);
+                        ay = fma(v, in[k].y, ay);
+                    }
+                }
+                base[j * step] = cmake(ax, ay);
+            }
+        }
+    } else {
+        // long fibres: real and imaginary parts are separate fibres (half the registers)
+        const int ntask = (H / m) * ncol * 2;
+        double* Td = reinterpret_cast<double*>(T);
+        for (int task = tid; task < ntask; task += HXG_THREADS) {
+            const int comp = task & 1, tk = task >> 1;
+            const int f = tk / ncol, c = c_lo + tk - f * ncol;
+            const int o = f / s, r = f - o * s;
+            double* base = Td + 2 * ((long long)(o * m * s + r) * ld + c) + comp;
+            double in[MAXM];
+#pragma unroll
+            for (int k = 0; k < MAXM; ++k)
+                if (k < m) in[k] = base[2 * k * step];
+            for (int j = 0; j < m; ++j) {
+                const double* vp = FWD ? sV + j : sV + j * m;
+                const int vs = FWD ? m : 1;
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < MAXM; ++k)
+                    if (k < m) acc = fma(vp[k * vs], in[k], acc);
+                base[2 * j * step] = acc;
+            }
+        }
+    }
+}
+
+template <bool FWD>
+__device__ __forceinline__ void hxg_transform_any(cplx* T, const double* sV, int m, int s, int H, int ld, int c_lo,
+                                                  int c_hi, int tid) {
+    if (m <= 4) hxg_transform<4, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 6) hxg_transform<6, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 8) hxg_transform<8, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 10) hxg_transform<10, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 12) hxg_transform<12, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 16) hxg_transform<16, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 20) hxg_transform<20, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 24) hxg_transform<24, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
+    else hxg_transform<32, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
+}
+
+__global__ void __launch_bounds__(HXG_THREADS, 1)
+hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__ Vcat, const double* __restrict__ lam,
+                  const cplx* __restrict__ etab, long long etab_stride_b, const double* __restrict__ g,
+                  const cplx* __restrict__ a, const double* __restrict__ fdiag, long long fdiag_stride_b,
+                  sqc_block_t X, sqc_block_t Y, int vmax, long long nitems) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int H = gm.H, C = gm.C, ld = gm.ld, T_ = gm.n_terms;
+    // shared memory: tile [H][ld] complex | phase table [T][H] complex | V matrices | lin[H] | column masks | mbarrier
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);
+    cplx* sPh = tile + (long long)H * ld;
+    double* sV = reinterpret_cast<double*>(sPh + (long long)max(T_, 1) * H);
+    double* sLin = sV + gm.vlen;
+    unsigned* sMask = reinterpret_cast<unsigned*>(sLin + H);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(
+        (reinterpret_cast<uintptr_t>(sMask + ld) + 7) & ~(uintptr_t)7);
+
+    for (int e = tid; e < gm.vlen; e += HXG_THREADS) sV[e] = Vcat[e];
+    if (tid == 0) hxg_mbar_init(bar, 1);
+    __syncthreads();
+
+    int last_b = -1, last_tile = -1;
+    unsigned phase = 0;
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int ti = (int)(item % gm.ntile);
+        const long long vec = item / gm.ntile;
+        const int b = (int)(vec / vmax), v = (int)(vec % vmax);
+        if (v >= blk_count(X, b)) continue;          // uniform over the CTA
+        const cplx* x = blk_vec(X, b, v, gm.N);
+        cplx* y = blk_vec(Y, b, v, gm.N);
+        // window [c0, c1) of this tile, loaded columns [l0, l1) (window + halo inside the vector)
+        const int c0 = ti * gm.ncore, c1 = min(C, c0 + gm.ncore);
+        const int l0 = max(0, c0 - gm.halo), l1 = min(C, c1 + gm.halo);
+        const int nld = l1 - l0;
+
+        // ---- 1. TMA loads: one bulk copy per row ----
+        if (tid < 32) {
+            if (tid == 0) hxg_mbar_expect_tx(bar, (unsigned)(H * nld * 16));
+            __syncwarp();
+            for (int h = tid; h < H; h += 32)
+                hxg_bulk_load(tile + (long long)h * ld, x + (long long)h * C + l0, (unsigned)(nld * 16), bar);
+        }
+        // ---- tables (while the copies fly): per sweep point the phases a_t prod_i etab_t[i][h_i] and the linear
+        // term of every row; per tile the in-range masks of every column ----
+        if (b != last_b) {
+            const cplx* et = etab + b * etab_stride_b;
+            const double* gb = g + (long long)b * gm.gcount;
+            for (int h = tid; h < H; h += HXG_THREADS) {
+                double lin = gb[0];
+                int hi[HXG_MAXH];
+#pragma unroll
+                for (int i = 0; i < HXG_MAXH; ++i) {
+                    if (i < gm.nh) {
+                        hi[i] = (h / gm.hs[i]) % gm.hm[i];
+                        lin = fma(gb[gm.hg[i]], lam[gm.htoff[i] + hi[i]], lin);
+                    }
+                }
+                sLin[h] = lin;
+                for (int t = 0; t < T_; ++t) {
+                    cplx ph = a[(long long)b * T_ + t];
+#pragma unroll
+                    for (int i = 0; i < HXG_MAXH; ++i)
+                        if (i < gm.nh) ph = cmul(ph, et[(long long)t * gm.tlen + gm.htoff[i] + hi[i]]);
+                    sPh[t * H + h] = ph;
+                }
+            }
+            last_b = b;
+        }
+        if (ti != last_tile) {
+            for (int cl = tid; cl < nld; cl += HXG_THREADS) {
+                const int c = l0 + cl;
+                unsigned mk = 0;
+                for (int t = 0; t < T_; ++t) {
+                    bool lo = true, hi = true;
+                    for (int j = 0; j < gm.nc; ++j) {
+                        const int ij = (c / gm.cs[j]) % gm.cd[j], w = gm.tsh[t][j];
+                        lo = lo && (ij - w >= 0) && (ij - w < gm.cd[j]);
+                        hi = hi && (ij + w >= 0) && (ij + w < gm.cd[j]);
+                    }
+                    mk |= (lo ? 1u : 0u) << (2 * t) | (hi ? 1u : 0u) << (2 * t + 1);
+                }
+                sMask[cl] = mk;
+            }
+            last_tile = ti;
+        }
+        hxg_mbar_wait(bar, phase);
+        phase ^= 1;
+        __syncthreads();
+
+        // ---- 2. forward transforms (all loaded columns: the halo is needed in the x basis too) ----
+        for (int i = 0; i < gm.nh; ++i) {
+            hxg_transform_any<true>(tile, sV + gm.hvoff[i], gm.hm[i], gm.hs[i], H, ld, 0, nld, tid);
+            __syncthreads();
+        }
+
+        // ---- 3. potential on the window columns.  It couples the columns of ONE row, so the rows are taken in
+        // groups of at most HXG_MAXE x 512 elements: gather the group's results in registers, synchronise,
+        // overwrite the group's rows (the next group reads other rows: no second barrier) ----
+        const int w0 = c0 - l0, nw = c1 - c0;            // window inside the loaded columns
+        const int rows_per = max(1, (HXG_MAXE * HXG_THREADS) / nw);
+        for (int h0 = 0; h0 < H; h0 += rows_per) {
+            const int nel = min(rows_per, H - h0) * nw;
+            cplx res[HXG_MAXE];
+#pragma unroll
+            for (int q = 0; q < HXG_MAXE; ++q) {
+                const int e = tid + q * HXG_THREADS;
+                if (e < nel) {
+                    const int hh = e / nw, cl = w0 + e - hh * nw, h = h0 + hh;
+                    const cplx* row = tile + (long long)h * ld;
+                    const cplx z = row[cl];
+                    const double lin = sLin[h];
+                    cplx acc = cmake(lin * z.x, lin * z.y);
+                    const unsigned mk = sMask[cl];
+#pragma unroll 1
+                    for (int t = 0; t < T_; ++t) {
+                        const cplx ph = sPh[t * H + h];
+                        const int d = gm.tdelta[t];
+                        if (mk >> (2 * t) & 1u) cfma(acc, ph, row[cl - d]);
+                        if (mk >> (2 * t + 1) & 1u) cfma(acc, cconj(ph), row[cl + d]);
+                    }
+                    res[q] = acc;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < HXG_MAXE; ++q) {
+                const int e = tid + q * HXG_THREADS;
+                if (e < nel) {
+                    const int hh = e / nw;
+                    tile[(long long)(h0 + hh) * ld + w0 + e - hh * nw] = res[q];
+                }
+            }
+        }
+        __syncthreads();
+        const int nel = H * nw;
+
+        // ---- 4. backward transforms on the window, epilogue, TMA stores ----
+        for (int i = gm.nh - 1; i >= 0; --i) {
+            hxg_transform_any<false>(tile, sV + gm.hvoff[i], gm.hm[i], gm.hs[i], H, ld, w0, w0 + nw, tid);
+            __syncthreads();
+        }
+        if (fdiag) {
+            const double* fd = fdiag + b * fdiag_stride_b;
+            for (int e = tid; e < nel; e += HXG_THREADS) {
+                const int h = e / nw, cc = e - h * nw;
+                const long long gi = (long long)h * C + c0 + cc;
+                const double d = fd[gi];
+                const cplx xv = x[gi];
+                cplx* p = tile + (long long)h * ld + w0 + cc;
+                cplx val = *p;
+                val.x = fma(d, xv.x, val.x);
+                val.y = fma(d, xv.y, val.y);
+                *p = val;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid < 32) {
+            for (int h = tid; h < H; h += 32)
+                hxg_bulk_store(y + (long long)h * C + c0, tile + (long long)h * ld + w0, (unsigned)(nw * 16));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the stores have read the tile
+        }
+        __syncthreads();
+    }
+    if (tid < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+extern "C" int sqc_hx_generic(const sqc_space_t* sp, const double* Vcat, const sqc_potential_t* pot,
+                              const double* fdiag, int64_t fdiag_stride_b, sqc_block_t X, sqc_block_t Y,
+                              int32_t B, void* stream) {
+    if (!sp || !pot || B <= 0 || X.cnt_fixed <= 0 || sp->n_modes < 1 || sp->n_modes > SQC_MAX_MODES) return SQC_EINVAL;
+    if (pot->diag || pot->n_terms < 0 || pot->n_terms > SQC_MAX_TERMS || X.ptr == Y.ptr) return SQC_EINVAL;
+    HxgGeom gm = {};
+    const int M = sp->n_modes;
+    // harmonic modes (more than one level) must lead the Kronecker order; modes of dimension one are transparent
+    int toff[SQC_MAX_MODES], off = 0;
+    bool seen_charge = false;
+    long long Hh = 1, Cc = 1;
+    for (int i = 0; i < M; ++i) {
+        toff[i] = off;
+        off += sp->dims[i];
+        if (sp->dims[i] <= 1) continue;
+        if (sp->harmonic[i]) {
+            if (seen_charge || gm.nh >= HXG_MAXH || sp->dims[i] > 32) return SQC_ELIMIT;
+            gm.hm[gm.nh] = sp->dims[i];
+            gm.htoff[gm.nh] = toff[i];
+            gm.hg[gm.nh] = 1 + i;
+            ++gm.nh;
+            Hh *= sp->dims[i];
+        } else {
+            seen_charge = true;
+            gm.cd[gm.nc] = sp->dims[i];
+            for (int t = 0; t < pot->n_terms; ++t) {
+                const int w = pot->shift[t][i];
+                if (w < -1 || w > 1) return SQC_ELIMIT;
+                gm.tsh[t][gm.nc] = w;
+            }
+            ++gm.nc;
+            Cc *= sp->dims[i];
+        }
+    }
+    if (gm.nh == 0 || Hh > 4096 || Cc > (1 << 24)) return SQC_ELIMIT;
+    gm.tlen = off;
+    gm.gcount = 1 + M;
+    gm.H = (int)Hh;
+    gm.C = (int)Cc;
+    gm.N = Hh * Cc;
+    int s = (int)Hh, vo = 0;
+    for (int i = 0; i < gm.nh; ++i) {
+        s /= gm.hm[i];
+        gm.hs[i] = s;
+        gm.hvoff[i] = vo;
+        vo += gm.hm[i] * gm.hm[i];
+    }
+    gm.vlen = vo;
+    int cs = (int)Cc;
+    for (int j = 0; j < gm.nc; ++j) {
+        cs /= gm.cd[j];
+        gm.cs[j] = cs;
+    }
+    gm.n_terms = pot->n_terms;
+    int halo = 0;
+    for (int t = 0; t < pot->n_terms; ++t) {
+        int d = 0;
+        for (int j = 0; j < gm.nc; ++j) d += gm.tsh[t][j] * gm.cs[j];
+        gm.tdelta[t] = d;
+        halo = max(halo, abs(d));
+    }
+    // tile geometry: as many window columns as shared memory and the register budget of the potential phase allow
+    const long long fixed = (long long)max(gm.n_terms, 1) * gm.H * 16 + (long long)gm.vlen * 8 + (long long)gm.H * 8 + 64;
+    const long long budget = 227 * 1024 - fixed;
+    auto bytes_for = [&](long long ncols) { return ncols * ((long long)gm.H * 16 + 4); };
+    int ncore, ntile;
+    if (bytes_for(gm.C) <= budget) {
+        ncore = gm.C;
+        ntile = 1;
+        gm.halo = 0;
+    } else {
+        const long long cap = budget / ((long long)gm.H * 16 + 4) - 2 * halo;
+        if (cap < halo || cap < 1) return SQC_ELIMIT;       // halo would dominate
+        ntile = (int)((gm.C + cap - 1) / cap);
+        ncore = (gm.C + ntile - 1) / ntile;
+        ntile = (gm.C + ncore - 1) / ncore;
+        gm.halo = halo;
+    }
+    gm.ncore = ncore;
+    gm.ntile = ntile;
+    gm.ld = ntile == 1 ? gm.C : min(gm.C, ncore + 2 * gm.halo);
+    const size_t smem = (size_t)((long long)gm.H * gm.ld * 16 + fixed + (long long)gm.ld * 4 + 16);
+    if (smem > 227 * 1024) return SQC_ELIMIT;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(hx_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long nitems = (long long)B * X.cnt_fixed * ntile;
+    const int grid = (int)(nitems < sms ? nitems : sms);
+    hx_generic_kernel<<<grid, HXG_THREADS, smem, (cudaStream_t)stream>>>(
+        gm, Vcat, pot->lam, (const cplx*)pot->etab, pot->etab_stride_b, pot->g, (const cplx*)pot->a, fdiag,
+        fdiag_stride_b, X, Y, X.cnt_fixed, nitems);
+    SQC_LAUNCHED();
+    return 0;
+}

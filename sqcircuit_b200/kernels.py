@@ -198,6 +198,17 @@ class Kernels:
         _lib.check(rc, 'sqc_hx_fused')
         return True
 
+    def hx_generic(self, sp, Vcat, pot, fdiag, X, Y):
+        """H.X in one kernel for layouts with leading harmonic modes (sqc_hx_generic); False when the layout is
+        not supported."""
+        fsb = 0 if fdiag is None or fdiag.shape[0] == 1 else fdiag.stride(0)
+        rc = self.lib.sqc_hx_generic(C.byref(sp), _p(Vcat), C.byref(pot), _p(fdiag), fsb, X.c(), Y.c(), X.B,
+                                     _stream(self.dev))
+        if rc == _lib.ELIMIT:
+            return False
+        _lib.check(rc, 'sqc_hx_generic')
+        return True
+
     def hx_fused_real(self, sp, Ve, Vo, pot, fdiag, X, Y, fdiag_sep=None):
         """Real-representation H.X (sqc_hx_fused_real); False when the layout / size is not supported.
         fdiag_sep: [m + inner] separable form of the same diagonal (used instead of fdiag when given)."""

@@ -111,6 +111,14 @@ class CircuitOperators:
             he, ho = (self.dims[0] + 1) // 2, self.dims[0] // 2
             self.Ve = Vfull[0::2, :he].contiguous()
             self.Vo = Vfull[1::2, :ho].contiguous()
+        # generic one-kernel H.X (csrc/hx_generic.cu): harmonic modes lead the Kronecker order, <= 4 of them,
+        # <= 32 levels each (circuits of several small modes: transmon-resonator-transmon, 4-mode candidates)
+        big = [i for i in range(self.M) if self.dims[i] > 1]
+        nh = len(self.tmodes)
+        self.generic = (not self.fused and 1 <= nh <= 4 and big[:nh] == self.tmodes
+                        and all(self.dims[i] <= 32 for i in self.tmodes) and self.T <= 16)
+        if self.generic:
+            self.Vcat = torch.cat([self.V[i].reshape(-1) for i in self.tmodes]).contiguous()
 
     # ---- tables --------------------------------------------------------------------------
     def _tables(self, s):
@@ -260,6 +268,10 @@ class CircuitOperators:
         if self.fused and self.use_fused:
             pot = self.potential_struct(a, g, etab, shift, None)
             if k.hx_fused(self.sp, self.Ve, self.Vo, pot, fock_diag, X, Y):
+                return
+        if self.generic and self.use_fused:
+            pot = self.potential_struct(a, g, etab, shift, None)
+            if k.hx_generic(self.sp, self.Vcat, pot, fock_diag, X, Y):
                 return
         if not self.tmodes:
             k.potential_apply(self.sp, self.potential_struct(a, g, etab, shift, fock_diag), X, Y)

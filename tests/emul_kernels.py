@@ -284,6 +284,9 @@ class EmulKernels:
     def hx_fused(self, sp, Ve, Vo, pot, fdiag, X, Y):
         return False      # not emulated: callers fall back to transform + potential + transform
 
+    def hx_generic(self, sp, Vcat, pot, fdiag, X, Y):
+        return False      # not emulated either: same fall-back
+
     # ---- real (time-reversal adapted) representation ------------------------------------------
     @staticmethod
     def _r2c(y, m, inner):

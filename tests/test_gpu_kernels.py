@@ -853,3 +853,132 @@ def test_gram_pair_real(kern, B, mm, p, N):
         got1, got2 = o1[b, :int(mtot[b]), :na].cpu(), o2[b, :int(mtot[b]), :na].cpu()
         assert float(got1.imag.abs().max()) == 0.0 and float(got2.imag.abs().max()) == 0.0
         assert relerr(got1.real, r1) < 1e-13 and relerr(got2.real, r2) < 1e-13, b
+
+
+# ---- sqc_hx_generic: one-kernel H.X for leading harmonic modes, against a plain torch fp64 restatement -------
+def _hx_torch_reference(dims, harm, Vs, lam_list, s, shifts, a, g, fd, X):
+    """Y = fd .* X + (x V_i) P ((x V_i^T) X) with dense torch tensor contractions (CPU, fp64)."""
+    B, nv, N = X.shape
+    M = len(dims)
+    Z = X.reshape((B, nv) + tuple(dims))
+    for i in range(M):
+        if harm[i] and dims[i] > 1:
+            Z = torch.movedim(torch.tensordot(Z, Vs[i].to(torch.complex128), dims=([2 + i], [0])), -1, 2 + i)
+    out = torch.zeros_like(Z)
+    lin = g[:, 0].reshape((B, 1) + (1,) * M).to(torch.complex128)
+    for i in range(M):
+        if harm[i]:
+            shp = [1] * (2 + M)
+            shp[2 + i] = dims[i]
+            lin = lin + g[:, 1 + i].reshape((B, 1) + (1,) * M) * lam_list[i].reshape(shp)
+    out = out + lin * Z
+    T = a.shape[1]
+    for t in range(T):
+        ph = a[:, t].reshape((B, 1) + (1,) * M)
+        for i in range(M):
+            if harm[i]:
+                shp = [1] * (2 + M)
+                shp[2 + i] = dims[i]
+                sb = s[:, t, i].reshape((-1, 1) + (1,) * M)
+                ph = ph * torch.exp(1j * sb * lam_list[i].reshape(shp))
+        # z(i - sh): roll forward by sh with zero fill; z(i + sh): roll back
+        lo, hi = Z, Z
+        for i in range(M):
+            w = int(shifts[t][i]) if not harm[i] else 0
+            if w:
+                lo = _shift(lo, 2 + i, w)
+                hi = _shift(hi, 2 + i, -w)
+        out = out + ph * lo + ph.conj() * hi
+    for i in range(M):
+        if harm[i] and dims[i] > 1:
+            out = torch.movedim(torch.tensordot(out, Vs[i].T.to(torch.complex128), dims=([2 + i], [0])), -1, 2 + i)
+    Y = out.reshape(B, nv, N)
+    if fd is not None:
+        Y = Y + fd.reshape(-1, 1, N) * X
+    return Y
+
+
+def _shift(Z, axis, w):
+    """out[..., i, ...] = Z[..., i - w, ...] (zero where i - w is out of range)."""
+    out = torch.zeros_like(Z)
+    n = Z.shape[axis]
+    if abs(w) >= n:
+        return out
+    src = [slice(None)] * Z.dim()
+    dst = [slice(None)] * Z.dim()
+    if w > 0:
+        src[axis], dst[axis] = slice(0, n - w), slice(w, n)
+    else:
+        src[axis], dst[axis] = slice(-w, n), slice(0, n + w)
+    out[tuple(dst)] = Z[tuple(src)]
+    return out
+
+
+@pytest.mark.parametrize('dims,harm,shifts,per_point', [
+    ([10, 9, 9], [1, 0, 0], [[0, 1, 0], [0, 0, 1]], False),                 # small transmon-resonator-transmon
+    ([10, 10, 9, 9], [1, 1, 0, 0], [[0, 0, 1, 0], [0, 0, 1, 0], [0, 0, 0, 1]], True),   # the 4-mode batch layout
+    ([10, 50, 50], [1, 0, 0], [[0, 1, 0], [0, 0, -1], [0, 1, 1]], False),  # column tiles with a halo of 51
+    ([3, 1, 7], [1, 1, 0], [[0, 0, 1]], False),                             # a harmonic mode truncated to one level
+    ([24, 5], [1, 0], [[0, 1]], False),                                     # long fibres (split re / im path)
+    ([32, 3], [1, 0], [[0, -1]], True),
+    ([6, 4, 5, 3, 3], [1, 1, 1, 0, 0], [[0, 0, 0, 1, -1], [0, 0, 0, 0, 1]], False)])
+def test_hx_generic_matches_torch_reference(kern, dims, harm, shifts, per_point):
+    from sqcircuit_b200._lib import Potential
+    M, N = len(dims), int(np.prod(dims))
+    B, nv, T = 3, 5, len(shifts)
+    sp = make_space(dims, harm)
+    toff = np.concatenate(([0], np.cumsum(dims)))[:-1]
+    tlen = int(np.sum(dims))
+    lam = torch.zeros(tlen, dtype=torch.float64)
+    Vs, lam_list = {}, {}
+    for i in range(M):
+        if harm[i] and dims[i] > 1:
+            Vd, ld = kern.xbasis(dims[i])
+            Vs[i], lam_list[i] = Vd.cpu(), ld.cpu()
+            lam[toff[i]:toff[i] + dims[i]] = ld.cpu()
+        else:
+            lam_list[i] = torch.zeros(dims[i], dtype=torch.float64)
+    gen = torch.Generator().manual_seed(11)
+    nb = B if per_point else 1
+    s = 0.4 * torch.randn((nb, T, M), dtype=torch.float64, generator=gen) * torch.tensor(harm, dtype=torch.float64)
+    etab = torch.empty((nb, T, tlen), dtype=torch.complex128, device='cuda')
+    kern.phase_tables(sp, T, lam.cuda(), s.cuda().contiguous(), etab)
+    a = rnd((B, T), 12)
+    g = torch.randn((B, 1 + M), dtype=torch.float64, generator=gen)
+    fd = torch.randn((B, N), dtype=torch.float64, generator=gen)
+    X = rnd((B, nv, N), 13)
+    cnt = torch.tensor([nv, 2, 0], dtype=torch.int32)
+    Vcat = torch.cat([Vs[i].reshape(-1) for i in range(M) if i in Vs]).cuda().contiguous()
+    pot = Potential()
+    pot.n_terms = T
+    for t in range(T):
+        for i in range(M):
+            pot.shift[t][i] = int(shifts[t][i])
+    lamd, ad, gd = lam.cuda(), a.cuda().contiguous(), g.cuda().contiguous()
+    pot.lam, pot.etab, pot.etab_stride_b = lamd.data_ptr(), etab.data_ptr(), (etab.stride(0) if per_point else 0)
+    pot.g, pot.a, pot.diag, pot.diag_stride_b = gd.data_ptr(), ad.data_ptr(), None, 0
+    for use_fd in (True, False):
+        ref = _hx_torch_reference(dims, harm, Vs, lam_list, s, shifts, a, g, fd if use_fd else None, X)
+        out = torch.full_like(X, 7.0).cuda()
+        ok = kern.hx_generic(sp, Vcat, pot, fd.cuda() if use_fd else None, BlockView(X.cuda(), cnt=cnt.cuda()),
+                             BlockView(out, cnt=cnt.cuda()))
+        assert ok
+        out = out.cpu()
+        for b in range(B):
+            n = int(cnt[b])
+            if n:
+                assert relerr(out[b, :n], ref[b, :n]) < 1e-13, (b, use_fd)
+            assert bool((out[b, n:] == 7.0).all())            # vectors beyond the count are not touched
+    # and the unfused kernel sequence the operator falls back to gives the same
+    s1, s2 = torch.zeros_like(X).cuda(), torch.zeros_like(X).cuda()
+    src = BlockView(X.cuda())
+    for i in range(M):
+        if i in Vs:
+            kern.mode_transform(sp, i, Vs[i].cuda(), 1, src, BlockView(s1), impl=1)
+            src = BlockView(s1)
+    kern.potential_apply(sp, pot, BlockView(s1), BlockView(s2))
+    for i in range(M):
+        if i in Vs:
+            kern.mode_transform(sp, i, Vs[i].cuda(), 0, BlockView(s2), BlockView(s2), impl=1)
+    ref2 = _hx_torch_reference(dims, harm, Vs, lam_list, s, shifts, a, g, None, X)
+    assert relerr(s2.cpu(), ref2) < 1e-13
