@@ -419,7 +419,7 @@ class ClockSampler:
 class TimedKernels:
     """Wraps the CUDA backend: CUDA events on the launching stream around every C-ABI call,
     so per-kernel device time is measured live inside the timed region (no profiler)."""
-    TIMED = ['hx_fused', 'hx_fused_real', 'real_to_complex', 'complex_to_real', 'mode_transform', 'potential_apply', 'gram', 'gram_pair', 'gen_rr', 'davidson_insert2',
+    TIMED = ['hx_fused', 'hx_fused_real', 'hx_generic', 'real_to_complex', 'complex_to_real', 'mode_transform', 'potential_apply', 'gram', 'gram_pair', 'gen_rr', 'davidson_insert2',
              'lowblock_assemble', 'hpd_inverse_c64', 'lowblock_apply', 'lowband_factor', 'lowband_apply', 'block_update', 'ritz_update', 'block_rightmul', 'heev',
              'residual_norms', 'precond_residual', 'restart_copy', 'svqb_coeffs', 'davidson_decide',
              'davidson_insert', 'diag_mul', 'ladder_apply']
@@ -592,7 +592,7 @@ def our_arm(args):
     # timed region: only the dominant kernel (the H.X apply) carries CUDA events -- bracketing all
     # ~900 C-ABI calls of a step costs ~60 ms of host time per step (measured), which would be
     # charged to `value`.  The full per-kernel breakdown comes from one extra, untimed step below.
-    kern.only = {'hx_fused', 'hx_fused_real', 'mode_transform', 'potential_apply', 'heev'}
+    kern.only = {'hx_fused', 'hx_fused_real', 'hx_generic', 'mode_transform', 'potential_apply', 'heev'}
     kern.enabled = True
     l0 = kern.launch_count()
     ms_dev, own_dev, last = timed(step, args.steps, False)
@@ -653,7 +653,7 @@ def our_arm(args):
     shares = {k: {'ms': round(v[0], 3), 'calls': v[1], 'share': round(v[0] / total_ms, 4)}
               for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}
     real_ms = hx_kernel.get('hx_fused_real', [0.0, 0])[0]
-    cplx_ms = sum(hx_kernel.get(k, [0, 0])[0] for k in ('hx_fused', 'mode_transform', 'potential_apply'))
+    cplx_ms = sum(hx_kernel.get(k, [0, 0])[0] for k in ('hx_fused', 'hx_generic', 'mode_transform', 'potential_apply'))
     heev_ms = hx_kernel.get('heev', [0.0, 0])[0]
     use_real = real_ms > cplx_ms
     m0 = cr.m[0]
@@ -678,6 +678,13 @@ def our_arm(args):
             kname = ('H.X apply, real representation (sqc_hx_fused_real: TMA load, transform + potential + '
                      'transform, TMA store)')
             flops_per_vec = 2.0 * m0 * N
+        elif hx_kernel.get('hx_generic', [0.0, 0])[0] > 0:
+            hx_ms, nv = hx_kernel['hx_generic'][0], nvec
+            hx_calls = hx_kernel['hx_generic'][1]
+            bytes_per_vec = 32 * N
+            kname = ('H.X apply, generic layout in one kernel (sqc_hx_generic: TMA-staged tile of all harmonic '
+                     'indices x a window of charge columns, transforms + potential + transforms in shared memory)')
+            flops_per_vec = 4.0 * sum(d for d, h in zip(cr.m, cr._operators().harm) if h and d > 1) * N
         elif hx_kernel.get('hx_fused', [0.0, 0])[0] > 0:
             hx_ms, nv = cplx_ms, nvec
             hx_calls = hx_kernel['hx_fused'][1]

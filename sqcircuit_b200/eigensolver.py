@@ -248,7 +248,7 @@ class RitzPairStart:
 
 DETAIL_STATS = None
 # entry points of op.apply: the only ones an instrumented backend may keep out of the CUDA graphs
-_APPLY_OPS = frozenset({'hx_fused', 'hx_fused_real', 'mode_transform', 'potential_apply'})
+_APPLY_OPS = frozenset({'hx_fused', 'hx_fused_real', 'hx_generic', 'mode_transform', 'potential_apply'})
 
 
 def solve_davidson_gen(kern, op, B, N, k, diag, p=None, mmax=None, tol=1e-9, maxit=300, x0=None,
