@@ -31,6 +31,7 @@ struct HxgGeom {
     int hs[HXG_MAXH];                // row stride of the mode inside [H]
     int htoff[HXG_MAXH];             // offset of the mode inside lam / etab rows
     int hvoff[HXG_MAXH];             // offset of V_i inside the concatenated matrices
+    int haoff[HXG_MAXH];             // offset of the padded (V, V^T) pair of the mode in shared memory
     int hg[HXG_MAXH];                // index of the mode's linear coefficient in g[b][:]
     int H, C;
     int nc;                          // charge modes with more than one state
@@ -39,8 +40,10 @@ struct HxgGeom {
     int n_terms;
     int tsh[SQC_MAX_TERMS][SQC_MAX_MODES];   // shift of term t on charge mode j
     int tdelta[SQC_MAX_TERMS];       // the same shift as a column offset
+    unsigned tpos[SQC_MAX_MODES];    // bit t: term t shifts charge mode j by +1
+    unsigned tneg[SQC_MAX_MODES];    // bit t: term t shifts charge mode j by -1
     int halo, ncore, ntile, ld;      // tile geometry: window columns, tiles per vector, row pitch (complex)
-    int tlen, gcount, vlen;
+    int tlen, gcount, vlen, alen;
     long long N;
 };
 
@@ -72,106 +75,142 @@ __device__ __forceinline__ void hxg_bulk_store(void* dst, const void* src, unsig
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(hxg_smem_u32(src)), "r"(bytes) : "memory");
 }
 
-// One harmonic mode, all fibres of the tile columns [c_lo, c_hi), in place.  FWD: out[j] = sum_k V[k][j] in[k]
-// (to the x basis); else out[k] = sum_j V[k][j] in[j].
-template <int MAXM, bool FWD>
-__device__ __forceinline__ void hxg_transform(cplx* __restrict__ T, const double* __restrict__ sV, int m, int s,
+// Thread layout of a phase that walks a [rows] x [n columns] piece of the tile: TC = n rounded up to whole warps
+// (at most the CTA), TR = 512 / TC row lanes; thread -> (tr, tc).  No division inside the loops.
+struct HxgLanes {
+    int TC, TR, tr, tc;
+    __device__ __forceinline__ HxgLanes(int n, int tid) {
+        TC = min(HXG_THREADS, (n + 31) & ~31);
+        TR = HXG_THREADS / TC;
+        tr = tid / TC;
+        tc = tid - tr * TC;
+        if (tr >= TR) tr = -1;                 // idle thread of this phase
+    }
+};
+
+// One harmonic mode, all fibres of the tile columns [c_lo, c_hi), in place: out[j] = sum_k A[k][j] in[k] with A the
+// padded matrix [m][mp] in shared memory (A = V: to the x basis; A = V^T: back).  A thread owns whole fibres: the m
+// inputs sit in registers, two outputs are formed at a time so that one 16-byte load of A feeds four FMAs.
+template <int MAXM>
+__device__ __forceinline__ void hxg_transform(cplx* __restrict__ T, const double* __restrict__ sA, int m, int mp, int s,
                                               int H, int ld, int c_lo, int c_hi, int tid) {
-    const int ncol = c_hi - c_lo;
+    const HxgLanes ln(c_hi - c_lo, tid);
+    if (ln.tr < 0) return;
     const long long step = (long long)s * ld;
+    const int nf = H / m;
     if (MAXM <= 12) {
-        // a thread owns complex fibres: one V element serves two FMAs
-        const int ntask = (H / m) * ncol;
-        for (int task = tid; task < ntask; task += HXG_THREADS) {
-            const int f = task / ncol, c = c_lo + task - f * ncol;
+        for (int f = ln.tr; f < nf; f += ln.TR) {
             const int o = f / s, r = f - o * s;
-            cplx* base = T + (long long)(o * m * s + r) * ld + c;
-            cplx in[MAXM];
+            for (int c = c_lo + ln.tc; c < c_hi; c += ln.TC) {
+                cplx* base = T + (long long)(o * m * s + r) * ld + c;
+                cplx in[MAXM];
 #pragma unroll
-            for (int k = 0; k < MAXM; ++k)
-                if (k < m) in[k] = base[k * step];
-            for (int j = 0; j < m; ++j) {
-                const double* vp = FWD ? sV + j : sV + j * m;
-                const int vs = FWD ? m : 1;
-                double ax = 0.0, ay = 0.0;
+                for (int k = 0; k < MAXM; ++k)
+                    if (k < m) in[k] = base[k * step];
+                for (int j = 0; j < m; j += 2) {
+                    const double2* ap = reinterpret_cast<const double2*>(sA + j);
+                    const int as = mp >> 1;
+                    double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
 #pragma unroll
-                for (int k = 0; k < MAXM; ++k) {
-                    if (k < m) {
-                        const double v = vp[k * vs];
-                        ax = fma(v, in[k].x, ax);
-                        ay = fma(v, in[k].y, ay);
+                    for (int k = 0; k < MAXM; ++k) {
+                        if (k < m) {
+                            const double2 v = ap[k * as];
+                            ax = fma(v.x, in[k].x, ax);
+                            ay = fma(v.x, in[k].y, ay);
+                            bx = fma(v.y, in[k].x, bx);
+                            by = fma(v.y, in[k].y, by);
+                        }
                     }
+                    base[j * step] = cmake(ax, ay);
+                    if (j + 1 < m) base[(j + 1) * step] = cmake(bx, by);
                 }
-                base[j * step] = cmake(ax, ay);
             }
         }
     } else {
         // long fibres: real and imaginary parts are separate fibres (half the registers)
-        const int ntask = (H / m) * ncol * 2;
         double* Td = reinterpret_cast<double*>(T);
-        for (int task = tid; task < ntask; task += HXG_THREADS) {
-            const int comp = task & 1, tk = task >> 1;
-            const int f = tk / ncol, c = c_lo + tk - f * ncol;
+        for (int f = ln.tr; f < nf; f += ln.TR) {
             const int o = f / s, r = f - o * s;
-            double* base = Td + 2 * ((long long)(o * m * s + r) * ld + c) + comp;
-            double in[MAXM];
+            for (int c = c_lo + ln.tc; c < c_hi; c += ln.TC) {
+#pragma unroll 1
+                for (int comp = 0; comp < 2; ++comp) {
+                    double* base = Td + 2 * ((long long)(o * m * s + r) * ld + c) + comp;
+                    double in[MAXM];
 #pragma unroll
-            for (int k = 0; k < MAXM; ++k)
-                if (k < m) in[k] = base[2 * k * step];
-            for (int j = 0; j < m; ++j) {
-                const double* vp = FWD ? sV + j : sV + j * m;
-                const int vs = FWD ? m : 1;
-                double acc = 0.0;
+                    for (int k = 0; k < MAXM; ++k)
+                        if (k < m) in[k] = base[2 * k * step];
+                    for (int j = 0; j < m; j += 2) {
+                        const double2* ap = reinterpret_cast<const double2*>(sA + j);
+                        const int as = mp >> 1;
+                        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                for (int k = 0; k < MAXM; ++k)
-                    if (k < m) acc = fma(vp[k * vs], in[k], acc);
-                base[2 * j * step] = acc;
+                        for (int k = 0; k < MAXM; ++k) {
+                            if (k < m) {
+                                const double2 v = ap[k * as];
+                                a0 = fma(v.x, in[k], a0);
+                                a1 = fma(v.y, in[k], a1);
+                            }
+                        }
+                        base[2 * j * step] = a0;
+                        if (j + 1 < m) base[2 * (j + 1) * step] = a1;
+                    }
+                }
             }
         }
     }
 }
 
-template <bool FWD>
-__device__ __forceinline__ void hxg_transform_any(cplx* T, const double* sV, int m, int s, int H, int ld, int c_lo,
-                                                  int c_hi, int tid) {
-    if (m <= 4) hxg_transform<4, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 6) hxg_transform<6, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 8) hxg_transform<8, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 10) hxg_transform<10, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 12) hxg_transform<12, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 16) hxg_transform<16, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 20) hxg_transform<20, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 24) hxg_transform<24, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
-    else hxg_transform<32, FWD>(T, sV, m, s, H, ld, c_lo, c_hi, tid);
+__device__ __forceinline__ void hxg_transform_any(cplx* T, const double* sA, int m, int mp, int s, int H, int ld,
+                                                  int c_lo, int c_hi, int tid) {
+    if (m <= 4) hxg_transform<4>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 6) hxg_transform<6>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 8) hxg_transform<8>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 10) hxg_transform<10>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 12) hxg_transform<12>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 16) hxg_transform<16>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 20) hxg_transform<20>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
+    else if (m <= 24) hxg_transform<24>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
+    else hxg_transform<32>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
 }
 
 __global__ void __launch_bounds__(HXG_THREADS, 1)
 hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__ Vcat, const double* __restrict__ lam,
                   const cplx* __restrict__ etab, long long etab_stride_b, const double* __restrict__ g,
                   const cplx* __restrict__ a, const double* __restrict__ fdiag, long long fdiag_stride_b,
-                  sqc_block_t X, sqc_block_t Y, int vmax, long long nitems) {
+                  sqc_block_t X, sqc_block_t Y, int vmax, long long nvec, long long nitems) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int H = gm.H, C = gm.C, ld = gm.ld, T_ = gm.n_terms;
-    // shared memory: tile [H][ld] complex | phase table [T][H] complex | V matrices | lin[H] | column masks | mbarrier
+    // shared memory: tile [H][ld] complex | phase table [T][H] complex | padded V and V^T per mode | lin[H] |
+    // column masks | mbarrier
     cplx* tile = reinterpret_cast<cplx*>(smem_raw);
     cplx* sPh = tile + (long long)H * ld;
-    double* sV = reinterpret_cast<double*>(sPh + (long long)max(T_, 1) * H);
-    double* sLin = sV + gm.vlen;
+    double* sA = reinterpret_cast<double*>(sPh + (long long)max(T_, 1) * H);
+    double* sLin = sA + gm.alen;
     unsigned* sMask = reinterpret_cast<unsigned*>(sLin + H);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(
         (reinterpret_cast<uintptr_t>(sMask + ld) + 7) & ~(uintptr_t)7);
 
-    for (int e = tid; e < gm.vlen; e += HXG_THREADS) sV[e] = Vcat[e];
+    for (int i = 0; i < gm.nh; ++i) {
+        const int m = gm.hm[i], mp = m + (m & 1);
+        double* A = sA + gm.haoff[i];
+        const double* V = Vcat + gm.hvoff[i];
+        for (int e = tid; e < m * mp; e += HXG_THREADS) {
+            const int k = e / mp, j = e - k * mp;
+            A[e] = j < m ? V[k * m + j] : 0.0;                    // forward:  out[j] = sum_k V[k][j] in[k]
+            A[m * mp + e] = j < m ? V[j * m + k] : 0.0;           // backward: out[j] = sum_k V[j][k] in[k]
+        }
+    }
     if (tid == 0) hxg_mbar_init(bar, 1);
     __syncthreads();
 
     int last_b = -1, last_tile = -1;
     unsigned phase = 0;
+    // items are tile-major: a CTA's consecutive items share the column window (masks), the point changes
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int ti = (int)(item % gm.ntile);
-        const long long vec = item / gm.ntile;
-        const int b = (int)(vec / vmax), v = (int)(vec % vmax);
+        const int ti = (int)(item / nvec);
+        const long long vec = item - (long long)ti * nvec;
+        const int b = (int)(vec / vmax), v = (int)(vec - (long long)b * vmax);
         if (v >= blk_count(X, b)) continue;          // uniform over the CTA
         const cplx* x = blk_vec(X, b, v, gm.N);
         cplx* y = blk_vec(Y, b, v, gm.N);
@@ -215,17 +254,16 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
         }
         if (ti != last_tile) {
             for (int cl = tid; cl < nld; cl += HXG_THREADS) {
-                const int c = l0 + cl;
-                unsigned mk = 0;
-                for (int t = 0; t < T_; ++t) {
-                    bool lo = true, hi = true;
-                    for (int j = 0; j < gm.nc; ++j) {
-                        const int ij = (c / gm.cs[j]) % gm.cd[j], w = gm.tsh[t][j];
-                        lo = lo && (ij - w >= 0) && (ij - w < gm.cd[j]);
-                        hi = hi && (ij + w >= 0) && (ij + w < gm.cd[j]);
-                    }
-                    mk |= (lo ? 1u : 0u) << (2 * t) | (hi ? 1u : 0u) << (2 * t + 1);
+                int rem = l0 + cl;
+                unsigned lo = 0xffffffffu, hi = 0xffffffffu;      // bit t: the shifted index stays inside the space
+                for (int j = 0; j < gm.nc; ++j) {
+                    const int ij = rem / gm.cs[j];
+                    rem -= ij * gm.cs[j];
+                    if (ij == 0) { lo &= ~gm.tpos[j]; hi &= ~gm.tneg[j]; }              // ij - 1 / ij + (-1) < 0
+                    if (ij == gm.cd[j] - 1) { lo &= ~gm.tneg[j]; hi &= ~gm.tpos[j]; }  // ij + 1 >= dim
                 }
+                unsigned mk = 0;
+                for (int t = 0; t < T_; ++t) mk |= (lo >> t & 1u) << (2 * t) | (hi >> t & 1u) << (2 * t + 1);
                 sMask[cl] = mk;
             }
             last_tile = ti;
@@ -236,68 +274,73 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
 
         // ---- 2. forward transforms (all loaded columns: the halo is needed in the x basis too) ----
         for (int i = 0; i < gm.nh; ++i) {
-            hxg_transform_any<true>(tile, sV + gm.hvoff[i], gm.hm[i], gm.hs[i], H, ld, 0, nld, tid);
+            const int m = gm.hm[i], mp = m + (m & 1);
+            hxg_transform_any(tile, sA + gm.haoff[i], m, mp, gm.hs[i], H, ld, 0, nld, tid);
             __syncthreads();
         }
 
-        // ---- 3. potential on the window columns.  It couples the columns of ONE row, so the rows are taken in
-        // groups of at most HXG_MAXE x 512 elements: gather the group's results in registers, synchronise,
-        // overwrite the group's rows (the next group reads other rows: no second barrier) ----
+        // ---- 3. potential on the window columns.  It couples the columns of ONE row, so whole rows are taken in
+        // passes of at most HXG_MAXE elements per thread: gather the pass's results in registers, synchronise,
+        // overwrite its rows (the next pass reads other rows: no second barrier) ----
         const int w0 = c0 - l0, nw = c1 - c0;            // window inside the loaded columns
-        const int rows_per = max(1, (HXG_MAXE * HXG_THREADS) / nw);
-        for (int h0 = 0; h0 < H; h0 += rows_per) {
-            const int nel = min(rows_per, H - h0) * nw;
+        const HxgLanes ln(nw, tid);
+        const int CS = (nw + ln.TC - 1) / ln.TC;         // column steps of a row (<= HXG_MAXE, see the launch code)
+        const int RG = max(1, HXG_MAXE / CS);            // row steps per pass
+        for (int h0 = 0; h0 < H; h0 += ln.TR * RG) {
             cplx res[HXG_MAXE];
+            int rg = 0, cs = 0;
 #pragma unroll
             for (int q = 0; q < HXG_MAXE; ++q) {
-                const int e = tid + q * HXG_THREADS;
-                if (e < nel) {
-                    const int hh = e / nw, cl = w0 + e - hh * nw, h = h0 + hh;
-                    const cplx* row = tile + (long long)h * ld;
-                    const cplx z = row[cl];
+                const int h = h0 + rg * ln.TR + ln.tr, cc = cs * ln.TC + ln.tc;
+                if (ln.tr >= 0 && rg < RG && h < H && cc < nw) {
+                    const cplx* row = tile + (long long)h * ld + w0;
+                    const cplx z = row[cc];
                     const double lin = sLin[h];
                     cplx acc = cmake(lin * z.x, lin * z.y);
-                    const unsigned mk = sMask[cl];
+                    const unsigned mk = sMask[w0 + cc];
 #pragma unroll 1
                     for (int t = 0; t < T_; ++t) {
                         const cplx ph = sPh[t * H + h];
                         const int d = gm.tdelta[t];
-                        if (mk >> (2 * t) & 1u) cfma(acc, ph, row[cl - d]);
-                        if (mk >> (2 * t + 1) & 1u) cfma(acc, cconj(ph), row[cl + d]);
+                        if (mk >> (2 * t) & 1u) cfma(acc, ph, row[cc - d]);
+                        if (mk >> (2 * t + 1) & 1u) cfma(acc, cconj(ph), row[cc + d]);
                     }
                     res[q] = acc;
                 }
+                if (++cs == CS) { cs = 0; ++rg; }
             }
             __syncthreads();
+            rg = 0;
+            cs = 0;
 #pragma unroll
             for (int q = 0; q < HXG_MAXE; ++q) {
-                const int e = tid + q * HXG_THREADS;
-                if (e < nel) {
-                    const int hh = e / nw;
-                    tile[(long long)(h0 + hh) * ld + w0 + e - hh * nw] = res[q];
-                }
+                const int h = h0 + rg * ln.TR + ln.tr, cc = cs * ln.TC + ln.tc;
+                if (ln.tr >= 0 && rg < RG && h < H && cc < nw) tile[(long long)h * ld + w0 + cc] = res[q];
+                if (++cs == CS) { cs = 0; ++rg; }
             }
         }
         __syncthreads();
-        const int nel = H * nw;
 
         // ---- 4. backward transforms on the window, epilogue, TMA stores ----
         for (int i = gm.nh - 1; i >= 0; --i) {
-            hxg_transform_any<false>(tile, sV + gm.hvoff[i], gm.hm[i], gm.hs[i], H, ld, w0, w0 + nw, tid);
+            const int m = gm.hm[i], mp = m + (m & 1);
+            hxg_transform_any(tile, sA + gm.haoff[i] + m * mp, m, mp, gm.hs[i], H, ld, w0, w0 + nw, tid);
             __syncthreads();
         }
-        if (fdiag) {
+        if (fdiag && ln.tr >= 0) {
             const double* fd = fdiag + b * fdiag_stride_b;
-            for (int e = tid; e < nel; e += HXG_THREADS) {
-                const int h = e / nw, cc = e - h * nw;
-                const long long gi = (long long)h * C + c0 + cc;
-                const double d = fd[gi];
-                const cplx xv = x[gi];
-                cplx* p = tile + (long long)h * ld + w0 + cc;
-                cplx val = *p;
-                val.x = fma(d, xv.x, val.x);
-                val.y = fma(d, xv.y, val.y);
-                *p = val;
+            for (int h = ln.tr; h < H; h += ln.TR) {
+                const long long g0 = (long long)h * C + c0;
+                cplx* trow = tile + (long long)h * ld + w0;
+#pragma unroll 4
+                for (int cc = ln.tc; cc < nw; cc += ln.TC) {
+                    const double d = fd[g0 + cc];
+                    const cplx xv = x[g0 + cc];
+                    cplx val = trow[cc];
+                    val.x = fma(d, xv.x, val.x);
+                    val.y = fma(d, xv.y, val.y);
+                    trow[cc] = val;
+                }
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -359,6 +402,8 @@ extern "C" int sqc_hx_generic(const sqc_space_t* sp, const double* Vcat, const s
         gm.hs[i] = s;
         gm.hvoff[i] = vo;
         vo += gm.hm[i] * gm.hm[i];
+        gm.haoff[i] = gm.alen;
+        gm.alen += 2 * gm.hm[i] * (gm.hm[i] + (gm.hm[i] & 1));
     }
     gm.vlen = vo;
     int cs = (int)Cc;
@@ -370,21 +415,26 @@ extern "C" int sqc_hx_generic(const sqc_space_t* sp, const double* Vcat, const s
     int halo = 0;
     for (int t = 0; t < pot->n_terms; ++t) {
         int d = 0;
-        for (int j = 0; j < gm.nc; ++j) d += gm.tsh[t][j] * gm.cs[j];
+        for (int j = 0; j < gm.nc; ++j) {
+            d += gm.tsh[t][j] * gm.cs[j];
+            if (gm.tsh[t][j] > 0) gm.tpos[j] |= 1u << t;
+            if (gm.tsh[t][j] < 0) gm.tneg[j] |= 1u << t;
+        }
         gm.tdelta[t] = d;
         halo = max(halo, abs(d));
     }
     // tile geometry: as many window columns as shared memory and the register budget of the potential phase allow
-    const long long fixed = (long long)max(gm.n_terms, 1) * gm.H * 16 + (long long)gm.vlen * 8 + (long long)gm.H * 8 + 64;
+    const long long fixed = (long long)max(gm.n_terms, 1) * gm.H * 16 + (long long)gm.alen * 8 + (long long)gm.H * 8 + 64;
     const long long budget = 227 * 1024 - fixed;
     auto bytes_for = [&](long long ncols) { return ncols * ((long long)gm.H * 16 + 4); };
     int ncore, ntile;
-    if (bytes_for(gm.C) <= budget) {
+    if (bytes_for(gm.C) <= budget && gm.C <= HXG_MAXE * HXG_THREADS) {
         ncore = gm.C;
         ntile = 1;
         gm.halo = 0;
     } else {
-        const long long cap = budget / ((long long)gm.H * 16 + 4) - 2 * halo;
+        long long cap = budget / ((long long)gm.H * 16 + 4) - 2 * halo;
+        if (cap > HXG_MAXE * HXG_THREADS) cap = HXG_MAXE * HXG_THREADS;      // column steps of the potential phase
         if (cap < halo || cap < 1) return SQC_ELIMIT;       // halo would dominate
         ntile = (int)((gm.C + cap - 1) / cap);
         ncore = (gm.C + ntile - 1) / ntile;
@@ -405,11 +455,12 @@ extern "C" int sqc_hx_generic(const sqc_space_t* sp, const double* Vcat, const s
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long nitems = (long long)B * X.cnt_fixed * ntile;
+    const long long nvec = (long long)B * X.cnt_fixed;
+    const long long nitems = nvec * ntile;
     const int grid = (int)(nitems < sms ? nitems : sms);
     hx_generic_kernel<<<grid, HXG_THREADS, smem, (cudaStream_t)stream>>>(
         gm, Vcat, pot->lam, (const cplx*)pot->etab, pot->etab_stride_b, pot->g, (const cplx*)pot->a, fdiag,
-        fdiag_stride_b, X, Y, X.cnt_fixed, nitems);
+        fdiag_stride_b, X, Y, X.cnt_fixed, nvec, nitems);
     SQC_LAUNCHED();
     return 0;
 }
