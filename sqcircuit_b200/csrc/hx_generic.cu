@@ -23,7 +23,6 @@
 
 #define HXG_THREADS 512
 #define HXG_MAXH 4          // harmonic modes
-#define HXG_MAXE 8         // tile elements per thread and pass of the potential phase
 
 struct HxgGeom {
     int nh;                          // harmonic modes with more than one level
@@ -43,6 +42,7 @@ struct HxgGeom {
     unsigned tpos[SQC_MAX_MODES];    // bit t: term t shifts charge mode j by +1
     unsigned tneg[SQC_MAX_MODES];    // bit t: term t shifts charge mode j by -1
     int halo, ncore, ntile, ld;      // tile geometry: window columns, tiles per vector, row pitch (complex)
+    int rp;                          // rows per pass of the potential phase = spare rows of the tile
     int tlen, gcount, vlen, alen;
     long long N;
 };
@@ -183,8 +183,9 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
     const int H = gm.H, C = gm.C, ld = gm.ld, T_ = gm.n_terms;
     // shared memory: tile [H][ld] complex | phase table [T][H] complex | padded V and V^T per mode | lin[H] |
     // column masks | mbarrier
-    cplx* tile = reinterpret_cast<cplx*>(smem_raw);
-    cplx* sPh = tile + (long long)H * ld;
+    cplx* tile = reinterpret_cast<cplx*>(smem_raw);           // [H + rp][ld]: final position of the vector
+    cplx* tload = tile + (long long)gm.rp * ld;               // where it is loaded and transformed forward
+    cplx* sPh = tile + (long long)(H + gm.rp) * ld;
     double* sA = reinterpret_cast<double*>(sPh + (long long)max(T_, 1) * H);
     double* sLin = sA + gm.alen;
     unsigned* sMask = reinterpret_cast<unsigned*>(sLin + H);
@@ -224,7 +225,7 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
             if (tid == 0) hxg_mbar_expect_tx(bar, (unsigned)(H * nld * 16));
             __syncwarp();
             for (int h = tid; h < H; h += 32)
-                hxg_bulk_load(tile + (long long)h * ld, x + (long long)h * C + l0, (unsigned)(nld * 16), bar);
+                hxg_bulk_load(tload + (long long)h * ld, x + (long long)h * C + l0, (unsigned)(nld * 16), bar);
         }
         // ---- tables (while the copies fly): per sweep point the phases a_t prod_i etab_t[i][h_i] and the linear
         // term of every row; per tile the in-range masks of every column ----
@@ -275,51 +276,39 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
         // ---- 2. forward transforms (all loaded columns: the halo is needed in the x basis too) ----
         for (int i = 0; i < gm.nh; ++i) {
             const int m = gm.hm[i], mp = m + (m & 1);
-            hxg_transform_any(tile, sA + gm.haoff[i], m, mp, gm.hs[i], H, ld, 0, nld, tid);
+            hxg_transform_any(tload, sA + gm.haoff[i], m, mp, gm.hs[i], H, ld, 0, nld, tid);
             __syncthreads();
         }
 
-        // ---- 3. potential on the window columns.  It couples the columns of ONE row, so whole rows are taken in
-        // passes of at most HXG_MAXE elements per thread: gather the pass's results in registers, synchronise,
-        // overwrite its rows (the next pass reads other rows: no second barrier) ----
+        // ---- 3. potential on the window columns, out of place with ONE spare group of rows: the vector was loaded
+        // gm.rp rows below its final position; pass p reads rows [p rp, (p+1) rp) at the loaded position and writes
+        // them rp rows higher -- into the spare rows first, then into the rows the previous pass has consumed (the
+        // potential couples the columns of one row only).  One barrier per pass, plain loops, no staging registers.
         const int w0 = c0 - l0, nw = c1 - c0;            // window inside the loaded columns
         const HxgLanes ln(nw, tid);
-        const int CS = (nw + ln.TC - 1) / ln.TC;         // column steps of a row (<= HXG_MAXE, see the launch code)
-        const int RG = max(1, HXG_MAXE / CS);            // row steps per pass
-        for (int h0 = 0; h0 < H; h0 += ln.TR * RG) {
-            cplx res[HXG_MAXE];
-            int rg = 0, cs = 0;
-#pragma unroll
-            for (int q = 0; q < HXG_MAXE; ++q) {
-                const int h = h0 + rg * ln.TR + ln.tr, cc = cs * ln.TC + ln.tc;
-                if (ln.tr >= 0 && rg < RG && h < H && cc < nw) {
-                    const cplx* row = tile + (long long)h * ld + w0;
-                    const cplx z = row[cc];
+        for (int h0 = 0; h0 < H; h0 += gm.rp) {
+            const int h1 = min(H, h0 + gm.rp);
+            if (ln.tr >= 0) {
+                for (int h = h0 + ln.tr; h < h1; h += ln.TR) {
+                    const cplx* row = tload + (long long)h * ld + w0;
+                    cplx* dst = tile + (long long)h * ld + w0;
                     const double lin = sLin[h];
-                    cplx acc = cmake(lin * z.x, lin * z.y);
-                    const unsigned mk = sMask[w0 + cc];
-#pragma unroll 1
-                    for (int t = 0; t < T_; ++t) {
-                        const cplx ph = sPh[t * H + h];
-                        const int d = gm.tdelta[t];
-                        if (mk >> (2 * t) & 1u) cfma(acc, ph, row[cc - d]);
-                        if (mk >> (2 * t + 1) & 1u) cfma(acc, cconj(ph), row[cc + d]);
+                    for (int cc = ln.tc; cc < nw; cc += ln.TC) {
+                        const cplx z = row[cc];
+                        cplx acc = cmake(lin * z.x, lin * z.y);
+                        const unsigned mk = sMask[w0 + cc];
+                        for (int t = 0; t < T_; ++t) {
+                            const cplx ph = sPh[t * H + h];
+                            const int d = gm.tdelta[t];
+                            if (mk >> (2 * t) & 1u) cfma(acc, ph, row[cc - d]);
+                            if (mk >> (2 * t + 1) & 1u) cfma(acc, cconj(ph), row[cc + d]);
+                        }
+                        dst[cc] = acc;
                     }
-                    res[q] = acc;
                 }
-                if (++cs == CS) { cs = 0; ++rg; }
             }
             __syncthreads();
-            rg = 0;
-            cs = 0;
-#pragma unroll
-            for (int q = 0; q < HXG_MAXE; ++q) {
-                const int h = h0 + rg * ln.TR + ln.tr, cc = cs * ln.TC + ln.tc;
-                if (ln.tr >= 0 && rg < RG && h < H && cc < nw) tile[(long long)h * ld + w0 + cc] = res[q];
-                if (++cs == CS) { cs = 0; ++rg; }
-            }
         }
-        __syncthreads();
 
         // ---- 4. backward transforms on the window, epilogue, TMA stores ----
         for (int i = gm.nh - 1; i >= 0; --i) {
@@ -423,20 +412,29 @@ extern "C" int sqc_hx_generic(const sqc_space_t* sp, const double* Vcat, const s
         gm.tdelta[t] = d;
         halo = max(halo, abs(d));
     }
-    // tile geometry: as many window columns as shared memory and the register budget of the potential phase allow
+    // tile geometry: as many window columns as shared memory allows.  Rows of the tile: H + rp (spare rows of the
+    // out-of-place potential phase); rp from the thread layout of a window of w columns: whole row lanes, about two
+    // elements per thread and pass.
     const long long fixed = (long long)max(gm.n_terms, 1) * gm.H * 16 + (long long)gm.alen * 8 + (long long)gm.H * 8 + 64;
     const long long budget = 227 * 1024 - fixed;
-    auto bytes_for = [&](long long ncols) { return ncols * ((long long)gm.H * 16 + 4); };
+    auto rows_per_pass = [&](long long w) {
+        const long long tc = w >= HXG_THREADS ? HXG_THREADS : ((w + 31) & ~31LL);
+        const long long tr = HXG_THREADS / tc, cs = (w + tc - 1) / tc;
+        const long long rp = tr * (cs >= 2 ? 1 : 2);
+        return (int)(rp < gm.H ? rp : gm.H);
+    };
+    auto bytes_for = [&](long long ncols, long long w) { return ncols * ((long long)(gm.H + rows_per_pass(w)) * 16 + 4); };
     int ncore, ntile;
-    if (bytes_for(gm.C) <= budget && gm.C <= HXG_MAXE * HXG_THREADS) {
+    if (bytes_for(gm.C, gm.C) <= budget) {
         ncore = gm.C;
         ntile = 1;
         gm.halo = 0;
     } else {
-        long long cap = budget / ((long long)gm.H * 16 + 4) - 2 * halo;
-        if (cap > HXG_MAXE * HXG_THREADS) cap = HXG_MAXE * HXG_THREADS;      // column steps of the potential phase
-        if (cap < halo || cap < 1) return SQC_ELIMIT;       // halo would dominate
-        ntile = (int)((gm.C + cap - 1) / cap);
+        // largest window w with (w + 2 halo) columns inside the budget
+        long long w = budget / ((long long)(gm.H + 1) * 16 + 4) - 2 * halo;
+        while (w > 0 && bytes_for(w + 2 * halo, w) > budget) --w;
+        if (w < halo || w < 1) return SQC_ELIMIT;       // halo would dominate
+        ntile = (int)((gm.C + w - 1) / w);
         ncore = (gm.C + ntile - 1) / ntile;
         ntile = (gm.C + ncore - 1) / ncore;
         gm.halo = halo;
@@ -444,7 +442,8 @@ extern "C" int sqc_hx_generic(const sqc_space_t* sp, const double* Vcat, const s
     gm.ncore = ncore;
     gm.ntile = ntile;
     gm.ld = ntile == 1 ? gm.C : min(gm.C, ncore + 2 * gm.halo);
-    const size_t smem = (size_t)((long long)gm.H * gm.ld * 16 + fixed + (long long)gm.ld * 4 + 16);
+    gm.rp = rows_per_pass(ncore);
+    const size_t smem = (size_t)((long long)(gm.H + gm.rp) * gm.ld * 16 + fixed + (long long)gm.ld * 4 + 16);
     if (smem > 227 * 1024) return SQC_ELIMIT;
     static bool attr_done = false;
     if (!attr_done) {
