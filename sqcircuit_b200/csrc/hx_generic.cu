@@ -21,8 +21,10 @@
 // Replaces the CSR mat-vec on the Hamiltonian of Circuit.hamiltonian() (circuit.py:2147-2164).
 #include "common.cuh"
 
-#define HXG_THREADS 512
 #define HXG_MAXH 4          // harmonic modes
+
+static int g_hxg_threads = 0;      // 0: choose; 512: force the 512-thread build (dev tool, tools/hxg_bench.py)
+extern "C" void sqc_debug_set_hxg_threads(int n) { g_hxg_threads = n; }
 
 struct HxgGeom {
     int nh;                          // harmonic modes with more than one level
@@ -79,9 +81,9 @@ __device__ __forceinline__ void hxg_bulk_store(void* dst, const void* src, unsig
 // (at most the CTA), TR = 512 / TC row lanes; thread -> (tr, tc).  No division inside the loops.
 struct HxgLanes {
     int TC, TR, tr, tc;
-    __device__ __forceinline__ HxgLanes(int n, int tid) {
-        TC = min(HXG_THREADS, (n + 31) & ~31);
-        TR = HXG_THREADS / TC;
+    __device__ __forceinline__ HxgLanes(int n, int tid, int nthreads) {
+        TC = min(nthreads, (n + 31) & ~31);
+        TR = nthreads / TC;
         tr = tid / TC;
         tc = tid - tr * TC;
         if (tr >= TR) tr = -1;                 // idle thread of this phase
@@ -93,8 +95,8 @@ struct HxgLanes {
 // inputs sit in registers, two outputs are formed at a time so that one 16-byte load of A feeds four FMAs.
 template <int MAXM>
 __device__ __forceinline__ void hxg_transform(cplx* __restrict__ T, const double* __restrict__ sA, int m, int mp, int s,
-                                              int H, int ld, int c_lo, int c_hi, int tid) {
-    const HxgLanes ln(c_hi - c_lo, tid);
+                                              int H, int ld, int c_lo, int c_hi, int tid, int nthreads) {
+    const HxgLanes ln(c_hi - c_lo, tid, nthreads);
     if (ln.tr < 0) return;
     const long long step = (long long)s * ld;
     const int nf = H / m;
@@ -160,20 +162,23 @@ __device__ __forceinline__ void hxg_transform(cplx* __restrict__ T, const double
     }
 }
 
+template <int MAXDIM>
 __device__ __forceinline__ void hxg_transform_any(cplx* T, const double* sA, int m, int mp, int s, int H, int ld,
-                                                  int c_lo, int c_hi, int tid) {
-    if (m <= 4) hxg_transform<4>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 6) hxg_transform<6>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 8) hxg_transform<8>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 10) hxg_transform<10>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 12) hxg_transform<12>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 16) hxg_transform<16>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 20) hxg_transform<20>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
-    else if (m <= 24) hxg_transform<24>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
-    else hxg_transform<32>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid);
+                                                  int c_lo, int c_hi, int tid, int nthreads) {
+    if (m <= 4) hxg_transform<4>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid, nthreads);
+    else if (m <= 6) hxg_transform<6>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid, nthreads);
+    else if (m <= 8) hxg_transform<8>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid, nthreads);
+    else if (m <= 10) hxg_transform<10>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid, nthreads);
+    else if (MAXDIM <= 10) return;
+    else if (m <= 12) hxg_transform<12>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid, nthreads);
+    else if (m <= 16) hxg_transform<16>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid, nthreads);
+    else if (m <= 20) hxg_transform<20>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid, nthreads);
+    else if (m <= 24) hxg_transform<24>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid, nthreads);
+    else hxg_transform<32>(T, sA, m, mp, s, H, ld, c_lo, c_hi, tid, nthreads);
 }
 
-__global__ void __launch_bounds__(HXG_THREADS, 1)
+template <int NTHREADS, int MAXDIM>
+__global__ void __launch_bounds__(NTHREADS, 1)
 hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__ Vcat, const double* __restrict__ lam,
                   const cplx* __restrict__ etab, long long etab_stride_b, const double* __restrict__ g,
                   const cplx* __restrict__ a, const double* __restrict__ fdiag, long long fdiag_stride_b,
@@ -196,7 +201,7 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
         const int m = gm.hm[i], mp = m + (m & 1);
         double* A = sA + gm.haoff[i];
         const double* V = Vcat + gm.hvoff[i];
-        for (int e = tid; e < m * mp; e += HXG_THREADS) {
+        for (int e = tid; e < m * mp; e += NTHREADS) {
             const int k = e / mp, j = e - k * mp;
             A[e] = j < m ? V[k * m + j] : 0.0;                    // forward:  out[j] = sum_k V[k][j] in[k]
             A[m * mp + e] = j < m ? V[j * m + k] : 0.0;           // backward: out[j] = sum_k V[j][k] in[k]
@@ -232,7 +237,7 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
         if (b != last_b) {
             const cplx* et = etab + b * etab_stride_b;
             const double* gb = g + (long long)b * gm.gcount;
-            for (int h = tid; h < H; h += HXG_THREADS) {
+            for (int h = tid; h < H; h += NTHREADS) {
                 double lin = gb[0];
                 int hi[HXG_MAXH];
 #pragma unroll
@@ -254,7 +259,7 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
             last_b = b;
         }
         if (ti != last_tile) {
-            for (int cl = tid; cl < nld; cl += HXG_THREADS) {
+            for (int cl = tid; cl < nld; cl += NTHREADS) {
                 int rem = l0 + cl;
                 unsigned lo = 0xffffffffu, hi = 0xffffffffu;      // bit t: the shifted index stays inside the space
                 for (int j = 0; j < gm.nc; ++j) {
@@ -276,7 +281,7 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
         // ---- 2. forward transforms (all loaded columns: the halo is needed in the x basis too) ----
         for (int i = 0; i < gm.nh; ++i) {
             const int m = gm.hm[i], mp = m + (m & 1);
-            hxg_transform_any(tload, sA + gm.haoff[i], m, mp, gm.hs[i], H, ld, 0, nld, tid);
+            hxg_transform_any<MAXDIM>(tload, sA + gm.haoff[i], m, mp, gm.hs[i], H, ld, 0, nld, tid, NTHREADS);
             __syncthreads();
         }
 
@@ -285,7 +290,7 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
         // them rp rows higher -- into the spare rows first, then into the rows the previous pass has consumed (the
         // potential couples the columns of one row only).  One barrier per pass, plain loops, no staging registers.
         const int w0 = c0 - l0, nw = c1 - c0;            // window inside the loaded columns
-        const HxgLanes ln(nw, tid);
+        const HxgLanes ln(nw, tid, NTHREADS);
         for (int h0 = 0; h0 < H; h0 += gm.rp) {
             const int h1 = min(H, h0 + gm.rp);
             if (ln.tr >= 0) {
@@ -293,17 +298,37 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
                     const cplx* row = tload + (long long)h * ld + w0;
                     cplx* dst = tile + (long long)h * ld + w0;
                     const double lin = sLin[h];
-                    for (int cc = ln.tc; cc < nw; cc += ln.TC) {
-                        const cplx z = row[cc];
-                        cplx acc = cmake(lin * z.x, lin * z.y);
-                        const unsigned mk = sMask[w0 + cc];
-                        for (int t = 0; t < T_; ++t) {
-                            const cplx ph = sPh[t * H + h];
-                            const int d = gm.tdelta[t];
-                            if (mk >> (2 * t) & 1u) cfma(acc, ph, row[cc - d]);
-                            if (mk >> (2 * t + 1) & 1u) cfma(acc, cconj(ph), row[cc + d]);
+                    // terms in blocks of four: phases and offsets of the row in registers, invalid neighbours (outside
+                    // the truncated charge range) enter with coefficient zero through a valid address -- no branches
+                    for (int t0 = 0; t0 == 0 || t0 < T_; t0 += 4) {
+                        cplx ph[4];
+                        int dl[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const bool on = t0 + u < T_;
+                            ph[u] = on ? sPh[(t0 + u) * H + h] : cmake(0.0, 0.0);
+                            dl[u] = on ? gm.tdelta[t0 + u] : 0;
                         }
-                        dst[cc] = acc;
+                        for (int cc = ln.tc; cc < nw; cc += ln.TC) {
+                            cplx acc;
+                            if (t0 == 0) {
+                                const cplx z = row[cc];
+                                acc = cmake(lin * z.x, lin * z.y);
+                            } else {
+                                acc = dst[cc];
+                            }
+                            const unsigned mk = sMask[w0 + cc] >> (2 * t0);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const bool lo = mk >> (2 * u) & 1u, hi = mk >> (2 * u + 1) & 1u;
+                                const cplx zl = row[lo ? cc - dl[u] : cc], zh = row[hi ? cc + dl[u] : cc];
+                                const cplx pl = lo ? ph[u] : cmake(0.0, 0.0);
+                                const cplx pc = hi ? cconj(ph[u]) : cmake(0.0, 0.0);
+                                cfma(acc, pl, zl);
+                                cfma(acc, pc, zh);
+                            }
+                            dst[cc] = acc;
+                        }
                     }
                 }
             }
@@ -313,7 +338,7 @@ hx_generic_kernel(const __grid_constant__ HxgGeom gm, const double* __restrict__
         // ---- 4. backward transforms on the window, epilogue, TMA stores ----
         for (int i = gm.nh - 1; i >= 0; --i) {
             const int m = gm.hm[i], mp = m + (m & 1);
-            hxg_transform_any(tile, sA + gm.haoff[i] + m * mp, m, mp, gm.hs[i], H, ld, w0, w0 + nw, tid);
+            hxg_transform_any<MAXDIM>(tile, sA + gm.haoff[i] + m * mp, m, mp, gm.hs[i], H, ld, w0, w0 + nw, tid, NTHREADS);
             __syncthreads();
         }
         if (fdiag && ln.tr >= 0) {
@@ -417,9 +442,15 @@ extern "C" int sqc_hx_generic(const sqc_space_t* sp, const double* Vcat, const s
     // elements per thread and pass.
     const long long fixed = (long long)max(gm.n_terms, 1) * gm.H * 16 + (long long)gm.alen * 8 + (long long)gm.H * 8 + 64;
     const long long budget = 227 * 1024 - fixed;
+    int maxdim = 0;
+    for (int i = 0; i < gm.nh; ++i) maxdim = max(maxdim, gm.hm[i]);
+    // Fibres of at most ten levels fit the 64-register budget of a 1024-thread CTA: twice the warps to hide the
+    // shared-memory and FP64 latencies of the in-place phases (measured: 2.23 -> 2.03 ms on 6144 vectors of a
+    // 10 x 10 x 9 x 9 space; no gain on 10 x 99 x 99, whose ten rows leave one fibre per column).
+    const int nthreads = (maxdim <= 10 && Hh >= 64 && g_hxg_threads != 512) ? 1024 : 512;
     auto rows_per_pass = [&](long long w) {
-        const long long tc = w >= HXG_THREADS ? HXG_THREADS : ((w + 31) & ~31LL);
-        const long long tr = HXG_THREADS / tc, cs = (w + tc - 1) / tc;
+        const long long tc = w >= nthreads ? nthreads : ((w + 31) & ~31LL);
+        const long long tr = nthreads / tc, cs = (w + tc - 1) / tc;
         const long long rp = tr * (cs >= 2 ? 1 : 2);
         return (int)(rp < gm.H ? rp : gm.H);
     };
@@ -430,13 +461,19 @@ extern "C" int sqc_hx_generic(const sqc_space_t* sp, const double* Vcat, const s
         ntile = 1;
         gm.halo = 0;
     } else {
-        // largest window w with (w + 2 halo) columns inside the budget
+        // largest window w whose balanced tiling (ncore columns per tile, its own rows per pass) fits the budget
         long long w = budget / ((long long)(gm.H + 1) * 16 + 4) - 2 * halo;
-        while (w > 0 && bytes_for(w + 2 * halo, w) > budget) --w;
-        if (w < halo || w < 1) return SQC_ELIMIT;       // halo would dominate
-        ntile = (int)((gm.C + w - 1) / w);
-        ncore = (gm.C + ntile - 1) / ntile;
-        ntile = (gm.C + ncore - 1) / ncore;
+        ncore = ntile = 0;
+        for (; w >= halo && w >= 1; --w) {
+            const int nt = (int)((gm.C + w - 1) / w);
+            const int nc = (gm.C + nt - 1) / nt;
+            if (bytes_for(nc + 2 * halo, nc) <= budget) {
+                ncore = nc;
+                ntile = (gm.C + nc - 1) / nc;
+                break;
+            }
+        }
+        if (ncore == 0) return SQC_ELIMIT;       // halo would dominate
         gm.halo = halo;
     }
     gm.ncore = ncore;
@@ -445,21 +482,28 @@ extern "C" int sqc_hx_generic(const sqc_space_t* sp, const double* Vcat, const s
     gm.rp = rows_per_pass(ncore);
     const size_t smem = (size_t)((long long)(gm.H + gm.rp) * gm.ld * 16 + fixed + (long long)gm.ld * 4 + 16);
     if (smem > 227 * 1024) return SQC_ELIMIT;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(hx_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long nvec = (long long)B * X.cnt_fixed;
     const long long nitems = nvec * ntile;
     const int grid = (int)(nitems < sms ? nitems : sms);
-    hx_generic_kernel<<<grid, HXG_THREADS, smem, (cudaStream_t)stream>>>(
-        gm, Vcat, pot->lam, (const cplx*)pot->etab, pot->etab_stride_b, pot->g, (const cplx*)pot->a, fdiag,
-        fdiag_stride_b, X, Y, X.cnt_fixed, nvec, nitems);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(hx_generic_kernel<1024, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(hx_generic_kernel<512, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    if (nthreads == 1024)
+        hx_generic_kernel<1024, 10><<<grid, 1024, smem, (cudaStream_t)stream>>>(
+            gm, Vcat, pot->lam, (const cplx*)pot->etab, pot->etab_stride_b, pot->g, (const cplx*)pot->a, fdiag,
+            fdiag_stride_b, X, Y, X.cnt_fixed, nvec, nitems);
+    else
+        hx_generic_kernel<512, 32><<<grid, 512, smem, (cudaStream_t)stream>>>(
+            gm, Vcat, pot->lam, (const cplx*)pot->etab, pot->etab_stride_b, pot->g, (const cplx*)pot->a, fdiag,
+            fdiag_stride_b, X, Y, X.cnt_fixed, nvec, nitems);
     SQC_LAUNCHED();
     return 0;
 }

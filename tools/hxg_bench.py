@@ -52,6 +52,10 @@ def run():
     assert k.hx_generic(sp, Vcat, pot, fd, BlockView(X), BlockView(Y))
 
 
+import ctypes
+force = int(os.environ.get('HXG_THREADS', '0'))
+k.lib.sqc_debug_set_hxg_threads.argtypes = [ctypes.c_int]
+k.lib.sqc_debug_set_hxg_threads(force)
 run()
 torch.cuda.synchronize()
 best = 1e9
@@ -63,6 +67,6 @@ for _ in range(5):
     torch.cuda.synchronize()
     best = min(best, s0.elapsed_time(e0))
 flops = 4.0 * sum(d for d, h in zip(dims, harm) if h) * N * p * B
-print(json.dumps({'layout': which, 'dims': dims, 'vectors': B * p, 'ms': round(best, 3),
+print(json.dumps({'layout': which, 'threads': force or 'auto', 'dims': dims, 'vectors': B * p, 'ms': round(best, 3),
                   'GBps': round(32.0 * N * p * B / best / 1e6, 1), 'TFLOPs': round(flops / best / 1e9, 2),
                   'us_per_vector_per_sm': round(best * 1e3 * 148 / (B * p), 2)}))
