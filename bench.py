@@ -131,37 +131,40 @@ class Fluxonium(Workload):
 
 class TransmonResonatorTransmon(Workload):
     name = 'trt1e5'
-    text = ('transmon-resonator-transmon, trunc_nums [10,50,50] (N=98010), 16x16 gate-charge grid per GPU, k=10, '
-            '3 T1/Tphi channels on (1,0)')
-    metric = 'diagonalisations/sec (k=10), transmon-resonator-transmon gate-charge grid'
+    text = ('transmon-resonator-(flux-tunable transmon), trunc_nums [10,50,50] (N=98010), 16x16 grid over (gate charge '
+            'of transmon 1) x (external flux of the SQUID of transmon 2) per GPU, k=10, 4 T1/Tphi channels on (1,0)')
+    metric = 'diagonalisations/sec (k=10), transmon-resonator-transmon gate-charge x flux grid'
     points = 256
     trunc = [10, 50, 50]
-    dec_types = ['capacitive', 'charge', 'cc']
+    dec_types = ['capacitive', 'charge', 'cc', 'flux']
 
     def build(self, sq, kern):
+        self.loop = sq.Loop()
         cr = sq.Circuit({(0, 1): [sq.Capacitor(0.5, 'GHz'), sq.Inductor(8.0, 'GHz')],
                          (0, 2): [sq.Capacitor(0.30, 'GHz'), sq.Junction(14.0, 'GHz')],
-                         (0, 3): [sq.Capacitor(0.27, 'GHz'), sq.Junction(17.0, 'GHz')],
+                         (0, 3): [sq.Capacitor(0.27, 'GHz'), sq.Junction(9.0, 'GHz', loops=[self.loop]),
+                                  sq.Junction(8.0, 'GHz', loops=[self.loop])],
                          (1, 2): [sq.Capacitor(12.0, 'GHz')], (1, 3): [sq.Capacitor(15.0, 'GHz')]}, kernels=kern)
         cr.set_trunc_nums(self.trunc)
         self.modes = [i + 1 for i in sorted(cr.charge_islands)]
         return cr
 
     def oracle(self, o):
+        lp = o.OLoop()
         c = o.OCircuit({(0, 1): [o.OCap(0.5, 'GHz'), o.OInd(8.0, 'GHz')],
                         (0, 2): [o.OCap(0.30, 'GHz'), o.OJJ(14.0, 'GHz')],
-                        (0, 3): [o.OCap(0.27, 'GHz'), o.OJJ(17.0, 'GHz')],
+                        (0, 3): [o.OCap(0.27, 'GHz'), o.OJJ(9.0, 'GHz', loops=[lp]), o.OJJ(8.0, 'GHz', loops=[lp])],
                         (1, 2): [o.OCap(12.0, 'GHz')], (1, 3): [o.OCap(15.0, 'GHz')]})
         c.set_trunc_nums(self.trunc)
         modes = [i + 1 for i in range(c.n) if c.is_charge(i)]
 
         def setter(prm):
-            for md, v in zip(modes, prm):
-                c.set_charge_offset(md, float(v))
+            c.set_charge_offset(modes[0], float(prm[0]))
+            lp.set_flux(float(prm[1]))
         return c, setter
 
     def grid(self, points, rank, world, strong=False):
-        # square grid over [0, 0.5)^2, row-major; the line index of _line walks the grid
+        # square grid over [0, 0.5)^2 (gate charge, flux), row-major; the line index of _line walks the grid
         side = int(round(np.sqrt(points)))
         t = self._line(side * side, rank, world, strong) * side * side      # fractional cell index
         cell = np.floor(t).astype(int)
@@ -169,7 +172,7 @@ class TransmonResonatorTransmon(Workload):
         return np.stack([((cell // side) + frac) / side * 0.5, ((cell % side) + 0.5) / side * 0.5], axis=1)
 
     def sweep_args(self, prm):
-        return {'charge_offsets': {self.modes[0]: prm[:, 0], self.modes[1]: prm[:, 1]}}
+        return {'charge_offsets': {self.modes[0]: prm[:, 0]}, 'loop_fluxes': {self.loop: prm[:, 1]}}
 
 
 class Discovery(Workload):

@@ -62,6 +62,23 @@ def trt(kernels=None):
     return cr, oc
 
 
+def trt_squid(kernels=None):
+    """Transmon - resonator - flux-tunable transmon (the second transmon is a SQUID: two junctions in a loop):
+    BASELINE configs[3] with a gate-charge AND a flux axis."""
+    lp = sq.Loop()
+    cr = sq.Circuit({(0, 1): [sq.Capacitor(0.5, 'GHz'), sq.Inductor(8.0, 'GHz')],
+                     (0, 2): [sq.Capacitor(0.30, 'GHz'), sq.Junction(14.0, 'GHz')],
+                     (0, 3): [sq.Capacitor(0.27, 'GHz'), sq.Junction(9.0, 'GHz', loops=[lp]),
+                              sq.Junction(8.0, 'GHz', loops=[lp])],
+                     (1, 2): [sq.Capacitor(12.0, 'GHz')], (1, 3): [sq.Capacitor(15.0, 'GHz')]}, kernels=kernels)
+    ol = o.OLoop()
+    oc = o.OCircuit({(0, 1): [o.OCap(0.5, 'GHz'), o.OInd(8.0, 'GHz')],
+                     (0, 2): [o.OCap(0.30, 'GHz'), o.OJJ(14.0, 'GHz')],
+                     (0, 3): [o.OCap(0.27, 'GHz'), o.OJJ(9.0, 'GHz', loops=[ol]), o.OJJ(8.0, 'GHz', loops=[ol])],
+                     (1, 2): [o.OCap(12.0, 'GHz')], (1, 3): [o.OCap(15.0, 'GHz')]})
+    return cr, lp, oc, ol
+
+
 def inductively_shunted(kernels=None):
     lp = sq.Loop()
     cr = sq.Circuit({(0, 1): [sq.Capacitor(20.3, 'fF')], (1, 2): [sq.Inductor(15.6, 'nH')],

@@ -341,6 +341,29 @@ def test_config3_transmon_resonator_transmon():
     _check(res, oc, setter, ngs, 10, ['capacitive', 'cc', 'charge'])
 
 
+def _grid_check(kernels, trunc, k, n_side):
+    """Gate charge of the first transmon x external flux of the SQUID transmon, n_side x n_side grid, against
+    the oracle point by point (eigenvalues, subspaces, four channels incl. flux dephasing)."""
+    cr, lp, oc, ol = cs.trt_squid(kernels)
+    cr.set_trunc_nums(trunc)
+    oc.set_trunc_nums(trunc)
+    m1 = sorted(cr.charge_islands)[0] + 1
+    a, b = np.meshgrid(np.linspace(0.0, 0.5, n_side), np.linspace(0.05, 0.45, n_side), indexing='ij')
+    ng, fl = a.ravel(), b.ravel()
+    res = cr.sweep_diag(k, charge_offsets={m1: ng}, loop_fluxes={lp: fl})
+
+    def setter(p):
+        oc.set_charge_offset(m1, float(p[0]))
+        ol.set_flux(float(p[1]))
+    _check(res, oc, setter, np.stack([ng, fl], axis=1), k, ['capacitive', 'cc', 'charge', 'flux'])
+    return res
+
+
+def test_config3_gate_charge_flux_grid():
+    """BASELINE configs[3], "ng/flux grid sweep": both axes at once on the flux-tunable variant."""
+    _grid_check(None, [6, 6, 6], 8, 3)
+
+
 def test_config3_full_size_dim_1e5():
     """BASELINE configs[3] at its named size: transmon-resonator-transmon, N = 10 x 99 x 99 = 98010,
     a 2-D gate-charge grid.  One grid point against the oracle (ARPACK on the CSR matrix), all

@@ -372,3 +372,10 @@ def test_low_block_sharing_only_between_neighbouring_points():
     rng = np.random.default_rng(0)
     assert group_of(rng.permutation(np.linspace(0.0, 1.0, 64))) == 1      # arbitrary order
     assert group_of([0.3]) == 1
+
+
+def test_gate_charge_flux_grid_three_modes_cpu():
+    """The body of the GPU test of BASELINE configs[3]'s ng x flux grid, kernels emulated, small truncation."""
+    from test_gpu_parity import _grid_check
+    res = _grid_check(EmulKernels(), [4, 4, 4], 5, 2)
+    assert res.converged

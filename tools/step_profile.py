@@ -11,8 +11,8 @@ loop = sq.Loop()
 C, CJ = sq.Capacitor(0.15, 'GHz'), sq.Capacitor(10, 'GHz')
 JJ, L = sq.Junction(5, 'GHz', loops=[loop]), sq.Inductor(0.13, 'GHz', loops=[loop])
 cr = sq.Circuit({(0, 1): [CJ, JJ], (0, 2): [L], (0, 3): [C], (1, 2): [C], (1, 3): [L], (2, 3): [CJ, JJ]})
-cr.set_trunc_nums([100, 50])
-fl = np.linspace(0.0, 1.0, points)
+cr.set_trunc_nums([100, 51])
+fl = (np.arange(points) + 0.5) / points
 DEC = ['capacitive', 'inductive', 'quasiparticle', 'charge', 'cc', 'flux']
 
 
