@@ -51,6 +51,61 @@ class SweepNoise:
                                ops.to_device(g, torch.float64), etab=etab, shift=shift)
         return Y
 
+    # ---- potential-type operators on the pair: matrix elements in the x basis ---------------------------
+    def _pair_x(self, states):
+        """The pair of ``_pair`` rotated to the x basis of every harmonic mode (once per pair): every
+        potential-type operator O = F^T P F then has <a|O|b> = <Fa| P |Fb> with P element-wise + shifts, so
+        the six channels of a T1 / Tphi query share ONE forward transform instead of paying a forward and a
+        backward transform per operator."""
+        key = tuple(int(x) for x in states)
+        if getattr(self, '_pairx_key', None) != key:
+            X = self._pair(states)
+            ops = self.ops
+            Z = X
+            if ops.tmodes:
+                Z = torch.empty_like(X)
+                src = BlockView(X)
+                for i in ops.tmodes:
+                    self.kern.mode_transform(ops.sp, i, ops.V[i], 1, src, BlockView(Z), impl=ops.impl)
+                    src = BlockView(Z)
+            self._pairx_val, self._pairx_key = Z, key
+            self._pairx_scratch = torch.empty_like(X)
+        return self._pairx_val
+
+    def _pot_elements(self, states, a, g, etab=None, shift=None):
+        """[B][2][2] matrix of the potential-type operator (a, g) between the two states (host array)."""
+        ops = self.ops
+        Z = self._pair_x(states)
+        S = self._pairx_scratch
+        g = np.broadcast_to(np.asarray(g, dtype=float).reshape(-1, 1 + ops.M), (self.B, 1 + ops.M))
+        pot = ops.potential_struct(ops.to_device(a, torch.complex128), ops.to_device(g, torch.float64),
+                                   ops.etab if etab is None else etab, shift, None)
+        self.kern.potential_apply(ops.sp, pot, BlockView(Z), BlockView(S))
+        return self._gram2(Z, S)
+
+    def _junction_elements(self, states, kind, w_id, b_id, weight=1.0):
+        """Matrix of the cos / sin / sin_half operator of one junction (circuit.py:1809-1825) on the pair."""
+        a = self._zeros_a()
+        zero_g = np.zeros(1 + self.ops.M)
+        if kind == 'cos':
+            a[:, w_id] = weight * self._phases(b_id) / 2
+            return self._pot_elements(states, a, zero_g)
+        if kind == 'sin':
+            a[:, w_id] = weight * self._phases(b_id) / 2j
+            return self._pot_elements(states, a, zero_g)
+        if kind == 'sin_half':
+            a[:, w_id] = weight * self._phases(b_id, 0.5) / 2j
+            return self._pot_elements(states, a, zero_g, etab=self.ops.etab_half(),
+                                      shift=np.zeros_like(self.ops.shift))
+        raise ValueError(kind)
+
+    def _coupling_elements(self, states, ctype, nodes):
+        if ctype == 'capacitive':
+            X = self._pair(states)
+            return self._gram2(X, self.apply_coupling(X, ctype, nodes))
+        k = self.ops.kcoef_b(ctype, nodes)
+        return self._pot_elements(states, self._zeros_a(), self.ops.phi_lin_b(k))
+
     def _apply_charge_comb(self, X, k):
         """Y = (sum_i k_i Q_i) X  with Q_i of circuit.py:1471-1497 (normalised by sqrt(hbar)); k: [M], or one
         row per point [B][M] (batched circuits)."""
@@ -109,15 +164,14 @@ class SweepNoise:
         raise ValueError(kind)
 
     def matrix_elements(self, ctype, nodes, states):
-        X = self._pair(states)
-        return self._gram2(X, self.apply_coupling(X, ctype, nodes))[:, 0, 1]
+        return self._coupling_elements(states, ctype, nodes)[:, 0, 1]
 
     # ---- decoherence ----------------------------------------------------------------------------
     @staticmethod
     def _dephasing(A, p_omega):
         return np.abs(p_omega * A) * np.sqrt(2 * np.abs(np.log(ENV['omega_low'] * ENV['t_exp'])))
 
-    def _partial_omega_loop(self, X, loop_idx):
+    def _partial_omega_loop(self, states, loop_idx):
         """<m|dH/dphi_loop|m> - <n|...|n>  (circuit.py:2749-2763)."""
         ops, t = self.ops, self.ops.topo
         g = np.zeros(1 + ops.M)
@@ -127,7 +181,7 @@ class SweepNoise:
         a = self._zeros_a()
         for _, jj, b_id, w_id in t.jj_keys:
             a[:, w_id] += t.B[b_id, loop_idx] * jj.si() * self._phases(b_id) / 2j
-        G = self._gram2(X, self._apply_pot(X, a, g))
+        G = self._pot_elements(states, a, g)
         return np.real(G[:, 0, 0] - G[:, 1, 1])
 
     def dec_rate(self, dec_type, states, total=True):
@@ -150,18 +204,18 @@ class SweepNoise:
                 for el in els:
                     cap = el if isinstance(el, Capacitor) else el.cap
                     if cap.Q:
-                        me = self._gram2(X, self.apply_coupling(X, 'capacitive', edge))[:, 0, 1]
+                        me = self._coupling_elements(states, 'capacitive', edge)[:, 0, 1]
                         decay += tempS * cap.si() / cap.Q(omega) * np.abs(me) ** 2
         elif dec_type == 'inductive':
             for edge, el, b_id in t.ind_keys:
                 Q = np.asarray(el.Q(omega, ENV['T']), dtype=float) * np.ones(self.B)
-                me = self._gram2(X, self.apply_coupling(X, 'inductive', edge))[:, 0, 1]
+                me = self._coupling_elements(states, 'inductive', edge)[:, 0, 1]
                 term = tempS / Q / el.si() * np.abs(me) ** 2
                 decay += np.where(np.isnan(Q), 0.0, term)
         elif dec_type == 'quasiparticle':
             for _, el, b_id, w_id in t.jj_keys:
                 Y = np.asarray(el.Y(omega, ENV['T']), dtype=float) * np.ones(self.B)
-                me = self._gram2(X, self.apply_junction_fn(X, 'sin_half', w_id, b_id))[:, 0, 1]
+                me = self._junction_elements(states, 'sin_half', w_id, b_id)[:, 0, 1]
                 term = tempS * Y * omega * el.si() * unt.hbar * np.abs(me) ** 2
                 decay += np.where(np.isnan(Y), 0.0, term)
         elif dec_type == 'charge':
@@ -174,12 +228,12 @@ class SweepNoise:
                 decay += self._dephasing(cr.charge_islands[i].A * 2 * unt.e, p_omega)
         elif dec_type == 'cc':
             for _, el, b_id, w_id in t.jj_keys:
-                G = self._gram2(X, self.apply_junction_fn(X, 'cos', w_id, b_id, weight=-1.0))
+                G = self._junction_elements(states, 'cos', w_id, b_id, weight=-1.0)
                 p_omega = np.real(G[:, 0, 0] - G[:, 1, 1])
                 decay += self._dephasing(el.A * el.si(), p_omega)
         elif dec_type == 'flux':
             for li, lp in enumerate(t.loops):
-                decay += self._dephasing(lp.A, self._partial_omega_loop(X, li))
+                decay += self._dephasing(lp.A, self._partial_omega_loop(states, li))
         else:
             raise ValueError(f'The decoherence type {dec_type} is not supported.')
         return decay
