@@ -556,6 +556,7 @@ def our_arm(args):
         t0.record()
         last = None
         for _ in range(nsteps):
+            last = None          # a sweep loop keeps the newest result only (two resident results double the peak)
             if DEBUG:
                 torch.cuda.synchronize()
                 ts = time.perf_counter()

@@ -5,6 +5,8 @@ Reference: Circuit.matrix_elements / dec_rate / _dec_rate_*_np / _get_partial_H
 interest of every sweep point at once; the inner products use the tensor-core Gram kernel;
 the closed-form rate expressions (a handful of flops per sweep point) are evaluated on the host.
 """
+import itertools
+
 import numpy as np
 import torch
 
@@ -14,8 +16,12 @@ from .kernels import BlockView
 from .noise import ENV
 
 
+_TOKENS = itertools.count(1)
+
+
 class SweepNoise:
     def __init__(self, kern, ops, hop, evals_rad, evecs, circuit):
+        self._token = next(_TOKENS)       # identity of this result in the shared workspace (ids are reused)
         self.kern, self.ops, self.hop = kern, ops, hop
         self.evals = evals_rad            # [B][k] tensor
         self.evecs = evecs                # [B][k][N] tensor
@@ -24,13 +30,23 @@ class SweepNoise:
         self.dev = evecs.device
 
     # ---- helpers ------------------------------------------------------------------------
+    def _buffer(self, name):
+        """[B][2][N] scratch from the backend's persistent workspace (GB-sized at bench scale: allocating it per
+        query makes the caching allocator grow new segments between sweeps, measured +170 ms on a 300 ms step).
+        The workspace is shared by every SweepNoise of the backend; ``owner`` tells whose data it holds."""
+        buf = self.kern.workspace('noise_' + name, (self.B, 2, self.evecs.shape[2]), torch.complex128)
+        owners = self.kern.__dict__.setdefault('_noise_owner', {})
+        mine = owners.get(name) == (self._token, getattr(self, '_pair_key', None))
+        return buf, mine, owners
+
     def _pair(self, states):
         key = tuple(int(x) for x in states)
-        if getattr(self, '_pair_key', None) != key:      # the six channels of a T1 / Tphi query share it
-            idx = torch.as_tensor(list(key), device=self.dev)
-            self._pair_val = self.evecs.index_select(1, idx).contiguous()        # [B][2][N]
+        buf, mine, owners = self._buffer('pair')
+        if getattr(self, '_pair_key', None) != key or not mine:      # the six channels of a query share it
             self._pair_key = key
-        return self._pair_val
+            torch.stack([self.evecs[:, key[0]], self.evecs[:, key[1]]], dim=1, out=buf)        # [B][2][N]
+            owners['pair'] = (self._token, key)
+        return buf
 
     def _gram2(self, X, Y):
         out = torch.empty((self.B, 2, 2), dtype=torch.complex128, device=self.dev)
@@ -57,26 +73,24 @@ class SweepNoise:
         potential-type operator O = F^T P F then has <a|O|b> = <Fa| P |Fb> with P element-wise + shifts, so
         the six channels of a T1 / Tphi query share ONE forward transform instead of paying a forward and a
         backward transform per operator."""
-        key = tuple(int(x) for x in states)
-        if getattr(self, '_pairx_key', None) != key:
-            X = self._pair(states)
-            ops = self.ops
-            Z = X
-            if ops.tmodes:
-                Z = torch.empty_like(X)
-                src = BlockView(X)
-                for i in ops.tmodes:
-                    self.kern.mode_transform(ops.sp, i, ops.V[i], 1, src, BlockView(Z), impl=ops.impl)
-                    src = BlockView(Z)
-            self._pairx_val, self._pairx_key = Z, key
-            self._pairx_scratch = torch.empty_like(X)
-        return self._pairx_val
+        X = self._pair(states)
+        ops = self.ops
+        if not ops.tmodes:
+            return X
+        buf, mine, owners = self._buffer('pairx')
+        if not mine:
+            src = BlockView(X)
+            for i in ops.tmodes:
+                self.kern.mode_transform(ops.sp, i, ops.V[i], 1, src, BlockView(buf), impl=ops.impl)
+                src = BlockView(buf)
+            owners['pairx'] = (self._token, self._pair_key)
+        return buf
 
     def _pot_elements(self, states, a, g, etab=None, shift=None):
         """[B][2][2] matrix of the potential-type operator (a, g) between the two states (host array)."""
         ops = self.ops
         Z = self._pair_x(states)
-        S = self._pairx_scratch
+        S = self._buffer('scratch')[0]
         g = np.broadcast_to(np.asarray(g, dtype=float).reshape(-1, 1 + ops.M), (self.B, 1 + ops.M))
         pot = ops.potential_struct(ops.to_device(a, torch.complex128), ops.to_device(g, torch.float64),
                                    ops.etab if etab is None else etab, shift, None)

@@ -47,15 +47,22 @@ class EmulKernels:
         self.launches = 0
 
     def workspace(self, key, shape, dtype):
-        return torch.empty(tuple(int(d) for d in shape), dtype=dtype)
+        """Persistent scratch per key, like Kernels.workspace (callers rely on getting the same storage back)."""
+        shape = tuple(int(d) for d in shape)
+        ws = self.__dict__.setdefault('_ws', {})
+        n = int(np.prod(shape))
+        buf = ws.get(key)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            ws[key] = buf = torch.empty(n, dtype=dtype)
+        return buf[:n].view(*shape)
+
+    def release_workspace(self):
+        self.__dict__['_ws'] = {}
 
     free_bytes_value = 1 << 60     # tests shrink it to exercise the memory guard of Circuit.sweep_diag
 
     def free_bytes(self):
         return self.free_bytes_value
-
-    def release_workspace(self):
-        pass
 
     def launch_count(self):
         return self.launches
