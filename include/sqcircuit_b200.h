@@ -176,6 +176,16 @@ int sqc_complex_to_real(const sqc_space_t* sp, sqc_block_t Zc, sqc_block_t Xr, i
 int sqc_potential_apply(const sqc_space_t* sp, const sqc_potential_t* pot, sqc_block_t X,
                         sqc_block_t Z, int32_t B, void* stream);
 
+/* out[b][i][j] = <z_i| P |z_j> for the first nv <= 4 vectors of every point (x/charge basis, P as documented at
+ * sqc_potential_t): one read of the vectors, no vector written.  The matrix elements of the potential-type
+ * operators of the noise code (cos / sin / sin_half of a junction, inductive coupling, dH/d phi_ext;
+ * circuit.py:2397-2647) between two eigenstates rotated to the x basis once.  out: device complex [B][nv][nv];
+ * work: device scratch of sqc_potential_elements_work_bytes() bytes (per-chunk partial sums, reduced in a fixed
+ * order).  Z.cnt must be NULL. */
+int64_t sqc_potential_elements_work_bytes(int64_t N, int32_t nv, int32_t B);
+int sqc_potential_elements(const sqc_space_t* sp, const sqc_potential_t* pot, sqc_block_t Z, int32_t nv, void* out,
+                           void* work, int32_t B, void* stream);
+
 /* Y = (accumulate ? Y : 0) + c_dn(b) * (a_m X) + c_up(b) * (a_m^dag X) on harmonic mode m
  * (charge / flux operators of harmonic modes, circuit.py:1471-1524).  c_*: device complex[B]. */
 int sqc_ladder_apply(const sqc_space_t* sp, int32_t mode, const void* c_dn, const void* c_up,

@@ -56,6 +56,8 @@ SIGNATURES = {
     'sqc_mode_transform': (c_i32, [C.POINTER(Space), c_i32, c_vp, c_i64, c_i32, Block, Block, c_vp,
                                    c_i64, Block, c_i32, c_i32, c_vp]),
     'sqc_potential_apply': (c_i32, [C.POINTER(Space), C.POINTER(Potential), Block, Block, c_i32, c_vp]),
+    'sqc_potential_elements_work_bytes': (c_i64, [c_i64, c_i32, c_i32]),
+    'sqc_potential_elements': (c_i32, [C.POINTER(Space), C.POINTER(Potential), Block, c_i32, c_vp, c_vp, c_i32, c_vp]),
     'sqc_ladder_apply': (c_i32, [C.POINTER(Space), c_i32, c_vp, c_vp, Block, Block, c_i32, c_i32, c_vp]),
     'sqc_gram_work_bytes': (c_i64, [c_i32, c_i32, c_i32, c_i64]),
     'sqc_gram': (c_i32, [Block, Block, c_i64, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_vp]),

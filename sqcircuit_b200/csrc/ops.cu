@@ -436,6 +436,161 @@ extern "C" int sqc_potential_apply(const sqc_space_t* sp, const sqc_potential_t*
 }
 
 // ---------------------------------------------------------------------------------------
+// (2b') matrix elements of a potential-type operator between a few x-basis vectors per point
+// ---------------------------------------------------------------------------------------
+// out[b][i][j] = sum_idx conj(z_i[idx]) (P z_j)[idx] for the nv <= 4 vectors of every point, P as in
+// sqc_potential_apply.  One pass over the vectors, nothing written but nv^2 numbers per point: the decoherence
+// channels of a T1 / Tphi query (circuit.py:2529-2647) each need the 2 x 2 matrix of one such operator between the
+// same pair of eigenstates, rotated to the x basis once (F^T P F between a and b = P between F a and F b).
+// Block = POTEL_CHUNK consecutive indices of one point; per-chunk partial sums in `work`, then a fixed-order
+// reduction over the chunks (deterministic).
+#define POTEL_THREADS 256
+#define POTEL_PER_THREAD 4
+#define POTEL_CHUNK (POTEL_THREADS * POTEL_PER_THREAD)
+#define POTEL_MAXV 4
+
+template <int NV>
+__global__ void __launch_bounds__(POTEL_THREADS)
+potential_elements_kernel(SpaceDev sp, PotDev pt, sqc_block_t Z, int nchunk, cplx* __restrict__ work) {
+    const int b = blockIdx.x / nchunk, ch = blockIdx.x - b * nchunk;
+    const int M = sp.n_modes;
+    const cplx* z[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) z[v] = blk_vec(Z, b, v, sp.N);
+    const double* gb = pt.g + (long long)b * (1 + M);
+    const cplx* et = pt.etab + b * pt.etab_stride_b;
+    cplx acc[NV][NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) acc[i][j] = cmake(0.0, 0.0);
+    for (int q = 0; q < POTEL_PER_THREAD; ++q) {
+        const long long idx = (long long)ch * POTEL_CHUNK + q * POTEL_THREADS + threadIdx.x;
+        if (idx >= sp.N) break;
+        int im[SQC_MAX_MODES];
+        long long r = idx;
+#pragma unroll
+        for (int m = 0; m < SQC_MAX_MODES; ++m) {
+            if (m < M) {
+                im[m] = (int)(r / sp.stride[m]);
+                r -= (long long)im[m] * sp.stride[m];
+            }
+        }
+        double lin = gb[0];
+        for (int m = 0; m < M; ++m)
+            if (sp.harm[m]) lin = fma(gb[1 + m], pt.lam[sp.toff[m] + im[m]], lin);
+        if (pt.diag) lin += pt.diag[b * pt.diag_stride_b + idx];
+        cplx pz[NV], zc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            zc[v] = z[v][idx];
+            pz[v] = cmake(lin * zc[v].x, lin * zc[v].y);
+        }
+        for (int t = 0; t < pt.n_terms; ++t) {
+            cplx ph = pt.a[(long long)b * pt.n_terms + t];
+            bool lo = true, hi = true;
+            for (int m = 0; m < M; ++m) {
+                if (sp.harm[m]) {
+                    ph = cmul(ph, et[(long long)t * sp.tlen + sp.toff[m] + im[m]]);
+                } else {
+                    const int w = pt.shift[t][m];
+                    lo = lo && (im[m] - w >= 0) && (im[m] - w < sp.dims[m]);
+                    hi = hi && (im[m] + w >= 0) && (im[m] + w < sp.dims[m]);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                if (lo) cfma(pz[v], ph, z[v][idx - pt.lin_shift[t]]);
+                if (hi) cfma(pz[v], cconj(ph), z[v][idx + pt.lin_shift[t]]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) cfmac(acc[i][j], zc[i], pz[j]);
+    }
+    // block reduction: warp shuffles, then one partial per warp through shared memory, fixed order
+    __shared__ double red[POTEL_THREADS / 32][2 * NV * NV];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const double re = warp_sum(acc[i][j].x), imv = warp_sum(acc[i][j].y);
+            if (lane == 0) {
+                red[wp][2 * (i * NV + j)] = re;
+                red[wp][2 * (i * NV + j) + 1] = imv;
+            }
+        }
+    __syncthreads();
+    if (threadIdx.x < 2 * NV * NV) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w_ = 0; w_ < POTEL_THREADS / 32; ++w_) sum += red[w_][threadIdx.x];
+        reinterpret_cast<double*>(work)[((long long)blockIdx.x) * 2 * NV * NV + threadIdx.x] = sum;
+    }
+}
+
+__global__ void potential_elements_reduce_kernel(const cplx* __restrict__ work, int nchunk, int nn, cplx* __restrict__ out) {
+    const int b = blockIdx.x, e = threadIdx.x;
+    if (e >= nn) return;
+    double re = 0.0, imv = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+        const cplx v = work[((long long)b * nchunk + c) * nn + e];
+        re += v.x;
+        imv += v.y;
+    }
+    out[(long long)b * nn + e] = cmake(re, imv);
+}
+
+extern "C" int64_t sqc_potential_elements_work_bytes(int64_t N, int32_t nv, int32_t B) {
+    if (N <= 0 || nv <= 0 || nv > POTEL_MAXV || B <= 0) return 0;
+    const int64_t nchunk = (N + POTEL_CHUNK - 1) / POTEL_CHUNK;
+    return (int64_t)B * nchunk * nv * nv * (int64_t)sizeof(cplx);
+}
+
+extern "C" int sqc_potential_elements(const sqc_space_t* sp, const sqc_potential_t* pot, sqc_block_t Z, int32_t nv,
+                                      void* out, void* work, int32_t B, void* stream) {
+    SpaceDev d;
+    int rc = make_space(sp, &d);
+    if (rc) return rc;
+    if (!pot || !out || !work || B <= 0 || nv <= 0 || nv > POTEL_MAXV || Z.cnt_fixed < nv || Z.cnt ||
+        pot->n_terms < 0 || pot->n_terms > SQC_MAX_TERMS)
+        return SQC_EINVAL;
+    PotDev pd;
+    pd.n_terms = pot->n_terms;
+    for (int t = 0; t < pot->n_terms; ++t) {
+        int ls = 0;
+        for (int m = 0; m < d.n_modes; ++m) {
+            pd.shift[t][m] = d.harm[m] ? 0 : pot->shift[t][m];
+            ls += pd.shift[t][m] * d.stride[m];
+        }
+        pd.lin_shift[t] = ls;
+    }
+    pd.lam = pot->lam;
+    pd.etab = (const cplx*)pot->etab;
+    pd.etab_stride_b = pot->etab_stride_b;
+    pd.g = pot->g;
+    pd.a = (const cplx*)pot->a;
+    pd.diag = pot->diag;
+    pd.diag_stride_b = pot->diag_stride_b;
+    const int nchunk = (int)((d.N + POTEL_CHUNK - 1) / POTEL_CHUNK);
+    const long long grid = (long long)B * nchunk;
+    if (grid > 0x7fffffffLL) return SQC_ELIMIT;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nv) {
+        case 1: potential_elements_kernel<1><<<(unsigned)grid, POTEL_THREADS, 0, st>>>(d, pd, Z, nchunk, (cplx*)work); break;
+        case 2: potential_elements_kernel<2><<<(unsigned)grid, POTEL_THREADS, 0, st>>>(d, pd, Z, nchunk, (cplx*)work); break;
+        case 3: potential_elements_kernel<3><<<(unsigned)grid, POTEL_THREADS, 0, st>>>(d, pd, Z, nchunk, (cplx*)work); break;
+        default: potential_elements_kernel<4><<<(unsigned)grid, POTEL_THREADS, 0, st>>>(d, pd, Z, nchunk, (cplx*)work); break;
+    }
+    SQC_LAUNCHED();
+    potential_elements_reduce_kernel<<<B, 32, 0, st>>>((const cplx*)work, nchunk, nv * nv, (cplx*)out);
+    SQC_LAUNCHED();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // (2c) ladder operators of a harmonic mode
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

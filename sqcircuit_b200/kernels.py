@@ -132,6 +132,14 @@ class Kernels:
         _lib.check(self.lib.sqc_potential_apply(C.byref(sp), C.byref(pot), X.c(), Z.c(), X.B,
                                                 _stream(self.dev)), 'sqc_potential_apply')
 
+    def potential_elements(self, sp, pot, Z, out):
+        """out[b][i][j] = <z_i| P |z_j> for the nv = out.shape[1] leading vectors of every point (x basis)."""
+        nv = out.shape[1]
+        nbytes = int(self.lib.sqc_potential_elements_work_bytes(Z.N, nv, Z.B))
+        work = self.workspace('potel_work', (max(nbytes, 16),), torch.uint8)
+        _lib.check(self.lib.sqc_potential_elements(C.byref(sp), C.byref(pot), Z.c(), nv, _p(out), _p(work), Z.B,
+                                                   _stream(self.dev)), 'sqc_potential_elements')
+
     def ladder_apply(self, sp, mode, c_dn, c_up, X, Y, accumulate):
         _lib.check(self.lib.sqc_ladder_apply(C.byref(sp), mode, _p(c_dn), _p(c_up), X.c(), Y.c(), X.B,
                                              int(accumulate), _stream(self.dev)), 'sqc_ladder_apply')

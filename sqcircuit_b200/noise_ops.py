@@ -90,12 +90,12 @@ class SweepNoise:
         """[B][2][2] matrix of the potential-type operator (a, g) between the two states (host array)."""
         ops = self.ops
         Z = self._pair_x(states)
-        S = self._buffer('scratch')[0]
         g = np.broadcast_to(np.asarray(g, dtype=float).reshape(-1, 1 + ops.M), (self.B, 1 + ops.M))
         pot = ops.potential_struct(ops.to_device(a, torch.complex128), ops.to_device(g, torch.float64),
                                    ops.etab if etab is None else etab, shift, None)
-        self.kern.potential_apply(ops.sp, pot, BlockView(Z), BlockView(S))
-        return self._gram2(Z, S)
+        out = torch.empty((self.B, 2, 2), dtype=torch.complex128, device=self.dev)
+        self.kern.potential_elements(ops.sp, pot, BlockView(Z), out)      # one read of the pair, nothing written
+        return out.cpu().numpy()
 
     def _junction_elements(self, states, kind, w_id, b_id, weight=1.0):
         """Matrix of the cos / sin / sin_half operator of one junction (circuit.py:1809-1825) on the pair."""

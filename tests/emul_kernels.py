@@ -137,6 +137,17 @@ class EmulKernels:
                 r = r + ediag[min(b, ediag.shape[0] - 1)].numpy()[None, :] * _get(EX, b)
             _set(Z, b, r)
 
+    def potential_elements(self, sp, pot, Z, out):
+        """out[b][i][j] = <z_i| P |z_j>: the contract of sqc_potential_elements, through the emulated apply."""
+        from sqcircuit_b200.kernels import BlockView
+        nv = out.shape[1]
+        S = torch.zeros_like(Z.tensor)
+        self.potential_apply(sp, pot, Z, BlockView(S))
+        for b in range(Z.B):
+            z = _get(Z, b)[:nv]
+            s = _get(BlockView(S), b)[:nv]
+            out[b] = torch.as_tensor(z.conj() @ s.T)
+
     def potential_apply(self, sp, pot, X, Z):
         a, g, etab, diag = pot._keep
         M = sp.n_modes

@@ -862,7 +862,7 @@ def _hx_torch_reference(dims, harm, Vs, lam_list, s, shifts, a, g, fd, X):
     M = len(dims)
     Z = X.reshape((B, nv) + tuple(dims))
     for i in range(M):
-        if harm[i] and dims[i] > 1:
+        if harm[i] and dims[i] > 1 and i in Vs:
             Z = torch.movedim(torch.tensordot(Z, Vs[i].to(torch.complex128), dims=([2 + i], [0])), -1, 2 + i)
     out = torch.zeros_like(Z)
     lin = g[:, 0].reshape((B, 1) + (1,) * M).to(torch.complex128)
@@ -890,7 +890,7 @@ def _hx_torch_reference(dims, harm, Vs, lam_list, s, shifts, a, g, fd, X):
                 hi = _shift(hi, 2 + i, -w)
         out = out + ph * lo + ph.conj() * hi
     for i in range(M):
-        if harm[i] and dims[i] > 1:
+        if harm[i] and dims[i] > 1 and i in Vs:
             out = torch.movedim(torch.tensordot(out, Vs[i].T.to(torch.complex128), dims=([2 + i], [0])), -1, 2 + i)
     Y = out.reshape(B, nv, N)
     if fd is not None:
@@ -982,3 +982,47 @@ def test_hx_generic_matches_torch_reference(kern, dims, harm, shifts, per_point)
             kern.mode_transform(sp, i, Vs[i].cuda(), 0, BlockView(s2), BlockView(s2), impl=1)
     ref2 = _hx_torch_reference(dims, harm, Vs, lam_list, s, shifts, a, g, None, X)
     assert relerr(s2.cpu(), ref2) < 1e-13
+
+
+@pytest.mark.parametrize('dims,harm,shifts,nv', [
+    ([100, 101], [1, 0], [[0, 1], [0, -1]], 2),
+    ([10, 9, 9], [1, 0, 0], [[0, 1, 0], [0, 0, 1], [0, 1, -1]], 2),
+    ([7, 5, 3, 3], [1, 1, 0, 0], [[0, 0, 1, 0]], 4),
+    ([33], [1], [[0]], 1),
+    ([41], [0], [[1]], 3)])
+def test_potential_elements_matches_torch_reference(kern, dims, harm, shifts, nv):
+    """out[b][i][j] = <z_i| P |z_j> (sqc_potential_elements) against P applied with dense torch index shifts
+    (the x-basis part of _hx_torch_reference: identity transforms) and a torch inner product."""
+    from sqcircuit_b200._lib import Potential
+    M, N = len(dims), int(np.prod(dims))
+    B, T = 5, len(shifts)
+    sp = make_space(dims, harm)
+    toff = np.concatenate(([0], np.cumsum(dims)))[:-1]
+    tlen = int(np.sum(dims))
+    gen = torch.Generator().manual_seed(3)
+    lam = torch.randn(tlen, dtype=torch.float64, generator=gen)
+    lam_list = {i: lam[toff[i]:toff[i] + dims[i]] * (1.0 if harm[i] else 0.0) for i in range(M)}
+    s = 0.4 * torch.randn((B, T, M), dtype=torch.float64, generator=gen) * torch.tensor(harm, dtype=torch.float64)
+    etab = torch.empty((B, T, tlen), dtype=torch.complex128, device='cuda')
+    kern.phase_tables(sp, T, lam.cuda(), s.cuda().contiguous(), etab)
+    a = rnd((B, T), 4)
+    g = torch.randn((B, 1 + M), dtype=torch.float64, generator=gen)
+    Z = rnd((B, nv + 1, N), 5)              # one more vector in the block than is used
+    # identity "transforms": harm flags off for the reference's rotation, on for the phases / linear terms
+    ref_pz = _hx_torch_reference(dims, harm, {}, lam_list, s, shifts, a, g, None, Z[:, :nv].contiguous())
+    ref = torch.einsum('bin,bjn->bij', Z[:, :nv].conj(), ref_pz)
+    pot = Potential()
+    pot.n_terms = T
+    for t in range(T):
+        for i in range(M):
+            pot.shift[t][i] = int(shifts[t][i])
+    lamd, ad, gd = lam.cuda(), a.cuda().contiguous(), g.cuda().contiguous()
+    pot.lam, pot.etab, pot.etab_stride_b = lamd.data_ptr(), etab.data_ptr(), etab.stride(0)
+    pot.g, pot.a, pot.diag, pot.diag_stride_b = gd.data_ptr(), ad.data_ptr(), None, 0
+    out = torch.zeros((B, nv, nv), dtype=torch.complex128, device='cuda')
+    kern.potential_elements(sp, pot, BlockView(Z.cuda()), out)
+    assert relerr(out.cpu(), ref) < 1e-13
+    # and the same numbers through sqc_potential_apply + sqc_gram
+    S = torch.zeros_like(Z).cuda()
+    kern.potential_apply(sp, pot, BlockView(Z.cuda()), BlockView(S))
+    assert relerr(out.cpu(), torch.einsum('bin,bjn->bij', Z[:, :nv].conj(), S.cpu()[:, :nv])) < 1e-13
