@@ -782,8 +782,14 @@ def our_arm(args):
 NCU_HX_TRAFFIC = {
     ('zeropi4096', 'complex'): (1.0855, 'ncu dram__bytes_read+write / algorithmic = 1.0855 '
                                         '(profiles/r01_ncu_full_v28_hx_fused.txt)'),
-    ('zeropi4096', 'real'): (0.98, 'ncu dram__bytes_read+write / algorithmic = 0.98: 996 MB + 950 MB for 12288 '
-                                   'vectors of 161.6 kB (profiles/r02_ncu_full_hx_real_v1.txt)'),
+    ('zeropi4096', 'real'): (0.87, 'ncu dram__bytes_read+write / algorithmic = 0.87: 247 MB read + 335 MB written by one '
+                                   'launch on 4140 vectors of 161.6 kB inside the bench -- part of the reads hit L2, the '
+                                   'block was written by the preceding kernel (profiles/r02_ncu_full_hx_real_final.txt; '
+                                   '0.98 on a cold 12288-vector launch, r02_ncu_full_hx_real_v1.txt)'),
+    ('trt1e5', 'complex'): (1.09, 'ncu dram__bytes_read+write / algorithmic = 1.09: 1.459 GB + 1.171 GB for 768 vectors '
+                                  'of 3.136 MB, halo columns read twice (profiles/r02_hx_generic.txt)'),
+    ('discovery512', 'complex'): (0.99, 'ncu dram__bytes_read+write / algorithmic = 0.99: 0.800 GB + 0.776 GB for 6144 '
+                                        'vectors of 259.2 kB (profiles/r02_hx_generic.txt)'),
 }
 HX_COUNTER = {'vectors': 0}
 DEBUG = bool(os.environ.get('SQC_BENCH_DEBUG'))
