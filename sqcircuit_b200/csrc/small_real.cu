@@ -10,26 +10,12 @@
 // for the latency of ONE problem (one round of 2x2 blocks per thread, three of eigenvector elements).
 #include <math.h>
 #include "common.cuh"
-#ifdef RRR_PROFILE      // dev build (tools/rrr_profile.sh): phase cycle counts of the first pencil, printed once
-#include <cstdio>
-__device__ long long g_rrr_t[16];
-#define RRR_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_rrr_t[i] = clock64(); } while (0)
-#else
-#define RRR_MARK(i) do {} while (0)
-#endif
 
 #define RRR_THREADS 384
 #define RRR_WARPS (RRR_THREADS / 32)
 #define RRR_BLK_THREADS 128       // threads that rotate the 2x2 blocks of A; the others rotate the rows of Z
 #define RRR_MAX_SWEEPS 30
 #define RRR_BIG 1.0e300
-
-// eigen-stage of sqc_gen_rr_real: 0 = tridiagonal path when only part of the spectrum is consumed (default),
-// 1 = tridiagonal path whenever possible, 2 = always the cyclic Jacobi (dev tool / tests)
-__device__ int g_rrr_eig = 0;
-extern "C" void sqc_debug_set_rrr_eig(int v) {
-    cudaMemcpyToSymbol(g_rrr_eig, &v, sizeof(int));
-}
 #define RRR_REG_BLOCKS 4          // blocks per thread whose (P, Q) indices are kept in registers
 
 // u-th block (P <= Q) of the upper triangle of a half x half block grid, row by row
@@ -183,278 +169,7 @@ __device__ void jacobi_syev_real(double* A, int n, int np, int lda, double* Zt, 
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Lowest `nev` eigenpairs of a real symmetric n x n matrix in shared memory WITHOUT the full Jacobi
-// diagonalisation: Householder tridiagonalisation, multisection (32 Sturm counts per round and eigenvalue, one warp
-// per eigenvalue), inverse iteration with the LAPACK dstein safeguards for clusters, back-transformation of the nev
-// vectors.  The Rayleigh-Ritz of the Davidson iteration consumes 12 of up to 40 pairs, and the cyclic Jacobi spends
-// ~250 barrier-separated steps of pure latency on all of them (0.31 ms per pencil); the
-// sequential depth here is ~35 reflector steps + ~11 multisection rounds + a tridiagonal solve.
-//   Ts : n x n (leading dim lda), destroyed: on exit its strict lower part holds the Householder vectors
-//   d, e, tau, vv, pp : scratch doubles [n];  lu : scratch [RRR_WARPS][5 n] doubles
-//   wl : [nev] eigenvalues, ascending;  Y : [nev][ldy] eigenvectors as rows;  flag : shared int, 0 on entry
-// Returns false (uniformly) when a vector fails its residual / orthogonality check: the caller then runs Jacobi.
-// All RRR_THREADS threads must call; n >= 3.
-__device__ bool tridiag_lowest(double* Ts, int n, int lda, int nev, double* d, double* e, double* tau, double* vv,
-                               double* pp, double* lu, double* wl, double* Y, int ldy, int* flag) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double eps = 2.220446049250313e-16;
-    // ---- 1. Householder tridiagonalisation (dsytd2, lower), the trailing block kept as a full symmetric matrix ----
-    for (int k = 0; k < n - 1; ++k) {
-        const int m = n - k - 1;                       // length of the column below the diagonal
-        if (warp == 0) {
-            double xn = 0.0;
-            for (int i = k + 2 + lane; i < n; i += 32) {
-                const double x = Ts[i * lda + k];
-                xn = fma(x, x, xn);
-            }
-            xn = warp_sum(xn);
-            const double alpha = Ts[(k + 1) * lda + k];
-            double t = 0.0, beta = alpha, scale = 0.0;
-            if (m > 1 && xn > 0.0) {
-                beta = -copysign(sqrt(fma(alpha, alpha, xn)), alpha);
-                t = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
-            }
-            for (int i = k + 1 + lane; i < n; i += 32) {
-                const double v = (i == k + 1) ? 1.0 : Ts[i * lda + k] * scale;
-                vv[i] = v;
-                if (i > k + 1) Ts[i * lda + k] = v;    // kept for the back-transformation
-            }
-            if (lane == 0) {
-                e[k] = beta;
-                tau[k] = t;
-            }
-        }
-        __syncthreads();
-        const double t = tau[k];
-        if (t != 0.0) {                                 // uniform
-            // p = tau A22 v, one warp per row
-            for (int i = k + 1 + warp; i < n; i += RRR_WARPS) {
-                double acc = 0.0;
-                for (int j = k + 1 + lane; j < n; j += 32) acc = fma(Ts[i * lda + j], vv[j], acc);
-                acc = warp_sum(acc);
-                if (lane == 0) pp[i] = t * acc;
-            }
-            __syncthreads();
-            // w = p - (tau / 2) (p . v) v   (every warp forms the dot product itself: no extra barrier)
-            double dot = 0.0;
-            for (int j = k + 1 + lane; j < n; j += 32) dot = fma(pp[j], vv[j], dot);
-            dot = warp_sum(dot);
-            const double a2 = -0.5 * t * dot;
-            // A22 -= v w^T + w v^T   (warp = rows, lanes = columns: no index arithmetic beyond adds)
-            for (int i = k + 1 + warp; i < n; i += RRR_WARPS) {
-                const double vi = vv[i], wi = fma(a2, vi, pp[i]);
-                for (int j = k + 1 + lane; j < n; j += 32) {
-                    const double vj = vv[j], wj = fma(a2, vj, pp[j]);
-                    Ts[i * lda + j] -= vi * wj + wi * vj;
-                }
-            }
-            __syncthreads();
-        }
-    }
-    for (int i = tid; i < n; i += RRR_THREADS) d[i] = Ts[i * lda + i];
-    __syncthreads();
-    RRR_MARK(5);
-    // ---- 2. multisection for the nev lowest eigenvalues (dstebz-style Sturm counts with pivmin) ----
-    double glo = 1e300, ghi = -1e300, emax = 0.0;
-    for (int i = lane; i < n; i += 32) {
-        const double el = i > 0 ? fabs(e[i - 1]) : 0.0, er = i < n - 1 ? fabs(e[i]) : 0.0;
-        glo = fmin(glo, d[i] - el - er);
-        ghi = fmax(ghi, d[i] + el + er);
-        emax = fmax(emax, er);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        glo = fmin(glo, __shfl_xor_sync(0xffffffffu, glo, o));
-        ghi = fmax(ghi, __shfl_xor_sync(0xffffffffu, ghi, o));
-        emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
-    }
-    const double tnorm = fmax(fabs(glo), fabs(ghi));
-    const double pivmin = fmax(2.2250738585072014e-308 * fmax(1.0, emax * emax), 1e-290);
-    glo -= 2.0 * tnorm * eps * n + 2.0 * pivmin;
-    ghi += 2.0 * tnorm * eps * n + 2.0 * pivmin;
-    for (int i = tid; i < n - 1; i += RRR_THREADS) pp[i] = e[i] * e[i];
-    __syncthreads();
-    for (int j = warp; j < nev; j += RRR_WARPS) {
-        double lo = glo, hi = ghi;
-        for (int round = 0; round < 16; ++round) {
-            const double width = hi - lo;
-            if (width <= 2.0 * eps * fmax(fabs(lo), fabs(hi)) + 2.0 * pivmin) break;
-            const double x = lo + width * (double)(lane + 1) * (1.0 / 33.0);
-            int cnt = 0;
-            double q = d[0] - x;
-            if (fabs(q) < pivmin) q = -pivmin;
-            cnt += q < 0.0;
-            for (int i = 1; i < n; ++i) {
-                // (a correctly rounded reciprocal is ample for a Sturm count and half the latency of a division)
-                q = fma(-pp[i - 1], __drcp_rn(q), d[i] - x);
-                if (fabs(q) < pivmin) q = -pivmin;
-                cnt += q < 0.0;
-            }
-            // lambda_j < x  <=>  count(x) >= j + 1
-            const unsigned bal = __ballot_sync(0xffffffffu, cnt >= j + 1);
-            const int s = bal ? __ffs(bal) - 1 : 32;
-            const double xs = __shfl_sync(0xffffffffu, x, s < 32 ? s : 31);
-            const double xp = __shfl_sync(0xffffffffu, x, s > 0 ? s - 1 : 0);
-            if (s < 32) hi = xs;
-            if (s > 0) lo = xp;
-        }
-        if (lane == 0) wl[j] = 0.5 * (lo + hi);
-    }
-    __syncthreads();
-    RRR_MARK(6);
-    // ---- 3. inverse iteration (dstein): clusters = runs of eigenvalues closer than 1e-3 ||T||; the r-th member of
-    // a cluster is computed in round r, orthogonalised against the members before it ----
-    const double ortol = 1e-3 * tnorm, pertol = 10.0 * eps * tnorm;
-    int maxr = 0;
-    {
-        int r = 0;
-        for (int j = 1; j < nev; ++j) {
-            r = (wl[j] - wl[j - 1] < ortol) ? r + 1 : 0;
-            maxr = max(maxr, r);
-        }
-    }
-    double* my = lu + (size_t)warp * 5 * n;            // a | b | c | dd | in  of dlagtf
-    for (int rr = 0; rr <= maxr; ++rr) {
-        for (int j = warp; j < nev; j += RRR_WARPS) {
-            int cs = j;
-            while (cs > 0 && wl[cs] - wl[cs - 1] < ortol) --cs;
-            if (j - cs != rr) continue;                 // uniform per warp
-            // separated shift inside a cluster (the members before j were shifted the same way)
-            double lam = wl[cs];
-            for (int q = cs + 1; q <= j; ++q) lam = fmax(wl[q], lam + pertol);
-            double* a = my, *b = my + n, *c = my + 2 * n, *dd = my + 3 * n, *in = my + 4 * n;
-            double* x = Y + (size_t)j * ldy;
-            // LU with partial pivoting of T - lam I (dlagtf), sequential: lane 0
-            if (lane == 0) {
-                for (int i = 0; i < n; ++i) a[i] = d[i] - lam;
-                for (int i = 0; i < n - 1; ++i) { b[i] = e[i]; c[i] = e[i]; }
-                const double tl = fmax(eps * tnorm, pivmin);
-                double scale1 = fabs(a[0]) + (n > 1 ? fabs(b[0]) : 0.0);
-                for (int k = 0; k < n - 1; ++k) {
-                    double scale2 = fabs(c[k]) + fabs(a[k + 1]);
-                    if (k < n - 2) scale2 += fabs(b[k + 1]);
-                    // pivot choice of dlagtf, |c| / scale2 <= |a| / scale1, without the divisions
-                    if (c[k] == 0.0 || (a[k] != 0.0 && fabs(c[k]) * scale1 <= fabs(a[k]) * scale2)) {
-                        in[k] = 0.0;
-                        scale1 = scale2;
-                        if (c[k] != 0.0) {
-                            c[k] = c[k] / a[k];
-                            a[k + 1] -= c[k] * b[k];
-                        }
-                        if (k < n - 2) dd[k] = 0.0;
-                    } else {
-                        in[k] = 1.0;
-                        const double mult = a[k] / c[k];
-                        a[k] = c[k];
-                        const double temp = a[k + 1];
-                        a[k + 1] = b[k] - mult * temp;
-                        if (k < n - 2) {
-                            dd[k] = b[k + 1];
-                            b[k + 1] = -mult * dd[k];
-                        }
-                        b[k] = temp;
-                        c[k] = mult;
-                    }
-                }
-                // zero pivots of U are replaced by +-tl when solving (dlagts job = -1); reciprocals for the solves
-                for (int i = 0; i < n; ++i) {
-                    double ai = a[i];
-                    if (fabs(ai) < tl) ai = copysign(tl, ai == 0.0 ? 1.0 : ai);
-                    a[i] = 1.0 / ai;
-                }
-            }
-            // deterministic start vector
-            for (int i = lane; i < n; i += 32) {
-                unsigned h = (unsigned)(i + 1) * 2654435761u ^ (unsigned)(j + 7) * 40503u ^ (unsigned)(rr + 3) * 69069u;
-                h ^= h >> 15;
-                x[i] = 1.0 + 0.5 * ((double)(h & 0xffffu) * (1.0 / 65536.0) - 0.5);
-            }
-            __syncwarp();
-            for (int it = 0; it < 3; ++it) {
-                // orthogonalise against the earlier members of the cluster (modified Gram-Schmidt)
-                for (int q = cs; q < j; ++q) {
-                    const double* yq = Y + (size_t)q * ldy;
-                    double dot = 0.0;
-                    for (int i = lane; i < n; i += 32) dot = fma(yq[i], x[i], dot);
-                    dot = warp_sum(dot);
-                    for (int i = lane; i < n; i += 32) x[i] = fma(-dot, yq[i], x[i]);
-                    __syncwarp();
-                }
-                if (it == 2) break;                     // last pass: only the re-orthogonalisation + norm below
-                // scale so that the solve cannot overflow, then x <- (P L U)^-1 x  (dlagts), lane 0
-                double nrm = 0.0;
-                for (int i = lane; i < n; i += 32) nrm = fmax(nrm, fabs(x[i]));
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, o));
-                const double sc = nrm > 0.0 ? 1.0 / nrm : 1.0;
-                for (int i = lane; i < n; i += 32) x[i] *= sc;
-                __syncwarp();
-                if (lane == 0) {
-                    for (int k = 1; k < n; ++k) {
-                        if (in[k - 1] == 0.0) {
-                            x[k] -= c[k - 1] * x[k - 1];
-                        } else {
-                            const double temp = x[k - 1];
-                            x[k - 1] = x[k];
-                            x[k] = temp - c[k - 1] * x[k];
-                        }
-                    }
-                    for (int k = n - 1; k >= 0; --k) {
-                        double temp = x[k];
-                        if (k <= n - 2) temp -= b[k] * x[k + 1];
-                        if (k <= n - 3) temp -= dd[k] * x[k + 2];
-                        x[k] = temp * a[k];
-                    }
-                }
-                __syncwarp();
-            }
-            double n2 = 0.0;
-            for (int i = lane; i < n; i += 32) n2 = fma(x[i], x[i], n2);
-            n2 = warp_sum(n2);
-            const double inv = n2 > 0.0 ? rsqrt(n2) : 0.0;
-            for (int i = lane; i < n; i += 32) x[i] *= inv;
-            __syncwarp();
-            // residual check on the tridiagonal matrix: || T x - lambda x ||_inf against ||T||
-            double res = 0.0;
-            for (int i = lane; i < n; i += 32) {
-                double r = (d[i] - wl[j]) * x[i];
-                if (i > 0) r = fma(e[i - 1], x[i - 1], r);
-                if (i < n - 1) r = fma(e[i], x[i + 1], r);
-                res = fmax(res, fabs(r));
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
-            if (lane == 0 && !(res <= 1e-10 * tnorm && n2 > 0.0)) atomicExch(flag, 1);
-        }
-        __syncthreads();
-    }
-    RRR_MARK(7);
-    if (*flag) return false;
-    // ---- 4. back-transformation y <- H_0 H_1 ... H_{n-2} y, one warp per vector ----
-    for (int j = warp; j < nev; j += RRR_WARPS) {
-        double* x = Y + (size_t)j * ldy;
-        // lane holds components lane and lane + 32 (n <= 64); the reflector vectors come from the columns of Ts
-        double x0 = lane < n ? x[lane] : 0.0, x1 = lane + 32 < n ? x[lane + 32] : 0.0;
-        for (int k = n - 2; k >= 0; --k) {
-            const double t = tau[k];
-            if (t == 0.0) continue;
-            const int i0 = lane, i1 = lane + 32;
-            const double v0 = i0 == k + 1 ? 1.0 : (i0 > k + 1 && i0 < n ? Ts[i0 * lda + k] : 0.0);
-            const double v1 = i1 == k + 1 ? 1.0 : (i1 > k + 1 && i1 < n ? Ts[i1 * lda + k] : 0.0);
-            const double dot = t * warp_sum(fma(v0, x0, v1 * x1));
-            x0 = fma(-dot, v0, x0);
-            x1 = fma(-dot, v1, x1);
-        }
-        if (lane < n) x[lane] = x0;
-        if (lane + 32 < n) x[lane + 32] = x1;
-    }
-    __syncthreads();
-    return true;
-}
-
-__global__ void __launch_bounds__(RRR_THREADS, 3)
+__global__ void __launch_bounds__(RRR_THREADS)
 gen_rr_real_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin, const int32_t* __restrict__ nArr,
                    int ld, double drop, double* __restrict__ w, cplx* __restrict__ Zout, int np_max, int n_out) {
     extern __shared__ double smem[];
@@ -472,16 +187,7 @@ gen_rr_real_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
     int* prs = reinterpret_cast<int*>(wv + np_max);
     int* rank = prs + np_max;
     int* dead = rank + np_max;
-    // scratch of the tridiagonal path: d | e | tau | vv | pp [np_max each], wl [16], Y [16][lda], lu [warps][5 np_max]
-    double* td = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(dead + np_max + 4) + 7) & ~(uintptr_t)7);
-    double* te = td + np_max;
-    double* ttau = te + np_max;
-    double* tvv = ttau + np_max;
-    double* tpp = tvv + np_max;
-    double* twl = tpp + np_max;
-    double* tY = twl + 16;
-    double* tlu = tY + (size_t)16 * lda;
-    __shared__ int s_na, s_flag;
+    __shared__ int s_na;
     const int tid = threadIdx.x;
     const cplx* ga = GAin + (int64_t)b * ld * ld;
     const cplx* gb = GBin + (int64_t)b * ld * ld;
@@ -496,7 +202,6 @@ gen_rr_real_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
         dead[i] = 0;
     }
     __syncthreads();
-    RRR_MARK(0);
     // ---- Cholesky (lower), in place; a pivot below drop * (original diagonal) removes the vector ----
     for (int j = 0; j < n; ++j) {
         if (tid == 0) {
@@ -528,7 +233,6 @@ gen_rr_real_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
         const int r = e / n, c = e % n;
         if (dead[r] || dead[c]) A[r * lda + c] = 0.0;
     }
-    RRR_MARK(1);
     // ---- Zs = L^-1 (lower triangular), one thread per column ----
     for (int c = tid; c < n; c += RRR_THREADS) {
         for (int i = 0; i < c; ++i) Zs[i * lda + c] = 0.0;
@@ -539,7 +243,6 @@ gen_rr_real_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
         }
     }
     __syncthreads();
-    RRR_MARK(2);
     // ---- Lm = Zs * A ;  A = Lm * Zs^T ----
     for (int e = tid; e < n * n; e += RRR_THREADS) {
         const int r = e / n, c = e % n;
@@ -554,7 +257,6 @@ gen_rr_real_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
         for (int k = 0; k <= c; ++k) acc = fma(Lm[r * lda + k], Zs[c * lda + k], acc);
         A[r * lda + c] = acc;
     }
-    RRR_MARK(3);
     // alive index list (compaction of the removed vectors)
     if (tid == 0) {
         int cnt = 0;
@@ -573,75 +275,35 @@ gen_rr_real_kernel(const cplx* __restrict__ GAin, const cplx* __restrict__ GBin,
     // dead[] is reused as the alive list: rank[] / prs[] are scratch of the Jacobi and the sort
     for (int i = tid; i < na; i += RRR_THREADS) dead[i] = rank[i];
     __syncthreads();
-    // Only the n_out lowest pairs are consumed.  When that is a proper subset, take them from the tridiagonal form
-    // (multisection + inverse iteration); the full cyclic Jacobi is the fall-back (a vector failing its residual
-    // check) and the path of small or fully requested pencils.
-    const int nev = n_out < na ? n_out : na;
-    RRR_MARK(4);
-    bool partial = g_rrr_eig != 2 && nev <= 16 && na >= 4 && (nev < na || g_rrr_eig == 1);
-    if (partial) {
-        if (tid == 0) s_flag = 0;
-        __syncthreads();
-        partial = tridiag_lowest(Lm, na, lda, nev, td, te, ttau, tvv, tpp, tlu, twl, tY, lda, &s_flag);
-        if (!partial) {
-            // restore the compacted matrix for the Jacobi fall-back (A still holds M)
-            for (int e = tid; e < na * na; e += RRR_THREADS) {
-                const int r = e / na, c = e % na;
-                Lm[r * lda + c] = 0.5 * (A[dead[r] * lda + dead[c]] + A[dead[c] * lda + dead[r]]);
-            }
-            __syncthreads();
-        }
+    jacobi_syev_real(Lm, na, npa, lda, A, lda, rot, prs, red);        // eigenvectors: rows of A
+    for (int i = tid; i < na; i += RRR_THREADS) wv[i] = Lm[i * lda + i];
+    __syncthreads();
+    for (int i = tid; i < na; i += RRR_THREADS) {
+        const double wi = wv[i];
+        int r = 0;
+        for (int j = 0; j < na; ++j) r += (wv[j] < wi) || (wv[j] == wi && j < i);
+        rank[i] = r;
     }
-    const double* Yv = A;                 // eigenvector rows
-    int nvec = na;                        // number of computed pairs
-    if (partial) {
-        for (int i = tid; i < nev; i += RRR_THREADS) {
-            wv[i] = twl[i];
-            rank[i] = i;
-        }
-        Yv = tY;
-        nvec = nev;
-    } else {
-        jacobi_syev_real(Lm, na, npa, lda, A, lda, rot, prs, red);        // eigenvectors: rows of A
-        for (int i = tid; i < na; i += RRR_THREADS) wv[i] = Lm[i * lda + i];
-        __syncthreads();
-        for (int i = tid; i < na; i += RRR_THREADS) {
-            const double wi = wv[i];
-            int r = 0;
-            for (int j = 0; j < na; ++j) r += (wv[j] < wi) || (wv[j] == wi && j < i);
-            rank[i] = r;
-        }
-    }
-    RRR_MARK(8);
     double* wout = w + (int64_t)b * ld;
     for (int i = tid; i < ld; i += RRR_THREADS) wout[i] = INFINITY;
     cplx* zg = Zout + (int64_t)b * ld * ld;
     const int nrows = n_out < n ? n_out : n;
     for (int e = tid; e < nrows * ld; e += RRR_THREADS) zg[e] = cmake(0.0, 0.0);
     __syncthreads();
-    for (int i = tid; i < nvec; i += RRR_THREADS) wout[rank[i]] = wv[i];
-    // c_j = L^-T y_j :  Zout[rank j][i] = sum_k' Zs[alive k'][i] * y_j[k'],  y_j = row j of the eigenvector array;
-    // only the n_out lowest pairs are consumed (Ritz block / thick restart)
-    for (int e = tid; e < nvec * n; e += RRR_THREADS) {
+    for (int i = tid; i < na; i += RRR_THREADS) wout[rank[i]] = wv[i];
+    // c_j = L^-T y_j :  Zout[rank j][i] = sum_k' Zs[alive k'][i] * y_j[k'],  y_j = row j of A; only the n_out
+    // lowest pairs are consumed (Ritz block / thick restart)
+    for (int e = tid; e < na * n; e += RRR_THREADS) {
         const int j = e / n, i = e % n;
         const int rj = rank[j];
         if (rj >= nrows) continue;
         double acc = 0.0;
         for (int kp = 0; kp < na; ++kp) {
             const int kk = dead[kp];
-            if (kk >= i) acc = fma(Zs[kk * lda + i], Yv[j * lda + kp], acc);
+            if (kk >= i) acc = fma(Zs[kk * lda + i], A[j * lda + kp], acc);
         }
         zg[rj * ld + i] = cmake(acc, 0.0);
     }
-#ifdef RRR_PROFILE
-    __syncthreads();
-    RRR_MARK(9);
-    if (blockIdx.x == 0 && tid == 0)
-        printf("[rrr n=%d] cholesky %lld  Linv %lld  products %lld  compact %lld  tridiag %lld  multisection %lld  inverse-it %lld  "
-               "back+sort %lld  output %lld  total %lld\n", n, g_rrr_t[1] - g_rrr_t[0], g_rrr_t[2] - g_rrr_t[1],
-               g_rrr_t[3] - g_rrr_t[2], g_rrr_t[4] - g_rrr_t[3], g_rrr_t[5] - g_rrr_t[4], g_rrr_t[6] - g_rrr_t[5],
-               g_rrr_t[7] - g_rrr_t[6], g_rrr_t[8] - g_rrr_t[7], g_rrr_t[9] - g_rrr_t[8], g_rrr_t[9] - g_rrr_t[0]);
-#endif
 }
 
 extern "C" int sqc_gen_rr_real(const void* GA, const void* GB, const int32_t* n, int32_t ld, double drop,
@@ -649,9 +311,7 @@ extern "C" int sqc_gen_rr_real(const void* GA, const void* GB, const int32_t* n,
     if (B <= 0 || ld <= 0 || ld > 68 || !n || n_out <= 0) return SQC_EINVAL;
     const int np_max = (ld + 1) & ~1;
     const size_t bytes = 3 * (size_t)np_max * (np_max | 1) * sizeof(double) + (3 * np_max + 2 * RRR_WARPS) * sizeof(double) +
-                         (3 * np_max + 4) * sizeof(int) + 16 +
-                         // tridiagonal path: five vectors, 16 eigenvalues, 16 eigenvector rows, LU scratch per warp
-                         (5 * (size_t)np_max + 16 + 16 * (size_t)(np_max | 1) + (size_t)RRR_WARPS * 5 * np_max) * sizeof(double) + 16;
+                         (3 * np_max + 4) * sizeof(int) + 16;
     cudaError_t e = cudaFuncSetAttribute(gen_rr_real_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
     gen_rr_real_kernel<<<B, RRR_THREADS, bytes, (cudaStream_t)stream>>>((const cplx*)GA, (const cplx*)GB, n, ld, drop,

@@ -721,17 +721,12 @@ def test_lowblock_assemble_real_is_the_rotated_complex_block(kern):
     assert torch.equal(outf, outr.real)
 
 
-@pytest.mark.parametrize('eig_mode', [0, 2])
 @pytest.mark.parametrize('mm,sizes', [(40, [40, 36, 24, 12, 1, 0, 33]), (64, [64, 61, 12]), (16, [16, 7])])
-def test_gen_rr_real(kern, mm, sizes, eig_mode):
-    """Real symmetric generalised Rayleigh-Ritz against scipy: the n_out lowest eigenvalues, GB-orthonormal
-    coefficient vectors, dependent basis vector removed, only the n_out lowest vectors written.  eig_mode 0: the
-    shipped path (tridiagonal form + multisection + inverse iteration when n_out < alive vectors, else Jacobi);
-    2: the cyclic Jacobi for every pencil (the fall-back)."""
-    import ctypes
+def test_gen_rr_real(kern, mm, sizes):
+    """Real symmetric generalised Rayleigh-Ritz (128-thread CTA per pencil) against scipy: eigenvalues,
+    GB-orthonormal coefficient vectors, dependent basis vector removed, only the n_out lowest vectors
+    written."""
     import scipy.linalg
-    kern.lib.sqc_debug_set_rrr_eig.argtypes = [ctypes.c_int]
-    kern.lib.sqc_debug_set_rrr_eig(eig_mode)
     B, n_out = len(sizes), 12
     g = torch.Generator().manual_seed(51)
     Q = torch.randn((B, mm, 150), dtype=torch.float64, generator=g)
@@ -758,12 +753,9 @@ def test_gen_rr_real(kern, mm, sizes, eig_mode):
         keep = [i for i in range(nb) if not (b == 1 and sizes[1] > 8 and i == 7)]
         wr = scipy.linalg.eigh(a[np.ix_(keep, keep)], gm[np.ix_(keep, keep)], eigvals_only=True)
         k = len(wr)
-        ko = min(k, n_out)
-        assert np.abs(w[b, :ko].numpy() - wr[:ko]).max() < 1e-10 * np.abs(wr).max(), (b, nb)
-        # beyond the consumed pairs an entry is either the eigenvalue or +inf; beyond the alive vectors +inf
-        rest = w[b, ko:k].numpy()
-        assert np.all(np.isinf(rest) | (np.abs(rest - wr[ko:k]) < 1e-10 * np.abs(wr).max()))
+        assert np.abs(w[b, :k].numpy() - wr).max() < 1e-10 * np.abs(wr).max(), (b, nb)
         assert np.all(np.isinf(w[b, k:].numpy()))
+        ko = min(k, n_out)
         c = Zt[b, :ko, :nb].numpy().T
         assert np.abs(c.imag).max() == 0.0
         c = c.real
@@ -771,46 +763,6 @@ def test_gen_rr_real(kern, mm, sizes, eig_mode):
         assert np.abs(a @ c - gm @ c * w[b, :ko].numpy()[None, :]).max() < 1e-9 * np.abs(wr).max() * np.abs(c).max()
         if nb > n_out:      # rows beyond n_out are not written
             assert complex(Zt[b, n_out, 0]) == 3.0 + 2.0j
-    kern.lib.sqc_debug_set_rrr_eig(0)
-
-
-def test_gen_rr_real_clustered_spectra(kern):
-    """The tridiagonal path on pencils with (nearly) degenerate wanted eigenvalues -- the 0-pi spectrum at half flux
-    has pairs split by 1e-6 and less: exact multiplicities, clusters of 1e-12 ... 1e-3 relative width, and a
-    cluster that straddles the n_out boundary.  Eigenvalues, GB-orthonormality and residuals as in the plain test."""
-    import scipy.linalg
-    mm, n, n_out = 40, 36, 12
-    rng = np.random.default_rng(5)
-    spectra = [np.concatenate(([1.0, 1.0, 1.0, 2.0, 2.0], np.linspace(3, 40, n - 5))),
-               np.concatenate(([1.0, 1.0 + 1e-12, 1.0 + 2e-12, 2.0, 2.0 + 1e-9, 3.0, 3.0 + 1e-6, 4.0, 4.0 + 1e-4],
-                               np.linspace(5, 50, n - 9))),
-               np.concatenate((np.linspace(1, 2, 10), [7.0] * 6, np.linspace(8, 30, n - 16))),     # cluster across n_out
-               np.concatenate((-np.ones(12), np.linspace(0, 10, n - 12))),
-               1e10 * np.concatenate(([-3.0, -3.0 + 1e-7], np.linspace(-2, 9, n - 2)))]
-    B = len(spectra)
-    GA = torch.zeros((B, mm, mm), dtype=torch.complex128)
-    GB = torch.zeros((B, mm, mm), dtype=torch.complex128)
-    refs = []
-    for b, sp_ in enumerate(spectra):
-        Qm, _ = np.linalg.qr(rng.standard_normal((n, n)))
-        M = (Qm * sp_) @ Qm.T
-        L = np.tril(rng.standard_normal((n, n))) * 0.2 + np.eye(n)
-        gb = L @ L.T
-        ga = L @ M @ L.T
-        GA[b, :n, :n] = torch.from_numpy(ga)
-        GB[b, :n, :n] = torch.from_numpy(gb)
-        refs.append((ga, gb, np.sort(sp_)))
-    nn = torch.full((B,), n, dtype=torch.int32)
-    w = torch.zeros((B, mm), dtype=torch.float64, device='cuda')
-    Zt = torch.zeros((B, mm, mm), dtype=torch.complex128, device='cuda')
-    kern.gen_rr(GA.cuda(), GB.cuda(), nn.cuda(), 1e-8, w, Zt, real=True, n_out=n_out)
-    w, Zt = w.cpu().numpy(), Zt.cpu().numpy()
-    for b, (ga, gb, wr) in enumerate(refs):
-        scale = np.abs(wr).max()
-        assert np.abs(w[b, :n_out] - wr[:n_out]).max() < 1e-9 * scale, (b, w[b, :n_out], wr[:n_out])
-        c = Zt[b, :n_out, :n].real.T
-        assert np.abs(c.T @ gb @ c - np.eye(n_out)).max() < 1e-8, b
-        assert np.abs(ga @ c - gb @ c * w[b, :n_out][None, :]).max() < 1e-8 * scale * np.abs(c).max(), b
 
 
 def test_lowband_real_factor_and_apply(kern):

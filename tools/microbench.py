@@ -108,16 +108,6 @@ if not only or 'pair' in only:
         nn = torch.full((B,), n, dtype=torch.int32, device=dev)
         ms = timeit(lambda: k.gen_rr(GA, GB, nn, 1e-8, w, Zt))
         report(f'gen_rr n={n}', ms, 0, 0)
-if only and 'rrr1' in only:
-    # one call per size (profiling build prints the phase cycles of the first pencil)
-    for n in (12, 24, 36):
-        Bq = 64
-        GAr = torch.randn((Bq, 40, 40), dtype=torch.float64, device=dev); GAr = GAr + GAr.transpose(1, 2)
-        Q = torch.randn((Bq, 40, 80), dtype=torch.float64, device=dev); GBr = Q @ Q.transpose(1, 2) / 80
-        w = torch.zeros((Bq, 40), dtype=torch.float64, device=dev); Zt = torch.zeros((Bq, 40, 40), dtype=torch.complex128, device=dev)
-        nn = torch.full((Bq,), n, dtype=torch.int32, device=dev)
-        k.gen_rr(GAr.to(torch.complex128), GBr.to(torch.complex128), nn, 1e-8, w, Zt, real=True, n_out=12)
-        torch.cuda.synchronize()
 if only and 'rrr' in only:
     # real generalised Rayleigh-Ritz: latency of one wave (<= 740 resident problems) and of several
     for Bq in (64, 740, 2048):
