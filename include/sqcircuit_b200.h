@@ -332,6 +332,15 @@ int sqc_lowblock_assemble(const sqc_space_t* sp, int32_t ns, const int32_t* S, i
                           const void* Dt, const sqc_potential_t* pot, const double* d,
                           int64_t d_stride_b, const double* sigma, double unit, void* out,
                           int32_t B, void* stream);
+
+/* The same block for ANY layout (multi-mode sweeps, batches of circuits): Dt holds per harmonic mode i with
+ * m_i > 1 the Fock-basis matrix of every junction term on that mode, V_i diag(etab_t^(i)) V_i^T, concatenated in mode
+ * order per term: device complex [(B or 1)][n_terms][sum_i m_i^2] (dt_stride_b = 0 when shared).  S: linear indices
+ * of the ns kept basis states, [(B or 1)][ns]. */
+int sqc_lowblock_assemble_generic(const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
+                                  const void* Dt, int64_t dt_stride_b, const sqc_potential_t* pot, const double* d,
+                                  int64_t d_stride_b, const double* sigma, double unit, void* out, int32_t B,
+                                  void* stream);
 int sqc_hpd_inverse_c64(void* A, int32_t ns, int32_t B, void* stream);
 int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
                        int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,

@@ -81,6 +81,8 @@ SIGNATURES = {
                                      c_i64, c_i32, c_vp]),
     'sqc_lowblock_assemble': (c_i32, [C.POINTER(Space), c_i32, c_vp, c_i64, c_vp, C.POINTER(Potential), c_vp, c_i64,
                                       c_vp, c_dbl, c_vp, c_i32, c_vp]),
+    'sqc_lowblock_assemble_generic': (c_i32, [C.POINTER(Space), c_i32, c_vp, c_i64, c_vp, c_i64, C.POINTER(Potential), c_vp,
+                                              c_i64, c_vp, c_dbl, c_vp, c_i32, c_vp]),
     'sqc_hpd_inverse_c64': (c_i32, [c_vp, c_i32, c_i32, c_vp]),
     'sqc_lowband_factor': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp]),
     'sqc_lowband_apply': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32,

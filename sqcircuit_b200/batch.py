@@ -58,7 +58,7 @@ class CircuitBatch:
         pts = [c._current_point() for c in self.circuits]
         return np.concatenate([p[0] for p in pts], axis=0), np.concatenate([p[1] for p in pts], axis=0)
 
-    def _solve(self, n_eig, tol=1e-9, maxit=300, stats=None) -> SweepResult:
+    def _solve(self, n_eig, tol=1e-9, maxit=300, stats=None, lowblock=160) -> SweepResult:
         ops = self._operators()
         kern = ops.kern
         lv, ng = self._points()
@@ -77,7 +77,8 @@ class CircuitBatch:
                 else:
                     sub = CircuitOperators(kern, [c._top for c in self.circuits[c0:c0 + chunk]], self.circuits[0].m)
                     op = HamiltonianOperator(sub, lv[c0:c0 + chunk], ng[c0:c0 + chunk])
-                parts.append(_davidson(kern, op, op.B, ops.N, n_eig, op.diag, tol=tol, maxit=maxit, stats=stats))
+                parts.append(_davidson(kern, op, op.B, ops.N, n_eig, op.diag, tol=tol, maxit=maxit, stats=stats,
+                                       lowblock_ns=lowblock))
             res = _cat_results(parts)
         if not res.converged:
             raise RuntimeError(f'batched Davidson did not converge after {res.iterations} iterations '

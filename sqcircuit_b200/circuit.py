@@ -360,7 +360,7 @@ class Circuit:
                     cls = RealHamiltonianOperator if real else HamiltonianOperator
                     op = cls(ops, lv[c0:c0 + chunk], ng if ng.shape[0] == 1 else ng[c0:c0 + chunk])
                 parts.append(_davidson(kern, op, op.B, Nv, n_eig, op.diag, p=block_size, mmax=max_basis,
-                                       tol=tol, maxit=maxit, stats=stats))
+                                       tol=tol, maxit=maxit, stats=stats, lowblock_ns=lowblock))
                 if not parts[-1].converged:
                     break
             res = _cat_results(parts)

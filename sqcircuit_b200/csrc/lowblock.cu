@@ -73,6 +73,125 @@ extern "C" int sqc_lowblock_assemble(const sqc_space_t* sp, int32_t ns, const in
     return 0;
 }
 
+// Any layout (up to SQC_MAX_MODES harmonic / charge modes): the same block from per-mode displacement tables
+//   Dt[b][t][off_i + n m_i + n'] = (V_i diag(etab_t^(i)) V_i^T)[n][n']   (harmonic modes with m_i > 1, concatenated),
+// the matrix of junction term t on mode i in the Fock basis.  H_SS[r][q] between the basis states r, q (multi-indices
+// decoded from the linear indices in S):  LC diagonal - sigma;  g_0 + sum_i g_i (a + a^dag)_i on states that differ
+// in harmonic mode i only;  a_t prod_i Dt_i[n_i][n'_i] where every charge index of q is that of r minus the shift
+// of term t, and the Hermitian conjugate.  Used by multi-mode sweeps and by batches of circuits (per-point tables).
+struct LbgGeom {
+    int M, ns, n_terms;
+    int dims[SQC_MAX_MODES], harm[SQC_MAX_MODES], stride[SQC_MAX_MODES], dtoff[SQC_MAX_MODES];
+    int shift[SQC_MAX_TERMS][SQC_MAX_MODES];
+    int dtlen;
+};
+
+__global__ void __launch_bounds__(256)
+lowblock_assemble_generic_kernel(const __grid_constant__ LbgGeom gm, const int32_t* __restrict__ S, long long s_stride_b,
+                                 const cplx* __restrict__ Dt, long long dt_stride_b, const cplx* __restrict__ a,
+                                 const double* __restrict__ g, const double* __restrict__ d, long long d_stride_b,
+                                 const double* __restrict__ sigma, double inv_unit, float2* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    const int ns = gm.ns, M = gm.M;
+    if (e >= ns * ns) return;
+    const int r = e / ns, q = e % ns;
+    const int32_t* s = S + b * s_stride_b;
+    int ir = s[r], iq = s[q];
+    int nr[SQC_MAX_MODES], nq[SQC_MAX_MODES];
+    int ndiff = 0, dmode = -1;                       // number of modes in which r and q differ, the last such mode
+    {
+        int xr = ir, xq = iq;
+#pragma unroll
+        for (int i = 0; i < SQC_MAX_MODES; ++i) {
+            if (i < M) {
+                nr[i] = xr / gm.stride[i];
+                xr -= nr[i] * gm.stride[i];
+                nq[i] = xq / gm.stride[i];
+                xq -= nq[i] * gm.stride[i];
+                if (nr[i] != nq[i]) {
+                    ++ndiff;
+                    dmode = i;
+                }
+            }
+        }
+    }
+    double vr = 0.0, vi = 0.0;
+    const double* gb = g + (long long)b * (1 + M);
+    if (ndiff == 0) vr += d[b * d_stride_b + ir] - sigma[b] + gb[0];
+    if (ndiff == 1 && gm.harm[dmode] && abs(nr[dmode] - nq[dmode]) == 1)
+        vr += gb[1 + dmode] * sqrt((double)max(nr[dmode], nq[dmode]));
+    const cplx* dt = Dt + b * dt_stride_b;
+    for (int t = 0; t < gm.n_terms; ++t) {
+        bool fw = true, bw = true;
+#pragma unroll
+        for (int i = 0; i < SQC_MAX_MODES; ++i) {
+            if (i < M && !gm.harm[i]) {
+                fw = fw && (nq[i] == nr[i] - gm.shift[t][i]);
+                bw = bw && (nq[i] == nr[i] + gm.shift[t][i]);
+            }
+        }
+        if (!fw && !bw) continue;
+        cplx pf = cmake(1.0, 0.0), pb = cmake(1.0, 0.0);      // prod_i Dt_i[n_r][n_q] and prod_i Dt_i[n_q][n_r]
+#pragma unroll
+        for (int i = 0; i < SQC_MAX_MODES; ++i) {
+            if (i < M && gm.harm[i]) {
+                if (gm.dims[i] > 1) {
+                    const cplx* di = dt + (long long)t * gm.dtlen + gm.dtoff[i];
+                    pf = cmul(pf, di[nr[i] * gm.dims[i] + nq[i]]);
+                    pb = cmul(pb, di[nq[i] * gm.dims[i] + nr[i]]);
+                }
+            }
+        }
+        const cplx at = a[(long long)b * gm.n_terms + t];
+        if (fw) {
+            const cplx w = cmul(at, pf);
+            vr += w.x;
+            vi += w.y;
+        }
+        if (bw) {
+            const cplx w = cmul(at, pb);
+            vr += w.x;
+            vi -= w.y;
+        }
+    }
+    out[(long long)b * ns * ns + e] = make_float2((float)(vr * inv_unit), (float)(vi * inv_unit));
+}
+
+extern "C" int sqc_lowblock_assemble_generic(const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
+                                             const void* Dt, int64_t dt_stride_b, const sqc_potential_t* pot,
+                                             const double* d, int64_t d_stride_b, const double* sigma, double unit,
+                                             void* out, int32_t B, void* stream) {
+    if (!sp || !pot || B <= 0 || ns <= 0 || sp->n_modes < 1 || sp->n_modes > SQC_MAX_MODES) return SQC_EINVAL;
+    if (pot->n_terms < 0 || pot->n_terms > SQC_MAX_TERMS) return SQC_EINVAL;
+    LbgGeom gm = {};
+    gm.M = sp->n_modes;
+    gm.ns = ns;
+    gm.n_terms = pot->n_terms;
+    long long N = 1;
+    for (int i = sp->n_modes - 1; i >= 0; --i) {
+        gm.dims[i] = sp->dims[i];
+        gm.harm[i] = sp->harmonic[i];
+        gm.stride[i] = (int)N;
+        N *= sp->dims[i];
+        if (N > 0x7fffffffLL) return SQC_ELIMIT;
+    }
+    int off = 0;
+    for (int i = 0; i < sp->n_modes; ++i) {
+        gm.dtoff[i] = off;
+        if (sp->harmonic[i] && sp->dims[i] > 1) off += sp->dims[i] * sp->dims[i];
+    }
+    gm.dtlen = off;
+    for (int t = 0; t < pot->n_terms; ++t)
+        for (int i = 0; i < sp->n_modes; ++i) gm.shift[t][i] = sp->harmonic[i] ? 0 : pot->shift[t][i];
+    dim3 grid((ns * ns + 255) / 256, B);
+    lowblock_assemble_generic_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        gm, S, s_stride_b, (const cplx*)Dt, dt_stride_b, (const cplx*)pot->a, pot->g, d, d_stride_b, sigma, 1.0 / unit,
+        (float2*)out);
+    SQC_LAUNCHED();
+    return 0;
+}
+
 // Real (time-reversal adapted) representation, see hx_real.cu: the index set holds REAL basis states
 // R = i * inner + j (Fock i; j = 0: charge 0, 1 <= j <= nc: cos-type (|n> + |-n>)/sqrt2, j > nc: sin-type
 // i(|n> - |-n>)/sqrt2 with n = j resp. j - nc).  H_r[R][R'] = sum_{s,s'} conj(u_s) u'_s' h(i, s n; i', s' n')

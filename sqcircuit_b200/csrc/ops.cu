@@ -367,12 +367,12 @@ potential_kernel(SpaceDev sp, PotDev pt, sqc_block_t X, sqc_block_t Z, int vmax,
     if (idx >= sp.N) return;
     const int M = sp.n_modes;
     int im[SQC_MAX_MODES];
-    long long r = idx;
+    int r = (int)idx;                      // N < 2^31 (make_space): 32-bit divisions, not the emulated 64-bit ones
 #pragma unroll
     for (int m = 0; m < SQC_MAX_MODES; ++m) {
         if (m < M) {
-            im[m] = (int)(r / sp.stride[m]);
-            r -= (long long)im[m] * sp.stride[m];
+            im[m] = r / sp.stride[m];
+            r -= im[m] * sp.stride[m];
         }
     }
     const cplx* x = blk_vec(X, b, v, sp.N);
@@ -468,12 +468,12 @@ potential_elements_kernel(SpaceDev sp, PotDev pt, sqc_block_t Z, int nchunk, cpl
         const long long idx = (long long)ch * POTEL_CHUNK + q * POTEL_THREADS + threadIdx.x;
         if (idx >= sp.N) break;
         int im[SQC_MAX_MODES];
-        long long r = idx;
+        int r = (int)idx;                  // N < 2^31 (make_space): 32-bit divisions, not the emulated 64-bit ones
 #pragma unroll
         for (int m = 0; m < SQC_MAX_MODES; ++m) {
             if (m < M) {
-                im[m] = (int)(r / sp.stride[m]);
-                r -= (long long)im[m] * sp.stride[m];
+                im[m] = r / sp.stride[m];
+                r -= im[m] * sp.stride[m];
             }
         }
         double lin = gb[0];

@@ -301,6 +301,16 @@ class Kernels:
                                                   _p(sigma), unit, _p(out), B, _stream(self.dev)),
                    'sqc_lowblock_assemble')
 
+    def lowblock_assemble_generic(self, sp, S, Dt, pot, d, sigma, unit, out):
+        """Low-energy block for any layout from per-mode displacement tables Dt [(B or 1)][T][sum m_i^2]."""
+        B, ns, _ = out.shape
+        ssb = 0 if S.shape[0] == 1 else S.stride(0)
+        dsb = 0 if d.shape[0] == 1 else d.stride(0)
+        tsb = 0 if Dt.shape[0] == 1 else Dt.stride(0)
+        _lib.check(self.lib.sqc_lowblock_assemble_generic(C.byref(sp), ns, _p(S), ssb, _p(Dt), tsb, C.byref(pot), _p(d),
+                                                          dsb, _p(sigma), unit, _p(out), B, _stream(self.dev)),
+                   'sqc_lowblock_assemble_generic')
+
     def hpd_inverse_c64(self, A):
         B, ns, _ = A.shape
         _lib.check(self.lib.sqc_hpd_inverse_c64(_p(A), ns, B, _stream(self.dev)), 'sqc_hpd_inverse_c64')

@@ -338,6 +338,22 @@ class CircuitOperators:
             self._Dt = torch.einsum('ni,ti,ki->tnk', V, e, V).contiguous()
         return self._Dt
 
+    def displacement_tables_generic(self):
+        """Per harmonic mode (more than one level) the Fock-basis matrix of every junction term on that mode,
+        V_i diag(etab_t^(i)) V_i^T, concatenated in mode order: [nb][T][sum m_i^2] (sqc_lowblock_assemble_generic)."""
+        if getattr(self, '_Dtg', None) is None:
+            nt = max(self.T, 1)
+            parts = []
+            for i in self.tmodes:
+                m, o = self.dims[i], int(self.toff[i])
+                V = self.V[i].to(torch.complex128)
+                e = self.etab[:, :, o:o + m]                                  # [nb][T][m]
+                parts.append(torch.einsum('ni,bti,ki->btnk', V, e, V).reshape(e.shape[0], nt, m * m))
+            if not parts:
+                parts = [torch.zeros((self.etab.shape[0], nt, 1), dtype=torch.complex128, device=self.device)]
+            self._Dtg = torch.cat(parts, dim=2).contiguous()
+        return self._Dtg
+
     def to_device(self, arr, dtype):
         arr = np.ascontiguousarray(arr)
         if not arr.flags.writeable:          # broadcast views: torch wants an array it may write to
@@ -367,8 +383,9 @@ class HamiltonianOperator:
         self.ops.apply_potential_op(X, Y, self.a, self.g, fock_diag=self.diag)
 
     def supports_lowblock(self):
-        # (the low block is assembled from one set of displacement tables: single-circuit sweeps only)
-        return bool(self.ops.fused and self.ops.T >= 1 and self.ops.nb == 1)
+        # harmonic x charge layouts of one circuit: the banded block of up to 512 states; every other layout
+        # (several modes, batches of circuits): the dense block of up to 160 states from per-mode tables
+        return bool(self.ops.T >= 1)
 
     def _auto_lowblock_group(self, max_group=8, budget=0.05):
         """Largest power-of-two group whose members differ by less than ``budget`` (relative) in the
@@ -404,6 +421,8 @@ class HamiltonianOperator:
             group = LOWBLOCK_GROUP or self._auto_lowblock_group()
         group = int(max(1, min(group, self.B)))
         unit = 2 * np.pi * 1e9
+        if not (ops.fused and ops.nb == 1):
+            return self._build_lowblock_generic(sigma, min(ns, 160), group, unit)
         if group == 1:
             a, g, diag, sig, nslot = self.a, self.g, self.diag, sigma.contiguous(), self.B
         else:
@@ -458,6 +477,31 @@ class HamiltonianOperator:
         else:
             kern.lowband_factor(Ainv, band[0], band[1], band[2])
         return {'S': S, 'Ainv': Ainv, 'unit': unit, 'ns': ns, 'group': group, 'band': band}
+
+
+    def _build_lowblock_generic(self, sigma, ns, group, unit):
+        """Dense low block (<= 160 states) of any layout: per-mode displacement tables, generic assembly,
+        complex64 inverse.  Per slot: the index set of its own LC diagonal, the tables of its own circuit."""
+        ops, kern = self.ops, self.ops.kern
+        ns = int(min(ns, ops.N // 2))
+        nslot = (self.B + group - 1) // group
+        if group == 1:
+            rep = None
+            a, g, diag, sig = self.a, self.g, self.diag, sigma.contiguous()
+        else:
+            rep = torch.clamp(torch.arange(nslot, device=self.device) * group + group // 2, max=self.B - 1)
+            a, g = self.a[rep].contiguous(), self.g[rep].contiguous()
+            diag = self.diag if self.diag.shape[0] == 1 else self.diag[rep].contiguous()
+            sig = sigma[rep].contiguous()
+        Dt = ops.displacement_tables_generic()
+        if Dt.shape[0] > 1 and rep is not None:
+            Dt = Dt[rep].contiguous()
+        S = torch.topk(diag, ns, dim=1, largest=False).indices.to(torch.int32).contiguous()
+        pot = ops.potential_struct(a, g, ops.etab)
+        Ainv = torch.empty((nslot, ns, ns), dtype=torch.complex64, device=self.device)
+        kern.lowblock_assemble_generic(ops.sp, S, Dt, pot, diag, sig, unit, Ainv)
+        kern.hpd_inverse_c64(Ainv)
+        return {'S': S, 'Ainv': Ainv, 'unit': unit, 'ns': ns, 'group': group, 'band': None}
 
 
 class RealHamiltonianOperator(HamiltonianOperator):

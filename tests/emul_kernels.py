@@ -583,6 +583,53 @@ class EmulKernels:
                 A += (c[None, :] == c[:, None] + sh) * np.conj(at * Dtn[t][n[None, :], n[:, None]])
             out[b] = torch.from_numpy((A / unit).astype(np.complex64))
 
+    def lowblock_assemble_generic(self, sp, S, Dt, pot, d, sigma, unit, out):
+        """Contract of sqc_lowblock_assemble_generic: H_SS - sigma for any layout from per-mode tables."""
+        a, g, etab, diag = pot._keep
+        M = sp.n_modes
+        dims = [sp.dims[i] for i in range(M)]
+        harm = [bool(sp.harmonic[i]) for i in range(M)]
+        strides = np.concatenate((np.cumprod(dims[::-1])[::-1][1:], [1])).astype(int)
+        dtoff, off = [], 0
+        for i in range(M):
+            dtoff.append(off)
+            if harm[i] and dims[i] > 1:
+                off += dims[i] * dims[i]
+        B, ns, _ = out.shape
+        for b in range(B):
+            s = S[min(b, S.shape[0] - 1)].numpy().astype(int)
+            dd = d[min(b, d.shape[0] - 1)].numpy()
+            dt = Dt[min(b, Dt.shape[0] - 1)].numpy()
+            idx = [(s // strides[i]) % dims[i] for i in range(M)]
+            differs = np.stack([idx[i][:, None] != idx[i][None, :] for i in range(M)])       # [M][ns][ns]
+            ndiff = differs.sum(axis=0)
+            A = np.zeros((ns, ns), complex)
+            A[np.arange(ns), np.arange(ns)] = dd[s] - float(sigma[b]) + float(g[b, 0])
+            for i in range(M):
+                if harm[i]:
+                    n, n2 = idx[i][:, None], idx[i][None, :]
+                    only = (ndiff == 1) & differs[i] & (np.abs(n - n2) == 1)
+                    A += only * float(g[b, 1 + i]) * np.sqrt(np.maximum(n, n2))
+            for t in range(pot.n_terms):
+                fw = np.ones((ns, ns), bool)
+                bw = np.ones((ns, ns), bool)
+                pf = np.ones((ns, ns), complex)
+                pb = np.ones((ns, ns), complex)
+                for i in range(M):
+                    n, n2 = idx[i][:, None], idx[i][None, :]
+                    if harm[i]:
+                        if dims[i] > 1:
+                            Di = dt[t, dtoff[i]:dtoff[i] + dims[i] ** 2].reshape(dims[i], dims[i])
+                            pf = pf * Di[n, n2]
+                            pb = pb * Di[n2, n]
+                    else:
+                        w = int(pot.shift[t][i])
+                        fw &= (n2 == n - w)
+                        bw &= (n2 == n + w)
+                at = complex(a[b, t])
+                A += fw * at * pf + bw * np.conj(at * pb)
+            out[b] = torch.from_numpy((A / unit).astype(np.complex64))
+
     def _lowblock_assemble_real(self, sp, S, Dt, pot, d, sigma, unit, out):
         """H_r = U^H H_c U on the real index set (each real state is a combination of charges +-n)."""
         a, g = pot._keep[0], pot._keep[1]
