@@ -23,6 +23,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -373,54 +374,57 @@ def reference_arm(args):
 # our arm
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
-             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (a polling
+    ``nvidia-smi -lms`` child was measured to stall the bench: single steps of 300 ms took up to 430 ms while it
+    ran -- profiles/r02_clock_sampler_stall.txt).  One light query set every 250 ms from a daemon thread."""
+    REASONS = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
-        self.p = None
+        self.sm, self.mx, self.reasons = [], [], set()
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _physical_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        ids = [x.strip() for x in vis.split(',') if x.strip()]
+        if ids and self.idx < len(ids) and ids[self.idx].isdigit():
+            return int(ids[self.idx])
+        return self.idx
 
     def start(self):
         try:
-            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
-                                       '-i', str(self.idx), '-lms', '200'], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            return
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.mx.append(mx)
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    for nm, bit in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(nm)
+                except Exception:
+                    pass
+                self._stop.wait(0.25)
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
-        if self.p is None:
+        if self._thread is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.f.read().strip().splitlines():
-            parts = [x.strip() for x in ln.split(',')]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[5:9]):
-                if val.lower().startswith('active'):
-                    reasons.add(nm)
-        if sm:
-            out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(np.max(mx)), 'reasons': sorted(reasons),
-                   'samples': len(sm)}
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if self.sm:
+            out = {'sm_mhz': float(np.median(self.sm)), 'sm_max_mhz': float(np.max(self.mx)),
+                   'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': 'NVML, 250 ms period'}
         return out
 
 
@@ -596,7 +600,7 @@ def our_arm(args):
     for _ in range(args.warmup):
         step(False)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get('SQC_BENCH_NO_SAMPLER'):      # (dev switch: is the poller perturbing the run?)
         sampler.start()
     # timed region: only the dominant kernel (the H.X apply) carries CUDA events -- bracketing all
     # ~900 C-ABI calls of a step costs ~60 ms of host time per step (measured), which would be

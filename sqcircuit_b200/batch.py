@@ -58,7 +58,7 @@ class CircuitBatch:
         pts = [c._current_point() for c in self.circuits]
         return np.concatenate([p[0] for p in pts], axis=0), np.concatenate([p[1] for p in pts], axis=0)
 
-    def _solve(self, n_eig, tol=1e-9, maxit=300, stats=None, lowblock=160) -> SweepResult:
+    def _solve(self, n_eig, tol=1e-9, maxit=300, stats=None, lowblock=512) -> SweepResult:
         ops = self._operators()
         kern = ops.kern
         lv, ng = self._points()
