@@ -452,6 +452,7 @@ class HamiltonianOperator:
         if group is None:
             group = LOWBLOCK_GROUP or self._auto_lowblock_group()
         group = int(max(1, min(group, self.B)))
+        self._last_group = group
         unit = 2 * np.pi * 1e9
         if not (ops.fused and ops.nb == 1):
             return self._build_lowblock_generic(sigma, min(ns, 512), group, unit)

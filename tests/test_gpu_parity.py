@@ -397,6 +397,27 @@ def test_config3_full_size_dim_1e5():
     assert 1 - o.subspace_overlap(v[:, :10], X[4].cpu().numpy().T, e[:10], w_next=e[10]) < 1e-10
 
 
+def test_config3_bench_grid_converges_without_the_orthogonalised_fallback(monkeypatch):
+    """The 16 x 16 gate-charge x flux grid of bench.py's trt1e5 at full size (N = 98010): every continuation level
+    must converge in the non-orthogonalised iteration (the orthogonalised safety net costs 3x the time and used
+    to be hit on every warm level: nearly dependent warm-start blocks, see eigensolver.solve_davidson_gen)."""
+    import sqcircuit_b200.circuit as C
+    cr, lp, oc, ol = cs.trt_squid()
+    cr.set_trunc_nums([10, 50, 50])
+    m1 = sorted(cr.charge_islands)[0] + 1
+    cell = np.arange(256)
+    ng, fl = (cell // 16) / 32.0, ((cell % 16) + 0.5) / 32.0
+
+    def no_fallback(*a, **k):
+        raise AssertionError('orthogonalised fall-back taken')
+    monkeypatch.setattr(C, 'solve_davidson', no_fallback)
+    res = cr.sweep_diag(10, charge_offsets={m1: ng}, loop_fluxes={lp: fl})
+    assert res.converged and float(res.resmax.max()) <= 1e-9 and res.iterations < 200
+    X = res.evecs
+    gram = X.conj() @ X.transpose(1, 2)
+    assert float((gram - torch.eye(10, device=X.device)).abs().max()) < 1e-10
+
+
 def test_other_reference_circuits():
     cr, lp, oc, ol = cs.coupled_fluxonium_transmon()
     cr.set_trunc_nums([30, 10])

@@ -379,3 +379,33 @@ def test_gate_charge_flux_grid_three_modes_cpu():
     from test_gpu_parity import _grid_check
     res = _grid_check(EmulKernels(), [4, 4, 4], 5, 2)
     assert res.converged
+
+
+def test_warm_start_from_nearly_dependent_neighbour_blocks_converges():
+    """BASELINE configs[3] at its named size (N = 98010), one point of the gate-charge x flux grid started from
+    the Ritz blocks of two neighbours that lie at the SAME gate charge: as raw basis vectors that union gave
+    cond(GB) ~ 1e8 and the non-orthogonalised iteration stalled at 1e-6 for ever (found on the GPU,
+    tools/stagnation_diag.py + tools/warm_point_diag.py); with the orthonormalised start block it converges in
+    < 25 iterations.  Kernels emulated."""
+    from sqcircuit_b200.eigensolver import RitzPairStart, solve_davidson_gen
+    from sqcircuit_b200.operators import HamiltonianOperator
+    K = EmulKernels()
+    cr, lp, oc, ol = cs.trt_squid(K)
+    cr.set_trunc_nums([10, 50, 50])
+    ops = cr._operators()
+    m1 = sorted(cr.charge_islands)[0]
+
+    def hop(pts):            # (gate-charge index, flux index) on the 16 x 16 grid of bench.py's trt1e5
+        lv = np.array([[2 * np.pi * (c + 0.5) / 32] for _, c in pts])
+        ng = np.zeros((len(pts), ops.M))
+        ng[:, m1] = [r / 32 for r, _ in pts]
+        return HamiltonianOperator(ops, lv, ng)
+    h = hop([(0, 1), (0, 2)])
+    cold = solve_davidson_gen(K, h, 2, ops.N, 10, h.diag, lowblock_ns=512)
+    assert cold.converged
+    h = hop([(2, 1)])
+    x0 = RitzPairStart(cold.ritz_block, torch.tensor([0]), torch.tensor([1]))
+    raw = solve_davidson_gen(K, h, 1, ops.N, 10, h.diag, lowblock_ns=512, x0=x0, maxit=30, orth_start=False)
+    assert not raw.converged and float(raw.resmax.max()) > 1e-7          # the failure mode this guards against
+    res = solve_davidson_gen(K, h, 1, ops.N, 10, h.diag, lowblock_ns=512, x0=x0, maxit=30)
+    assert res.converged and res.iterations < 25 and float(res.resmax.max()) <= 1e-9
