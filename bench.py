@@ -374,16 +374,25 @@ def reference_arm(args):
 # our arm
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (a polling
-    ``nvidia-smi -lms`` child was measured to stall the bench: single steps of 300 ms took up to 430 ms while it
-    ran -- profiles/r02_clock_sampler_stall.txt).  One light query set every 250 ms from a daemon thread."""
+    """SM clock and throttle reasons of the timed regions, in-process through NVML.
+
+    Measured on this pool (profiles/r02_clock_sampler_stall.txt): a polling ``nvidia-smi -lms 200`` child, or
+    nvmlDeviceGetCurrentClocksEventReasons called from a thread every 50-100 ms, stall single 300 ms steps of the
+    bench by up to 200 ms (the query serialises with kernel launches in the driver); nvmlDeviceGetClockInfo does
+    not.  So: the SM clock is sampled every 250 ms DURING the regions by a daemon thread; the event reasons are
+    read right before the first and right after the last timed step, and throttling in between is caught by the
+    cumulative NVML violation counters (thermal / power / reliability / board limit), whose deltas over the
+    regions are reported."""
     REASONS = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
+    POLICIES = {'sw_power_cap': 0, 'sw_thermal_slowdown': 1, 'hw_slowdown': 5}   # NVML_PERF_POLICY_POWER / THERMAL / RELIABILITY
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.sm, self.mx, self.reasons = [], [], set()
         self._stop = threading.Event()
         self._thread = None
+        self._nvml = self._h = None
+        self._viol0 = {}
 
     def _physical_index(self):
         vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
@@ -392,27 +401,46 @@ class ClockSampler:
             return int(ids[self.idx])
         return self.idx
 
+    def _read_reasons(self):
+        try:
+            mask = int(self._nvml.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+            for nm, bit in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(nm)
+        except Exception:
+            pass
+
+    def _violations(self):
+        out = {}
+        for nm, pol in self.POLICIES.items():
+            try:
+                out[nm] = int(self._nvml.nvmlDeviceGetViolationStatus(self._h, pol).violationTime)
+            except Exception:
+                pass
+        return out
+
     def start(self):
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self._nvml = pynvml
+            self._h = h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
             mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
+            self._nvml = None
             return
+        self._read_reasons()
+        self._viol0 = self._violations()
+        period = float(os.environ.get('SQC_SAMPLER_PERIOD', '0.25'))
 
         def loop():
             while not self._stop.is_set():
                 try:
                     self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                     self.mx.append(mx)
-                    mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                    for nm, bit in self.REASONS.items():
-                        if mask & bit:
-                            self.reasons.add(nm)
                 except Exception:
                     pass
-                self._stop.wait(0.25)
+                self._stop.wait(period)
         self._thread = threading.Thread(target=loop, daemon=True)
         self._thread.start()
 
@@ -422,9 +450,18 @@ class ClockSampler:
             return out
         self._stop.set()
         self._thread.join(timeout=2)
+        self._read_reasons()
+        viol = {}
+        for nm, t1 in self._violations().items():
+            dt = t1 - self._viol0.get(nm, t1)
+            viol[nm] = dt
+            if dt > 0:
+                self.reasons.add(nm)
         if self.sm:
             out = {'sm_mhz': float(np.median(self.sm)), 'sm_max_mhz': float(np.max(self.mx)),
-                   'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': 'NVML, 250 ms period'}
+                   'reasons': sorted(self.reasons), 'samples': len(self.sm),
+                   'source': 'NVML: SM clock every 250 ms during the timed regions; event reasons before / after '
+                             'them + violation-counter deltas (ns) over them', 'violation_ns': viol}
         return out
 
 

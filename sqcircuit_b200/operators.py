@@ -373,6 +373,7 @@ class HamiltonianOperator:
         self.device = ops.device
         self.B = loop_vals.shape[0]
         a, g = ops.hamiltonian_coeffs(loop_vals)
+        self.a_host, self.g_host = a, g          # host copies: decisions on them cost no device round trip
         self.a = ops.to_device(a, torch.complex128)
         self.g = ops.to_device(g, torch.float64)
         self.diag = ops.lc_diagonal(ng)          # [1 or B][N]
@@ -394,12 +395,15 @@ class HamiltonianOperator:
         if self.B < 2:
             return 1
         step = 0.0
-        if self.a.numel():
-            da = (self.a[1:] - self.a[:-1]).abs().amax(dim=0)
-            step = float((da / self.a.abs().amax(dim=0).clamp_min(1e-300)).max())
-        if self.g.numel():
-            dg = (self.g[1:] - self.g[:-1]).abs().amax(dim=0)
-            step = max(step, float((dg / self.g.abs().amax(dim=0).clamp_min(1e-300)).max()))
+        a, g = getattr(self, 'a_host', None), getattr(self, 'g_host', None)
+        if a is None:
+            a, g = self.a.cpu().numpy(), self.g.cpu().numpy()
+        if a.size:
+            da = np.abs(a[1:] - a[:-1]).max(axis=0)
+            step = float((da / np.maximum(np.abs(a).max(axis=0), 1e-300)).max())
+        if g.size:
+            dg = np.abs(g[1:] - g[:-1]).max(axis=0)
+            step = max(step, float((dg / np.maximum(np.abs(g).max(axis=0), 1e-300)).max()))
         if self.diag.shape[0] > 1:
             dd = (self.diag[1:] - self.diag[:-1]).abs().amax()
             step = max(step, float(dd / self.diag.abs().amax().clamp_min(1e-300)))
@@ -554,6 +558,7 @@ class RealHamiltonianOperator(HamiltonianOperator):
         else:           # share the coefficient tables of an existing complex operator of the same points
             self.ops, self.device, self.B = ops, ops.device, base.B
             self.a, self.g, self.diag, self.loop_vals, self.ng = base.a, base.g, base.diag, base.loop_vals, base.ng
+            self.a_host, self.g_host = getattr(base, 'a_host', None), getattr(base, 'g_host', None)
         m, inner = ops.dims
         self.N = ops.N
         self.Nc = (ops.N + 1) // 2
