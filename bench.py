@@ -376,23 +376,21 @@ def reference_arm(args):
 class ClockSampler:
     """SM clock and throttle reasons of the timed regions, in-process through NVML.
 
-    Measured on this pool (profiles/r02_clock_sampler_stall.txt): a polling ``nvidia-smi -lms 200`` child, or
-    nvmlDeviceGetCurrentClocksEventReasons called from a thread every 50-100 ms, stall single 300 ms steps of the
-    bench by up to 200 ms (the query serialises with kernel launches in the driver); nvmlDeviceGetClockInfo does
-    not.  So: the SM clock is sampled every 250 ms DURING the regions by a daemon thread; the event reasons are
-    read right before the first and right after the last timed step, and throttling in between is caught by the
-    cumulative NVML violation counters (thermal / power / reliability / board limit), whose deltas over the
-    regions are reported."""
+    Measured on this pool (profiles/r02_clock_sampler_stall.txt): a polling ``nvidia-smi -lms 200`` child, or NVML
+    queries from a polling thread, stall single 300 ms steps of the bench by 30-200 ms (the query serialises with
+    kernel launches in the driver; nvmlDeviceGetCurrentClocksEventReasons is the worst).  So the timed loop itself
+    reads the SM clock once per step, right after enqueueing it; the event reasons are read right before the
+    first and right after the last timed step, and throttling in between is caught by the cumulative NVML
+    violation counters (thermal / power / reliability), whose deltas over the regions are reported."""
     REASONS = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
     POLICIES = {'sw_power_cap': 0, 'sw_thermal_slowdown': 1, 'hw_slowdown': 5}   # NVML_PERF_POLICY_POWER / THERMAL / RELIABILITY
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.sm, self.mx, self.reasons = [], [], set()
-        self._stop = threading.Event()
-        self._thread = None
         self._nvml = self._h = None
         self._viol0 = {}
+        self._cost = 0.0
 
     def _physical_index(self):
         vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
@@ -424,32 +422,33 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self._nvml = pynvml
-            self._h = h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
-            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self._nvml = None
             return
         self._read_reasons()
         self._viol0 = self._violations()
-        period = float(os.environ.get('SQC_SAMPLER_PERIOD', '0.25'))
+        self._cost = 0.0
 
-        def loop():
-            while not self._stop.is_set():
-                try:
-                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                    self.mx.append(mx)
-                except Exception:
-                    pass
-                self._stop.wait(period)
-        self._thread = threading.Thread(target=loop, daemon=True)
-        self._thread.start()
+    def sample(self):
+        """One SM-clock reading, called by the timed loop right after it has enqueued a step (inside the timed
+        region, from the launching thread itself: nothing races with the launches; the GPU is busy with the
+        step just enqueued, so the reading is taken under load)."""
+        if self._nvml is None:
+            return
+        t = time.perf_counter()
+        try:
+            self.sm.append(float(self._nvml.nvmlDeviceGetClockInfo(self._h, self._nvml.NVML_CLOCK_SM)))
+            self.mx.append(self._max)
+        except Exception:
+            pass
+        self._cost += time.perf_counter() - t
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
-        if self._thread is None:
+        if self._nvml is None:
             return out
-        self._stop.set()
-        self._thread.join(timeout=2)
         self._read_reasons()
         viol = {}
         for nm, t1 in self._violations().items():
@@ -460,8 +459,9 @@ class ClockSampler:
         if self.sm:
             out = {'sm_mhz': float(np.median(self.sm)), 'sm_max_mhz': float(np.max(self.mx)),
                    'reasons': sorted(self.reasons), 'samples': len(self.sm),
-                   'source': 'NVML: SM clock every 250 ms during the timed regions; event reasons before / after '
-                             'them + violation-counter deltas (ns) over them', 'violation_ns': viol}
+                   'source': 'NVML: SM clock read by the timed loop after every enqueued step (GPU under load); '
+                             'event reasons before / after the timed regions + violation-counter deltas (ns) '
+                             'over them', 'violation_ns': viol, 'sampling_ms_total': round(1e3 * self._cost, 2)}
         return out
 
 
@@ -551,6 +551,8 @@ def our_arm(args):
     from sqcircuit_b200.sharding import gather_to_root
     sq.set_device(dev)
     kern = TimedKernels(Kernels(dev))
+    if DEBUG:
+        _debug_level_times()
     if args.no_graphs:
         kern._k.use_graphs = False
 
@@ -578,8 +580,18 @@ def our_arm(args):
                 if world > 1:
                     gather_to_root(ef.contiguous(), n_total)
                 return (ef.cpu() if e2e else ef), grads, res
+            if DEBUG:
+                torch.cuda.synchronize()
+                t0_ = time.perf_counter()
             res = cr.sweep_diag(N_EIG, **wl.sweep_args(prm), **solver_kw)
+            if DEBUG:
+                torch.cuda.synchronize()
+                t1_ = time.perf_counter()
             rates = [res.dec_rate(d, states=STATES) for d in wl.dec_types]
+            if DEBUG:
+                torch.cuda.synchronize()
+                print(f'[debug] sweep_diag {1e3 * (t1_ - t0_):.1f} ms (levels {sum(_LEVEL_MS):.1f}), rates '
+                      f'{1e3 * (time.perf_counter() - t1_):.1f} ms', file=sys.stderr)
             if world > 1:
                 # the only collective of the path: final gather of the per-point results to rank 0
                 gather_to_root(res.efreqs.contiguous(), n_total)
@@ -592,6 +604,8 @@ def our_arm(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    sampler = None
 
     def timed(step, nsteps, e2e):
         """K steps bracketed by barrier + synchronize; returns (max over ranks of the device time, this
@@ -606,10 +620,14 @@ def our_arm(args):
             if DEBUG:
                 torch.cuda.synchronize()
                 ts = time.perf_counter()
+                _LEVEL_MS.clear()
             last = step(e2e)
+            if sampler is not None:
+                sampler.sample()
             if DEBUG:
                 torch.cuda.synchronize()
                 st_ = torch.cuda.memory_stats()
+                print(f'[debug] levels (ms, host wall): {[round(x, 1) for x in _LEVEL_MS]}', file=sys.stderr)
                 print(f'[debug] step e2e={e2e} {1e3 * (time.perf_counter() - ts):.1f} ms  cudaMalloc segments '
                       f'{st_["segment.all.allocated"]} retries {st_["num_alloc_retries"]} reserved '
                       f'{st_["reserved_bytes.all.current"] / 2**30:.1f} GiB peak-alloc '
@@ -637,7 +655,7 @@ def our_arm(args):
     for _ in range(args.warmup):
         step(False)
     sampler = ClockSampler(local)
-    if rank == 0 and not os.environ.get('SQC_BENCH_NO_SAMPLER'):      # (dev switch: is the poller perturbing the run?)
+    if rank == 0 and not os.environ.get('SQC_BENCH_NO_SAMPLER'):      # (dev switch: is the sampling perturbing the run?)
         sampler.start()
     # timed region: only the dominant kernel (the H.X apply) carries CUDA events -- bracketing all
     # ~900 C-ABI calls of a step costs ~60 ms of host time per step (measured), which would be
@@ -834,6 +852,20 @@ NCU_HX_TRAFFIC = {
 }
 HX_COUNTER = {'vectors': 0}
 DEBUG = bool(os.environ.get('SQC_BENCH_DEBUG'))
+_LEVEL_MS = []
+
+
+def _debug_level_times():
+    """SQC_BENCH_DEBUG: host wall time of every batched Davidson call of a step (one per continuation level)."""
+    import sqcircuit_b200.circuit as C
+    inner = C._davidson
+
+    def timed_davidson(*a, **kw):
+        t = time.perf_counter()
+        r = inner(*a, **kw)
+        _LEVEL_MS.append(1e3 * (time.perf_counter() - t))
+        return r
+    C._davidson = timed_davidson
 
 
 def _install_hx_counter():
@@ -856,6 +888,9 @@ def _install_hx_counter():
 
 
 def main():
+    if os.environ.get('SQC_BENCH_NOGC'):
+        import gc
+        gc.disable()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)

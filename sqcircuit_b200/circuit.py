@@ -444,7 +444,7 @@ class Circuit:
                 # Ritz blocks (all p vectors) of solved points, kept until the last level starts
                 ritz = {int(i): j for j, i in enumerate(idx)}
                 ritz_store = [r.ritz_block]
-                ii = torch.as_tensor(idx, device=dev)
+                ii = kern.upload(idx)
                 evals[ii], evecs[ii], resmax[ii] = r.evals, r.evecs, r.resmax
                 iters, conv = r.iterations, r.converged
             else:
@@ -462,11 +462,10 @@ class Circuit:
                 new_blocks = []
                 for c0 in range(0, len(idx), chunk):
                     sel = slice(c0, c0 + chunk)
-                    x0 = RitzPairStart(store, torch.as_tensor(pos[nb[sel, 0]], device=dev),
-                                       torch.as_tensor(pos[nb[sel, 1]], device=dev))
+                    x0 = RitzPairStart(store, kern.upload(pos[nb[sel, 0]]), kern.upload(pos[nb[sel, 1]]))
                     r = solve(idx[sel], x0, st)
                     del x0
-                    ii = torch.as_tensor(idx[sel], device=dev)
+                    ii = kern.upload(idx[sel])
                     evals[ii], evecs[ii], resmax[ii] = r.evals, r.evecs, r.resmax
                     iters += r.iterations
                     conv = conv and r.converged

@@ -139,7 +139,7 @@ class SweepNoise:
             vals = (np.arange(-nmax, nmax + 1)[None, :] - ng[:, i:i + 1]) * (k[:, i:i + 1] * c)
             shape = [vals.shape[0]] + [1] * ops.M
             shape[1 + i] = ops.dims[i]
-            dvec += torch.as_tensor(vals, dtype=torch.float64, device=self.dev).reshape(shape)
+            dvec += self.kern.upload(vals, torch.float64).reshape(shape)
         first = True
         if any_charge:
             self.kern.diag_mul(BlockView(X), BlockView(Y), dvec.reshape(Bn, ops.N).contiguous(), False)

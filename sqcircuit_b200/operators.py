@@ -126,7 +126,7 @@ class CircuitOperators:
         nt = max(self.T, 1)
         s = np.asarray(s, dtype=float).reshape(-1, nt, self.M)
         etab = torch.empty((s.shape[0], nt, self.tlen), dtype=torch.complex128, device=self.device)
-        sd = torch.as_tensor(s, dtype=torch.float64, device=self.device).contiguous()
+        sd = self.kern.upload(s, torch.float64)
         self.kern.phase_tables(self.sp, nt, self.lam, sd, etab)
         return etab
 
@@ -224,9 +224,9 @@ class CircuitOperators:
         B = max(ng.shape[0], self.nb)
         dev = self.device
         out = torch.empty((B, self.N), dtype=torch.float64, device=dev)
-        om = torch.as_tensor(np.broadcast_to(omega, (B, self.M)).copy(), dtype=torch.float64, device=dev)
-        qq = torch.as_tensor(np.broadcast_to(q, (B, self.M, self.M)).copy(), dtype=torch.float64, device=dev)
-        ngd = torch.as_tensor(np.broadcast_to(ng, (B, self.M)).copy(), dtype=torch.float64, device=dev)
+        om = self.kern.upload(np.broadcast_to(omega, (B, self.M)), torch.float64)
+        qq = self.kern.upload(np.broadcast_to(q, (B, self.M, self.M)), torch.float64)
+        ngd = self.kern.upload(np.broadcast_to(ng, (B, self.M)), torch.float64)
         self.kern.lc_diagonal(self.sp, om, qq, ngd, out)
         return out
 
@@ -355,10 +355,7 @@ class CircuitOperators:
         return self._Dtg
 
     def to_device(self, arr, dtype):
-        arr = np.ascontiguousarray(arr)
-        if not arr.flags.writeable:          # broadcast views: torch wants an array it may write to
-            arr = arr.copy()
-        return torch.as_tensor(arr, dtype=dtype, device=self.device).contiguous()
+        return self.kern.upload(arr, dtype)
 
 
 # sweep points per shared low-block inverse of the two-level preconditioner (see build_lowblock)
@@ -441,7 +438,7 @@ class HamiltonianOperator:
             off[r, :len(st)] = st
         if rows == 1 and nslot > 1:      # LC diagonal shared by all sweep points (flux sweeps)
             off, nblk = np.repeat(off, nslot, axis=0), np.repeat(nblk, nslot)
-        return (torch.as_tensor(off, device=self.device), torch.as_tensor(nblk, device=self.device), nbmax,
+        return (self.ops.kern.upload(off), self.ops.kern.upload(nblk), nbmax,
                 torch.argsort(S, dim=1).to(torch.int32).contiguous())
 
     def build_lowblock(self, sigma, ns, group=None):
@@ -563,7 +560,7 @@ class RealHamiltonianOperator(HamiltonianOperator):
         self.N = ops.N
         self.Nc = (ops.N + 1) // 2
         self.diag_c = self.diag
-        cmap = torch.as_tensor(ops.real_index_map(), device=self.device)
+        cmap = ops.kern.upload(ops.real_index_map())
         dr = self.diag_c.reshape(-1, m, inner)[:, :, cmap].reshape(-1, ops.N)
         if 2 * self.Nc != ops.N:       # padding amplitude: never selected as a low-energy state, stays zero
             dr = torch.cat([dr, torch.full((dr.shape[0], 1), 1e300, dtype=dr.dtype, device=self.device)], dim=1)
@@ -649,7 +646,7 @@ class RealHamiltonianOperator(HamiltonianOperator):
             if n:
                 idx.append(i * inner + nc + n)
         starts = np.array([b[1] for b in blocks] + [len(idx)])
-        S = torch.as_tensor(np.array(idx, dtype=np.int32), device=self.device).reshape(1, -1).contiguous()
+        S = self.ops.kern.upload(np.array(idx, dtype=np.int32)).reshape(1, -1).contiguous()
         if len(idx) <= 160:
             return S, None, None, 0, None
         # neighbouring small blocks (the thin ends of the low-energy ellipse) are merged up to one warp's
@@ -666,7 +663,7 @@ class RealHamiltonianOperator(HamiltonianOperator):
         if nbmax > 64:
             # blocks too large for the banded kernels: dense block on the 160 lowest states instead
             return self._real_low_set(160, m, inner, nc)
-        off = torch.as_tensor(starts.astype(np.int32), device=self.device).reshape(1, -1)
-        nblk = torch.as_tensor(np.array([len(starts) - 1], dtype=np.int32), device=self.device)
+        off = self.ops.kern.upload(starts.astype(np.int32)).reshape(1, -1)
+        nblk = self.ops.kern.upload(np.array([len(starts) - 1], dtype=np.int32))
         perm = torch.argsort(S, dim=1).to(torch.int32).contiguous()
         return S, off, nblk, nbmax, perm

@@ -467,6 +467,10 @@ class EmulKernels:
             setattr(st, k, v)
         return st
 
+    def upload(self, arr, dtype=None):
+        t = torch.as_tensor(np.array(arr))
+        return t.to(dtype) if dtype is not None else t
+
     def davidson_decide(self, st, B):
         st.n_not_done[0] = 0
         p, k = st.p, st.k
