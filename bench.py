@@ -469,7 +469,7 @@ class TimedKernels:
     """Wraps the CUDA backend: CUDA events on the launching stream around every C-ABI call,
     so per-kernel device time is measured live inside the timed region (no profiler)."""
     TIMED = ['hx_fused', 'hx_fused_real', 'hx_generic', 'real_to_complex', 'complex_to_real', 'mode_transform', 'potential_apply', 'potential_elements', 'gram', 'gram_pair', 'gen_rr', 'davidson_insert2',
-             'lowblock_assemble', 'hpd_inverse_c64', 'lowblock_apply', 'lowband_factor', 'lowband_apply', 'block_update', 'ritz_update', 'block_rightmul', 'heev',
+             'lowblock_assemble', 'lowblock_assemble_generic', 'hamiltonian_dense', 'hpd_inverse_c64', 'lowblock_apply', 'lowband_factor', 'lowband_apply', 'block_update', 'ritz_update', 'block_rightmul', 'heev',
              'residual_norms', 'precond_residual', 'restart_copy', 'svqb_coeffs', 'davidson_decide',
              'davidson_insert', 'diag_mul', 'ladder_apply']
 

@@ -341,6 +341,12 @@ int sqc_lowblock_assemble_generic(const sqc_space_t* sp, int32_t ns, const int32
                                   const void* Dt, int64_t dt_stride_b, const sqc_potential_t* pot, const double* d,
                                   int64_t d_stride_b, const double* sigma, double unit, void* out, int32_t B,
                                   void* stream);
+/* The whole Hamiltonian of every sweep point as a dense matrix, out[b][r][q] = <r|H(b)|q> (complex128,
+ * [B][N][N], N = prod dims <= 4096), assembled from the same per-mode tables as above -- what the reference
+ * materialises in Circuit.hamiltonian() (circuit.py:2147-2164) before a dense / sparse eigensolve.  Feeds
+ * sqc_heev on the dense path (N <= 112). */
+int sqc_hamiltonian_dense(const sqc_space_t* sp, const void* Dt, int64_t dt_stride_b, const sqc_potential_t* pot,
+                          const double* d, int64_t d_stride_b, void* out, int32_t B, void* stream);
 int sqc_hpd_inverse_c64(void* A, int32_t ns, int32_t B, void* stream);
 int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
                        int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,

@@ -86,18 +86,21 @@ struct LbgGeom {
     int dtlen;
 };
 
+// DENSE: the whole Hamiltonian in complex128 (S = all states in natural order, no shift, no scaling) for the
+// dense eigensolver path (sqc_hamiltonian_dense).
+template <bool DENSE>
 __global__ void __launch_bounds__(256)
 lowblock_assemble_generic_kernel(const __grid_constant__ LbgGeom gm, const int32_t* __restrict__ S, long long s_stride_b,
                                  const cplx* __restrict__ Dt, long long dt_stride_b, const cplx* __restrict__ a,
                                  const double* __restrict__ g, const double* __restrict__ d, long long d_stride_b,
-                                 const double* __restrict__ sigma, double inv_unit, float2* __restrict__ out) {
+                                 const double* __restrict__ sigma, double inv_unit, void* __restrict__ out_) {
     const int b = blockIdx.y;
     const int e = blockIdx.x * 256 + threadIdx.x;
     const int ns = gm.ns, M = gm.M;
     if (e >= ns * ns) return;
     const int r = e / ns, q = e % ns;
-    const int32_t* s = S + b * s_stride_b;
-    int ir = s[r], iq = s[q];
+    const int32_t* s = DENSE ? nullptr : S + b * s_stride_b;
+    int ir = DENSE ? r : s[r], iq = DENSE ? q : s[q];
     int nr[SQC_MAX_MODES], nq[SQC_MAX_MODES];
     int ndiff = 0, dmode = -1;                       // number of modes in which r and q differ, the last such mode
     {
@@ -118,7 +121,7 @@ lowblock_assemble_generic_kernel(const __grid_constant__ LbgGeom gm, const int32
     }
     double vr = 0.0, vi = 0.0;
     const double* gb = g + (long long)b * (1 + M);
-    if (ndiff == 0) vr += d[b * d_stride_b + ir] - sigma[b] + gb[0];
+    if (ndiff == 0) vr += d[b * d_stride_b + ir] - (DENSE ? 0.0 : sigma[b]) + gb[0];
     if (ndiff == 1 && gm.harm[dmode] && abs(nr[dmode] - nq[dmode]) == 1)
         vr += gb[1 + dmode] * sqrt((double)max(nr[dmode], nq[dmode]));
     const cplx* dt = Dt + b * dt_stride_b;
@@ -155,13 +158,14 @@ lowblock_assemble_generic_kernel(const __grid_constant__ LbgGeom gm, const int32
             vi -= w.y;
         }
     }
-    out[(long long)b * ns * ns + e] = make_float2((float)(vr * inv_unit), (float)(vi * inv_unit));
+    if (DENSE) reinterpret_cast<cplx*>(out_)[(long long)b * ns * ns + e] = cmake(vr, vi);
+    else reinterpret_cast<float2*>(out_)[(long long)b * ns * ns + e] = make_float2((float)(vr * inv_unit), (float)(vi * inv_unit));
 }
 
-extern "C" int sqc_lowblock_assemble_generic(const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
-                                             const void* Dt, int64_t dt_stride_b, const sqc_potential_t* pot,
-                                             const double* d, int64_t d_stride_b, const double* sigma, double unit,
-                                             void* out, int32_t B, void* stream) {
+static int lbg_launch(bool dense, const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
+                      const void* Dt, int64_t dt_stride_b, const sqc_potential_t* pot,
+                      const double* d, int64_t d_stride_b, const double* sigma, double unit,
+                      void* out, int32_t B, void* stream) {
     if (!sp || !pot || B <= 0 || ns <= 0 || sp->n_modes < 1 || sp->n_modes > SQC_MAX_MODES) return SQC_EINVAL;
     if (pot->n_terms < 0 || pot->n_terms > SQC_MAX_TERMS) return SQC_EINVAL;
     LbgGeom gm = {};
@@ -184,12 +188,35 @@ extern "C" int sqc_lowblock_assemble_generic(const sqc_space_t* sp, int32_t ns, 
     gm.dtlen = off;
     for (int t = 0; t < pot->n_terms; ++t)
         for (int i = 0; i < sp->n_modes; ++i) gm.shift[t][i] = sp->harmonic[i] ? 0 : pot->shift[t][i];
+    if (dense && (long long)ns != N) return SQC_EINVAL;
     dim3 grid((ns * ns + 255) / 256, B);
-    lowblock_assemble_generic_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        gm, S, s_stride_b, (const cplx*)Dt, dt_stride_b, (const cplx*)pot->a, pot->g, d, d_stride_b, sigma, 1.0 / unit,
-        (float2*)out);
+    if (dense)
+        lowblock_assemble_generic_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            gm, S, s_stride_b, (const cplx*)Dt, dt_stride_b, (const cplx*)pot->a, pot->g, d, d_stride_b, sigma, 1.0, out);
+    else
+        lowblock_assemble_generic_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            gm, S, s_stride_b, (const cplx*)Dt, dt_stride_b, (const cplx*)pot->a, pot->g, d, d_stride_b, sigma, 1.0 / unit,
+            out);
     SQC_LAUNCHED();
     return 0;
+}
+
+extern "C" int sqc_lowblock_assemble_generic(const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
+                                             const void* Dt, int64_t dt_stride_b, const sqc_potential_t* pot,
+                                             const double* d, int64_t d_stride_b, const double* sigma, double unit,
+                                             void* out, int32_t B, void* stream) {
+    if (!S || !sigma) return SQC_EINVAL;
+    return lbg_launch(false, sp, ns, S, s_stride_b, Dt, dt_stride_b, pot, d, d_stride_b, sigma, unit, out, B, stream);
+}
+
+extern "C" int sqc_hamiltonian_dense(const sqc_space_t* sp, const void* Dt, int64_t dt_stride_b,
+                                     const sqc_potential_t* pot, const double* d, int64_t d_stride_b, void* out,
+                                     int32_t B, void* stream) {
+    if (!sp) return SQC_EINVAL;
+    long long N = 1;
+    for (int i = 0; i < sp->n_modes; ++i) N *= sp->dims[i];
+    if (N > 4096) return SQC_ELIMIT;
+    return lbg_launch(true, sp, (int32_t)N, nullptr, 0, Dt, dt_stride_b, pot, d, d_stride_b, nullptr, 1.0, out, B, stream);
 }
 
 // Real (time-reversal adapted) representation, see hx_real.cu: the index set holds REAL basis states

@@ -37,6 +37,17 @@ class EigResult:
 
 def solve_dense(kern, op, B, N, k):
     dev = op.device
+    if hasattr(op, 'dense_matrix'):
+        # H(b) assembled directly from the per-mode Fock-basis tables (sqc_hamiltonian_dense): one small kernel
+        # instead of pushing the identity through the matrix-free operator (measured on the 1024-point fluxonium
+        # sweep: 23 ms of transform passes on 102 400 unit vectors)
+        H = op.dense_matrix()
+        w = torch.empty((B, N), dtype=torch.float64, device=dev)
+        Zt = torch.empty((B, N, N), dtype=torch.complex128, device=dev)
+        kern.heev(H, N, w, Zt)
+        k = min(k, N)
+        return EigResult(w[:, :k].contiguous(), Zt[:, :k, :].contiguous(), 0,
+                         torch.zeros(B, dtype=torch.float64, device=dev), True)
     eye = torch.eye(N, dtype=torch.complex128, device=dev).unsqueeze(0).expand(B, N, N).contiguous()
     HX = torch.empty_like(eye)
     op.apply(BlockView(eye), BlockView(HX))

@@ -341,6 +341,14 @@ class Kernels:
                                                           dsb, _p(sigma), unit, _p(out), B, _stream(self.dev)),
                    'sqc_lowblock_assemble_generic')
 
+    def hamiltonian_dense(self, sp, Dt, pot, d, out):
+        """out[b] = H(b) as a dense complex128 matrix (sqc_hamiltonian_dense)."""
+        B = out.shape[0]
+        dsb = 0 if d.shape[0] == 1 else d.stride(0)
+        tsb = 0 if Dt.shape[0] == 1 else Dt.stride(0)
+        _lib.check(self.lib.sqc_hamiltonian_dense(C.byref(sp), _p(Dt), tsb, C.byref(pot), _p(d), dsb, _p(out), B,
+                                                  _stream(self.dev)), 'sqc_hamiltonian_dense')
+
     def hpd_inverse_c64(self, A):
         B, ns, _ = A.shape
         _lib.check(self.lib.sqc_hpd_inverse_c64(_p(A), ns, B, _stream(self.dev)), 'sqc_hpd_inverse_c64')

@@ -380,6 +380,15 @@ class HamiltonianOperator:
     def apply(self, X: BlockView, Y: BlockView):
         self.ops.apply_potential_op(X, Y, self.a, self.g, fock_diag=self.diag)
 
+    def dense_matrix(self):
+        """H(b) of every point as a dense [B][N][N] complex128 matrix, H[b][r][q] = <r|H(b)|q> (small Hilbert
+        spaces: the dense eigensolver path)."""
+        ops = self.ops
+        H = torch.empty((self.B, ops.N, ops.N), dtype=torch.complex128, device=self.device)
+        pot = ops.potential_struct(self.a, self.g, ops.etab)
+        ops.kern.hamiltonian_dense(ops.sp, ops.displacement_tables_generic(), pot, self.diag, H)
+        return H
+
     def supports_lowblock(self):
         # harmonic x charge layouts of one circuit: the banded block of up to 512 states; every other layout
         # (several modes, batches of circuits): the dense block of up to 160 states from per-mode tables

@@ -632,7 +632,13 @@ class EmulKernels:
                         bw &= (n2 == n + w)
                 at = complex(a[b, t])
                 A += fw * at * pf + bw * np.conj(at * pb)
-            out[b] = torch.from_numpy((A / unit).astype(np.complex64))
+            out[b] = torch.from_numpy((A / unit).astype(np.complex64 if out.dtype == torch.complex64 else np.complex128))
+
+    def hamiltonian_dense(self, sp, Dt, pot, d, out):
+        """Contract of sqc_hamiltonian_dense: the whole H of every point, complex128, from per-mode tables."""
+        B, N, _ = out.shape
+        S = torch.arange(N, dtype=torch.int32).reshape(1, N)
+        self.lowblock_assemble_generic(sp, S, Dt, pot, d, torch.zeros(B, dtype=torch.float64), 1.0, out)
 
     def _lowblock_assemble_real(self, sp, S, Dt, pot, d, sigma, unit, out):
         """H_r = U^H H_c U on the real index set (each real state is a combination of charges +-n)."""

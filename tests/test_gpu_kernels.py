@@ -1094,6 +1094,10 @@ def test_lowblock_assemble_generic_matches_dense_operator(kern, dims, harm, shif
         idx = S[b].long()
         ref = (H[b][idx][:, idx] - sigma[b] * torch.eye(ns, device='cuda')) / unit
         assert relerr(out[b].to(torch.complex128).cpu(), ref.cpu()) < 1e-6           # complex64 storage
+    # the whole matrix in complex128 (sqc_hamiltonian_dense: the dense eigensolver path)
+    Hd = torch.empty((B, N, N), dtype=torch.complex128, device='cuda')
+    kern.hamiltonian_dense(sp, Dt, pot, d, Hd)
+    assert relerr(Hd.cpu(), H.cpu()) < 1e-13
     # the emulated contract gives the same block
     pot._keep = (a.cpu(), g.cpu(), etab.cpu(), None)
     oute = torch.zeros((B, ns, ns), dtype=torch.complex64)

@@ -1,7 +1,7 @@
 """Dev tool: where the HOST time of a bench step goes (cProfile of the Python thread over a few steps of a
 workload, GPU running asynchronously; blocking waits show up as synchronize / item / cpu).
 
-    python tools/host_profile.py [zeropi4096] [steps]
+    python tools/host_profile.py [zeropi4096] [steps] [points]
 """
 import cProfile
 import io
@@ -26,7 +26,7 @@ def main():
     kern = Kernels('cuda:0')
     wl = bench.WORKLOADS[name]()
     cr = wl.build(sq, kern)
-    prm = wl.grid(wl.points, 0, 1)
+    prm = wl.grid(int(sys.argv[3]) if len(sys.argv) > 3 else wl.points, 0, 1)
 
     def step():
         res = cr.sweep_diag(10, **wl.sweep_args(prm))
