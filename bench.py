@@ -469,7 +469,7 @@ class TimedKernels:
     """Wraps the CUDA backend: CUDA events on the launching stream around every C-ABI call,
     so per-kernel device time is measured live inside the timed region (no profiler)."""
     TIMED = ['hx_fused', 'hx_fused_real', 'hx_generic', 'real_to_complex', 'complex_to_real', 'mode_transform', 'potential_apply', 'potential_elements', 'gram', 'gram_pair', 'gen_rr', 'davidson_insert2',
-             'lowblock_assemble', 'lowblock_assemble_generic', 'hamiltonian_dense', 'hpd_inverse_c64', 'lowblock_apply', 'lowband_factor', 'lowband_apply', 'block_update', 'ritz_update', 'block_rightmul', 'heev',
+             'lowblock_assemble', 'lowblock_assemble_generic', 'hamiltonian_dense', 'hpd_inverse_c64', 'lowblock_apply', 'lowband_factor', 'lowband_apply', 'block_update', 'ritz_update', 'block_rightmul', 'heev', 'syev',
              'residual_norms', 'precond_residual', 'restart_copy', 'svqb_coeffs', 'davidson_decide',
              'davidson_insert', 'diag_mul', 'ladder_apply']
 
@@ -660,7 +660,7 @@ def our_arm(args):
     # timed region: only the dominant kernel (the H.X apply) carries CUDA events -- bracketing all
     # ~900 C-ABI calls of a step costs ~60 ms of host time per step (measured), which would be
     # charged to `value`.  The full per-kernel breakdown comes from one extra, untimed step below.
-    kern.only = {'hx_fused', 'hx_fused_real', 'hx_generic', 'mode_transform', 'potential_apply', 'heev'}
+    kern.only = {'hx_fused', 'hx_fused_real', 'hx_generic', 'mode_transform', 'potential_apply', 'heev', 'syev'}
     kern.enabled = True
     l0 = kern.launch_count()
     ms_dev, own_dev, last = timed(step, args.steps, False)
@@ -727,21 +727,28 @@ def our_arm(args):
     real_ms = hx_kernel.get('hx_fused_real', [0.0, 0])[0]
     cplx_ms = sum(hx_kernel.get(k, [0, 0])[0] for k in ('hx_fused', 'hx_generic', 'mode_transform', 'potential_apply'))
     heev_ms = hx_kernel.get('heev', [0.0, 0])[0]
+    syev_ms = hx_kernel.get('syev', [0.0, 0])[0]
     use_real = real_ms > cplx_ms
     m0 = cr.m[0]
-    if heev_ms > max(real_ms, cplx_ms):
+    if max(heev_ms, syev_ms) > max(real_ms, cplx_ms):
         # dense path (N <= 112): the batched Jacobi eigensolver dominates; judged against the FP64 pipe.
-        # Algorithmic work of a Hermitian eigendecomposition with vectors: ~9 n^3 complex multiply-adds
-        # (tridiagonalisation 4/3 + QR with vectors ~6 + back-transformation 2) = 72 n^3 real flop
-        calls = hx_kernel['heev'][1]
+        # Algorithmic work of a Hermitian eigendecomposition with vectors: ~9 n^3 multiply-adds
+        # (tridiagonalisation 4/3 + QR with vectors ~6 + back-transformation 2): 72 n^3 real flop for a complex
+        # matrix (sqc_heev), 18 n^3 for a real symmetric one (sqc_syev: circuits without charge modes)
+        sym = syev_ms > heev_ms
+        name, ev_ms, per_mat = ('syev', syev_ms, 18.0 * N ** 3) if sym else ('heev', heev_ms, 72.0 * N ** 3)
+        calls = hx_kernel[name][1]
         nmat = points * args.steps
-        flops = 72.0 * N ** 3 * nmat
-        roof = {'bound': 'tensor', 'kernel': 'sqc_heev (batched Hermitian Jacobi eigensolver, one CTA per sweep '
-                'point; SIMT FP64 -- there is no FP64 tcgen05, the FP64 pipe is the bound)', 'unit': 'TFLOP/s',
+        flops = per_mat * nmat
+        roof = {'bound': 'tensor', 'kernel': ('sqc_syev (batched real symmetric Jacobi eigensolver, matrix and '
+                                              'eigenvectors in shared memory' if sym else
+                                              'sqc_heev (batched Hermitian Jacobi eigensolver') +
+                ', one CTA per sweep point; SIMT FP64 -- there is no FP64 tcgen05, the FP64 pipe is the bound)',
+                'unit': 'TFLOP/s',
                 'peak': 37.1, 'peak_source': 'measured FP64 DMMA/DFMA issue rate (tools/cu/dmma_peak.cu, '
                 'profiles/r01_dmma_peak.txt); MEASURED_PEAKS.json has no FP64 figure',
-                'achieved': flops / (heev_ms / 1e3) / 1e12, 'traffic': None, 'calls': calls, 'ms': heev_ms,
-                'algorithmic_flops_per_matrix': 72.0 * N ** 3, 'matrices': nmat}
+                'achieved': flops / (ev_ms / 1e3) / 1e12, 'traffic': None, 'calls': calls, 'ms': ev_ms,
+                'algorithmic_flops_per_matrix': per_mat, 'matrices': nmat}
         roof['frac'] = roof['achieved'] / roof['peak']
     else:
         if use_real:

@@ -344,9 +344,16 @@ int sqc_lowblock_assemble_generic(const sqc_space_t* sp, int32_t ns, const int32
 /* The whole Hamiltonian of every sweep point as a dense matrix, out[b][r][q] = <r|H(b)|q> (complex128,
  * [B][N][N], N = prod dims <= 4096), assembled from the same per-mode tables as above -- what the reference
  * materialises in Circuit.hamiltonian() (circuit.py:2147-2164) before a dense / sparse eigensolve.  Feeds
- * sqc_heev on the dense path (N <= 112). */
+ * sqc_heev (or, real_out, sqc_syev) on the dense path (N <= 112). */
 int sqc_hamiltonian_dense(const sqc_space_t* sp, const void* Dt, int64_t dt_stride_b, const sqc_potential_t* pot,
-                          const double* d, int64_t d_stride_b, void* out, int32_t B, void* stream);
+                          const double* d, int64_t d_stride_b, void* out, int32_t real_out, int32_t B, void* stream);
+/* real_out != 0: out is double [B][N][N] (layouts without charge modes only: there a_t D_t + h.c. = 2 Re(a_t D_t),
+ * H is real symmetric), the input of sqc_syev: batched real symmetric eigensolver (parallel cyclic Jacobi, matrix
+ * and eigenvectors in shared memory, one CTA per matrix).  A: device double [B][ld][ld] (read only), n <= 112 the
+ * size of every matrix, w: device [B][ld] ascending eigenvalues (entries >= n set to +inf), Zt: device double
+ * [B][ld][ld], Zt[j][i] = component i of eigenvector j.  Replaces the eigs / eigh call of Circuit._diag_np
+ * (circuit.py:1938-1986) for small real Hamiltonians. */
+int sqc_syev(const double* A, int32_t n, int32_t ld, double* w, double* Zt, int32_t B, void* stream);
 int sqc_hpd_inverse_c64(void* A, int32_t ns, int32_t B, void* stream);
 int sqc_lowblock_apply(sqc_block_t X, sqc_block_t HX, sqc_block_t T, const double* theta,
                        int32_t ld_theta, const int32_t* act, int32_t ld_act, const int32_t* S,

@@ -83,7 +83,8 @@ SIGNATURES = {
                                       c_vp, c_dbl, c_vp, c_i32, c_vp]),
     'sqc_lowblock_assemble_generic': (c_i32, [C.POINTER(Space), c_i32, c_vp, c_i64, c_vp, c_i64, C.POINTER(Potential), c_vp,
                                               c_i64, c_vp, c_dbl, c_vp, c_i32, c_vp]),
-    'sqc_hamiltonian_dense': (c_i32, [C.POINTER(Space), c_vp, c_i64, C.POINTER(Potential), c_vp, c_i64, c_vp, c_i32, c_vp]),
+    'sqc_hamiltonian_dense': (c_i32, [C.POINTER(Space), c_vp, c_i64, C.POINTER(Potential), c_vp, c_i64, c_vp, c_i32, c_i32, c_vp]),
+    'sqc_syev': (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     'sqc_hpd_inverse_c64': (c_i32, [c_vp, c_i32, c_i32, c_vp]),
     'sqc_lowband_factor': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp]),
     'sqc_lowband_apply': (c_i32, [Block, Block, Block, c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32,

@@ -86,9 +86,10 @@ struct LbgGeom {
     int dtlen;
 };
 
-// DENSE: the whole Hamiltonian in complex128 (S = all states in natural order, no shift, no scaling) for the
-// dense eigensolver path (sqc_hamiltonian_dense).
-template <bool DENSE>
+// DENSE = 1: the whole Hamiltonian in complex128 (S = all states in natural order, no shift, no scaling) for the
+// dense eigensolver path (sqc_hamiltonian_dense); DENSE = 2: its real part as doubles (layouts without charge
+// modes: H is real symmetric in the Fock basis).
+template <int DENSE>
 __global__ void __launch_bounds__(256)
 lowblock_assemble_generic_kernel(const __grid_constant__ LbgGeom gm, const int32_t* __restrict__ S, long long s_stride_b,
                                  const cplx* __restrict__ Dt, long long dt_stride_b, const cplx* __restrict__ a,
@@ -158,11 +159,12 @@ lowblock_assemble_generic_kernel(const __grid_constant__ LbgGeom gm, const int32
             vi -= w.y;
         }
     }
-    if (DENSE) reinterpret_cast<cplx*>(out_)[(long long)b * ns * ns + e] = cmake(vr, vi);
+    if (DENSE == 2) reinterpret_cast<double*>(out_)[(long long)b * ns * ns + e] = vr;
+    else if (DENSE == 1) reinterpret_cast<cplx*>(out_)[(long long)b * ns * ns + e] = cmake(vr, vi);
     else reinterpret_cast<float2*>(out_)[(long long)b * ns * ns + e] = make_float2((float)(vr * inv_unit), (float)(vi * inv_unit));
 }
 
-static int lbg_launch(bool dense, const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
+static int lbg_launch(int dense, const sqc_space_t* sp, int32_t ns, const int32_t* S, int64_t s_stride_b,
                       const void* Dt, int64_t dt_stride_b, const sqc_potential_t* pot,
                       const double* d, int64_t d_stride_b, const double* sigma, double unit,
                       void* out, int32_t B, void* stream) {
@@ -190,11 +192,14 @@ static int lbg_launch(bool dense, const sqc_space_t* sp, int32_t ns, const int32
         for (int i = 0; i < sp->n_modes; ++i) gm.shift[t][i] = sp->harmonic[i] ? 0 : pot->shift[t][i];
     if (dense && (long long)ns != N) return SQC_EINVAL;
     dim3 grid((ns * ns + 255) / 256, B);
-    if (dense)
-        lowblock_assemble_generic_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    if (dense == 2)
+        lowblock_assemble_generic_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            gm, S, s_stride_b, (const cplx*)Dt, dt_stride_b, (const cplx*)pot->a, pot->g, d, d_stride_b, sigma, 1.0, out);
+    else if (dense == 1)
+        lowblock_assemble_generic_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(
             gm, S, s_stride_b, (const cplx*)Dt, dt_stride_b, (const cplx*)pot->a, pot->g, d, d_stride_b, sigma, 1.0, out);
     else
-        lowblock_assemble_generic_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        lowblock_assemble_generic_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(
             gm, S, s_stride_b, (const cplx*)Dt, dt_stride_b, (const cplx*)pot->a, pot->g, d, d_stride_b, sigma, 1.0 / unit,
             out);
     SQC_LAUNCHED();
@@ -206,17 +211,20 @@ extern "C" int sqc_lowblock_assemble_generic(const sqc_space_t* sp, int32_t ns, 
                                              const double* d, int64_t d_stride_b, const double* sigma, double unit,
                                              void* out, int32_t B, void* stream) {
     if (!S || !sigma) return SQC_EINVAL;
-    return lbg_launch(false, sp, ns, S, s_stride_b, Dt, dt_stride_b, pot, d, d_stride_b, sigma, unit, out, B, stream);
+    return lbg_launch(0, sp, ns, S, s_stride_b, Dt, dt_stride_b, pot, d, d_stride_b, sigma, unit, out, B, stream);
 }
 
 extern "C" int sqc_hamiltonian_dense(const sqc_space_t* sp, const void* Dt, int64_t dt_stride_b,
                                      const sqc_potential_t* pot, const double* d, int64_t d_stride_b, void* out,
-                                     int32_t B, void* stream) {
+                                     int32_t real_out, int32_t B, void* stream) {
     if (!sp) return SQC_EINVAL;
+    if (real_out)       // only layouts without charge modes have a real symmetric H in this basis
+        for (int i = 0; i < sp->n_modes; ++i)
+            if (!sp->harmonic[i] && sp->dims[i] > 1) return SQC_EINVAL;
     long long N = 1;
     for (int i = 0; i < sp->n_modes; ++i) N *= sp->dims[i];
     if (N > 4096) return SQC_ELIMIT;
-    return lbg_launch(true, sp, (int32_t)N, nullptr, 0, Dt, dt_stride_b, pot, d, d_stride_b, nullptr, 1.0, out, B, stream);
+    return lbg_launch(real_out ? 2 : 1, sp, (int32_t)N, nullptr, 0, Dt, dt_stride_b, pot, d, d_stride_b, nullptr, 1.0, out, B, stream);
 }
 
 // Real (time-reversal adapted) representation, see hx_real.cu: the index set holds REAL basis states

@@ -319,3 +319,182 @@ extern "C" int sqc_gen_rr_real(const void* GA, const void* GB, const int32_t* n,
     SQC_LAUNCHED();
     return 0;
 }
+
+// =====================================================================================
+// Batched real symmetric eigensolver for the dense path (sqc_syev): the Hamiltonian of a circuit WITHOUT
+// charge modes is real symmetric in the Fock basis (a_t D_t + h.c. = 2 Re(a_t D_t) for the complex-symmetric
+// displacement tables D_t = V diag(e^{i s lam}) V^T), so the 1024-point fluxonium sweep of BASELINE configs[1]
+// needs a quarter of the flops of sqc_heev and holds BOTH the matrix and the eigenvectors in shared memory
+// (2 x 81 KB at n = 100; the complex kernel keeps the eigenvectors in global memory).
+// Same parallel cyclic Jacobi as above, with the thread split of the large complex kernel (small.cu): the
+// 2 x 2 blocks of the upper triangle and the eigenvector rows are rotated side by side by two teams.
+// =====================================================================================
+#define SYV_THREADS 1024
+
+__device__ void jacobi_syev_big(double* A, int n, int np, int lda, double* Zt, int ldz, double* rot, int* prs,
+                                double* red) {
+    const int tid = threadIdx.x, nt = SYV_THREADS;
+    const int half = np >> 1;
+    for (int e = tid; e < np * np; e += nt) {
+        const int r = e / np, c = e % np;
+        if (r >= n || c >= n) A[r * lda + c] = (r == c) ? RRR_BIG : 0.0;
+        Zt[r * ldz + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int ntri = half * (half + 1) / 2;
+    // a 2 x 2 block costs about four eigenvector elements: split the threads accordingly
+    int na_thr = (int)((long long)nt * 4 * ntri / (4LL * ntri + (long long)half * n));
+    na_thr = (na_thr + 31) & ~31;
+    if (na_thr < 32) na_thr = 32;
+    if (na_thr > nt - 32) na_thr = nt - 32;
+    int P0 = 0, Q0 = 0;
+    if (tid < ntri && tid < na_thr) rrr_tri_index(tid, half, P0, Q0);
+    bool polish = false;
+    for (int sweep = 0; sweep < RRR_MAX_SWEEPS; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int e = tid; e < n * n; e += nt) {
+            const int r = e / n, c = e % n;
+            const double v = A[r * lda + c];
+            if (r == c) dg = fma(v, v, dg); else off = fma(v, v, off);
+        }
+        off = warp_sum(off);
+        dg = warp_sum(dg);
+        if ((tid & 31) == 0) {
+            red[tid >> 5] = off;
+            red[32 + (tid >> 5)] = dg;
+        }
+        __syncthreads();
+        double o = 0.0, d = 0.0;
+        for (int w_ = 0; w_ < nt / 32; ++w_) {
+            o += red[w_];
+            d += red[32 + w_];
+        }
+        __syncthreads();
+        if (o == 0.0 || polish) break;
+        if (o <= 1e-22 * (d + o)) polish = true;
+        const bool fast_angle = o > 1e-8 * (d + o);
+
+        for (int step = 0; step < np - 1; ++step) {
+            if (tid < half) {
+                const int k = tid;
+                int p = (k == 0) ? np - 1 : (step + k) % (np - 1);
+                int q = (step - k + (np - 1)) % (np - 1);
+                if (p > q) { const int t_ = p; p = q; q = t_; }
+                prs[2 * k] = p;
+                prs[2 * k + 1] = q;
+                const double a = A[p * lda + p], dd = A[q * lda + q], b = A[p * lda + q];
+                double c = 1.0, s = 0.0;
+                const double lim = 1e-17 * (fabs(a) + fabs(dd));
+                if (fabs(b) > lim && b != 0.0 && p < n && q < n) {
+                    double t;
+                    const float bf = (float)b;
+                    if (fast_angle && fabsf(bf) > 1e-15f && fabsf(bf) < 1e15f) {
+                        const float thf = 0.5f * (float)(dd - a) / bf;
+                        t = (double)(copysignf(1.0f, thf) / (fabsf(thf) + sqrtf(fmaf(thf, thf, 1.0f))));
+                    } else {
+                        const double th = 0.5 * (dd - a) / b;
+                        t = copysign(1.0, th) / (fabs(th) + sqrt(fma(th, th, 1.0)));
+                    }
+                    c = rsqrt(fma(t, t, 1.0));
+                    s = t * c;
+                }
+                rot[2 * k] = c;
+                rot[2 * k + 1] = s;
+            }
+            __syncthreads();
+            if (tid < na_thr) {
+                for (int u = tid; u < ntri; u += na_thr) {
+                    int P = P0, Q = Q0;
+                    if (u != tid) rrr_tri_index(u, half, P, Q);
+                    const double cP = rot[2 * P], sP = rot[2 * P + 1], cQ = rot[2 * Q], sQ = rot[2 * Q + 1];
+                    if (sP == 0.0 && sQ == 0.0) continue;
+                    const int p = prs[2 * P], q = prs[2 * P + 1], pc = prs[2 * Q], qc = prs[2 * Q + 1];
+                    const double a00 = A[p * lda + pc], a01 = A[p * lda + qc];
+                    const double a10 = A[q * lda + pc], a11 = A[q * lda + qc];
+                    const double r00 = cP * a00 - sP * a10, r01 = cP * a01 - sP * a11;
+                    const double r10 = sP * a00 + cP * a10, r11 = sP * a01 + cP * a11;
+                    double o00 = cQ * r00 - sQ * r01, o01 = sQ * r00 + cQ * r01;
+                    double o10 = cQ * r10 - sQ * r11, o11 = sQ * r10 + cQ * r11;
+                    if (P == Q && sP != 0.0) {
+                        o01 = fast_angle ? o01 : 0.0;
+                        o10 = o01;
+                    }
+                    A[p * lda + pc] = o00;
+                    A[p * lda + qc] = o01;
+                    A[q * lda + pc] = o10;
+                    A[q * lda + qc] = o11;
+                    if (P != Q) {
+                        A[pc * lda + p] = o00;
+                        A[qc * lda + p] = o01;
+                        A[pc * lda + q] = o10;
+                        A[qc * lda + q] = o11;
+                    }
+                }
+            } else {
+                for (int e = tid - na_thr; e < half * n; e += nt - na_thr) {
+                    const int P = e / n, i = e - P * n;
+                    const double sP = rot[2 * P + 1];
+                    if (sP == 0.0) continue;
+                    const int p = prs[2 * P], q = prs[2 * P + 1];
+                    const double cP = rot[2 * P];
+                    const double zp = Zt[p * ldz + i], zq = Zt[q * ldz + i];
+                    Zt[p * ldz + i] = cP * zp - sP * zq;
+                    Zt[q * ldz + i] = sP * zp + cP * zq;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SYV_THREADS, 1)
+syev_kernel(const double* __restrict__ Ain, int n, int ld, double* __restrict__ w, double* __restrict__ Zout) {
+    extern __shared__ double smem[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int np = (n + 1) & ~1;
+    const int lda = np | 1;
+    double* A = smem;
+    double* Zs = A + (size_t)np * lda;
+    double* rot = Zs + (size_t)np * lda;       // [np]
+    double* red = rot + np;                    // [64]
+    double* wv = red + 64;                     // [np]
+    int* prs = reinterpret_cast<int*>(wv + np);
+    int* rank = prs + np;
+    const double* a = Ain + (int64_t)b * ld * ld;
+    for (int e = tid; e < n * n; e += SYV_THREADS) {
+        const int r = e / n, c = e % n;
+        A[r * lda + c] = 0.5 * (a[r * ld + c] + a[c * ld + r]);
+    }
+    __syncthreads();
+    jacobi_syev_big(A, n, np, lda, Zs, lda, rot, prs, red);
+    for (int i = tid; i < n; i += SYV_THREADS) wv[i] = A[i * lda + i];
+    __syncthreads();
+    for (int i = tid; i < n; i += SYV_THREADS) {
+        const double wi = wv[i];
+        int r = 0;
+        for (int j = 0; j < n; ++j) r += (wv[j] < wi) || (wv[j] == wi && j < i);
+        rank[i] = r;
+    }
+    __syncthreads();
+    double* wout = w + (int64_t)b * ld;
+    for (int i = tid; i < ld; i += SYV_THREADS) wout[i] = INFINITY;
+    __syncthreads();
+    for (int i = tid; i < n; i += SYV_THREADS) wout[rank[i]] = wv[i];
+    double* zg = Zout + (int64_t)b * ld * ld;
+    for (int e = tid; e < n * n; e += SYV_THREADS) {
+        const int j = e / n, i = e - j * n;
+        zg[rank[j] * ld + i] = Zs[j * lda + i];
+    }
+}
+
+extern "C" int sqc_syev(const double* A, int32_t n, int32_t ld, double* w, double* Zt, int32_t B, void* stream) {
+    if (!A || !w || !Zt || B <= 0 || n <= 0 || ld < n || n > 112) return SQC_EINVAL;
+    const int np = (n + 1) & ~1;
+    const size_t bytes = ((size_t)2 * np * (np | 1) + 2 * np + 64) * sizeof(double) + 2 * np * sizeof(int) + 16;
+    if (bytes > 227 * 1024) return SQC_ELIMIT;
+    cudaError_t e = cudaFuncSetAttribute(syev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    syev_kernel<<<B, SYV_THREADS, bytes, (cudaStream_t)stream>>>(A, n, ld, w, Zt);
+    SQC_LAUNCHED();
+    return 0;
+}

@@ -342,12 +342,18 @@ class Kernels:
                    'sqc_lowblock_assemble_generic')
 
     def hamiltonian_dense(self, sp, Dt, pot, d, out):
-        """out[b] = H(b) as a dense complex128 matrix (sqc_hamiltonian_dense)."""
+        """out[b] = H(b) as a dense matrix: complex128, or float64 for layouts without charge modes."""
         B = out.shape[0]
         dsb = 0 if d.shape[0] == 1 else d.stride(0)
         tsb = 0 if Dt.shape[0] == 1 else Dt.stride(0)
-        _lib.check(self.lib.sqc_hamiltonian_dense(C.byref(sp), _p(Dt), tsb, C.byref(pot), _p(d), dsb, _p(out), B,
-                                                  _stream(self.dev)), 'sqc_hamiltonian_dense')
+        _lib.check(self.lib.sqc_hamiltonian_dense(C.byref(sp), _p(Dt), tsb, C.byref(pot), _p(d), dsb, _p(out),
+                                                  int(out.dtype == torch.float64), B, _stream(self.dev)),
+                   'sqc_hamiltonian_dense')
+
+    def syev(self, A, w, Zt):
+        """Batched real symmetric eigensolver: A [B][n][n] float64, w [B][n], Zt [B][n][n] (rows = eigenvectors)."""
+        B, n, _ = A.shape
+        _lib.check(self.lib.sqc_syev(_p(A), n, n, _p(w), _p(Zt), B, _stream(self.dev)), 'sqc_syev')
 
     def hpd_inverse_c64(self, A):
         B, ns, _ = A.shape

@@ -381,10 +381,12 @@ class HamiltonianOperator:
         self.ops.apply_potential_op(X, Y, self.a, self.g, fock_diag=self.diag)
 
     def dense_matrix(self):
-        """H(b) of every point as a dense [B][N][N] complex128 matrix, H[b][r][q] = <r|H(b)|q> (small Hilbert
-        spaces: the dense eigensolver path)."""
+        """H(b) of every point as a dense [B][N][N] matrix, H[b][r][q] = <r|H(b)|q> (small Hilbert spaces: the
+        dense eigensolver path): float64 for layouts without charge modes, else complex128."""
         ops = self.ops
-        H = torch.empty((self.B, ops.N, ops.N), dtype=torch.complex128, device=self.device)
+        # without charge modes H is real symmetric in the Fock basis (a_t D_t + h.c. = 2 Re(a_t D_t))
+        real = not any((not h) and d > 1 for h, d in zip(ops.harm, ops.dims))
+        H = torch.empty((self.B, ops.N, ops.N), dtype=torch.float64 if real else torch.complex128, device=self.device)
         pot = ops.potential_struct(self.a, self.g, ops.etab)
         ops.kern.hamiltonian_dense(ops.sp, ops.displacement_tables_generic(), pot, self.diag, H)
         return H

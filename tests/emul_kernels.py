@@ -638,7 +638,20 @@ class EmulKernels:
         """Contract of sqc_hamiltonian_dense: the whole H of every point, complex128, from per-mode tables."""
         B, N, _ = out.shape
         S = torch.arange(N, dtype=torch.int32).reshape(1, N)
-        self.lowblock_assemble_generic(sp, S, Dt, pot, d, torch.zeros(B, dtype=torch.float64), 1.0, out)
+        if out.dtype == torch.float64:
+            tmp = torch.empty(out.shape, dtype=torch.complex128)
+            self.lowblock_assemble_generic(sp, S, Dt, pot, d, torch.zeros(B, dtype=torch.float64), 1.0, tmp)
+            out.copy_(tmp.real)
+        else:
+            self.lowblock_assemble_generic(sp, S, Dt, pot, d, torch.zeros(B, dtype=torch.float64), 1.0, out)
+
+    def syev(self, A, w, Zt):
+        """Contract of sqc_syev."""
+        for b in range(A.shape[0]):
+            a = A[b].numpy()
+            ev, vec = np.linalg.eigh(0.5 * (a + a.T))
+            w[b] = torch.from_numpy(ev)
+            Zt[b] = torch.from_numpy(np.ascontiguousarray(vec.T))
 
     def _lowblock_assemble_real(self, sp, S, Dt, pot, d, sigma, unit, out):
         """H_r = U^H H_c U on the real index set (each real state is a combination of charges +-n)."""

@@ -118,6 +118,32 @@ def test_heev(kern, ld, sizes):
         assert np.abs(a @ Z - Z * w[b, :nb].numpy()[None, :]).max() < 2e-13 * scale * np.sqrt(nb)
 
 
+@pytest.mark.parametrize('n', [2, 7, 50, 100, 111, 112])
+def test_syev(kern, n):
+    """Batched real symmetric Jacobi eigensolver (sqc_syev) against torch.linalg.eigh in float64: eigenvalues,
+    residuals, orthonormality; includes a matrix with degenerate eigenvalues and a diagonal one."""
+    B = 5
+    gen = torch.Generator().manual_seed(100 + n)
+    A = torch.randn((B, n, n), dtype=torch.float64, generator=gen)
+    A = A + A.transpose(1, 2)
+    A[1] = torch.diag(torch.arange(n, dtype=torch.float64) - 3.0)                      # already diagonal
+    q, _ = torch.linalg.qr(torch.randn((n, n), dtype=torch.float64, generator=gen))
+    A[2] = q @ torch.diag(torch.tensor([1.0, 1.0] + [float(i // 2) for i in range(2, n)], dtype=torch.float64)[:n]) @ q.T
+    A[3] = A[3] * 1e9                                                                  # circuit-like scale (rad/s)
+    Ad = A.cuda().contiguous()
+    w = torch.empty((B, n), dtype=torch.float64, device='cuda')
+    Zt = torch.empty((B, n, n), dtype=torch.float64, device='cuda')
+    kern.syev(Ad, w, Zt)
+    ref = torch.linalg.eigvalsh(0.5 * (A + A.transpose(1, 2)))
+    for b in range(B):
+        scale = float(ref[b].abs().max())
+        assert float((w[b].cpu() - ref[b]).abs().max()) < 1e-12 * scale
+        Z = Zt[b].cpu()
+        assert float((Z @ Z.T - torch.eye(n, dtype=torch.float64)).abs().max()) < 1e-12
+        As = 0.5 * (A[b] + A[b].T)
+        assert float((Z @ As - w[b].cpu()[:, None] * Z).abs().max()) < 1e-11 * scale
+
+
 @pytest.mark.parametrize('m', [2, 9, 25, 100, 101, 112])
 def test_xbasis(kern, m):
     V, lam = kern.xbasis(m)
@@ -1032,7 +1058,8 @@ def test_potential_elements_matches_torch_reference(kern, dims, harm, shifts, nv
     ([6, 5, 5], [1, 0, 0], [[0, 1, 0], [0, 0, 1]]),
     ([5, 4, 3, 3], [1, 1, 0, 0], [[0, 0, 1, 0], [0, 0, 1, -1], [0, 0, 0, 1]]),
     ([7, 1, 5], [1, 1, 0], [[0, 0, 1]]),
-    ([12, 9], [1, 0], [[0, 1], [0, -1]])])
+    ([12, 9], [1, 0], [[0, 1], [0, -1]]),
+    ([9, 6], [1, 1], [[0, 0], [0, 0]])])
 def test_lowblock_assemble_generic_matches_dense_operator(kern, dims, harm, shifts):
     """(H_SS - sigma) / unit from the per-mode displacement tables (sqc_lowblock_assemble_generic) against the dense
     matrix of the same operator -- H applied to the identity by the transform / potential kernels -- restricted to
@@ -1098,6 +1125,12 @@ def test_lowblock_assemble_generic_matches_dense_operator(kern, dims, harm, shif
     Hd = torch.empty((B, N, N), dtype=torch.complex128, device='cuda')
     kern.hamiltonian_dense(sp, Dt, pot, d, Hd)
     assert relerr(Hd.cpu(), H.cpu()) < 1e-13
+    if all(harm):
+        # no charge modes: H is real symmetric in the Fock basis, real output for sqc_syev
+        assert float(H.imag.abs().max()) < 1e-13 * float(H.abs().max())
+        Hr = torch.empty((B, N, N), dtype=torch.float64, device='cuda')
+        kern.hamiltonian_dense(sp, Dt, pot, d, Hr)
+        assert relerr(Hr.cpu().to(torch.complex128), H.cpu()) < 1e-13
     # the emulated contract gives the same block
     pot._keep = (a.cpu(), g.cpu(), etab.cpu(), None)
     oute = torch.zeros((B, ns, ns), dtype=torch.complex64)
