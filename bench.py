@@ -551,8 +551,7 @@ def our_arm(args):
     from sqcircuit_b200.sharding import gather_to_root
     sq.set_device(dev)
     kern = TimedKernels(Kernels(dev))
-    if DEBUG:
-        _debug_level_times()
+    _debug_level_times()
     if args.no_graphs:
         kern._k.use_graphs = False
 
@@ -564,6 +563,18 @@ def our_arm(args):
                      real=(False if args.complex else None))
     if args.strides:
         solver_kw['coarse_stride'] = tuple(int(x) for x in args.strides.split(','))
+
+    host_out = {}
+    stage_wall = []
+
+    def to_host(t):
+        """D2H of a step's result into pinned host memory (the read of the result the e2e contract asks for)."""
+        key = (tuple(t.shape), t.dtype)
+        if key not in host_out:
+            host_out[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        host_out[key].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host_out[key]
 
     def make_step(prm_host, n_total):
         """One pass of the hot path over this rank's points.  e2e=True: host parameter array in, host
@@ -579,11 +590,12 @@ def our_arm(args):
                 ef, grads, res = wl.step(prm, torch)
                 if world > 1:
                     gather_to_root(ef.contiguous(), n_total)
-                return (ef.cpu() if e2e else ef), grads, res
+                return (to_host(ef) if e2e else ef), grads, res
             if DEBUG:
                 torch.cuda.synchronize()
-                t0_ = time.perf_counter()
+            t0_ = time.perf_counter()
             res = cr.sweep_diag(N_EIG, **wl.sweep_args(prm), **solver_kw)
+            ta_ = time.perf_counter()
             if DEBUG:
                 torch.cuda.synchronize()
                 t1_ = time.perf_counter()
@@ -596,7 +608,14 @@ def our_arm(args):
                 # the only collective of the path: final gather of the per-point results to rank 0
                 gather_to_root(res.efreqs.contiguous(), n_total)
             if e2e:
-                return res.efreqs.cpu(), rates, res
+                tb_ = time.perf_counter()
+                out = to_host(res.efreqs)
+                # host wall clock of the stages of this step: sweep_diag (returns once its last level has been
+                # judged on the host), decay rates (every channel ends with a host read), final D2H
+                stage_wall.append([round(1e3 * (ta_ - t0_), 1), round(1e3 * (tb_ - ta_), 1),
+                                   round(1e3 * (time.perf_counter() - tb_), 1),
+                                   [round(x, 1) for x in _LEVEL_MS[-4:]]])
+                return out, rates, res
             return res.efreqs, rates, res
         return step
 
@@ -606,6 +625,7 @@ def our_arm(args):
         torch.cuda.synchronize()
 
     sampler = None
+    step_wall = []         # host wall time of every step of the last timed region (an e2e step ends with a host read)
 
     def timed(step, nsteps, e2e):
         """K steps bracketed by barrier + synchronize; returns (max over ranks of the device time, this
@@ -615,15 +635,18 @@ def our_arm(args):
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         last = None
+        step_wall.clear()
         for _ in range(nsteps):
+            tw = time.perf_counter()
             last = None          # a sweep loop keeps the newest result only (two resident results double the peak)
             if DEBUG:
                 torch.cuda.synchronize()
                 ts = time.perf_counter()
-                _LEVEL_MS.clear()
+            _LEVEL_MS.clear()
             last = step(e2e)
             if sampler is not None:
                 sampler.sample()
+            step_wall.append(round(1e3 * (time.perf_counter() - tw), 1))
             if DEBUG:
                 torch.cuda.synchronize()
                 st_ = torch.cuda.memory_stats()
@@ -673,7 +696,12 @@ def our_arm(args):
     iters = last[2].iterations
     del last                      # (its GB of eigenvectors would stay resident during the next region)
     step(True)                    # one untimed pass of the end-to-end path (pinned-memory copies, host reads)
+    ms0_ = torch.cuda.memory_stats()
     ms_e2e, own_e2e, last_e2e = timed(step, args.steps, True)
+    ms1_ = torch.cuda.memory_stats()
+    alloc_events = {k: int(ms1_.get(k, 0) - ms0_.get(k, 0)) for k in ('num_device_alloc', 'num_device_free',
+                                                                       'num_alloc_retries', 'num_ooms')}
+    e2e_step_wall = list(step_wall)
     del last_e2e
     clocks = sampler.stop() if rank == 0 else None
     rank_ms = per_rank(own_dev / args.steps)
@@ -830,7 +858,8 @@ def our_arm(args):
                    'parallelism': f'every one of the {world} GPU(s) sweeps the same range with {points} points '
                                   '(offset by a fraction of the spacing): identical work per GPU, final NCCL gather'},
         'e2e': {'value': e2e_value, 'unit': 'diag/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': ms_e2e / args.steps},
+                'ms_per_step': ms_e2e / args.steps, 'step_wall_ms': e2e_step_wall, 'allocator_events': alloc_events,
+                'stage_wall_ms(sweep_diag, rates, d2h)': stage_wall[-args.steps:]},
         'gpu_launches': int(launches),
         'per_rank': {'ms_per_step': [round(x, 2) for x in rank_ms], 'iterations': [int(x) for x in rank_iters]},
         'strong': strong,
@@ -895,9 +924,6 @@ def _install_hx_counter():
 
 
 def main():
-    if os.environ.get('SQC_BENCH_NOGC'):
-        import gc
-        gc.disable()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=3)

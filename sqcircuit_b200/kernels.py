@@ -62,7 +62,8 @@ class Kernels:
             raise _lib.SqcLibraryError('sqcircuit_b200 kernels need a CUDA device')
         self._gram_work = None
         self._ws = {}
-        self._pin, self._pin_off = None, 0
+        self._pin, self._pin_off, self._pin_down = None, 0, None
+        self._free_ref, self._free_calls = None, 0
         self.graph_launches = 0        # kernel launches replayed through CUDA graphs (not seen by the C counter)
         self.use_graphs = True         # solver iterations are captured into CUDA graphs (see eigensolver.py)
         self._capture_stream = None
@@ -109,18 +110,43 @@ class Kernels:
         self._pin_off = off + n
         return out
 
+    def download(self, t):
+        """Small device tensor -> numpy array through pinned staging (the counterpart of ``upload``: a pageable
+        ``.cpu()`` / ``.item()`` is the same synchronous driver copy).  Blocks until the data has arrived."""
+        t = t.detach()
+        if not t.is_contiguous():
+            t = t.contiguous()
+        n = t.numel() * t.element_size()
+        if n == 0 or n > self._PIN_BYTES // 4:
+            return t.cpu().numpy()
+        if self._pin_down is None:
+            self._pin_down = torch.empty(self._PIN_BYTES // 4, dtype=torch.uint8).pin_memory()
+        stage = self._pin_down[:n].view(t.dtype).view(t.shape)
+        stage.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return stage.numpy().copy()
+
     def release_workspace(self):
         self._ws = {}
 
     def free_bytes(self):
         """Device bytes a new batched solve may claim: free device memory, the caching allocator's unused
-        reserve, and the persistent workspace (the next solve reuses it)."""
-        free, _ = torch.cuda.mem_get_info(self.dev)
-        cached = torch.cuda.memory_reserved(self.dev) - torch.cuda.memory_allocated(self.dev)
-        ws = sum(int(b.numel()) for b in self._ws.values() if b is not None)
-        return int(free) + int(cached) + ws
+        reserve, and the persistent workspace (the next solve reuses it).
 
-    # ---- (1) operators ---------------------------------------------------
+        cudaMemGetInfo is asked once and then only every 64th call: in between, the driver's free figure is
+        tracked through the caching allocator's own reserve counter (this process is the device's only tenant on
+        the path).  The driver call was measured to block for up to 96 ms now and then when issued between the
+        levels of a sweep (profiles/r02_step_time_noise.txt)."""
+        reserved = torch.cuda.memory_reserved(self.dev)
+        if self._free_ref is None or self._free_calls % 64 == 0:
+            free, _ = torch.cuda.mem_get_info(self.dev)
+            self._free_ref = (int(free), int(reserved))
+        self._free_calls += 1
+        free = self._free_ref[0] - (int(reserved) - self._free_ref[1])
+        cached = reserved - torch.cuda.memory_allocated(self.dev)
+        ws = sum(int(b.numel()) for b in self._ws.values() if b is not None)
+        return max(0, int(free)) + int(cached) + ws
+
     def xbasis(self, m):
         V = torch.empty((m, m), dtype=torch.float64, device=self.dev)
         lam = torch.empty((m,), dtype=torch.float64, device=self.dev)

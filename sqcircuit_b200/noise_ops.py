@@ -51,7 +51,7 @@ class SweepNoise:
     def _gram2(self, X, Y):
         out = torch.empty((self.B, 2, 2), dtype=torch.complex128, device=self.dev)
         self.kern.gram(BlockView(X), BlockView(Y), out)
-        return out.cpu().numpy()
+        return self.kern.download(out)
 
     def _phases(self, b_id, scale=1.0):
         return np.exp(1j * scale * self.ops.ext_flux(self.hop.loop_vals, b_id))
@@ -95,7 +95,7 @@ class SweepNoise:
                                    ops.etab if etab is None else etab, shift, None)
         out = torch.empty((self.B, 2, 2), dtype=torch.complex128, device=self.dev)
         self.kern.potential_elements(ops.sp, pot, BlockView(Z), out)      # one read of the pair, nothing written
-        return out.cpu().numpy()
+        return self.kern.download(out)
 
     def _junction_elements(self, states, kind, w_id, b_id, weight=1.0):
         """Matrix of the cos / sin / sin_half operator of one junction (circuit.py:1809-1825) on the pair."""
@@ -200,7 +200,7 @@ class SweepNoise:
 
     def dec_rate(self, dec_type, states, total=True):
         cr, ops, t = self.cr, self.ops, self.ops.topo
-        w = self.evals.cpu().numpy()
+        w = self.kern.download(self.evals)
         omega = np.abs(w[:, states[1]] - w[:, states[0]])
         X = self._pair(states)
         alpha = unt.hbar * omega / (unt.k_B * ENV['T'])

@@ -484,7 +484,7 @@ class HamiltonianOperator:
             S = torch.topk(diag, ns, dim=1, largest=False).indices
             key = torch.sort((S % inner) * m + S // inner, dim=1).values
             S = ((key % m) * inner + key // m).to(torch.int32).contiguous()
-            band = self._band_layout((key // m).cpu().numpy(), S, nslot)
+            band = self._band_layout(kern.download(key // m), S, nslot)
             if band is None:
                 ns = 160          # blocks too large for the banded kernels: dense 160 x 160 instead
         if band is None:
@@ -533,7 +533,7 @@ class HamiltonianOperator:
                     stride = int(np.prod(ops.dims[i + 1:]))
                     key = torch.sort(((low[:, :nb] // stride) % ops.dims[i]) * ops.N + low[:, :nb], dim=1).values
                     Sb = (key % ops.N).to(torch.int32).contiguous()
-                    lay = self._band_layout((key // ops.N).cpu().numpy(), Sb, nslot)
+                    lay = self._band_layout(kern.download(key // ops.N), Sb, nslot)
                     if lay is not None and (best is None or lay[2] < best[0][2]):
                         best = (lay, Sb)
                 if best is not None:
@@ -582,7 +582,8 @@ class RealHamiltonianOperator(HamiltonianOperator):
         if self.diag.shape[0] == 1:
             d2 = dr[0, :ops.N].reshape(m, inner)
             dh, dc = d2[:, 0] - d2[0, 0], d2[0, :]
-            if float((d2 - dh[:, None] - dc[None, :]).abs().max()) <= 4e-16 * float(d2.abs().max()):
+            chk = ops.kern.download(torch.stack([(d2 - dh[:, None] - dc[None, :]).abs().max(), d2.abs().max()]))
+            if float(chk[0]) <= 4e-16 * float(chk[1]):
                 self.diag_sep = torch.cat([dh, dc]).contiguous()
 
     def apply(self, X: BlockView, Y: BlockView):
@@ -639,7 +640,7 @@ class RealHamiltonianOperator(HamiltonianOperator):
         """Index set (device int32 [1][ns']), block offsets, block count, largest block, address-sorting
         permutation.  Host work, done once per circuit and size (the LC diagonal does not depend on the
         sweep point at zero gate charge)."""
-        d = self.diag_c[0].reshape(m, inner).cpu().numpy()
+        d = self.ops.kern.download(self.diag_c[0].reshape(m, inner))
         units = sorted(((d[i, nc + n], n, i) for i in range(m) for n in range(nc + 1)))
         chosen, cnt = [], 0
         for e, n, i in units:

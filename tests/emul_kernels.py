@@ -467,6 +467,9 @@ class EmulKernels:
             setattr(st, k, v)
         return st
 
+    def download(self, t):
+        return t.detach().cpu().numpy().copy()
+
     def upload(self, arr, dtype=None):
         t = torch.as_tensor(np.array(arr))
         return t.to(dtype) if dtype is not None else t
