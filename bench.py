@@ -480,6 +480,7 @@ class TimedKernels:
         self.enabled = False
         self.only = None       # restrict the instrumentation to these entry points
         self.records = []      # (name, start_event, stop_event, meta)
+        self._pool = []        # pre-created event pairs
         for name in self.TIMED:
             setattr(self, name, self._wrap(name))
 
@@ -499,13 +500,26 @@ class TimedKernels:
         def call(*a, **kw):
             if not self.enabled or (self.only is not None and name not in self.only):
                 return fn(*a, **kw)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if self._pool:
+                s, e = self._pool.pop()
+            else:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             r = fn(*a, **kw)
             e.record()
             self.records.append((name, s, e))
             return r
         return call
+
+    def reserve(self, n):
+        """Create (and record once, so that the driver objects exist) n event pairs outside the timed region:
+        cudaEventCreate inside it would be charged to `value`."""
+        torch = self._torch
+        while len(self._pool) < n:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            e.record()
+            self._pool.append((s, e))
 
     def summary(self):
         tot = {}
@@ -684,15 +698,22 @@ def our_arm(args):
     # ~900 C-ABI calls of a step costs ~60 ms of host time per step (measured), which would be
     # charged to `value`.  The full per-kernel breakdown comes from one extra, untimed step below.
     kern.only = {'hx_fused', 'hx_fused_real', 'hx_generic', 'mode_transform', 'potential_apply', 'heev', 'syev'}
+    kern.reserve(512 * (max(args.steps, 1) + 1))
     kern.enabled = True
+    # one more untimed step in exactly the mode of the timed region (H.X outside the iteration's CUDA graphs, which
+    # are then captured in two pieces): its first-time costs showed up in `value` on a fresh box otherwise
+    step(False)
+    torch.cuda.synchronize()
+    kern.records = []
+    for key_ in list(HX_COUNTER):
+        HX_COUNTER[key_] = 0
     l0 = kern.launch_count()
     ms_dev, own_dev, last = timed(step, args.steps, False)
     launches = kern.launch_count() - l0
     kern.enabled = False
     hx_kernel = kern.summary()
-    nvec = HX_COUNTER.get('vectors', 0) + (int(HX_COUNTER['vectors_dev'].item()) if 'vectors_dev' in HX_COUNTER else 0)
-    nvec_real = HX_COUNTER.get('real_vectors', 0) + (int(HX_COUNTER['real_vectors_dev'].item())
-                                                      if 'real_vectors_dev' in HX_COUNTER else 0)
+    nvec = int(HX_COUNTER.get('vectors', 0)) + int(HX_COUNTER.get('vectors_dev', 0))
+    nvec_real = int(HX_COUNTER.get('real_vectors', 0)) + int(HX_COUNTER.get('real_vectors_dev', 0))
     iters = last[2].iterations
     del last                      # (its GB of eigenvectors would stay resident during the next region)
     step(True)                    # one untimed pass of the end-to-end path (pinned-memory copies, host reads)
