@@ -1136,3 +1136,27 @@ def test_lowblock_assemble_generic_matches_dense_operator(kern, dims, harm, shif
     oute = torch.zeros((B, ns, ns), dtype=torch.complex64)
     EmulKernels().lowblock_assemble_generic(sp, S.cpu(), Dt.cpu(), pot, d.cpu(), sigma.cpu(), unit, oute)
     assert relerr(out.cpu().to(torch.complex128), oute.to(torch.complex128)) < 1e-6
+
+
+def test_pinned_staging_upload_download_and_free_memory_tracking(kern):
+    """Kernels.upload / download (pinned staging instead of pageable driver copies) round-trip every dtype the
+    host code sends, survive the wrap-around of the staging arena, fall back to a plain copy for large arrays;
+    free_bytes follows the allocator between its rare cudaMemGetInfo calls."""
+    rng = np.random.default_rng(5)
+    for arr in (rng.standard_normal((3, 7)), rng.integers(0, 1000, 33), rng.standard_normal(5) + 1j * rng.standard_normal(5),
+                np.arange(12, dtype=np.int32).reshape(3, 4)[:, ::2], np.broadcast_to(np.arange(4.0), (3, 4)), np.zeros((0,))):
+        t = kern.upload(arr)
+        assert t.device.type == 'cuda' and tuple(t.shape) == arr.shape
+        assert np.array_equal(kern.download(t), np.asarray(arr))
+    assert kern.upload(np.arange(5), torch.float64).dtype == torch.float64
+    big = rng.standard_normal(kern._PIN_BYTES // 8)                      # > a quarter of the arena: plain copy
+    assert np.array_equal(kern.download(kern.upload(big)), big)
+    chunk = rng.standard_normal(kern._PIN_BYTES // 40)                   # forces several wrap-arounds
+    outs = [kern.upload(chunk + i) for i in range(30)]
+    for i, t in enumerate(outs):
+        assert np.array_equal(t.cpu().numpy(), chunk + i)
+    f0 = kern.free_bytes()
+    hold = torch.empty(1 << 30, dtype=torch.uint8, device='cuda')
+    f1 = kern.free_bytes()
+    assert f1 <= f0 and f0 - f1 <= (1 << 30) + (64 << 20)                # the new GiB is held; the rest is slack
+    del hold
