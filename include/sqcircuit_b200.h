@@ -76,7 +76,7 @@ typedef struct {
 } sqc_potential_t;
 
 /* ---- library ---------------------------------------------------------- */
-int         sqc_abi_version(void);
+int         sqc_abi_version(void);   /* 4 */
 const char* sqc_error_string(int code);
 /* number of kernels launched by this library since load (bench.py gpu_launches) */
 int64_t     sqc_launch_count(void);

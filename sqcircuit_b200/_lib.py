@@ -147,7 +147,7 @@ def load():
             raise SqcLibraryError(f'{LIB_PATH} does not export {name}') from e
         fn.restype = res
         fn.argtypes = args
-    if lib.sqc_abi_version() != 3:
+    if lib.sqc_abi_version() != 4:
         raise SqcLibraryError('sqcircuit_b200 ABI version mismatch')
     built, here = lib.sqc_source_hash().decode(), source_hash()
     if built != here:

@@ -1032,7 +1032,7 @@ extern "C" int sqc_diag_mul(sqc_block_t X, sqc_block_t Y, const double* diag, in
     return 0;
 }
 
-extern "C" int sqc_abi_version(void) { return 3; }
+extern "C" int sqc_abi_version(void) { return 4; }
 extern "C" int64_t sqc_launch_count(void) { return g_sqc_launches; }
 extern "C" const char* sqc_error_string(int code) {
     if (code == 0) return "ok";

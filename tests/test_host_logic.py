@@ -26,7 +26,7 @@ def test_abi_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().sqc_abi_version() == 3
+    assert _lib.load().sqc_abi_version() == 4
     assert _lib.load().sqc_error_string(-1).decode().startswith('sqcircuit_b200')
 
 
