@@ -33,6 +33,12 @@
 #define HXR_MARK(i) do {} while (0)
 #endif
 
+#ifndef HXR_LAG_SEP        // (tuning knobs of the epilogue pipeline, tools/hxr_variants.sh; measured at the bench
+#define HXR_LAG_SEP 2      //  geometry, 12288 vectors: 4 -> 1.994 ms, 3 -> 1.963, 2 -> 1.907, 1 -> 1.930, no pipeline 2.007)
+#endif
+#ifndef HXR_PIPE
+#define HXR_PIPE 1
+#endif
 #define HXR_MAXT 4
 #define HXR_MAX_WARPS 28    // warps per CTA (registers: 65536 / (28 * 32) = 73 per thread)
 #define HXR_MAX_TEAMS 4
@@ -97,8 +103,8 @@ __device__ __forceinline__ void hxr_pass(const double* __restrict__ sV, double* 
                                          const double* __restrict__ fd, const double* __restrict__ sDh) {
     constexpr int KP = 4 * KS, NRT = (KS + 1) / 2;
     constexpr int VLD = (KP % 8 == 4) ? KP : KP + 4;
-    constexpr int LAG = SEP ? 4 : 2;      // row tiles in flight (registers: 2 resp. 4 doubles per tile)
-    constexpr bool PIPE = KS >= NRT + LAG;
+    constexpr int LAG = SEP ? HXR_LAG_SEP : 2;      // row tiles in flight (registers: 2 resp. 4 doubles per tile)
+    constexpr bool PIPE = HXR_PIPE && KS >= NRT + LAG;
     const int pp = gm.pp, inner = gm.inner;
     const int hcnt = par ? gm.ho : gm.he;
     double acc[NRT][2];
@@ -281,7 +287,7 @@ hx_real_kernel(HxrGeom gm, const double* __restrict__ Ve, const double* __restri
         }
         const double* xv = reinterpret_cast<const double*>(blk_vec(X, b, v, gm.vstride / 2));
         double* yv = reinterpret_cast<double*>(blk_vec(Y, b, v, gm.vstride / 2));
-        mbar_wait(bar, phase);
+        mbar_wait(bar, phase);     // (letting warp 0 alone poll, the others sleeping in a team barrier: 2 % slower)
         phase ^= 1;
         HXR_MARK(1);
 
