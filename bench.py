@@ -898,10 +898,13 @@ def our_arm(args):
 NCU_HX_TRAFFIC = {
     ('zeropi4096', 'complex'): (1.0855, 'ncu dram__bytes_read+write / algorithmic = 1.0855 '
                                         '(profiles/r01_ncu_full_v28_hx_fused.txt)'),
-    ('zeropi4096', 'real'): (0.87, 'ncu dram__bytes_read+write / algorithmic = 0.87: 247 MB read + 335 MB written by one '
-                                   'launch on 4140 vectors of 161.6 kB inside the bench -- part of the reads hit L2, the '
-                                   'block was written by the preceding kernel (profiles/r02_ncu_full_hx_real_final.txt; '
-                                   '0.98 on a cold 12288-vector launch, r02_ncu_full_hx_real_v1.txt)'),
+    ('zeropi4096', 'real'): (1.28, 'ncu dram__bytes_read+write / algorithmic = 1.28 on the launches that carry most of a '
+                                   "step's bytes: 2.27 GB read + 2.82 GB written by one launch on 24576 vectors of 161.6 kB "
+                                   '(largest continuation level, profiles/r02_ncu_full_hx_real_lag2.txt; the excess over '
+                                   'the 1.99 GB of results is write-back traffic the kernel does not ask for by count -- '
+                                   'presumably its 268 B of register-spill stores per thread); 0.87 on a 4140-vector '
+                                   'launch whose input still sits in L2 (r02_ncu_full_hx_real_final.txt), 0.98 on a cold '
+                                   '12288-vector launch (r02_ncu_full_hx_real_v1.txt)'),
     ('trt1e5', 'complex'): (1.09, 'ncu dram__bytes_read+write / algorithmic = 1.09: 1.459 GB + 1.171 GB for 768 vectors '
                                   'of 3.136 MB, halo columns read twice (profiles/r02_hx_generic.txt)'),
     ('discovery512', 'complex'): (0.99, 'ncu dram__bytes_read+write / algorithmic = 0.99: 0.800 GB + 0.776 GB for 6144 '
