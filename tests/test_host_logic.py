@@ -409,3 +409,39 @@ def test_warm_start_from_nearly_dependent_neighbour_blocks_converges():
     assert not raw.converged and float(raw.resmax.max()) > 1e-7          # the failure mode this guards against
     res = solve_davidson_gen(K, h, 1, ops.N, 10, h.diag, lowblock_ns=512, x0=x0, maxit=30)
     assert res.converged and res.iterations < 25 and float(res.resmax.max()) <= 1e-9
+
+
+def test_generic_low_block_is_block_tridiagonal_in_one_charge_mode():
+    """Two-level preconditioner of a layout with several charge modes (transmon - resonator - SQUID transmon): the
+    index set ordered by the value of ONE charge mode makes H_SS block tridiagonal (every junction term shifts a
+    charge by at most one), which is what the banded factorisation relies on.  Checks the assembled block against
+    the block offsets handed to sqc_lowband_factor, per slot (the gate charge, hence the index set, differs per
+    point)."""
+    from sqcircuit_b200.operators import HamiltonianOperator
+    K = EmulKernels()
+    cr, lp, oc, ol = cs.trt_squid(K)
+    cr.set_trunc_nums([4, 12, 12])
+    ops = cr._operators()
+    m1 = sorted(cr.charge_islands)[0]
+    lv = 2 * np.pi * np.array([[0.1], [0.33]])
+    ng = np.zeros((2, ops.M))
+    ng[:, m1] = [0.05, 0.4]
+    hop = HamiltonianOperator(ops, lv, ng)
+    seen = {}
+    factor = K.lowband_factor
+
+    def spy(A, off, nblk, nbmax):
+        seen['A'], seen['off'], seen['nblk'], seen['nbmax'] = A.clone(), off.clone(), nblk.clone(), nbmax
+        return factor(A, off, nblk, nbmax)
+    K.lowband_factor = spy
+    sigma = torch.full((2,), -1e12, dtype=torch.float64)
+    lb = hop.build_lowblock(sigma, 512, group=1)
+    assert lb['band'] is not None and lb['ns'] > 160 and seen['nbmax'] <= 64
+    for b in range(2):
+        A = seen['A'][b].numpy()
+        off = seen['off'][b].numpy()[:int(seen['nblk'][b]) + 1]
+        blk = np.searchsorted(off, np.arange(lb['ns']), side='right') - 1
+        far = np.abs(blk[:, None] - blk[None, :]) > 1
+        assert np.abs(A[far]).max() == 0.0 and np.abs(A[~far]).max() > 0.0
+        assert len(set(lb['S'][b].tolist())) == lb['ns']
+    assert not torch.equal(lb['S'][0], lb['S'][1])          # per-point index sets (different gate charge)
